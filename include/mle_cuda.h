@@ -1,0 +1,143 @@
+/* mle_cuda.h -- C ABI of libmle_cuda, the B200 (sm_100a) sampling engine behind MultilevelEstimators.jl.
+ *
+ * The library replaces ONE path of the reference: the per-index, per-shift sample batch that
+ * `parallel_sample!` drives (src/sample.jl:39-56 MC, :79-102 QMC) together with the statistics that
+ * `mean/var/varest` later recompute from the stored samples (src/methods.jl:44-68, :282).  Everything else
+ * (index sets, the adaptive loop, History) stays host code.  All `file:line` citations are relative to the
+ * reference repository root.
+ *
+ * Conventions
+ *   - every function returns an `int` status (MLE_OK == 0, negative = error); no exception crosses the boundary;
+ *     `mle_last_error(ctx)` gives the message.  Argument errors correspond to the reference's `ArgumentError`
+ *     (src/check_input.jl:9-25), CUDA / NCCL failures to an `ErrorException`.
+ *   - all pointers are caller-owned HOST memory unless the name says `_dev`; the library never returns memory
+ *     it allocated.  Handles are opaque and freed by the matching `*_destroy`.
+ *   - arrays are dense, first index fastest (Julia / column-major order) and documented as [fastest x ... x slowest].
+ *   - one context per process and GPU; calls on one context are blocking and not re-entrant
+ *     (the reference has a single caller too: `sample!` <- `update_samples` <- `_run`, src/sample.jl:8-34).
+ *   - there is NO CPU fallback: every entry point that computes fails with MLE_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MLE_CUDA_H
+#define MLE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLE_ABI_VERSION 1
+
+typedef struct mle_ctx_s *mle_ctx;
+typedef struct mle_lattice_s *mle_lattice;
+typedef struct mle_dists_s *mle_dists;
+typedef struct mle_model_s *mle_model;
+
+enum mle_status {
+    MLE_OK = 0,
+    MLE_ERR_ARG = -1,    /* invalid argument (ArgumentError in the reference)                              */
+    MLE_ERR_CUDA = -2,   /* CUDA runtime / no usable device / kernel failure                               */
+    MLE_ERR_RANGE = -3,  /* point number beyond the lattice size n: the reference returns rand(s) there
+                            (src/lattice.jl:166,175), which cannot be reproduced -- refused instead          */
+    MLE_ERR_STATE = -4,  /* model not fully configured (e.g. KL basis missing for the requested level)      */
+    MLE_ERR_NOMEM = -5
+};
+
+/* Distribution kinds of src/distribution.jl and their parameters p[0..3]:
+ *   MLE_UNIFORM      {a, b}            transform = a + (b - a) x                               (:84)
+ *   MLE_NORMAL       {mu, sigma}       transform = mu + sigma * sqrt(2) erfinv(2x - 1)          (:112, :151)
+ *   MLE_TRUNCNORMAL  {mu, sigma, a, b} transform = mu + sigma * Phi^-1(Phi(al) + (Phi(be)-Phi(al)) x)   (:145-149)
+ *   MLE_WEIBULL      {k, lambda}       transform = lambda * (-log(1 - x))^(1/k)                 (:182)          */
+enum mle_dist_kind { MLE_UNIFORM = 0, MLE_NORMAL = 1, MLE_TRUNCNORMAL = 2, MLE_WEIBULL = 3 };
+typedef struct mle_dist {
+    int32_t kind;
+    int32_t reserved;
+    double p[4];
+} mle_dist;
+
+/* ---- context -------------------------------------------------------------------------------------------------- */
+int mle_abi_version(void);
+/* Create a context on CUDA device `device` (ordinal as seen by this process).  Replaces nothing in the reference:
+ * it is where the `pmap` worker pool of src/sample.jl:43-45 / :89-91 turns into one GPU. */
+int mle_init(int device, mle_ctx *ctx);
+int mle_destroy(mle_ctx ctx);
+/* Message of the last failing call on `ctx` (ctx == NULL: last failing mle_init of this thread). */
+const char *mle_last_error(mle_ctx ctx);
+/* SM count, HBM bytes and compute capability (major*10 + minor) of the context's device. */
+int mle_device_info(mle_ctx ctx, int *sm_count, size_t *hbm_bytes, int *cc);
+/* The CUDA stream (cudaStream_t) all work of this context is issued on, for callers that time with events. */
+int mle_stream(mle_ctx ctx, void **stream);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+int mle_launch_count(mle_ctx ctx, uint64_t *count);
+
+/* ---- stage 1: rank-1 lattice rule  (LatticeRule32{s}, src/lattice.jl:11-14, :48-50, :88-90) -------------------- */
+/* The published generating vectors the reference ships in src/generating_vectors/ ("K_3600_32", "CKN_250_20"),
+ * embedded in the library.  `*z` points to static storage. */
+int mle_genvec(const char *name, const uint32_t **z, int *len);
+/* LatticeRule32(z, s, n): first `s` entries of `z`, at most `nmax` points (reference default typemax(UInt32)).
+ * z == NULL selects the default rule LatticeRule32(s) = first s entries of K_3600_32 (src/lattice.jl:88, s <= 3600). */
+int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_t nmax, mle_lattice *lat);
+int mle_lattice_destroy(mle_ctx ctx, mle_lattice lat);
+
+/* ---- stage 2: distributions  (Vector{<:AbstractDistribution}, src/estimator.jl:116, src/sample.jl:42,88) -------- */
+int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists *dists);
+int mle_dists_destroy(mle_ctx ctx, mle_dists dists);
+
+/* ---- stage 3: device model registry (replaces the Julia closure `sample_function(index, xi)`,
+ *      src/estimator.jl:115, called at src/sample.jl:42,88) ------------------------------------------------------
+ *   "expsum"       Q_l = exp(sum_{j<m_l} a_j xi_j), m_l = min(m, m0 2^l); params = {m0, a_1..a_m}; 1 QoI; ndims = 1
+ *   "problem18"    the reference's own analytic test function, test/regression.jl:17-46 (ndims = 1) and
+ *                  :69-103 (ndims = 2) with the multi-index difference of src/index.jl:49-58; 13 QoI; no params
+ *   "lognormal1d"  -(a u')' = 1 on (0,1), u(0)=u(1)=0, log a = KL expansion; level l has n0 2^l cells; params = {n0};
+ *                  structure of docs/src/example.md:106-128 (coarse field = even nodes of the fine field, QoI = u(1/2));
+ *                  needs mle_model_set_basis for every level used; 1 QoI; ndims = 1
+ * Every model returns (dQ, Qf) per sample exactly like the reference's sample functions. */
+int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *model);
+/* KL basis of one level: phi[cols x rows] = row-major [rows = nodes][cols = KL terms], log a(node i) = sum_k phi[i][k] xi_k */
+int mle_model_set_basis(mle_ctx ctx, mle_model model, int level, int rows, int cols, const double *phi);
+int mle_model_nqoi(mle_model model, int *nqoi);
+int mle_model_destroy(mle_ctx ctx, mle_model model);
+
+/* ---- parity hook for stages 1-2:  transform.(D[1:m], get_point(gen[r], k)[1:m])  (src/sample.jl:84-88) ----------
+ * out[m x n x R]: out[(r*n + i)*m + j] = coordinate j of point k0+i of shift r (k zero-based, src/sample.jl:84).
+ *   lat == NULL   -> MC: counter-based uniforms keyed by (mc_seed, k, j) instead of lattice points (R must be 1)
+ *   dists == NULL -> raw points in [0,1) (no transform)
+ *   shifts        -> [s x R] (shift r at shifts + r*s, the `shift` field of ShiftedLatticeRule, src/lattice.jl:132-137);
+ *                    NULL -> unshifted rule, R must be 1 (src/lattice.jl:142-145)
+ * Fails with MLE_ERR_RANGE if k0+n-1 > nmax, MLE_ERR_ARG if m > s (the reference pads with rand(), src/sample.jl:85). */
+int mle_points(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts, int R, uint64_t k0, uint64_t n,
+               int m, uint64_t mc_seed, double *out);
+/* Same, device-resident: `shifts_dev` and `out_dev` are device pointers; asynchronous on the context's stream. */
+int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts_dev, int R, uint64_t k0,
+                   uint64_t n, int m, uint64_t mc_seed, double *out_dev);
+
+/* ---- the hot path: one `parallel_sample!` call  (src/sample.jl:39-56, :79-102) ---------------------------------
+ * Evaluates (dQ, Qf) = model(index, xi) for every (shift r, point k0..k0+n-1) and reduces them on the device.
+ *   index[d]       the level / multi-index (zero-based like the reference's Index)
+ *   moments        [3 x 2 x q x R]: moments[((r*q + c)*2 + X)*3 + {0,1,2}] = {n, mean, M2 = sum (x-mean)^2} of the n
+ *                  values of X (0: dQ, 1: Qf) for QoI c and shift r -- the sufficient statistics from which
+ *                  mean/var/varest of src/methods.jl:44-68,282 follow (var = M2/(n-1), Chan-mergeable across calls)
+ *   samples        optional [n x 2 x q x R] (same ordering, n fastest): the raw samples that `append_samples!`
+ *                  stores (src/sample.jl:104-111); NULL to skip (the default: nothing is written to HBM per sample)
+ *   gpu_seconds    optional: device time of the call's kernels (CUDA events) -- the reference uses the wall time of
+ *                  this call as its default cost model (src/sample.jl:27, src/internals.jl:106)
+ * lat / dists / shifts / mc_seed as for mle_points. */
+int mle_sample_batch(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                     const double *shifts, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed, double *moments,
+                     double *samples, double *gpu_seconds);
+/* Same with device-resident shifts / moments / samples, asynchronous on the context's stream (no host copies). */
+int mle_sample_batch_dev(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                         const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
+                         double *moments_dev, double *samples_dev);
+/* Block until everything issued on the context's stream has finished. */
+int mle_sync(mle_ctx ctx);
+
+/* Merge (n, mean, M2) triplets: acc <- acc (+) part, `count` triplets (Chan et al.); pure host arithmetic used by the
+ * host layers to accumulate calls and ranks in a fixed order. */
+int mle_moments_merge(double *acc, const double *part, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLE_CUDA_H */

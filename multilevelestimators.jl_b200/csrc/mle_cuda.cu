@@ -1,0 +1,636 @@
+// mle_cuda.cu -- C ABI of libmle_cuda (see include/mle_cuda.h).  Host side: handles, argument checks mirroring the
+// reference's ArgumentErrors, device buffers, kernel launches.  There is no CPU fallback anywhere in this file.
+#include "../../include/mle_cuda.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mle_kernels.cuh"
+#include "../../include/mle_genvec_data.inc"
+
+using namespace mle;
+
+// ---------------------------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------------------------
+struct mle_ctx_s {
+    int device = -1;
+    int sm_count = 0;
+    int cc = 0;
+    size_t hbm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // reusable device / pinned scratch
+    Moment *d_partials = nullptr;
+    size_t partials_cap = 0;  // in Moments
+    double *d_shifts = nullptr;
+    size_t shifts_cap = 0;
+    double *d_moments = nullptr;
+    size_t moments_cap = 0;
+    double *h_pinned = nullptr;
+    size_t pinned_cap = 0;  // doubles
+};
+
+struct mle_lattice_s {
+    int s = 0;
+    uint64_t nmax = 0;
+    double *d_z = nullptr;  // z as Float64 (exact)
+};
+
+struct mle_dists_s {
+    int m = 0;
+    int mode = GEN_GENERAL;
+    int *d_kind = nullptr;
+    double *d_par = nullptr;  // [m][6]
+};
+
+static const int MLE_MAX_LEVELS = 16;
+struct mle_model_s {
+    int kind = 0, ndims = 1, nqoi = 1, n0 = 0;
+    int nweights = 0;
+    double *d_weights = nullptr;
+    // lognormal: per-level permuted / chunked basis
+    double *d_basis[MLE_MAX_LEVELS] = {};
+    int basis_rows[MLE_MAX_LEVELS] = {};
+    int basis_cols[MLE_MAX_LEVELS] = {};
+    int basis_mpad[MLE_MAX_LEVELS] = {};
+    int basis_nchunks[MLE_MAX_LEVELS] = {};
+};
+
+static thread_local std::string g_init_err;
+
+static int fail(mle_ctx ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_init_err = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            (void)cudaGetLastError();                                                                      \
+            return fail(ctx, MLE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+        }                                                                                                  \
+    } while (0)
+
+template <typename T>
+static int ensure_dev(mle_ctx ctx, T **p, size_t *cap, size_t need) {
+    if (*cap >= need) return MLE_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 2 + 64;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), want * sizeof(T));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc failed (scratch)"); }
+    *cap = want;
+    return MLE_OK;
+}
+
+static int ensure_pinned(mle_ctx ctx, size_t need) {
+    if (ctx->pinned_cap >= need) return MLE_OK;
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr; ctx->pinned_cap = 0;
+    size_t want = need + need / 2 + 64;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_pinned), want * sizeof(double));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMallocHost failed"); }
+    ctx->pinned_cap = want;
+    return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mle_abi_version(void) { return MLE_ABI_VERSION; }
+
+extern "C" int mle_init(int device, mle_ctx *out) {
+    if (!out) return fail(nullptr, MLE_ERR_ARG, "mle_init: ctx is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, MLE_ERR_CUDA, std::string("mle_init: no CUDA device (") +
+                                               (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) +
+                                               "); libmle_cuda has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, MLE_ERR_ARG, "mle_init: device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, MLE_ERR_CUDA, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, MLE_ERR_CUDA, "mle_init: libmle_cuda is built for sm_100a only (device is sm_" +
+                                               std::to_string(prop.major * 10 + prop.minor) + ")");
+    mle_ctx ctx = new (std::nothrow) mle_ctx_s();
+    if (!ctx) return fail(nullptr, MLE_ERR_NOMEM, "mle_init: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc = prop.major * 10 + prop.minor;
+    ctx->hbm = prop.totalGlobalMem;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete ctx;
+        return fail(nullptr, MLE_ERR_CUDA, "mle_init: stream / event creation failed");
+    }
+    // opt in to large dynamic shared memory once
+    cudaFuncSetAttribute(points_kernel<POINTS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(sample_simple_kernel<MODEL_EXPSUM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(sample_simple_kernel<MODEL_PROBLEM18, 26>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lognormal1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
+    *out = ctx;
+    return MLE_OK;
+}
+
+extern "C" int mle_destroy(mle_ctx ctx) {
+    if (!ctx) return MLE_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_partials) cudaFree(ctx->d_partials);
+    if (ctx->d_shifts) cudaFree(ctx->d_shifts);
+    if (ctx->d_moments) cudaFree(ctx->d_moments);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MLE_OK;
+}
+
+extern "C" const char *mle_last_error(mle_ctx ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+extern "C" int mle_device_info(mle_ctx ctx, int *sm_count, size_t *hbm_bytes, int *cc) {
+    if (!ctx) return MLE_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm;
+    if (cc) *cc = ctx->cc;
+    return MLE_OK;
+}
+
+extern "C" int mle_stream(mle_ctx ctx, void **stream) {
+    if (!ctx || !stream) return MLE_ERR_ARG;
+    *stream = reinterpret_cast<void *>(ctx->stream);
+    return MLE_OK;
+}
+
+extern "C" int mle_launch_count(mle_ctx ctx, uint64_t *count) {
+    if (!ctx || !count) return MLE_ERR_ARG;
+    *count = ctx->launches;
+    return MLE_OK;
+}
+
+extern "C" int mle_sync(mle_ctx ctx) {
+    if (!ctx) return MLE_ERR_ARG;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// lattice rule
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mle_genvec(const char *name, const uint32_t **z, int *len) {
+    if (!name || !z || !len) return MLE_ERR_ARG;
+    if (!strcmp(name, "K_3600_32")) { *z = MLE_GENVEC_K3600; *len = MLE_GENVEC_K3600_LEN; return MLE_OK; }
+    if (!strcmp(name, "CKN_250_20")) { *z = MLE_GENVEC_CKN250; *len = MLE_GENVEC_CKN250_LEN; return MLE_OK; }
+    return MLE_ERR_ARG;
+}
+
+extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_t nmax, mle_lattice *out) {
+    if (!ctx || !out) return MLE_ERR_ARG;
+    *out = nullptr;
+    // check_args, src/lattice.jl:181-185: s > 0, s <= length(z) (caller's contract), n <= 2^32
+    if (s <= 0) return fail(ctx, MLE_ERR_ARG, "LatticeRule32: number of dimensions s must be larger than 0");
+    if (nmax > 0xffffffffull) return fail(ctx, MLE_ERR_ARG, "LatticeRule32: maximum number of points n must be smaller than or equal to 2^32");
+    if (!z) {  // LatticeRule32(s): src/lattice.jl:88, check_arg :187
+        if (s > MLE_GENVEC_K3600_LEN)
+            return fail(ctx, MLE_ERR_ARG, "LatticeRule32: number of dimensions s must be smaller than or equal to 3600, please supply your own generating vector z to proceed");
+        z = MLE_GENVEC_K3600;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    mle_lattice L = new (std::nothrow) mle_lattice_s();
+    if (!L) return fail(ctx, MLE_ERR_NOMEM, "out of host memory");
+    L->s = s;
+    L->nmax = nmax;
+    std::vector<double> zd((size_t)s);
+    for (int j = 0; j < s; ++j) zd[(size_t)j] = (double)z[j];
+    if (cudaMalloc(&L->d_z, sizeof(double) * (size_t)s) != cudaSuccess) { delete L; (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(z)"); }
+    cudaError_t e = cudaMemcpyAsync(L->d_z, zd.data(), sizeof(double) * (size_t)s, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(L->d_z); delete L; return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = L;
+    return MLE_OK;
+}
+
+extern "C" int mle_lattice_destroy(mle_ctx ctx, mle_lattice lat) {
+    if (!lat) return MLE_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(lat->d_z);
+    delete lat;
+    return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// distributions
+// ---------------------------------------------------------------------------------------------------------------
+static double host_normcdf(double x) {  // Phi(x) = 1/2*(1 + erf(x/sqrt(2)))              src/distribution.jl:153
+    volatile double q = x / 1.4142135623730951;
+    volatile double e = 1.0 + std::erf(q);
+    return 0.5 * e;
+}
+
+extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists *out) {
+    if (!ctx || !out) return MLE_ERR_ARG;
+    *out = nullptr;
+    if (!d || m <= 0) return fail(ctx, MLE_ERR_ARG, "distributions: need at least one distribution");
+    std::vector<int> kind((size_t)m);
+    std::vector<double> par((size_t)m * 6, 0.0);
+    bool all_std = true;
+    for (int j = 0; j < m; ++j) {
+        const mle_dist &D = d[j];
+        const double *p = D.p;
+        double *o = &par[(size_t)j * 6];
+        auto finite = [](double v) { return std::isfinite(v); };
+        switch (D.kind) {  // constructor checks of src/distribution.jl:36-40, :104-108, :134-141, :173-178
+        case MLE_UNIFORM:
+            if (!finite(p[0]) || !finite(p[1])) return fail(ctx, MLE_ERR_ARG, "Uniform: a and b must be finite");
+            if (!(p[0] < p[1])) return fail(ctx, MLE_ERR_ARG, "Uniform: a must be smaller than b");
+            break;
+        case MLE_NORMAL:
+            if (!finite(p[0]) || !finite(p[1])) return fail(ctx, MLE_ERR_ARG, "Normal: mu and sigma must be finite");
+            if (!(p[1] > 0)) return fail(ctx, MLE_ERR_ARG, "Normal: sigma must be larger than 0");
+            break;
+        case MLE_TRUNCNORMAL: {
+            if (!finite(p[0]) || !finite(p[1]) || !finite(p[2]) || !finite(p[3])) return fail(ctx, MLE_ERR_ARG, "TruncatedNormal: parameters must be finite");
+            if (!(p[1] > 0)) return fail(ctx, MLE_ERR_ARG, "TruncatedNormal: sigma must be larger than 0");
+            if (!(p[2] < p[3])) return fail(ctx, MLE_ERR_ARG, "TruncatedNormal: a must be smaller than b");
+            // per-distribution constants of src/distribution.jl:146-148 (depend on the parameters only)
+            volatile double al = (p[2] - p[0]) / p[1], be = (p[3] - p[0]) / p[1];
+            double Fa = host_normcdf(al), Fb = host_normcdf(be);
+            volatile double dF = Fb - Fa;
+            o[4] = Fa; o[5] = dF;
+            break;
+        }
+        case MLE_WEIBULL:
+            if (!finite(p[0]) || !finite(p[1])) return fail(ctx, MLE_ERR_ARG, "Weibull: k and lambda must be finite");
+            if (!(p[0] > 0) || !(p[1] > 0)) return fail(ctx, MLE_ERR_ARG, "Weibull: k and lambda must be larger than 0");
+            break;
+        default:
+            return fail(ctx, MLE_ERR_ARG, "distributions: unknown kind");
+        }
+        kind[(size_t)j] = D.kind;
+        for (int t = 0; t < 4; ++t) o[t] = p[t];
+        if (!(D.kind == MLE_NORMAL && p[0] == 0.0 && p[1] == 1.0)) all_std = false;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    mle_dists S = new (std::nothrow) mle_dists_s();
+    if (!S) return fail(ctx, MLE_ERR_NOMEM, "out of host memory");
+    S->m = m;
+    S->mode = all_std ? GEN_STDNORMAL : GEN_GENERAL;
+    cudaError_t e = cudaMalloc(&S->d_kind, sizeof(int) * (size_t)m);
+    if (e == cudaSuccess) e = cudaMalloc(&S->d_par, sizeof(double) * (size_t)m * 6);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(S->d_kind, kind.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(S->d_par, par.data(), sizeof(double) * (size_t)m * 6, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(S->d_kind); cudaFree(S->d_par); delete S;
+        return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = S;
+    return MLE_OK;
+}
+
+extern "C" int mle_dists_destroy(mle_ctx ctx, mle_dists dists) {
+    if (!dists) return MLE_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(dists->d_kind);
+    cudaFree(dists->d_par);
+    delete dists;
+    return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// model registry
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *out) {
+    if (!ctx || !out || !name) return MLE_ERR_ARG;
+    *out = nullptr;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    mle_model M = new (std::nothrow) mle_model_s();
+    if (!M) return fail(ctx, MLE_ERR_NOMEM, "out of host memory");
+    M->ndims = ndims;
+    if (!strcmp(name, "expsum")) {
+        if (ndims != 1 || nparams < 2 || !params || params[0] < 1) { delete M; return fail(ctx, MLE_ERR_ARG, "expsum: ndims = 1, params = {m0 >= 1, a_1..a_m}"); }
+        M->kind = MODEL_EXPSUM;
+        M->n0 = (int)params[0];
+        M->nweights = nparams - 1;
+        cudaError_t e = cudaMalloc(&M->d_weights, sizeof(double) * (size_t)M->nweights);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(M->d_weights, params + 1, sizeof(double) * (size_t)M->nweights, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(M->d_weights); delete M; return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e)); }
+    } else if (!strcmp(name, "problem18")) {
+        if (ndims != 1 && ndims != 2) { delete M; return fail(ctx, MLE_ERR_ARG, "problem18: ndims must be 1 or 2"); }
+        M->kind = MODEL_PROBLEM18;
+        M->nqoi = 13;
+    } else if (!strcmp(name, "lognormal1d")) {
+        int n0 = (nparams > 0 && params) ? (int)params[0] : 16;
+        if (ndims != 1 || n0 < 4 || (n0 & 1)) { delete M; return fail(ctx, MLE_ERR_ARG, "lognormal1d: ndims = 1, params = {n0}, n0 even and >= 4"); }
+        M->kind = MODEL_LOGNORMAL1D;
+        M->n0 = n0;
+    } else {
+        delete M;
+        return fail(ctx, MLE_ERR_ARG, std::string("unknown model '") + name + "'");
+    }
+    *out = M;
+    return MLE_OK;
+}
+
+extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows, int cols, const double *phi) {
+    if (!ctx || !M || !phi) return MLE_ERR_ARG;
+    if (M->kind != MODEL_LOGNORMAL1D) return fail(ctx, MLE_ERR_ARG, "set_basis: model takes no KL basis");
+    if (level < 0 || level >= MLE_MAX_LEVELS) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
+    const long long N = (long long)M->n0 << level;
+    if (rows != N + 1) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be n0*2^level + 1 (nodes of the level's grid)");
+    if (cols < 1 || cols > 4 * LN_RC) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 256");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // Row r' = 2*i' + side: side 0 -> node i', side 1 -> mirrored node N - i' (i' = 0..N/2), so both elimination sweeps
+    // read rows in ascending order.  Stored chunked and k-major: [chunk][k][RC], zero padded.
+    const int Mh = (int)(N / 2);
+    const int nrows = 2 * (Mh + 1);
+    const int nchunks = (nrows + LN_RC - 1) / LN_RC;
+    const int mpad = (cols + 3) & ~3;
+    std::vector<double> packed((size_t)nchunks * mpad * LN_RC, 0.0);
+    for (int rp = 0; rp < nrows; ++rp) {
+        const int ip = rp >> 1, side = rp & 1;
+        const long long node = side ? N - ip : ip;
+        const int c = rp / LN_RC, rr = rp % LN_RC;
+        for (int k = 0; k < cols; ++k) packed[((size_t)c * mpad + k) * LN_RC + rr] = phi[(size_t)node * cols + k];
+    }
+    double *d = nullptr;
+    if (cudaMalloc(&d, packed.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
+    cudaError_t e = cudaMemcpyAsync(d, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d); return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e)); }
+    if (M->d_basis[level]) cudaFree(M->d_basis[level]);
+    M->d_basis[level] = d;
+    M->basis_rows[level] = rows;
+    M->basis_cols[level] = cols;
+    M->basis_mpad[level] = mpad;
+    M->basis_nchunks[level] = nchunks;
+    return MLE_OK;
+}
+
+extern "C" int mle_model_nqoi(mle_model M, int *nqoi) {
+    if (!M || !nqoi) return MLE_ERR_ARG;
+    *nqoi = M->nqoi;
+    return MLE_OK;
+}
+
+extern "C" int mle_model_destroy(mle_ctx ctx, mle_model M) {
+    if (!M) return MLE_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(M->d_weights);
+    for (int l = 0; l < MLE_MAX_LEVELS; ++l) cudaFree(M->d_basis[l]);
+    delete M;
+    return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// common argument handling for the point / batch entry points
+// ---------------------------------------------------------------------------------------------------------------
+static int make_gen_args(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts_dev, int R, uint64_t k0,
+                         uint64_t n, int m, uint64_t seed, GenArgs *g) {
+    if (R < 1) return fail(ctx, MLE_ERR_ARG, "number of shifts must be at least 1");
+    if (m < 1) return fail(ctx, MLE_ERR_ARG, "nb_of_uncertainties must be at least 1");
+    if (n > 0xffffffffull) return fail(ctx, MLE_ERR_ARG, "at most 2^32 points per call");
+    if (lat) {
+        if (m > lat->s) return fail(ctx, MLE_ERR_ARG, "nb_of_uncertainties exceeds the lattice dimension s (the reference pads with rand(), src/sample.jl:85, which is not reproducible)");
+        if (n && (k0 + n - 1 > lat->nmax || k0 + n - 1 > 0xffffffffull))
+            return fail(ctx, MLE_ERR_RANGE, "point number beyond the lattice size n (the reference returns rand(s) there, src/lattice.jl:166,175)");
+        if (!shifts_dev && R != 1) return fail(ctx, MLE_ERR_ARG, "an unshifted lattice rule has a single 'shift'");
+    } else {
+        if (R != 1) return fail(ctx, MLE_ERR_ARG, "MC sampling has a single 'shift' slot (src/internals.jl:41)");
+        if (shifts_dev) return fail(ctx, MLE_ERR_ARG, "MC sampling takes no shifts");
+    }
+    if (dists && m > dists->m) return fail(ctx, MLE_ERR_ARG, "nb_of_uncertainties exceeds the number of distributions");
+    g->zd = lat ? lat->d_z : nullptr;
+    g->shifts = shifts_dev;
+    g->kind = dists ? dists->d_kind : nullptr;
+    g->par = dists ? dists->d_par : nullptr;
+    g->seed = seed;
+    g->k0 = k0;
+    g->n = n;
+    g->s = lat ? lat->s : 0;
+    g->m = m;
+    g->R = R;
+    g->mode = dists ? dists->mode : GEN_RAW;
+    return MLE_OK;
+}
+
+static int upload_shifts(mle_ctx ctx, mle_lattice lat, const double *shifts, int R, const double **dev) {
+    *dev = nullptr;
+    if (!shifts) return MLE_OK;
+    if (!lat) return fail(ctx, MLE_ERR_ARG, "MC sampling takes no shifts");
+    const size_t cnt = (size_t)R * (size_t)lat->s;
+    int rc = ensure_dev(ctx, &ctx->d_shifts, &ctx->shifts_cap, cnt);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, cnt + 4096);
+    if (rc) return rc;
+    memcpy(ctx->h_pinned, shifts, cnt * sizeof(double));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_shifts, ctx->h_pinned, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = ctx->d_shifts;
+    return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 1-2 parity hook
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts_dev, int R, uint64_t k0,
+                              uint64_t n, int m, uint64_t mc_seed, double *out_dev) {
+    if (!ctx || !out_dev) return MLE_ERR_ARG;
+    GenArgs g;
+    int rc = make_gen_args(ctx, lat, dists, shifts_dev, R, k0, n, m, mc_seed, &g);
+    if (rc) return rc;
+    if (n == 0) return MLE_OK;
+    if (m > POINTS_TILE_CAP) return fail(ctx, MLE_ERR_ARG, "mle_points: at most 4096 dimensions");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int P = POINTS_TILE_CAP / m > 0 ? POINTS_TILE_CAP / m : 1;
+    const long long tps = (long long)((n + (uint64_t)P - 1) / (uint64_t)P);
+    const long long ntiles = tps * R;
+    const size_t smem = 2 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + 16;
+    long long grid = (long long)ctx->sm_count * 3;
+    if (grid > ntiles) grid = ntiles;
+    points_kernel<POINTS_THREADS><<<(unsigned)grid, POINTS_THREADS, smem, ctx->stream>>>(g, out_dev, P, tps, ntiles);
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaGetLastError());
+    return MLE_OK;
+}
+
+extern "C" int mle_points(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts, int R, uint64_t k0, uint64_t n,
+                          int m, uint64_t mc_seed, double *out) {
+    if (!ctx || !out) return MLE_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (R < 1 || m < 1) return fail(ctx, MLE_ERR_ARG, "R and m must be positive");
+    const double *sh_dev = nullptr;
+    int rc = upload_shifts(ctx, lat, shifts, R, &sh_dev);
+    if (rc) return rc;
+    if (n == 0) return MLE_OK;
+    const size_t cnt = (size_t)R * n * (size_t)m;
+    double *d_out = nullptr;
+    if (cudaMalloc(&d_out, cnt * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "mle_points: cudaMalloc(out)"); }
+    rc = mle_points_dev(ctx, lat, dists, sh_dev, R, k0, n, m, mc_seed, d_out);
+    if (rc == MLE_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, MLE_ERR_CUDA, std::string("mle_points: ") + cudaGetErrorString(e)); }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------------------------------
+static long long grid_x_for(mle_ctx ctx, long long tiles_per_shift, int R, int ctas_per_sm) {
+    // persistent-style: about ctas_per_sm CTAs per SM in total, split evenly over the R shifts
+    long long total = (long long)ctx->sm_count * ctas_per_sm;
+    long long gx = (total + R - 1) / R;
+    if (gx < 1) gx = 1;
+    if (gx > tiles_per_shift) gx = tiles_per_shift;
+    return gx;
+}
+
+extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                                    const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
+                                    double *moments_dev, double *samples_dev) {
+    if (!ctx || !M || !index || !moments_dev) return MLE_ERR_ARG;
+    if (d != M->ndims) return fail(ctx, MLE_ERR_ARG, "index dimension does not match the model");
+    for (int t = 0; t < d; ++t)
+        if (index[t] < 0) return fail(ctx, MLE_ERR_ARG, "index must be non-negative");
+    if (n == 0) return fail(ctx, MLE_ERR_ARG, "sample!: number of samples must be positive");
+    GenArgs g;
+    int rc = make_gen_args(ctx, lat, dists, shifts_dev, R, k0, n, m, mc_seed, &g);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int V = 2 * M->nqoi;
+    long long gx = 0;
+    if (M->kind == MODEL_EXPSUM || M->kind == MODEL_PROBLEM18) {
+        const long long tps = (long long)((n + SIMPLE_THREADS - 1) / SIMPLE_THREADS);
+        gx = grid_x_for(ctx, tps, R, 4);
+        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+        if (rc) return rc;
+        SimpleModelArgs ma{};
+        ma.weights = M->d_weights;
+        ma.nweights = M->nweights;
+        ma.ndims = M->ndims;
+        ma.idx0 = index[0];
+        ma.idx1 = d > 1 ? index[1] : 0;
+        const int W = SIMPLE_THREADS / 32;
+        const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_LD * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Moment) +
+                            (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + 16;
+        dim3 grid((unsigned)gx, (unsigned)R);
+        if (M->kind == MODEL_EXPSUM) {
+            if (index[0] > 30) return fail(ctx, MLE_ERR_ARG, "expsum: level too large");
+            long long ml = (long long)M->n0 << index[0];
+            if (ml > m) ml = m;
+            if (ml > M->nweights) ml = M->nweights;
+            long long mlc = 0;
+            if (index[0] > 0) {
+                mlc = (long long)M->n0 << (index[0] - 1);
+                if (mlc > m) mlc = m;
+                if (mlc > M->nweights) mlc = M->nweights;
+            }
+            ma.ml = (int)ml;
+            ma.mlc = (int)mlc;
+            sample_simple_kernel<MODEL_EXPSUM, 2><<<grid, SIMPLE_THREADS, smem, ctx->stream>>>(g, ma, ctx->d_partials, samples_dev, tps);
+        } else {
+            if (m < M->ndims) return fail(ctx, MLE_ERR_ARG, "problem18: needs one uncertainty per index dimension");
+            sample_simple_kernel<MODEL_PROBLEM18, 26><<<grid, SIMPLE_THREADS, smem, ctx->stream>>>(g, ma, ctx->d_partials, samples_dev, tps);
+        }
+    } else if (M->kind == MODEL_LOGNORMAL1D) {
+        const int level = index[0];
+        if (level >= MLE_MAX_LEVELS || !M->d_basis[level]) return fail(ctx, MLE_ERR_STATE, "lognormal1d: no KL basis set for this level (mle_model_set_basis)");
+        if (m != M->basis_cols[level]) return fail(ctx, MLE_ERR_ARG, "lognormal1d: nb_of_uncertainties must equal the number of KL terms of the level's basis");
+        Lognormal1dArgs la{};
+        la.basis = M->d_basis[level];
+        la.N = M->n0 << level;
+        la.mpad = M->basis_mpad[level];
+        la.nchunks = M->basis_nchunks[level];
+        la.level = level;
+        la.h2 = 1.0 / ((double)la.N * (double)la.N);
+        la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
+        const long long tps = (long long)((n + LN_BT - 1) / LN_BT);
+        gx = grid_x_for(ctx, tps, R, 2);
+        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+        if (rc) return rc;
+        const int W = LN_THREADS / 32;
+        const size_t smem = (size_t)la.mpad * LN_BT * 8 + (size_t)2 * LN_KC * LN_RC * 8 + (size_t)LN_RC * LN_BT * 8 +
+                            (size_t)3 * 2 * W * 8 + 2 * sizeof(Moment) + (size_t)2 * LN_BT * sizeof(SweepState) + 16 + 16;
+        dim3 grid((unsigned)gx, (unsigned)R);
+        lognormal1d_kernel<<<grid, LN_THREADS, smem, ctx->stream>>>(g, la, ctx->d_partials, samples_dev, tps);
+    } else {
+        return fail(ctx, MLE_ERR_ARG, "unknown model kind");
+    }
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaGetLastError());
+    const int RV = R * V;
+    const int warps_per_block = 4;
+    finalize_kernel<<<(RV + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->stream>>>(ctx->d_partials, (int)gx, RV, moments_dev);
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaGetLastError());
+    return MLE_OK;
+}
+
+extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                                const double *shifts, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed, double *moments,
+                                double *samples, double *gpu_seconds) {
+    if (!ctx || !M || !moments) return MLE_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (R < 1) return fail(ctx, MLE_ERR_ARG, "number of shifts must be at least 1");
+    const double *sh_dev = nullptr;
+    int rc = upload_shifts(ctx, lat, shifts, R, &sh_dev);
+    if (rc) return rc;
+    const size_t nm = (size_t)R * 2 * (size_t)M->nqoi * 3;
+    rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, nm);
+    if (rc) return rc;
+    double *d_samples = nullptr;
+    const size_t ns = samples ? (size_t)R * 2 * (size_t)M->nqoi * n : 0;
+    if (samples && ns) {
+        if (cudaMalloc(&d_samples, ns * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(samples)"); }
+    }
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    rc = mle_sample_batch_dev(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, ctx->d_moments, d_samples);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (rc == MLE_OK) {
+        cudaError_t e = cudaMemcpyAsync(moments, ctx->d_moments, nm * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && d_samples) e = cudaMemcpyAsync(samples, d_samples, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_batch: ") + cudaGetErrorString(e)); }
+        if (rc == MLE_OK && gpu_seconds) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            *gpu_seconds = (double)ms * 1e-3;
+        }
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (d_samples) cudaFree(d_samples);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side moment algebra
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mle_moments_merge(double *acc, const double *part, size_t count) {
+    if (!acc || !part) return MLE_ERR_ARG;
+    for (size_t i = 0; i < count; ++i) {
+        Moment a{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]}, b{part[3 * i], part[3 * i + 1], part[3 * i + 2]};
+        Moment o = moment_merge(a, b);
+        acc[3 * i] = o.n; acc[3 * i + 1] = o.mean; acc[3 * i + 2] = o.m2;
+    }
+    return MLE_OK;
+}

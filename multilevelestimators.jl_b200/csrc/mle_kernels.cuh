@@ -1,0 +1,487 @@
+// mle_kernels.cuh -- the CUDA kernels of libmle_cuda (sm_100a only).
+//
+//   points_kernel        K1/K2: lattice (or counter-RNG) point -> shift -> inverse CDF -> dense [m x n x R] in HBM,
+//                        tile staged in shared memory and written with one TMA bulk store per tile
+//   sample_simple_kernel K5+K6: fused generate -> analytic sample function -> per-CTA moments (no per-sample HBM traffic)
+//   lognormal1d_kernel   K1+K3+K4+K6 fused: generate xi tile -> KL contraction (FP64 register-tiled GEMM fed by TMA bulk
+//                        loads of the basis) -> exp -> two-sided Thomas sweeps for fine and coarse grids -> moments
+//   finalize_kernel      fixed-order Chan merge of the per-CTA partial moments
+#pragma once
+#include "mle_device.cuh"
+
+namespace mle {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMA (bulk async copy) helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ===================================================================================================================
+// K1 / K2: points -> HBM
+//   out[(r*n + i)*m + j].  One tile = P consecutive points of one shift = P*m consecutive doubles of `out`.
+//   Persistent CTAs loop over tiles; two shared-memory tile buffers so the TMA store of tile t overlaps tile t+1.
+//   Algorithmic traffic: 8 B written per coordinate (z and the shifts stay in L1/L2).
+// ===================================================================================================================
+constexpr int POINTS_THREADS = 256;
+constexpr int POINTS_TILE_CAP = 4096;  // elements per tile buffer (32 KB)
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__restrict__ out, int P,
+                                                         long long tiles_per_shift, long long ntiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *buf0 = reinterpret_cast<double *>(smem_raw);
+    double *buf1 = buf0 + POINTS_TILE_CAP;
+    GenScratch sc;
+    sc.queue = reinterpret_cast<unsigned short *>(buf1 + POINTS_TILE_CAP);
+    sc.cnt = reinterpret_cast<int *>(sc.queue + POINTS_TILE_CAP);
+
+    const int m = g.m;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int r = (int)(tile / tiles_per_shift);
+        const long long ti = tile - (long long)r * tiles_per_shift;
+        const unsigned long long i0 = (unsigned long long)ti * (unsigned long long)P;
+        const unsigned long long left = g.n - i0;
+        const int Pt = left < (unsigned long long)P ? (int)left : P;
+        double *buf = (it & 1) ? buf1 : buf0;
+        // the bulk store issued two iterations ago read this buffer: wait until at most one store is still reading
+        if (threadIdx.x == 0) bulk_wait_read<1>();
+        gen_tile<THREADS, false>(buf, m, 1, Pt, 0, m, g.k0 + i0, g, r, sc);
+        double *dst = out + ((size_t)r * g.n + i0) * (size_t)m;
+        const uint32_t bytes = (uint32_t)Pt * (uint32_t)m * 8u;
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0;
+        if (tma_ok) {
+            fence_proxy_async_smem();  // make this thread's generic-proxy writes visible to the async proxy
+            __syncthreads();
+            if (threadIdx.x == 0) { bulk_store_s2g(dst, buf, bytes); bulk_commit(); }
+        } else {  // odd m with an odd starting element: plain coalesced stores
+            for (int e = threadIdx.x; e < Pt * m; e += THREADS) dst[e] = buf[e];
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_all<0>();
+}
+
+// ===================================================================================================================
+// analytic sample functions (one sample per thread), fused with generation and moments
+// ===================================================================================================================
+enum : int { MODEL_EXPSUM = 0, MODEL_PROBLEM18 = 1, MODEL_LOGNORMAL1D = 2 };
+
+struct SimpleModelArgs {
+    const double *weights;  // expsum: a_j
+    int nweights;
+    int ml;    // expsum: active dims at this level
+    int mlc;   // expsum: active dims at level-1 (0: no coarse term)
+    int ndims; // problem18
+    int idx0, idx1;
+};
+
+constexpr int SIMPLE_THREADS = 128;
+constexpr int SIMPLE_MC = 64;             // dims per chunk
+constexpr int SIMPLE_LD = SIMPLE_MC + 1;  // odd stride: conflict-free per-thread row reads
+
+// problem_18                                                      test/regression.jl:17-36 (1-d), :69-103 (2-d)
+__device__ __forceinline__ double p18_coef(int l, double xj) {
+    if (l == 3) return 1.0;
+    if (l == 2) return 1.1;
+    if (l == 1) return __dadd_rn(__ddiv_rn(xj, 60.0), 1.2);
+    return 1.5;
+}
+__device__ __forceinline__ void problem18_eval(int ndims, int i0, int i1, double xi0, double xi1, double *f) {
+    double x13 = __dmul_rn(__dmul_rn(xi0, xi0), xi0);
+    double x23 = (ndims == 2) ? __dmul_rn(__dmul_rn(xi1, xi1), xi1) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+        double xj = 0.5 * j;  // range(0, 6, 13)[j]
+        double fj;
+        if (xj <= 3.0) fj = (xj - 2.0) * (xj - 2.0);           // exact small constants
+        else fj = __dadd_rn(__dmul_rn(2.0, log(xj - 2.0)), 1.0);
+        double acc = __dadd_rn(fj, __dmul_rn(p18_coef(i0, xj), x13));
+        if (ndims == 2) {
+            acc = __dadd_rn(acc, __dmul_rn(p18_coef(i1, xj), x23));
+            if (i0 > 0 && i1 > 0) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(0.03125, x13), x23));
+        }
+        f[j] = acc;
+    }
+}
+
+// Batched corrected two-pass moments of V values per thread; thread 0 merges them into acc[V] (shared memory).
+template <int THREADS, int V>
+__device__ __forceinline__ void block_moments_merge(const double (&x)[V], int cnt, double *red /* [3][V][W] */,
+                                                    Moment *acc) {
+    constexpr int W = THREADS / 32;
+    const bool valid = (int)threadIdx.x < cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *r0 = red, *r1 = red + V * W, *r2 = red + 2 * V * W;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        double s = warp_sum(valid ? x[v] : 0.0);
+        if (lane == 0) r0[v * W + warp] = s;
+    }
+    __syncthreads();
+    double d[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) t += r0[v * W + w];
+        double mean0 = t / (double)cnt;
+        d[v] = valid ? x[v] - mean0 : 0.0;
+        double sd = warp_sum(d[v]), sdd = warp_sum(d[v] * d[v]);
+        if (lane == 0) { r1[v * W + warp] = sd; r2[v * W + warp] = sdd; }
+    }
+    __syncthreads();
+    if (threadIdx.x < V) {
+        const int v = threadIdx.x;
+        double t = 0.0, sd = 0.0, sdd = 0.0;
+        for (int w = 0; w < W; ++w) { t += r0[v * W + w]; sd += r1[v * W + w]; sdd += r2[v * W + w]; }
+        Moment o;
+        o.n = (double)cnt;
+        o.mean = t / (double)cnt + sd / (double)cnt;
+        o.m2 = fmax(sdd - sd * sd / (double)cnt, 0.0);
+        acc[v] = moment_merge(acc[v], o);
+    }
+    __syncthreads();
+}
+
+// grid = (G, R).  CTA (g, r) handles point tiles g, g+G, ... of shift r, SIMPLE_THREADS points per tile, dims in chunks.
+// partials[(r*V + v)*G + g] = merged (n, mean, M2) of this CTA.  samples (optional): [(r*V + v)*n + i].
+template <int MODEL, int V>
+__global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g, SimpleModelArgs ma,
+                                                                       Moment *__restrict__ partials,
+                                                                       double *__restrict__ samples,
+                                                                       long long tiles_per_shift) {
+    constexpr int THREADS = SIMPLE_THREADS;
+    constexpr int W = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *tile = reinterpret_cast<double *>(smem_raw);                    // [THREADS][SIMPLE_LD]
+    double *red = tile + THREADS * SIMPLE_LD;                               // [3][V][W]
+    Moment *acc = reinterpret_cast<Moment *>(red + 3 * V * W);              // [V]
+    GenScratch sc;
+    sc.queue = reinterpret_cast<unsigned short *>(acc + V);                 // [THREADS*SIMPLE_MC]
+    sc.cnt = reinterpret_cast<int *>(sc.queue + THREADS * SIMPLE_MC);
+
+    const int r = blockIdx.y;
+    const int tid = threadIdx.x;
+    if (tid < V) acc[tid] = Moment{0.0, 0.0, 0.0};
+    __syncthreads();
+
+    for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
+        const unsigned long long i0 = (unsigned long long)ti * THREADS;
+        const unsigned long long left = g.n - i0;
+        const int Pt = left < (unsigned long long)THREADS ? (int)left : THREADS;
+        double val[V];
+        double s_acc = 0.0, s_coarse = 0.0;
+        double xi0 = 0.0, xi1 = 0.0;
+        for (int j0 = 0; j0 < g.m; j0 += SIMPLE_MC) {
+            const int mc = min(SIMPLE_MC, g.m - j0);
+            gen_tile<THREADS, false>(tile, SIMPLE_LD, 1, Pt, j0, mc, g.k0 + i0, g, r, sc);
+            if (tid < Pt) {
+                const double *row = tile + tid * SIMPLE_LD;
+                if (MODEL == MODEL_EXPSUM) {
+                    for (int jj = 0; jj < mc; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < ma.ml) s_acc = __fma_rn(__ldg(ma.weights + j), row[jj], s_acc);
+                        if (j == ma.mlc - 1) s_coarse = s_acc;
+                    }
+                } else {
+                    if (j0 == 0) { xi0 = row[0]; if (mc > 1) xi1 = row[1]; }
+                }
+            }
+            // gen_tile starts with a barrier after resetting its counters, but the tile itself is overwritten in pass 1:
+            __syncthreads();
+        }
+        if (MODEL == MODEL_EXPSUM) {
+            double qf = exp(s_acc);
+            val[1] = qf;
+            val[0] = ma.mlc > 0 ? __dsub_rn(qf, exp(s_coarse)) : qf;
+        } else {
+            // (dQ, Qf): dQ = Qf + sum over diff(index) of +-Q_kappa         src/index.jl:49-58, test/regression.jl:39-46
+            double f[13], dq[13];
+            problem18_eval(ma.ndims, ma.idx0, ma.idx1, xi0, xi1, f);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) dq[j] = f[j];
+            const int lo0 = ma.idx0 > 0 ? ma.idx0 - 1 : 0;
+            const int hi1 = ma.ndims == 2 ? ma.idx1 : 0;
+            const int lo1 = (ma.ndims == 2 && ma.idx1 > 0) ? ma.idx1 - 1 : 0;
+            for (int b = lo1; b <= hi1; ++b)
+                for (int a = lo0; a <= ma.idx0; ++a) {
+                    if (a == ma.idx0 && b == hi1) continue;
+                    const double sgn = (((ma.idx0 - a) + (hi1 - b)) & 1) ? -1.0 : 1.0;
+                    double fc[13];
+                    problem18_eval(ma.ndims, a, b, xi0, xi1, fc);
+#pragma unroll
+                    for (int j = 0; j < 13; ++j) dq[j] = __dadd_rn(dq[j], __dmul_rn(sgn, fc[j]));
+                }
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+                if (2 * j + 1 < V) { val[2 * j] = dq[j]; val[2 * j + 1] = f[j]; }
+            }
+        }
+        if (samples && tid < Pt) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) samples[((size_t)r * V + v) * g.n + i0 + tid] = val[v];
+        }
+        block_moments_merge<THREADS, V>(val, Pt, red, acc);
+    }
+    if (tid < V) partials[((size_t)r * V + tid) * gridDim.x + blockIdx.x] = acc[tid];
+}
+
+// ===================================================================================================================
+// finalize: merge the G per-CTA partials of every (shift, value) in a fixed order -> moments[(r*V + v)*3 + {n,mean,M2}]
+// one warp per (r, v): lane l merges partials [l*chunk, (l+1)*chunk) in order, then a fixed shuffle tree.
+// ===================================================================================================================
+__global__ void finalize_kernel(const Moment *__restrict__ partials, int G, int RV, double *__restrict__ moments) {
+    const int rv = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (rv >= RV) return;
+    const int lane = threadIdx.x & 31;
+    const int chunk = (G + 31) / 32;
+    Moment a{0.0, 0.0, 0.0};
+    const Moment *p = partials + (size_t)rv * G;
+    for (int i = lane * chunk; i < min(G, (lane + 1) * chunk); ++i) a = moment_merge(a, p[i]);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Moment b;
+        b.n = __shfl_down_sync(0xffffffffu, a.n, o);
+        b.mean = __shfl_down_sync(0xffffffffu, a.mean, o);
+        b.m2 = __shfl_down_sync(0xffffffffu, a.m2, o);
+        if ((lane & (2 * o - 1)) == 0) a = moment_merge(a, b);
+    }
+    if (lane == 0) {
+        moments[(size_t)rv * 3 + 0] = a.n;
+        moments[(size_t)rv * 3 + 1] = a.mean;
+        moments[(size_t)rv * 3 + 2] = a.m2;
+    }
+}
+
+// ===================================================================================================================
+// 1-D lognormal diffusion, fully fused (see oracle/mle_oracle.c for the model definition)
+//
+//  per CTA tile: BT samples of one shift.
+//   A. xi tile [mpad][BT] (k-major, sample fastest) generated in shared memory (lattice -> shift -> Phi^-1).
+//   B. the field is produced in row chunks of RC rows; a "row" is (half-node i', side): side 0 = node i', side 1 = the
+//      mirrored node N-i', so that BOTH elimination sweeps of the two-sided Thomas solve consume rows in ascending order.
+//      G[row][sample] = sum_k A[row][k] xi[k][sample], k ascending with fused multiply-adds (bit-identical to the oracle);
+//      A arrives by TMA bulk loads in k-chunks [KC][RC] (double-buffered, mbarrier-tracked); every thread owns an
+//      8-row x 4-sample register tile.  Epilogue: a = exp(G) -> F[row][sample] in shared memory.
+//   C. sweeps: thread (side, sample) advances the fine elimination by one row per half-node and the coarse one on every
+//      even half-node (coarse field = even nodes of the fine field, docs/src/example.md:120); only running scalars are
+//      kept -- the field never leaves the SM and nothing per-sample is written to HBM.
+//   D. the two sides meet at the mid node: Qf, Qc, dQ = Qf - Qc; corrected two-pass block moments; Chan merge.
+// ===================================================================================================================
+struct Lognormal1dArgs {
+    const double *basis;  // [nchunks][mpad][RC] permuted, chunked, k-major basis of this level
+    int N;                // fine cells
+    int mpad;             // KL terms padded to a multiple of 4
+    int nchunks;          // row chunks
+    int level;
+    double h2, h2c;       // 1/N^2, 1/(N/2)^2
+};
+
+constexpr int LN_THREADS = 128;
+constexpr int LN_BT = 64;   // samples per tile
+constexpr int LN_RC = 64;   // rows per chunk (32 half-nodes x 2 sides)
+constexpr int LN_KC = 20;   // k per A chunk
+
+struct SweepState {
+    double a_prev, k_prev, p, y;
+};
+
+// one elimination step on arrival of node value `a` (node number ip on this side, ascending); rows 1..M-1
+__device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, double h2) {
+    if (ip == 0) { s.a_prev = a; return; }
+    double k_new = __dmul_rn(0.5, __dadd_rn(s.a_prev, a));
+    if (ip >= 2) {
+        double b = __dadd_rn(s.k_prev, k_new);
+        if (ip == 2) { s.p = b; s.y = h2; }
+        else {
+            double w = __ddiv_rn(s.k_prev, s.p);
+            s.p = __fma_rn(-w, s.k_prev, b);
+            s.y = __fma_rn(w, s.y, h2);
+        }
+    }
+    s.k_prev = k_new;
+    s.a_prev = a;
+}
+
+// combine the left state L and the right (mirrored) state Rr at the mid node; M = number of half-cells per side
+__device__ __forceinline__ double sweep_combine(const SweepState &L, const SweepState &Rr, int M, double h2) {
+    double den = __dadd_rn(L.k_prev, Rr.k_prev), num = h2;
+    if (M >= 2) {
+        double w = __ddiv_rn(L.k_prev, L.p);
+        den = __fma_rn(-w, L.k_prev, den);
+        num = __fma_rn(w, L.y, num);
+        w = __ddiv_rn(Rr.k_prev, Rr.p);
+        den = __fma_rn(-w, Rr.k_prev, den);
+        num = __fma_rn(w, Rr.y, num);
+    }
+    return __ddiv_rn(num, den);
+}
+
+__global__ void __launch_bounds__(LN_THREADS) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la,
+                                                                 Moment *__restrict__ partials,
+                                                                 double *__restrict__ samples,
+                                                                 long long tiles_per_shift) {
+    constexpr int THREADS = LN_THREADS, BT = LN_BT, RC = LN_RC, KC = LN_KC, W = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int mpad = la.mpad;
+    double *xi = reinterpret_cast<double *>(smem_raw);       // [mpad][BT]
+    double *As = xi + (size_t)mpad * BT;                     // [2][KC][RC]
+    double *F = As + 2 * KC * RC;                            // [RC][BT]   (aliased by the generator queue)
+    double *red = F + RC * BT;                               // [3][2][W]
+    Moment *acc = reinterpret_cast<Moment *>(red + 3 * 2 * W);  // [2]
+    SweepState *xch = reinterpret_cast<SweepState *>(acc + 2);  // [2][BT] right-side states (fine, coarse)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xch + 2 * BT);  // [2]
+    GenScratch sc;
+    sc.queue = reinterpret_cast<unsigned short *>(F);        // BT*mpad*2 bytes <= RC*BT*8 needs mpad <= 4*RC (host-checked)
+    sc.cnt = reinterpret_cast<int *>(bars + 2);
+
+    const int tid = threadIdx.x, r = blockIdx.y;
+    const int ty = tid >> 4, tx = tid & 15;  // 8 row groups x 16 sample groups
+    const int M = la.N / 2;                  // mid node
+    const int nkc = (mpad + KC - 1) / KC;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (tid < 2) acc[tid] = Moment{0.0, 0.0, 0.0};
+    // zero the k-padding rows of xi once (gen_tile never writes them)
+    for (int e = tid; e < (mpad - g.m) * BT; e += THREADS) xi[(size_t)g.m * BT + e] = 0.0;
+    __syncthreads();
+    uint32_t phase[2] = {0u, 0u};
+
+    for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
+        const unsigned long long i0 = (unsigned long long)ti * BT;
+        const unsigned long long left = g.n - i0;
+        const int Pt = left < (unsigned long long)BT ? (int)left : BT;
+        // A. inputs (always a full tile: surplus points are masked out of the statistics)
+        gen_tile<THREADS, true>(xi, 1, BT, BT, 0, g.m, g.k0 + i0, g, r, sc);
+
+        SweepState sf{0, 0, 0, 0}, scs{0, 0, 0, 0};
+        const int side = tid / BT, b = tid - side * BT;
+
+        // first A chunk of this tile
+        int it = 0;  // running (row chunk, k chunk) counter within the tile
+        if (tid == 0) {
+            const int kc0 = min(KC, mpad);
+            mbar_expect_tx(&bars[0], (uint32_t)(kc0 * RC * 8));
+            bulk_load_g2s(As, la.basis, (uint32_t)(kc0 * RC * 8), &bars[0]);
+        }
+        for (int c = 0; c < la.nchunks; ++c) {
+            double accr[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int jx = 0; jx < 4; ++jx) accr[i][jx] = 0.0;
+            for (int kci = 0; kci < nkc; ++kci, ++it) {
+                const int st = it & 1;
+                const int kbeg = kci * KC, kc = min(KC, mpad - kbeg);
+                // prefetch the next (row chunk, k chunk) block into the other stage
+                if (tid == 0) {
+                    int nc = c, nk = kci + 1;
+                    if (nk == nkc) { nk = 0; ++nc; }
+                    if (nc < la.nchunks) {
+                        const int nkb = nk * KC, nkcnt = min(KC, mpad - nkb);
+                        const double *src = la.basis + ((size_t)nc * mpad + nkb) * RC;
+                        mbar_expect_tx(&bars[st ^ 1], (uint32_t)(nkcnt * RC * 8));
+                        bulk_load_g2s(As + (st ^ 1) * KC * RC, src, (uint32_t)(nkcnt * RC * 8), &bars[st ^ 1]);
+                    }
+                }
+                mbar_wait(&bars[st], phase[st]);
+                phase[st] ^= 1u;
+                const double *Ak = As + st * KC * RC + 8 * ty;
+                const double *Xk = xi + (size_t)kbeg * BT + 2 * tx;
+#pragma unroll 4
+                for (int k = 0; k < kc; ++k) {
+                    double a[8], x[4];
+                    const double2 *ap = reinterpret_cast<const double2 *>(Ak + k * RC);
+                    double2 a01 = ap[0], a23 = ap[1], a45 = ap[2], a67 = ap[3];
+                    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+                    a[4] = a45.x; a[5] = a45.y; a[6] = a67.x; a[7] = a67.y;
+                    double2 x01 = *reinterpret_cast<const double2 *>(Xk + k * BT);
+                    double2 x23 = *reinterpret_cast<const double2 *>(Xk + k * BT + 32);
+                    x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int jx = 0; jx < 4; ++jx) accr[i][jx] = __fma_rn(a[i], x[jx], accr[i][jx]);
+                }
+                __syncthreads();  // everyone is done with stage st (refilled two iterations later) -- and with F
+            }
+            // epilogue: a = exp(G) -> F[row][sample]; thread owns rows 8ty..8ty+7, samples {2tx, 2tx+1, 32+2tx, 32+2tx+1}
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double2 lo, hi;
+                lo.x = exp(accr[i][0]); lo.y = exp(accr[i][1]);
+                hi.x = exp(accr[i][2]); hi.y = exp(accr[i][3]);
+                double *frow = F + (8 * ty + i) * BT + 2 * tx;
+                *reinterpret_cast<double2 *>(frow) = lo;
+                *reinterpret_cast<double2 *>(frow + 32) = hi;
+            }
+            __syncthreads();
+            // C. sweeps over the RC/2 half-nodes of this chunk
+            const int ip0 = c * (RC / 2);
+#pragma unroll 4
+            for (int q = 0; q < RC / 2; ++q) {
+                const int ip = ip0 + q;
+                if (ip <= M) {
+                    const double a = F[(2 * q + side) * BT + b];
+                    sweep_step(sf, ip, a, la.h2);
+                    if (la.level > 0 && (ip & 1) == 0) sweep_step(scs, ip >> 1, a, la.h2c);
+                }
+            }
+            // (the k-chunk barriers of the next row chunk order these reads before F is rewritten)
+        }
+        // D. meet in the middle
+        if (side == 1) { xch[b] = sf; xch[BT + b] = scs; }
+        __syncthreads();
+        double val[2] = {0.0, 0.0};
+        if (side == 0) {
+            const double qf = sweep_combine(sf, xch[b], M, la.h2);
+            val[1] = qf;
+            val[0] = qf;
+            if (la.level > 0) val[0] = __dsub_rn(qf, sweep_combine(scs, xch[BT + b], M / 2, la.h2c));
+            if (samples && b < Pt) {
+                samples[((size_t)r * 2 + 0) * g.n + i0 + b] = val[0];
+                samples[((size_t)r * 2 + 1) * g.n + i0 + b] = val[1];
+            }
+        }
+        block_moments_merge<THREADS, 2>(val, Pt, red, acc);  // valid threads: tid < Pt <= BT (side 0)
+    }
+    if (tid < 2) partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = acc[tid];
+}
+
+}  // namespace mle

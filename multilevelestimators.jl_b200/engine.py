@@ -1,0 +1,233 @@
+"""Thin object layer over the C ABI (include/mle_cuda.h): one `Engine` per GPU, handles for lattice rules,
+distribution vectors and device models, and the two hot-path calls `points` / `sample_batch`.
+
+This is host plumbing only -- every number is produced by the CUDA kernels in csrc/.  The calls mirror
+`parallel_sample!` (src/sample.jl:39-56, :79-102 of the reference): zero-based point numbers, one shift vector
+per (index, shift), `m = nb_of_uncertainties(index)` leading coordinates.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_dp = C.POINTER(C.c_double)
+
+
+class MLEError(RuntimeError):
+    """CUDA / state failure inside libmle_cuda (ErrorException in the Julia wrapper)."""
+
+
+class MLEArgumentError(ValueError):
+    """Invalid argument (the reference's ArgumentError, src/check_input.jl)."""
+
+
+def _as_dp(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+class _Handle:
+    def __init__(self, engine, handle, destroy):
+        self.engine, self.handle, self._destroy = engine, handle, destroy
+
+    def close(self):
+        if self.handle is not None and self.engine.ctx is not None:
+            self._destroy(self.engine.ctx, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceLattice(_Handle):
+    s = 0
+    nmax = 0
+
+
+class DeviceDists(_Handle):
+    m = 0
+
+
+class DeviceModel(_Handle):
+    """Handle of a built-in CUDA sample function (stands where the Julia closure `sample_function` stood)."""
+    name = ""
+    ndims = 1
+    nqoi = 1
+
+    def set_basis(self, level, phi):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        self.engine._check(self.engine.lib.mle_model_set_basis(self.engine.ctx, self.handle, int(level), phi.shape[0],
+                                                               phi.shape[1], _as_dp(phi)))
+        return self
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        ctx = C.c_void_p()
+        rc = self.lib.mle_init(int(device), C.byref(ctx))
+        if rc != _lib.MLE_OK:
+            msg = self.lib.mle_last_error(None).decode()
+            raise MLEError("mle_init failed (%d): %s" % (rc, msg))
+        self.ctx = ctx
+        self.device = device
+        sm, hbm, cc = C.c_int(), C.c_size_t(), C.c_int()
+        self.lib.mle_device_info(self.ctx, C.byref(sm), C.byref(hbm), C.byref(cc))
+        self.sm_count, self.hbm_bytes, self.cc = sm.value, hbm.value, cc.value
+
+    # ---- plumbing ----------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == _lib.MLE_OK:
+            return
+        msg = self.lib.mle_last_error(self.ctx).decode()
+        if rc in (_lib.MLE_ERR_ARG, _lib.MLE_ERR_RANGE):
+            raise MLEArgumentError(msg)
+        raise MLEError("libmle_cuda error %d: %s" % (rc, msg))
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            self.lib.mle_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        self._check(self.lib.mle_stream(self.ctx, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def launch_count(self):
+        c = C.c_uint64()
+        self._check(self.lib.mle_launch_count(self.ctx, C.byref(c)))
+        return c.value
+
+    def sync(self):
+        self._check(self.lib.mle_sync(self.ctx))
+
+    # ---- handles -----------------------------------------------------------------------------------------------
+    def genvec(self, name="K_3600_32"):
+        p, n = C.POINTER(C.c_uint32)(), C.c_int()
+        rc = self.lib.mle_genvec(name.encode(), C.byref(p), C.byref(n))
+        if rc:
+            raise MLEArgumentError("unknown generating vector %r" % name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).astype(np.uint32)
+
+    def lattice(self, z=None, s=None, nmax=2**32 - 1):
+        """LatticeRule32(z, s, n); z None -> the default rule LatticeRule32(s) (src/lattice.jl:88)"""
+        zp = None
+        if z is not None:
+            z = np.ascontiguousarray(z, dtype=np.uint32)
+            s = len(z) if s is None else s
+            if s > len(z):
+                raise MLEArgumentError("LatticeRule32: number of dimensions s must be smaller than or equal to the "
+                                       "length of the generating vector z")
+            zp = z.ctypes.data_as(C.POINTER(C.c_uint32))
+        h = C.c_void_p()
+        self._check(self.lib.mle_lattice_create(self.ctx, zp, int(s), int(nmax), C.byref(h)))
+        L = DeviceLattice(self, h, self.lib.mle_lattice_destroy)
+        L.s, L.nmax = int(s), int(nmax)
+        return L
+
+    def dists(self, dists):
+        """dists: sequence of (kind, params) pairs"""
+        arr = (_lib.mle_dist * len(dists))()
+        for j, (kind, pars) in enumerate(dists):
+            arr[j].kind = int(kind)
+            for t, v in enumerate(pars):
+                arr[j].p[t] = float(v)
+        h = C.c_void_p()
+        self._check(self.lib.mle_dists_create(self.ctx, arr, len(dists), C.byref(h)))
+        D = DeviceDists(self, h, self.lib.mle_dists_destroy)
+        D.m = len(dists)
+        return D
+
+    def model(self, name, ndims=1, params=()):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        h = C.c_void_p()
+        self._check(self.lib.mle_model_create(self.ctx, name.encode(), int(ndims), _as_dp(p) if len(p) else None, len(p),
+                                              C.byref(h)))
+        M = DeviceModel(self, h, self.lib.mle_model_destroy)
+        q = C.c_int()
+        self.lib.mle_model_nqoi(h, C.byref(q))
+        M.name, M.ndims, M.nqoi = name, int(ndims), q.value
+        return M
+
+    # ---- stage 1-2 parity hook -------------------------------------------------------------------------------------
+    def points(self, lattice, dists, shifts, k0, n, m=None, mc_seed=0):
+        """-> float64[R, n, m]: transform.(D[1:m], get_point(gen[r], k)[1:m]) for k = k0 .. k0+n-1 (zero-based)"""
+        if shifts is not None:
+            shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+            if lattice is None or shifts.ndim != 2 or shifts.shape[1] != lattice.s:
+                raise MLEArgumentError("shifts must have shape [R, s]")
+            R = shifts.shape[0]
+        else:
+            R = 1
+        if m is None:
+            m = dists.m if dists is not None else lattice.s
+        out = np.empty((R, int(n), int(m)))
+        self._check(self.lib.mle_points(self.ctx, lattice.handle if lattice else None, dists.handle if dists else None,
+                                        _as_dp(shifts), R, int(k0), int(n), int(m), int(mc_seed), _as_dp(out)))
+        return out
+
+    def points_dev(self, lattice, dists, shifts_ptr, R, k0, n, m, out_ptr, mc_seed=0):
+        """device-pointer variant (asynchronous on self.stream)"""
+        self._check(self.lib.mle_points_dev(self.ctx, lattice.handle if lattice else None,
+                                            dists.handle if dists else None, shifts_ptr, int(R), int(k0), int(n),
+                                            int(m), int(mc_seed), out_ptr))
+
+    # ---- the hot path ----------------------------------------------------------------------------------------------
+    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m=None, mc_seed=0, want_samples=False,
+                     want_time=False):
+        """One `parallel_sample!` call.  -> moments float64[R, nqoi, 2, 3] = (n, mean, M2) for X in (dQ, Qf)
+        [, samples float64[R, nqoi, 2, n]] [, gpu_seconds]"""
+        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.int32)
+        if shifts is not None:
+            shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+            if lattice is None or shifts.ndim != 2 or shifts.shape[1] != lattice.s:
+                raise MLEArgumentError("shifts must have shape [R, s]")
+            R = shifts.shape[0]
+        else:
+            R = 1
+        if m is None:
+            m = dists.m if dists is not None else lattice.s
+        mom = np.empty((R, model.nqoi, 2, 3))
+        smp = np.empty((R, model.nqoi, 2, int(n))) if want_samples else None
+        t = C.c_double(0.0)
+        self._check(self.lib.mle_sample_batch(self.ctx, model.handle, lattice.handle if lattice else None,
+                                              dists.handle if dists else None, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              len(idx), _as_dp(shifts), R, int(k0), int(n), int(m), int(mc_seed),
+                                              _as_dp(mom), _as_dp(smp), C.byref(t)))
+        out = (mom,)
+        if want_samples:
+            out += (smp,)
+        if want_time:
+            out += (t.value,)
+        return out[0] if len(out) == 1 else out
+
+    def sample_batch_dev(self, model, lattice, dists, index, shifts_ptr, R, k0, n, m, moments_ptr, samples_ptr=None,
+                         mc_seed=0):
+        """device-pointer variant: asynchronous on self.stream, nothing crosses PCIe"""
+        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.int32)
+        self._check(self.lib.mle_sample_batch_dev(self.ctx, model.handle, lattice.handle if lattice else None,
+                                                  dists.handle if dists else None,
+                                                  idx.ctypes.data_as(C.POINTER(C.c_int32)), len(idx), shifts_ptr, int(R),
+                                                  int(k0), int(n), int(m), int(mc_seed), moments_ptr, samples_ptr))
+
+
+def moments_merge(acc, part):
+    """acc <- acc (+) part for arrays of (n, mean, M2) triplets (last axis 3); fixed-order Chan merge in libmle_cuda"""
+    lib = _lib.load()
+    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    part = np.ascontiguousarray(part, dtype=np.float64)
+    assert acc.shape == part.shape and acc.shape[-1] == 3
+    lib.mle_moments_merge(_as_dp(acc), _as_dp(part), acc.size // 3)
+    return acc

@@ -1,0 +1,17 @@
+"""Synthetic Karhunen-Loeve bases for the lognormal-diffusion device models (host-side input preparation).
+
+In the reference workflow the user builds one `GaussianRandomField` per level with GaussianRandomFields.jl
+(docs/src/example.md:73-80) and the sample function evaluates `sample(grf, xi = omega)`.  The device models take the
+same object in matrix form: Phi_l[node, k] = sqrt(lambda_k) * phi_k(x_node), log a = Phi_l @ xi.  Any basis can be
+supplied; this helper provides the smooth synthetic spectrum used by the tests and the benchmark:
+sqrt(lambda_k) phi_k(x) = sigma * k^(-decay) * sqrt(2) * cos(pi k x), k = 1..m  (SURVEY.md 8d).
+"""
+import numpy as np
+
+
+def kl_basis_1d(level, m=100, n0=16, sigma=0.5, decay=1.5):
+    """-> float64[N+1, m] for the level's grid of N = n0 * 2^level cells on [0, 1]"""
+    N = n0 << level
+    x = np.arange(N + 1, dtype=np.float64) / N
+    k = np.arange(1, m + 1, dtype=np.float64)
+    return np.ascontiguousarray(sigma * np.sqrt(2.0) * k**(-decay) * np.cos(np.pi * np.outer(x, k)))

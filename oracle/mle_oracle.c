@@ -1,0 +1,561 @@
+/* mle_oracle.c -- CPU restatement of the MultilevelEstimators.jl sampling hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (multilevelestimators.jl_b200/,
+ * libmle_cuda) may link, import or call this file; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs do, and only as the checker / CPU baseline.
+ *
+ * What it restates (file:line relative to /root/reference):
+ *   stage 1  rank-1 lattice points            src/lattice.jl:142-145 (unshifted), :168-171 (shifted),
+ *                                             :166,:175 (k > n), :178 (reversebits)
+ *   stage 2  inverse-CDF transforms           src/distribution.jl:84 (Uniform), :112 (Normal),
+ *                                             :145-149 (TruncatedNormal), :151 (Phi^-1), :153 (Phi), :182 (Weibull)
+ *            erfinv                           SpecialFunctions.jl (compat "2", Project.toml:25; NOT in the tree):
+ *                                             Blair-Edwards-Johnson rational approximants, @horner = fused muladd chain
+ *   stage 3  sample functions                 test/regression.jl:17-46, :69-103 (problem_18, the only executable sample
+ *                                             function in the reference); docs/src/example.md:106-128 (structure of the
+ *                                             lognormal-diffusion function: fine field, coarse = stride-2 view, QoI at the
+ *                                             mid index, return (dQ, Qf)); src/index.jl:49-58 (diff signs)
+ *   stage 4  per-(qoi, shift) statistics      src/sample.jl:39-56, :79-111 (loop order, zero-based k, (shift, k) product);
+ *                                             src/methods.jl:44-57, :282 (mean / corrected var per shift)
+ *
+ * Parity pinning: stages 1-2 are pinned by the reference's doctest golden vectors (tests/golden/, SURVEY.md 8c:
+ * G1, G2, G4 bit-exact; G5-G8 to the reference's own tolerance).  problem_18 restates reference test code.
+ * The lognormal-diffusion models are NOT in the reference tree (they live in GaussianRandomFields.jl /
+ * SimpleMultigrid.jl): for those this oracle is "parity unpinned" -- it defines the model that the CUDA path must match.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off -mfma; every fused multiply-add is an explicit fma()).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* the published generating vectors the reference reads at src/lattice.jl:88-90 (embedded, see tools/embed_genvecs.py) */
+#include "../include/mle_genvec_data.inc"
+ORC_API const uint32_t *orc_genvec(int which, int *len) {
+    if (which == 0) { *len = MLE_GENVEC_K3600_LEN; return MLE_GENVEC_K3600; }
+    if (which == 1) { *len = MLE_GENVEC_CKN250_LEN; return MLE_GENVEC_CKN250; }
+    *len = 0;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* stage 1: lattice points                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* src/lattice.jl:178  reversebits(n) = parse(U, reverse(bitstring(n)), base=2) */
+ORC_API uint32_t orc_reversebits32(uint32_t v) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
+    return r;
+}
+
+/* src/lattice.jl:143 / :169   phi = reversebits(xor(k, k >> 1)) */
+ORC_API uint32_t orc_phi(uint32_t k) { return orc_reversebits32(k ^ (k >> 1)); }
+
+/* One coordinate.  src/lattice.jl:144 (shift == NULL):  phi * 2.0^(-32) * z .% 1
+ *                  src/lattice.jl:170:                  (phi * 2.0^(-32) * z .+ shift) .% 1
+ * phi*2^-32 is exact; the product with z is rounded once; the shift is added to the UNREDUCED product
+ * and rounded again; `% 1` on Float64 is fmod (exact). */
+static inline double orc_coord(uint32_t phi, uint32_t zj, const double *shiftj) {
+    double t = (double)phi * 0x1p-32;
+    double p = t * (double)zj; /* separately rounded (built with -ffp-contract=off) */
+    if (shiftj) {
+        double s = p + *shiftj;
+        return fmod(s, 1.0);
+    }
+    return fmod(p, 1.0);
+}
+
+/* get_point(rule, k) for one (shift, k): x[0..s-1].  Returns -1 when k > nmax (the reference then returns
+ * rand(s), src/lattice.jl:166,175 -- not reproducible, treated as an argument error by the engine). */
+ORC_API int orc_get_point(const uint32_t *z, int s, uint64_t nmax, const double *shift, uint64_t k, double *x) {
+    if (k > nmax || k > 0xffffffffull) return -1;
+    uint32_t phi = orc_phi((uint32_t)k);
+    for (int j = 0; j < s; ++j) x[j] = orc_coord(phi, z[j], shift ? shift + j : NULL);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* stage 2: transforms                                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* @horner(t, c0, c1, ..., cn): acc = cn; acc = muladd(t, acc, c_{n-1}) ... (fused on every FMA machine) */
+static inline double horner(double t, const double *c, int n) {
+    double acc = c[n - 1];
+    for (int i = n - 2; i >= 0; --i) acc = fma(t, acc, c[i]);
+    return acc;
+}
+
+static const double P1[7] = {0.16030495584406622931e2, -0.9078495926296032665e2, 0.18644914861620987391e3,
+                             -0.16900142734642382420e3, 0.654546628479448704e2, -0.86421301158724779e1,
+                             0.17605878213905900};
+static const double Q1[7] = {0.14780647071513831611e2, -0.9137416702426031394e2, 0.21015790486205317714e3,
+                             -0.22210254121855132366e3, 0.10760453916055123830e3, -0.20601073032826544e2, 1.0};
+static const double P2[8] = {-0.15238926344072612e-1, 0.3444556924136125216, -0.29344398672542478687e1,
+                             0.11763505705217827302e2, -0.22655292823101104193e2, 0.19121334396580330163e2,
+                             -0.5478927619598318769e1, 0.237516689024448};
+static const double Q2[8] = {-0.10846516960205995e-1, 0.2610628885843078511, -0.24068318104393757995e1,
+                             0.10695129973387014469e2, -0.23716715521596581025e2, 0.24640158943917284883e2,
+                             -0.10014376349783070835e2, 1.0};
+static const double P3[9] = {0.10501311523733438116e-3, 0.1053261131423333816425e-1, 0.26987802736243283544516,
+                             0.23268695788919690806414e1, 0.71678547949107996810001e1, 0.85475611822167827825185e1,
+                             0.68738088073543839802913e1, 0.3627002483095870893002e1, 0.886062739296515468149};
+static const double Q3[10] = {0.10501266687030337690e-3, 0.1053286230093332753111e-1, 0.27019862373751554845553,
+                              0.23501436397970253259123e1, 0.76078028785801277064351e1, 0.111815861040569078273451e2,
+                              0.119487879184353966678438e2, 0.81922409747269907893913e1, 0.4099387907636801536145e1,
+                              1.0};
+
+/* SpecialFunctions.erfinv(::Float64) -- see the header comment; |x| > 1 returns NaN here (DomainError there). */
+ORC_API double orc_erfinv(double x) {
+    double a = fabs(x);
+    if (a >= 1.0) {
+        if (x == 1.0) return INFINITY;
+        if (x == -1.0) return -INFINITY;
+        return NAN;
+    }
+    if (a <= 0.75) {
+        double xx = x * x;
+        double t = xx - 0.5625;
+        double num = x * horner(t, P1, 7);
+        return num / horner(t, Q1, 7);
+    }
+    if (a <= 0.9375) {
+        double xx = x * x;
+        double t = xx - 0.87890625;
+        double num = x * horner(t, P2, 8);
+        return num / horner(t, Q2, 8);
+    }
+    double t = 1.0 / sqrt(-log1p(-a));
+    double den = copysign(t, x) * horner(t, Q3, 10);
+    return horner(t, P3, 9) / den;
+}
+
+/* src/distribution.jl:151   Phi^-1(x) = sqrt(2) * erfinv(2*x - 1) */
+ORC_API double orc_norminv(double x) {
+    double u = 2.0 * x - 1.0; /* 2*x is exact, so one rounding either way */
+    return 1.4142135623730951 * orc_erfinv(u);
+}
+
+/* src/distribution.jl:153   Phi(x) = 1/2*(1 + erf(x/sqrt(2))) */
+ORC_API double orc_normcdf(double x) {
+    double q = x / 1.4142135623730951;
+    double e = 1.0 + erf(q);
+    return 0.5 * e;
+}
+
+enum { ORC_UNIFORM = 0, ORC_NORMAL = 1, ORC_TRUNCNORMAL = 2, ORC_WEIBULL = 3 };
+
+/* transform(D, x).  p = {a,b} | {mu,sigma} | {mu,sigma,a,b} | {k,lambda}.  Every operation individually rounded
+ * (Julia does not contract a + b*c). */
+ORC_API double orc_transform(int kind, const double *p, double x) {
+    switch (kind) {
+    case ORC_UNIFORM: { /* :84  a + (b - a)*x */
+        double w = p[1] - p[0];
+        double wx = w * x;
+        return p[0] + wx;
+    }
+    case ORC_NORMAL: { /* :112  mu + sigma*Phi^-1(x) */
+        double sy = p[1] * orc_norminv(x);
+        return p[0] + sy;
+    }
+    case ORC_TRUNCNORMAL: { /* :145-149 */
+        double al = (p[2] - p[0]) / p[1];
+        double be = (p[3] - p[0]) / p[1];
+        double Fa = orc_normcdf(al);
+        double Fb = orc_normcdf(be);
+        double d = Fb - Fa;
+        double dx = d * x;
+        double arg = Fa + dx;
+        double sy = p[1] * orc_norminv(arg);
+        return p[0] + sy;
+    }
+    case ORC_WEIBULL: { /* :182  lambda * (-log(1 - x))^(1/k) */
+        double om = 1.0 - x;
+        double l = -log(om);
+        double ik = 1.0 / p[0];
+        double pw = pow(l, ik);
+        return p[1] * pw;
+    }
+    default:
+        return x; /* identity: raw points */
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* MC uniforms: counter-based SplitMix64.  The reference draws rand(m) from Julia's task-local Xoshiro     */
+/* (src/sample.jl:42) which is not reproducible outside Julia; the engine defines its own counter stream.  */
+/* u(seed, k, j) = ((mix(seed + GOLDEN*(k*m + j + 1)) >> 12) + 0.5) * 2^-52  in (0, 1).                     */
+/* ------------------------------------------------------------------------------------------------ */
+ORC_API uint64_t orc_splitmix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+ORC_API double orc_mc_uniform(uint64_t seed, uint64_t k, uint32_t m, uint32_t j) {
+    uint64_t ctr = k * (uint64_t)m + j + 1ull;
+    uint64_t v = orc_splitmix64(seed + 0x9e3779b97f4a7c15ull * ctr);
+    return ((double)(v >> 12) + 0.5) * 0x1p-52;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* points for a whole (shift, k) rectangle: the parity hook for stages 1-2                             */
+/* out[(r*n + i)*m + j],  k = k0 + i.  kinds == NULL -> raw points.  z == NULL -> MC uniforms (R = 1). */
+/* ------------------------------------------------------------------------------------------------ */
+ORC_API int orc_points(const uint32_t *z, int s, uint64_t nmax, const int *kinds, const double *pars /*4 per dim*/,
+                       int m, const double *shifts /* [R][s] or NULL */, int R, uint64_t k0, uint64_t n,
+                       uint64_t mc_seed, double *out) {
+    if (z && m > s) return -2; /* reference pads with rand(): not reproducible (src/sample.jl:85) */
+    if (z && n && (k0 + n - 1 > nmax || k0 + n - 1 > 0xffffffffull)) return -1;
+    for (int r = 0; r < R; ++r) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            uint64_t k = k0 + (uint64_t)i;
+            double *o = out + ((size_t)r * n + (size_t)i) * m;
+            uint32_t phi = z ? orc_phi((uint32_t)k) : 0;
+            for (int j = 0; j < m; ++j) {
+                double x = z ? orc_coord(phi, z[j], shifts ? shifts + (size_t)r * s + j : NULL)
+                             : orc_mc_uniform(mc_seed, k, (uint32_t)m, (uint32_t)j);
+                o[j] = kinds ? orc_transform(kinds[j], pars + 4 * j, x) : x;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* stage 3: sample functions (the device-model registry, restated on the CPU)                        */
+/* ------------------------------------------------------------------------------------------------ */
+enum { ORC_MODEL_EXPSUM = 0, ORC_MODEL_PROBLEM18 = 1, ORC_MODEL_LOGNORMAL1D = 2, ORC_MODEL_LOGNORMAL2D = 3 };
+
+#define ORC_MAX_LEVELS 16
+typedef struct {
+    int kind;
+    int nqoi;
+    int ndims;     /* dimension of the index (1 = multilevel, 2 = multi-index) */
+    int n0;        /* coarsest number of cells per direction (lognormal) / coarsest active dims (expsum) */
+    int nweights;  /* expsum */
+    double *weights;
+    /* lognormal: KL basis per level, row-major [nodes][m] */
+    int basis_rows[ORC_MAX_LEVELS];
+    int basis_cols[ORC_MAX_LEVELS];
+    double *basis[ORC_MAX_LEVELS];
+} orc_model;
+
+ORC_API orc_model *orc_model_create(int kind, int ndims, const double *params, int nparams) {
+    orc_model *M = (orc_model *)calloc(1, sizeof(orc_model));
+    M->kind = kind;
+    M->ndims = ndims;
+    M->nqoi = 1;
+    if (kind == ORC_MODEL_EXPSUM) { /* params = {m0, a_1 ... a_m} */
+        M->n0 = (int)params[0];
+        M->nweights = nparams - 1;
+        M->weights = (double *)malloc(sizeof(double) * (size_t)(nparams - 1));
+        memcpy(M->weights, params + 1, sizeof(double) * (size_t)(nparams - 1));
+    } else if (kind == ORC_MODEL_PROBLEM18) {
+        M->nqoi = 13;
+    } else { /* lognormal: params = {n0} */
+        M->n0 = nparams > 0 ? (int)params[0] : 16;
+    }
+    return M;
+}
+
+ORC_API int orc_model_set_basis(orc_model *M, int level, int rows, int cols, const double *phi) {
+    if (level < 0 || level >= ORC_MAX_LEVELS) return -1;
+    free(M->basis[level]);
+    M->basis[level] = (double *)malloc(sizeof(double) * (size_t)rows * cols);
+    memcpy(M->basis[level], phi, sizeof(double) * (size_t)rows * cols);
+    M->basis_rows[level] = rows;
+    M->basis_cols[level] = cols;
+    return 0;
+}
+
+ORC_API void orc_model_destroy(orc_model *M) {
+    if (!M) return;
+    free(M->weights);
+    for (int l = 0; l < ORC_MAX_LEVELS; ++l) free(M->basis[l]);
+    free(M);
+}
+
+ORC_API int orc_model_nqoi(const orc_model *M) { return M->nqoi; }
+
+/* --- expsum: Q_l(xi) = exp(sum_{j < m_l} a_j xi_j), m_l = min(m, m0 * 2^l); dQ = Q_l - Q_{l-1} ---------- */
+static double expsum_q(const orc_model *M, int level, const double *xi, int m) {
+    long ml = (long)M->n0 << level;
+    if (ml > m) ml = m;
+    if (ml > M->nweights) ml = M->nweights;
+    double acc = 0.0;
+    for (long j = 0; j < ml; ++j) acc = fma(M->weights[j], xi[j], acc);
+    return exp(acc);
+}
+
+/* --- problem_18: test/regression.jl:17-36 (1-d), :69-103 (2-d) --------------------------------------- */
+static double p18_coef(int l, double xj) { /* the level-dependent factor of xi^3 */
+    if (l == 3) return 1.0;
+    if (l == 2) return 1.1;
+    if (l == 1) {
+        double q = xj / 60.0;
+        return q + 1.2;
+    }
+    return 1.5; /* 3/2 */
+}
+
+static void problem18_eval(int ndims, const int *idx, const double *xi, double *f) {
+    const int n = 13;
+    double x1sq = xi[0] * xi[0];
+    double x13 = x1sq * xi[0]; /* xi * xi * xi, left to right */
+    double x23 = 0.0;
+    if (ndims == 2) {
+        double x2sq = xi[1] * xi[1];
+        double t = x2sq * xi[1];
+        x23 = t;
+    }
+    for (int j = 0; j < n; ++j) {
+        /* range(0, 6, 13)[j] = j * 0.5 exactly */
+        double xj = 0.5 * j;
+        double fj;
+        if (xj <= 3.0) {
+            fj = (xj - 2.0) * (xj - 2.0);
+        } else {
+            double lg = 2.0 * log(xj - 2.0);
+            fj = lg + 1.0;
+        }
+        double t1 = p18_coef(idx[0], xj) * x13;
+        double acc = fj + t1;
+        if (ndims == 2) {
+            double t2 = p18_coef(idx[1], xj) * x23;
+            acc = acc + t2;
+            if (idx[0] > 0 && idx[1] > 0) {
+                double c = 0.03125 * x13; /* 1/32 * xi13 * xi23, left to right */
+                double t3 = c * x23;
+                acc = acc + t3;
+            }
+        }
+        f[j] = acc;
+    }
+}
+
+/* --- lognormal diffusion, 1-D:  -(a u')' = 1 on (0,1), u(0) = u(1) = 0 ------------------------------------
+ * level l: N = n0 * 2^l cells, nodes 0..N; log a at node i = sum_k Phi_l[i][k] xi_k (k ascending, fused);
+ * interface coefficient kappa_{i+1/2} = 0.5*(a_i + a_{i+1});
+ * (kappa_{i-1/2} + kappa_{i+1/2}) u_i - kappa_{i-1/2} u_{i-1} - kappa_{i+1/2} u_{i+1} = h^2, i = 1..N-1, h = 1/N;
+ * QoI = u at node N/2.  The mid value comes from a two-sided (twisted) Thomas elimination: left sweep up to
+ * N/2 - 1, right sweep down to N/2 + 1, then the 1x1 system at N/2.  The coarse problem uses the even nodes of
+ * the fine field (docs/src/example.md:120) with N/2 cells. */
+static double tridiag_mid(const double *a /* node values, stride st */, int st, int N) {
+    int M = N / 2;
+    double h2 = 1.0 / ((double)N * (double)N);
+#define KAPPA(i) (0.5 * (a[(size_t)(i) * st] + a[(size_t)((i) + 1) * st])) /* kappa_{i+1/2} */
+    /* left sweep: rows 1 .. M-1 */
+    double p = 0.0, y = 0.0;
+    int have_left = 0;
+    for (int i = 1; i <= M - 1; ++i) {
+        double km = KAPPA(i - 1), kp = KAPPA(i);
+        double b = km + kp;
+        if (!have_left) { p = b; y = h2; have_left = 1; }
+        else {
+            double w = km / p;
+            p = fma(-w, km, b);
+            y = fma(w, y, h2);
+        }
+    }
+    /* right sweep: rows N-1 .. M+1 */
+    double q = 0.0, zz = 0.0;
+    int have_right = 0;
+    for (int i = N - 1; i >= M + 1; --i) {
+        double km = KAPPA(i - 1), kp = KAPPA(i);
+        double b = km + kp;
+        if (!have_right) { q = b; zz = h2; have_right = 1; }
+        else {
+            double w = kp / q;
+            q = fma(-w, kp, b);
+            zz = fma(w, zz, h2);
+        }
+    }
+    double km = KAPPA(M - 1), kp = KAPPA(M);
+    double den = km + kp, num = h2;
+    if (have_left) { double w = km / p; den = fma(-w, km, den); num = fma(w, y, num); }
+    if (have_right) { double w = kp / q; den = fma(-w, kp, den); num = fma(w, zz, num); }
+#undef KAPPA
+    return num / den;
+}
+
+/* full Thomas solve (all unknowns) -- used by tests to cross-check the twisted mid value */
+ORC_API double orc_tridiag_mid_full(const double *a, int N) {
+    int n = N - 1;
+    double *c = (double *)malloc(sizeof(double) * (size_t)n), *d = (double *)malloc(sizeof(double) * (size_t)n);
+    double h2 = 1.0 / ((double)N * (double)N);
+    for (int i = 1; i <= n; ++i) {
+        double km = 0.5 * (a[i - 1] + a[i]), kp = 0.5 * (a[i] + a[i + 1]);
+        double b = km + kp, lo = -km, up = -kp;
+        if (i == 1) { c[0] = up / b; d[0] = h2 / b; }
+        else {
+            double den = b - lo * c[i - 2];
+            c[i - 1] = up / den;
+            d[i - 1] = (h2 - lo * d[i - 2]) / den;
+        }
+    }
+    double *u = (double *)malloc(sizeof(double) * (size_t)n);
+    u[n - 1] = d[n - 1];
+    for (int i = n - 2; i >= 0; --i) u[i] = d[i] - c[i] * u[i + 1];
+    double r = u[N / 2 - 1];
+    free(c); free(d); free(u);
+    return r;
+}
+
+ORC_API double orc_tridiag_mid(const double *a, int st, int N) { return tridiag_mid(a, st, N); }
+
+static int lognormal1d_eval(const orc_model *M, int level, const double *xi, int m, double *dQ, double *Qf,
+                            double *work /* >= nodes */) {
+    const double *Phi = M->basis[level];
+    if (!Phi) return -3;
+    int N = M->n0 << level;
+    if (M->basis_rows[level] != N + 1 || M->basis_cols[level] < m) return -3;
+    int ld = M->basis_cols[level];
+    for (int i = 0; i <= N; ++i) {
+        double g = 0.0;
+        const double *row = Phi + (size_t)i * ld;
+        for (int k = 0; k < m; ++k) g = fma(row[k], xi[k], g);
+        work[i] = exp(g);
+    }
+    double qf = tridiag_mid(work, 1, N);
+    *Qf = qf;
+    *dQ = qf;
+    if (level > 0) {
+        double qc = tridiag_mid(work, 2, N / 2);
+        *dQ = qf - qc;
+    }
+    return 0;
+}
+
+/* f(index, xi) -> (dQ[nqoi], Qf[nqoi]).   dQ = Qf + sum_{(kappa, +-1) in diff(index)} +- Q_kappa  (src/index.jl:49-58) */
+ORC_API int orc_model_eval(const orc_model *M, const int *index, const double *xi, int m, double *dQ, double *Qf) {
+    switch (M->kind) {
+    case ORC_MODEL_EXPSUM: {
+        double qf = expsum_q(M, index[0], xi, m);
+        Qf[0] = qf;
+        dQ[0] = index[0] > 0 ? qf - expsum_q(M, index[0] - 1, xi, m) : qf;
+        return 0;
+    }
+    case ORC_MODEL_PROBLEM18: {
+        double f[13];
+        problem18_eval(M->ndims, index, xi, Qf);
+        for (int j = 0; j < 13; ++j) dQ[j] = Qf[j];
+        /* diff(index): all I in [max(0, index-1), index] except index itself, sign -1 if |index - I|_1 odd.
+         * Dict iteration order in Julia is unspecified; for d = 2 the three terms are added here in the order
+         * (i-1, j-1), (i, j-1), (i-1, j)  [column-major CartesianIndices order]. */
+        int lo0 = index[0] > 0 ? index[0] - 1 : 0;
+        int lo1 = (M->ndims == 2) ? (index[1] > 0 ? index[1] - 1 : 0) : 0;
+        int hi1 = (M->ndims == 2) ? index[1] : 0;
+        for (int b = lo1; b <= hi1; ++b)
+            for (int a = lo0; a <= index[0]; ++a) {
+                if (a == index[0] && b == hi1) continue;
+                int I[2] = {a, b};
+                int dist = (index[0] - a) + (hi1 - b);
+                double sgn = (dist & 1) ? -1.0 : 1.0;
+                problem18_eval(M->ndims, I, xi, f);
+                for (int j = 0; j < 13; ++j) {
+                    double t = sgn * f[j];
+                    dQ[j] = dQ[j] + t;
+                }
+            }
+        return 0;
+    }
+    case ORC_MODEL_LOGNORMAL1D: {
+        int N = M->n0 << index[0];
+        double *work = (double *)malloc(sizeof(double) * (size_t)(N + 1));
+        int rc = lognormal1d_eval(M, index[0], xi, m, dQ, Qf, work);
+        free(work);
+        return rc;
+    }
+    default:
+        return -4;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* stage 4: the whole batch, the way the reference runs it                                           */
+/*   for (r, i) in product(1:R, Istart:Iend):  xi = transform.(D[1:m], get_point(gen[r], i-1)[1:m])    */
+/*                                             (dQ, Qf) = f(index, xi)           src/sample.jl:79-102 */
+/*   then per (shift, qoi): mean and corrected variance of the n values        src/methods.jl:44-57  */
+/* moments[((r*nqoi + q)*2 + X)*3 + {0,1,2}] = {n, mean, M2 = sum (x - mean)^2},  X = 0: dQ, 1: Qf      */
+/* samples (optional) [((r*nqoi + q)*2 + X)*n + i]                                                     */
+/* Sums are carried in long double so the oracle is (much) closer to the exact statistics than 1e-12.  */
+/* ------------------------------------------------------------------------------------------------ */
+ORC_API int orc_sample_batch(const orc_model *M, const uint32_t *z, int s, uint64_t nmax, const int *kinds,
+                             const double *pars, int m, const int *index, const double *shifts, int R, uint64_t k0,
+                             uint64_t n, uint64_t mc_seed, double *moments, double *samples_or_null) {
+    int q = M->nqoi;
+    if (z && m > s) return -2;
+    if (z && n && (k0 + n - 1 > nmax || k0 + n - 1 > 0xffffffffull)) return -1;
+    size_t per = (size_t)2 * q * n;
+    double *buf = samples_or_null ? samples_or_null : (double *)malloc(sizeof(double) * per * (size_t)R);
+    if (!buf) return -5;
+    int rc_all = 0;
+#pragma omp parallel
+    {
+        double *xi = (double *)malloc(sizeof(double) * (size_t)m);
+        double *dq = (double *)malloc(sizeof(double) * (size_t)q * 2);
+        double *qf = dq + q;
+        /* the reference farms out one (shift, k) item at a time (pmap, batch_size = 1, src/sample.jl:93-95) */
+#pragma omp for schedule(dynamic, 8) collapse(2)
+        for (int r = 0; r < R; ++r)
+            for (int64_t i = 0; i < (int64_t)n; ++i) {
+                uint64_t k = k0 + (uint64_t)i;
+                uint32_t phi = z ? orc_phi((uint32_t)k) : 0;
+                for (int j = 0; j < m; ++j) {
+                    double x = z ? orc_coord(phi, z[j], shifts ? shifts + (size_t)r * s + j : NULL)
+                                 : orc_mc_uniform(mc_seed, k, (uint32_t)m, (uint32_t)j);
+                    xi[j] = kinds ? orc_transform(kinds[j], pars + 4 * j, x) : x;
+                }
+                int rc = orc_model_eval(M, index, xi, m, dq, qf);
+                if (rc) {
+#pragma omp atomic write
+                    rc_all = rc;
+                }
+                for (int c = 0; c < q; ++c) {
+                    buf[(((size_t)r * q + c) * 2 + 0) * n + (size_t)i] = dq[c];
+                    buf[(((size_t)r * q + c) * 2 + 1) * n + (size_t)i] = qf[c];
+                }
+            }
+        free(xi);
+        free(dq);
+    }
+    if (rc_all) { if (!samples_or_null) free(buf); return rc_all; }
+    for (size_t v = 0; v < (size_t)R * q * 2; ++v) {
+        const double *x = buf + v * n;
+        long double sum = 0.0L;
+        for (uint64_t i = 0; i < n; ++i) sum += x[i];
+        long double mean = n ? sum / (long double)n : 0.0L;
+        long double m2 = 0.0L;
+        for (uint64_t i = 0; i < n; ++i) { long double d = x[i] - mean; m2 += d * d; }
+        moments[v * 3 + 0] = (double)n;
+        moments[v * 3 + 1] = (double)mean;
+        moments[v * 3 + 2] = (double)m2;
+    }
+    if (!samples_or_null) free(buf);
+    return 0;
+}
+
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* Returns 1 when this object was compiled WITHOUT floating-point contraction (required: every fused operation in this
+ * file is an explicit fma()).  a*b + c below differs between the fused and the separately rounded evaluation. */
+ORC_API int orc_selftest_nocontract(void) {
+    volatile double a = 1.0 + 0x1p-30, b = 1.0 - 0x1p-30, c = -1.0;
+    double r = a * b + c; /* exact product 1 - 2^-60 rounds to 1.0 -> r == 0 when not contracted */
+    return r == 0.0;
+}

@@ -1,0 +1,82 @@
+"""CPU tests of the drop-in boundary: libmle_cuda.so loads without a GPU, exports every symbol that
+include/mle_cuda.h declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "mle_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mle_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    import mle_b200
+    lib = mle_b200._lib.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libmle_cuda.so does not export %s" % n
+        assert n in mle_b200._lib.SIGNATURES, "no ctypes prototype for %s" % n
+    assert lib.mle_abi_version() == 1
+
+
+def test_no_torch_types_in_the_boundary():
+    hdr = open(os.path.join(ROOT, "include", "mle_cuda.h")).read()
+    assert "torch" not in hdr and "at::" not in hdr and "std::" not in hdr
+
+
+def test_embedded_generating_vectors_match_the_oracle(oracle):
+    import mle_b200
+    lib = mle_b200._lib.load()
+    for name, n in (("K_3600_32", 3600), ("CKN_250_20", 250)):
+        p, ln = C.POINTER(C.c_uint32)(), C.c_int()
+        assert lib.mle_genvec(name.encode(), C.byref(p), C.byref(ln)) == 0 and ln.value == n
+        z = np.ctypeslib.as_array(p, shape=(n,))
+        assert np.array_equal(z, oracle.genvec(name))
+        assert z[0] == 1
+    z = oracle.genvec("K_3600_32")
+    assert z.max() == 521301 and oracle.genvec("CKN_250_20").max() < 2**20
+
+
+def test_moments_merge_is_chan(oracle):
+    import mle_b200
+    rng = np.random.default_rng(0)
+    x = rng.normal(3.0, 2.0, size=1000)
+    parts = np.split(x, [10, 11, 500])
+    acc = np.zeros((1, 3))
+    for p in parts:
+        acc = mle_b200.moments_merge(acc, np.array([[len(p), p.mean(), ((p - p.mean())**2).sum()]]))
+    assert acc[0, 0] == 1000
+    assert abs(acc[0, 1] - x.mean()) < 1e-14 * abs(x.mean())
+    assert abs(acc[0, 2] - ((x - x.mean())**2).sum()) < 1e-12 * acc[0, 2]
+
+
+def test_fails_loudly_without_a_gpu():
+    import torch
+    import mle_b200
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mle_b200.MLEError) as e:
+        mle_b200.Engine(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_uses_the_oracle():
+    """the product path must not import, include, link or dlopen anything under oracle/ (comments may cite it)"""
+    pkg = os.path.join(ROOT, "multilevelestimators.jl_b200")
+    bad = re.compile(r"(^\s*(import|from)\s+oracle\b|#include\s*[\"<][^\">]*oracle|libmle_oracle|\borc_[a-z])", re.M)
+    seen = 0
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                seen += 1
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not bad.search(src), fn
+    assert seen >= 5

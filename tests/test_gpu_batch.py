@@ -1,0 +1,148 @@
+"""GPU parity, stages 3-4 (through the C ABI): per-(qoi, shift) moments of one `parallel_sample!` call against the
+oracle run on identical points.  North star: level means and variances within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from conftest import splitmix_uniforms
+
+pytestmark = pytest.mark.gpu
+
+NORMAL01 = (1, [0.0, 1.0])
+RTOL = 1e-12  # north star: means and variances within 1e-12 relative for identical points
+
+
+def check_moments(got, want, smp_got=None, smp_want=None, rtol=RTOL):
+    assert got.shape == want.shape
+    assert np.array_equal(got[..., 0], want[..., 0])
+    scale = np.sqrt(want[..., 2] / np.maximum(want[..., 0], 1)) + np.abs(want[..., 1])  # mean error relative to |mean| + std
+    assert np.all(np.abs(got[..., 1] - want[..., 1]) <= rtol * scale)
+    assert np.all(np.abs(got[..., 2] - want[..., 2]) <= rtol * np.abs(want[..., 2]) + 1e-300)
+    if smp_got is not None:
+        assert np.allclose(smp_got, smp_want, rtol=1e-13, atol=1e-16)
+
+
+def expsum_setup(engine, oracle, s, m0=4):
+    z = oracle.genvec("K_3600_32", s)
+    w = [0.5 / (j + 1) for j in range(s)]
+    return (z, engine.lattice(z, s), [NORMAL01] * s, engine.dists([NORMAL01] * s),
+            engine.model("expsum", 1, [m0] + w), oracle.Model(oracle.MODEL_EXPSUM, 1, [m0] + w))
+
+
+@pytest.mark.parametrize("s,R,level,k0,n", [(16, 1, 0, 0, 1), (16, 4, 0, 0, 2), (16, 16, 2, 0, 127), (100, 16, 3, 0, 128),
+                                            (100, 3, 6, 1000, 129), (100, 16, 1, 7, 5000), (130, 2, 9, 0, 777)])
+def test_expsum_qmc(engine, oracle, s, R, level, k0, n):
+    z, lat, dl, d, gm, om = expsum_setup(engine, oracle, s)
+    sh = splitmix_uniforms(2024, R * s).reshape(R, s)
+    got, smp = engine.sample_batch(gm, lat, d, [level], sh, k0, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, k0, n, want_samples=True)
+    if n > 1:
+        check_moments(got, want, smp, smp_w)
+    else:
+        assert np.allclose(got[..., 1], want[..., 1], rtol=1e-14) and (got[..., 2] == 0).all()
+
+
+def test_expsum_mc_and_closed_form(engine, oracle):
+    """config C1: SL/MC on 16 Normal() inputs, Q = exp(sum a_j xi_j), E[Q] = exp(sum a_j^2 / 2)"""
+    s = 16
+    w = [0.5 / (j + 1) for j in range(s)]
+    d = engine.dists([NORMAL01] * s)
+    gm = engine.model("expsum", 1, [s] + w)
+    om = oracle.Model(oracle.MODEL_EXPSUM, 1, [s] + w)
+    n = 200000
+    got = engine.sample_batch(gm, None, d, [0], None, 0, n, mc_seed=1)
+    want = oracle.sample_batch(om, None, [NORMAL01] * s, [0], None, 0, n, mc_seed=1)
+    check_moments(got, want)
+    exact = np.exp(0.5 * np.sum(np.square(w)))
+    se = np.sqrt(got[0, 0, 1, 2] / (n - 1) / n)
+    assert abs(got[0, 0, 1, 1] - exact) < 5 * se
+
+
+def test_batches_merge_like_one_call(engine, oracle):
+    """samples persist across calls in the reference: merging the moments of consecutive k-ranges
+    must equal the moments of the union"""
+    import mle_b200
+    z, lat, dl, d, gm, om = expsum_setup(engine, oracle, 32)
+    sh = splitmix_uniforms(4, 5 * 32).reshape(5, 32)
+    whole = engine.sample_batch(gm, lat, d, [2], sh, 0, 3000)
+    acc = engine.sample_batch(gm, lat, d, [2], sh, 0, 1)
+    for k0, n in [(1, 9), (10, 990), (1000, 2000)]:
+        acc = mle_b200.moments_merge(acc, engine.sample_batch(gm, lat, d, [2], sh, k0, n))
+    check_moments(acc, whole)
+    check_moments(acc, oracle.sample_batch(om, z, dl, [2], sh, 0, 3000))
+
+
+@pytest.mark.parametrize("ndims,index,R,n", [(1, [0], 4, 300), (1, [3], 16, 1000), (2, [0, 0], 2, 257), (2, [2, 1], 4, 640),
+                                             (2, [3, 3], 3, 100), (2, [0, 2], 1, 50)])
+def test_problem18_reference_test_function(engine, oracle, ndims, index, R, n):
+    """test/regression.jl: problem_18 with Uniform(-0.5, 0.5) inputs, 13 QoI, multi-index differences"""
+    z = oracle.genvec("K_3600_32", ndims)
+    lat = engine.lattice(z, ndims)
+    dl = [(0, [-0.5, 0.5])] * ndims
+    d = engine.dists(dl)
+    gm = engine.model("problem18", ndims)
+    om = oracle.Model(oracle.MODEL_PROBLEM18, ndims)
+    assert gm.nqoi == 13
+    sh = splitmix_uniforms(31, R * ndims).reshape(R, ndims)
+    got, smp = engine.sample_batch(gm, lat, d, index, sh, 0, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, index, sh, 0, n, want_samples=True)
+    assert got.shape == (R, 13, 2, 3)
+    assert np.allclose(smp, smp_w, rtol=0, atol=4e-16)  # log() of a handful of constants may differ by an ulp
+    check_moments(got, want, rtol=1e-11)  # dQ of several QoI is ~1e-2 * xi^3 on O(1) values: absolute rounding dominates
+
+
+def test_problem18_mc(engine, oracle):
+    d = engine.dists([(0, [-0.5, 0.5])])
+    gm = engine.model("problem18", 1)
+    om = oracle.Model(oracle.MODEL_PROBLEM18, 1)
+    got = engine.sample_batch(gm, None, d, [1], None, 0, 5000, mc_seed=3)
+    want = oracle.sample_batch(om, None, [(0, [-0.5, 0.5])], [1], None, 0, 5000, mc_seed=3)
+    check_moments(got, want, rtol=1e-11)
+
+
+def lognormal_setup(engine, oracle, m, levels, n0=16):
+    import mle_b200.kl as kl
+    z = oracle.genvec("K_3600_32", m)
+    gm = engine.model("lognormal1d", 1, [n0])
+    om = oracle.Model(oracle.MODEL_LOGNORMAL1D, 1, [float(n0)])
+    for lev in levels:
+        phi = kl.kl_basis_1d(lev, m=m, n0=n0)
+        gm.set_basis(lev, phi)
+        om.set_basis(lev, phi)
+    return z, engine.lattice(z, m), [NORMAL01] * m, engine.dists([NORMAL01] * m), gm, om
+
+
+@pytest.mark.parametrize("level,R,k0,n", [(0, 16, 0, 1), (0, 2, 0, 64), (1, 3, 5, 65), (2, 16, 0, 200), (3, 2, 0, 127),
+                                          (4, 16, 100, 32), (5, 2, 0, 70), (6, 2, 0, 40)])
+def test_lognormal1d_levels(engine, oracle, level, R, k0, n):
+    """config C2 shape: 100 KL terms, grid 2^(l+4), levels 0-6, randomly shifted lattice"""
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 100, [level])
+    sh = splitmix_uniforms(2024, R * 100).reshape(R, 100)
+    got, smp = engine.sample_batch(gm, lat, d, [level], sh, k0, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, k0, n, want_samples=True)
+    # per-sample values: identical elimination order, exp() from a different libm -> a few 1e-16 relative on Qf
+    assert np.allclose(smp[:, 0, 1], smp_w[:, 0, 1], rtol=1e-13, atol=0)
+    assert np.allclose(smp[:, 0, 0], smp_w[:, 0, 0], rtol=0, atol=1e-15)
+    if n > 1:
+        check_moments(got, want, rtol=1e-11 if level >= 4 else RTOL)
+
+
+def test_lognormal1d_small_kl_and_errors(engine, oracle):
+    import mle_b200
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 10, [0, 1])
+    sh = splitmix_uniforms(8, 2 * 10).reshape(2, 10)
+    got = engine.sample_batch(gm, lat, d, [1], sh, 0, 500)
+    check_moments(got, oracle.sample_batch(om, z, dl, [1], sh, 0, 500))
+    with pytest.raises(mle_b200.MLEError):
+        engine.sample_batch(gm, lat, d, [2], sh, 0, 10)   # no basis for level 2
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.sample_batch(gm, lat, d, [1, 0], sh, 0, 10)  # wrong index dimension
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.sample_batch(gm, lat, d, [1], sh, 0, 0)    # n must be positive
+
+
+def test_moments_are_deterministic(engine, oracle):
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 100, [2])
+    sh = splitmix_uniforms(3, 16 * 100).reshape(16, 100)
+    a = engine.sample_batch(gm, lat, d, [2], sh, 0, 3000)
+    b = engine.sample_batch(gm, lat, d, [2], sh, 0, 3000)
+    assert np.array_equal(a, b)

@@ -1,0 +1,202 @@
+"""CPU tests: the oracle (oracle/mle_oracle.c) against every golden vector the reference holds for the hot path
+(SURVEY.md 8c), plus internal consistency of the oracle's own model definitions.  No GPU needed."""
+import numpy as np
+import pytest
+
+from conftest import splitmix_uniforms, ulp_diff
+
+
+def f(strs):
+    return np.array([float(s) for s in strs])
+
+
+def test_G1_fibonacci_point(oracle, goldens):
+    g = goldens["G1"]  # src/lattice.jl:33-39
+    x = oracle.get_point(g["z"], g["k"], nmax=g["nmax"])
+    assert np.array_equal(x, f(g["point"]))
+
+
+def test_G1_beyond_n_is_refused(oracle, goldens):
+    g = goldens["G1"]  # src/lattice.jl:41-44: get_point(rule, 56) is rand(s) -- cannot be reproduced
+    with pytest.raises(ValueError):
+        oracle.get_point(g["z"], 56, nmax=g["nmax"])
+
+
+def test_G2_default_rule_point_123(oracle, goldens):
+    g = goldens["G2"]  # src/lattice.jl:61-84
+    z = oracle.genvec(g["genvec"], g["s"])
+    assert np.array_equal(oracle.get_point(z, g["k"]), f(g["point"]))
+
+
+def test_G3_shifted_point_zero_is_the_shift(oracle, goldens):
+    g = goldens["G3"]  # src/lattice.jl:101-128
+    z = oracle.genvec(g["genvec"], g["s"])
+    shift = f(g["point_equals_shift"])
+    assert np.array_equal(oracle.get_point(z, 0, shift=shift), shift)
+
+
+def test_G4_normal_transform_bit_exact(oracle, goldens):
+    g = goldens["G4"]  # src/distribution.jl:57-81 -- covers all three erfinv branches
+    got = np.array([oracle.transform(oracle.NORMAL, [0.0, 1.0], float(x)) for x in g["x"]])
+    assert np.array_equal(got, f(g["y"]))
+    u = 2 * f(g["x"]) - 1
+    assert (np.abs(u) <= 0.75).any() and ((np.abs(u) > 0.75) & (np.abs(u) <= 0.9375)).any() and (np.abs(u) > 0.9375).any()
+
+
+@pytest.mark.parametrize("key", ["G5", "G6", "G7"])
+def test_G5_G7_quantile_fixtures(oracle, goldens, key):
+    g = goldens[key]  # test/distribution.jl:35-39, :60-64, :81-85 -- the reference asserts isapprox (rtol sqrt(eps))
+    got = np.array([oracle.transform(g["kind"], g["pars"], float(x)) for x in g["x"]])
+    want = f(g["y"])
+    assert np.allclose(got, want, rtol=1.5e-8, atol=1e-15)
+    # our restatement is in fact far closer than the reference's tolerance
+    assert np.max(np.abs(got - want)) < 1e-15
+
+
+def test_G8_uniform_identity(oracle):
+    for x in np.linspace(0, 1, 11):  # test/distribution.jl:18-20
+        assert oracle.transform(oracle.UNIFORM, [0.0, 1.0], x) == x
+
+
+def test_points_in_unit_interval_and_lengths(oracle):
+    z = oracle.genvec("K_3600_32", 100)  # test/lattice.jl:9-20
+    sh = splitmix_uniforms(7, 300).reshape(3, 100)
+    pts = oracle.points(z, None, sh, 0, 257)
+    assert pts.shape == (3, 257, 100)
+    assert (pts >= 0).all() and (pts < 1).all()
+    raw = oracle.points(z, None, None, 0, 64)
+    assert (raw >= 0).all() and (raw < 1).all() and (raw[0, 0] == 0).all()
+
+
+def test_unshifted_point_is_integer_arithmetic(oracle):
+    """for z < 2^21 the unshifted point equals ((phi*z) mod 2^32) * 2^-32 bit for bit"""
+    z = oracle.genvec("K_3600_32", 3600)
+    rng = np.random.default_rng(1)
+    for k in rng.integers(0, 2**32, size=50):
+        phi = int(oracle.lib().orc_phi(int(k)))
+        want = ((phi * z.astype(np.uint64)) % (1 << 32)).astype(np.float64) * 2.0**-32
+        assert np.array_equal(oracle.get_point(z, int(k)), want)
+
+
+def test_shift_is_added_before_reduction(oracle):
+    """reduce-then-shift is NOT what the reference computes; the oracle must keep the reference's order"""
+    z = oracle.genvec("K_3600_32", 64)
+    sh = splitmix_uniforms(3, 64)
+    k = 123457
+    got = oracle.get_point(z, k, shift=sh)
+    raw = oracle.get_point(z, k)
+    alt = np.fmod(raw + sh, 1.0)
+    assert np.max(np.abs(got - alt)) < 1e-9  # same lattice point ...
+    assert (got != alt).any()                # ... but not the same bits
+
+
+def test_reversebits(oracle):
+    L = oracle.lib()
+    for v in [0, 1, 2, 0x80000000, 0xDEADBEEF, 0xFFFFFFFF, 0x46]:
+        assert L.orc_reversebits32(v) == int(format(v, "032b")[::-1], 2)  # src/lattice.jl:178
+    assert L.orc_phi(123) == 0x62000000
+
+
+def test_erfinv_against_mpmath(oracle):
+    """the restated erfinv is an approximation (a few ulp, up to ~19 ulp in the tail branch); sanity-check it"""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    L = oracle.lib()
+    for u in [-0.999, -0.95, -0.8, -0.5, -1e-3, 1e-9, 0.3, 0.74, 0.76, 0.93, 0.94, 0.99999]:
+        ref = float(mp.erfinv(mp.mpf(u)))
+        assert abs(L.orc_erfinv(u) - ref) <= 32 * np.spacing(abs(ref))
+    assert L.orc_erfinv(1.0) == np.inf and L.orc_erfinv(-1.0) == -np.inf
+
+
+def test_mc_uniform_stream(oracle):
+    L = oracle.lib()
+    u = np.array([L.orc_mc_uniform(5, k, 16, j) for k in range(200) for j in range(16)])
+    assert (u > 0).all() and (u < 1).all()
+    assert abs(u.mean() - 0.5) < 0.02 and len(np.unique(u)) == len(u)
+
+
+def test_twisted_thomas_matches_full_solve(oracle):
+    rng = np.random.default_rng(0)
+    L = oracle.lib()
+    import ctypes as C
+    for N in [4, 8, 16, 64, 1024]:
+        a = np.exp(rng.normal(size=N + 1))
+        p = a.ctypes.data_as(C.POINTER(C.c_double))
+        mid = L.orc_tridiag_mid(p, 1, N)
+        full = L.orc_tridiag_mid_full(p, N)
+        # white-noise coefficients: cond(A) ~ N^2 * contrast, so the two elimination orders differ by rounding only
+        assert abs(mid - full) <= 1e-15 * N * N * abs(full)
+        # against a dense solve
+        kap = 0.5 * (a[:-1] + a[1:])
+        A = np.diag(kap[:-1] + kap[1:]) - np.diag(kap[1:-1], 1) - np.diag(kap[1:-1], -1)
+        u = np.linalg.solve(A, np.full(N - 1, 1.0 / N**2))
+        assert abs(mid - u[N // 2 - 1]) <= 1e-15 * N * N * abs(mid) + 1e-13 * abs(mid)
+
+
+def test_constant_coefficient_gives_parabola(oracle):
+    import ctypes as C
+    a = np.ones(65)
+    mid = oracle.lib().orc_tridiag_mid(a.ctypes.data_as(C.POINTER(C.c_double)), 1, 64)
+    assert abs(mid - 0.125) < 1e-14  # u = x(1-x)/2 at x = 1/2, exact for the 3-point stencil
+
+
+def test_problem18_definition(oracle):
+    """test/regression.jl:17-46: level 0 value and the telescoping difference"""
+    M = oracle.Model(oracle.MODEL_PROBLEM18, 1)
+    xi = np.array([0.3])
+    dq0, qf0 = M.eval([0], xi)
+    x = np.linspace(0, 6, 13)
+    base = np.where(x <= 3, (x - 2)**2, 2 * np.log(np.maximum(x - 2, 1e-300)) + 1)
+    assert np.allclose(qf0, base + 1.5 * 0.3**3, rtol=1e-15) and np.array_equal(dq0, qf0)
+    dq2, qf2 = M.eval([2], xi)
+    _, qf1 = M.eval([1], xi)
+    assert np.allclose(dq2, qf2 - qf1, rtol=0, atol=1e-15)
+    M2 = oracle.Model(oracle.MODEL_PROBLEM18, 2)
+    xi2 = np.array([0.3, -0.2])
+    dq, qf = M2.eval([2, 1], xi2)
+    q = lambda i, j: M2.eval([i, j], xi2)[1]
+    assert np.allclose(dq, q(2, 1) - q(1, 1) - q(2, 0) + q(1, 0), atol=1e-14)  # src/index.jl:49-58
+
+
+def test_sample_batch_statistics(oracle):
+    """moments of orc_sample_batch == numpy on the returned samples; k-ranges continue across calls"""
+    z = oracle.genvec("K_3600_32", 8)
+    sh = splitmix_uniforms(11, 4 * 8).reshape(4, 8)
+    dists = [(oracle.NORMAL, [0.0, 1.0])] * 8
+    M = oracle.Model(oracle.MODEL_EXPSUM, 1, [2.0] + [0.5 / (j + 1) for j in range(8)])
+    mom, smp = oracle.sample_batch(M, z, dists, [1], sh, 0, 300, want_samples=True)
+    assert mom.shape == (4, 1, 2, 3) and smp.shape == (4, 1, 2, 300)
+    assert np.allclose(mom[..., 0], 300)
+    assert np.allclose(mom[..., 1], smp.mean(axis=-1), rtol=1e-14)
+    assert np.allclose(mom[..., 2], smp.var(axis=-1) * 300, rtol=1e-12)
+    _, smp_a = oracle.sample_batch(M, z, dists, [1], sh, 0, 100, want_samples=True)
+    _, smp_b = oracle.sample_batch(M, z, dists, [1], sh, 100, 200, want_samples=True)
+    assert np.array_equal(np.concatenate([smp_a, smp_b], axis=-1), smp)
+    # level 1 of expsum: dQ = exp(sum over 4 dims) - exp(sum over 2 dims)
+    xi = oracle.points(z, dists, sh, 0, 300)
+    w = np.array([0.5 / (j + 1) for j in range(8)])
+    qf = np.exp(xi[..., :4] @ w[:4])
+    qc = np.exp(xi[..., :2] @ w[:2])
+    assert np.allclose(smp[:, 0, 1], qf, rtol=1e-14) and np.allclose(smp[:, 0, 0], qf - qc, atol=1e-14)
+
+
+def test_lognormal1d_oracle_model(oracle):
+    import mle_b200.kl as kl
+    M = oracle.Model(oracle.MODEL_LOGNORMAL1D, 1, [16.0])
+    for lev in range(3):
+        M.set_basis(lev, kl.kl_basis_1d(lev, m=20))
+    xi = np.zeros(20)
+    dq, qf = M.eval([0], xi)
+    assert abs(qf[0] - 0.125) < 1e-14 and dq[0] == qf[0]  # a == 1: u = x(1-x)/2
+    rng = np.random.default_rng(2)
+    xi = rng.normal(size=20)
+    dq1, qf1 = M.eval([1], xi)
+    # the coarse solve of level 1 uses the even nodes of the level-1 field
+    a = np.exp(kl.kl_basis_1d(1, m=20) @ xi)
+    import ctypes as C
+    ac = np.ascontiguousarray(a[::2])
+    qc = oracle.lib().orc_tridiag_mid(ac.ctypes.data_as(C.POINTER(C.c_double)), 1, 16)
+    assert abs(dq1[0] - (qf1[0] - qc)) < 1e-16
+    # discretisation error decays: |dQ| shrinks with the level
+    dq2, _ = M.eval([2], xi)
+    assert abs(dq2[0]) < abs(dq1[0])
