@@ -128,10 +128,10 @@ __device__ __forceinline__ void problem18_eval(int ndims, int i0, int i1, double
     double x23 = (ndims == 2) ? __dmul_rn(__dmul_rn(xi1, xi1), xi1) : 0.0;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
-        double xj = 0.5 * j;  // range(0, 6, 13)[j]
-        double fj;
-        if (xj <= 3.0) fj = (xj - 2.0) * (xj - 2.0);           // exact small constants
-        else fj = __dadd_rn(__dmul_rn(2.0, log(xj - 2.0)), 1.0);
+        const double xj = 0.5 * j;  // range(0, 6, 13)[j]
+        // f_j = x_j <= 3 ? (x_j - 2)^2 : 2*log(x_j - 2) + 1: thirteen constants (correctly rounded logs, generated table)
+        constexpr double base[13] = MLE_P18_BASE_INIT;
+        const double fj = base[j];
         double acc = __dadd_rn(fj, __dmul_rn(p18_coef(i0, xj), x13));
         if (ndims == 2) {
             acc = __dadd_rn(acc, __dmul_rn(p18_coef(i1, xj), x23));
@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g
             __syncthreads();
         }
         if (MODEL == MODEL_EXPSUM) {
-            double qf = exp(s_acc);
+            double qf = exp_det(s_acc);
             val[1] = qf;
-            val[0] = ma.mlc > 0 ? __dsub_rn(qf, exp(s_coarse)) : qf;
+            val[0] = ma.mlc > 0 ? __dsub_rn(qf, exp_det(s_coarse)) : qf;
         } else {
             // (dQ, Qf): dQ = Qf + sum over diff(index) of +-Q_kappa         src/index.jl:49-58, test/regression.jl:39-46
             double f[13], dq[13];
@@ -445,8 +445,8 @@ __global__ void __launch_bounds__(LN_THREADS) lognormal1d_kernel(GenArgs g, Logn
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 double2 lo, hi;
-                lo.x = exp(accr[i][0]); lo.y = exp(accr[i][1]);
-                hi.x = exp(accr[i][2]); hi.y = exp(accr[i][3]);
+                lo.x = exp_det(accr[i][0]); lo.y = exp_det(accr[i][1]);
+                hi.x = exp_det(accr[i][2]); hi.y = exp_det(accr[i][3]);
                 double *frow = F + (8 * ty + i) * BT + 2 * tx;
                 *reinterpret_cast<double2 *>(frow) = lo;
                 *reinterpret_cast<double2 *>(frow + 32) = hi;

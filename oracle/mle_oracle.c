@@ -45,6 +45,78 @@ ORC_API const uint32_t *orc_genvec(int which, int *len) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Elementary functions the reference takes from Julia's runtime (Base.log1p, Base.exp -- not in the tree). */
+/* Any two 1-ulp implementations of them differ in the last bit now and then, and the erfinv tail approximant  */
+/* amplifies a 1-ulp difference of the logarithm to ~10 ulp.  To make "the same arithmetic" checkable bit for */
+/* bit, the oracle and the CUDA kernels both use the algorithms defined here (tables: tools/gen_math_tables.py, */
+/* include/mle_math_tables.inc); tests/ checks them against mpmath / libm.                                      */
+/* ------------------------------------------------------------------------------------------------ */
+#include "../include/mle_math_tables.inc"
+static const double LOGT[3 * MLE_LOGT_ROWS] = MLE_LOGT_TABLE_INIT;
+
+static inline double u64_as_double(uint64_t b) { double d; memcpy(&d, &b, 8); return d; }
+static inline uint64_t double_as_u64(double d) { uint64_t b; memcpy(&b, &d, 8); return b; }
+
+/* log(w) for a normal double w in (0, 1/16]; error ~2^-66 absolute on |log w| >= 2.77 (correctly rounded except
+ * with probability ~1e-4).  w = 2^e m, m in [1,2); c = table centre of m's 1/128 bin; m/c - 1 = r exactly as
+ * r_hi + p_lo (two-product); log w = e ln2 + log c + log1p(r). */
+ORC_API double orc_log_tail(double w) {
+    uint64_t bits = double_as_u64(w);
+    int e = (int)(bits >> 52) - 1023;
+    double m = u64_as_double((bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+    int i = (int)((bits >> 45) & 127);
+    double invc = LOGT[3 * i], logc_hi = LOGT[3 * i + 1], logc_lo = LOGT[3 * i + 2];
+    double p_hi = m * invc;
+    double p_lo = fma(m, invc, -p_hi); /* exact */
+    double r_hi = p_hi - 1.0;          /* exact */
+    double r = r_hi + p_lo;
+    double q = -0.125;                 /* log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + ... - r^6/8) */
+    q = fma(q, r, 0x1.2492492492492p-3);  /* 1/7 */
+    q = fma(q, r, -0x1.5555555555555p-3); /* 1/6 */
+    q = fma(q, r, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 0x1.5555555555555p-2);  /* 1/3 */
+    q = fma(q, r, -0.5);
+    q = (r * r) * q;
+    double ed = (double)e;
+    double A = ed * MLE_LOGT_LN2_HI + logc_hi; /* both exact: 32-bit ln2_hi, logc_hi multiple of 2^-40 */
+    double s = A + r_hi;
+    double err = r_hi - (s - A);               /* Fast2Sum, |A| > |r_hi| */
+    double lo = fma(ed, MLE_LOGT_LN2_LO, logc_lo) + p_lo;
+    lo = lo + q;
+    lo = lo + err;
+    return s + lo;
+}
+
+/* exp(x): k = rint(x log2 e), r = x - k ln2 (two-step), degree-13 Taylor polynomial, scaling by 2^k in two exact-then-
+ * rounded steps.  Error < 1 ulp; the lognormal / expsum models are DEFINED with this exp on both sides. */
+ORC_API double orc_exp(double x) {
+    if (x != x) return x;
+    if (x > 710.0) x = 710.0;
+    if (x < -746.0) x = -746.0;
+    double kd = rint(x * 0x1.71547652b82fep+0);
+    double r = fma(kd, -MLE_LOGT_LN2_HI, x);
+    r = fma(kd, -MLE_LOGT_LN2_LO, r);
+    double p = 0x1.6124613a86d09p-33;      /* 1/13! */
+    p = fma(p, r, 0x1.1eed8eff8d898p-29);  /* 1/12! */
+    p = fma(p, r, 0x1.ae64567f544e4p-26);  /* 1/11! */
+    p = fma(p, r, 0x1.27e4fb7789f5cp-22);  /* 1/10! */
+    p = fma(p, r, 0x1.71de3a556c734p-19);  /* 1/9! */
+    p = fma(p, r, 0x1.a01a01a01a01ap-16);  /* 1/8! */
+    p = fma(p, r, 0x1.a01a01a01a01ap-13);  /* 1/7! */
+    p = fma(p, r, 0x1.6c16c16c16c17p-10);  /* 1/6! */
+    p = fma(p, r, 0x1.1111111111111p-7);   /* 1/5! */
+    p = fma(p, r, 0x1.5555555555555p-5);   /* 1/4! */
+    p = fma(p, r, 0x1.5555555555555p-3);   /* 1/3! */
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int k = (int)kd, k1 = k / 2, k2 = k - k1;
+    double s1 = u64_as_double((uint64_t)(k1 + 1023) << 52), s2 = u64_as_double((uint64_t)(k2 + 1023) << 52);
+    return (p * s1) * s2;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* stage 1: lattice points                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -131,7 +203,7 @@ ORC_API double orc_erfinv(double x) {
         double num = x * horner(t, P2, 8);
         return num / horner(t, Q2, 8);
     }
-    double t = 1.0 / sqrt(-log1p(-a));
+    double t = 1.0 / sqrt(-orc_log_tail(1.0 - a)); /* log1p(-a): 1 - a is exact for a >= 1/2 */
     double den = copysign(t, x) * horner(t, Q3, 10);
     return horner(t, P3, 9) / den;
 }
@@ -293,7 +365,7 @@ static double expsum_q(const orc_model *M, int level, const double *xi, int m) {
     if (ml > M->nweights) ml = M->nweights;
     double acc = 0.0;
     for (long j = 0; j < ml; ++j) acc = fma(M->weights[j], xi[j], acc);
-    return exp(acc);
+    return orc_exp(acc);
 }
 
 /* --- problem_18: test/regression.jl:17-36 (1-d), :69-103 (2-d) --------------------------------------- */
@@ -320,13 +392,9 @@ static void problem18_eval(int ndims, const int *idx, const double *xi, double *
     for (int j = 0; j < n; ++j) {
         /* range(0, 6, 13)[j] = j * 0.5 exactly */
         double xj = 0.5 * j;
-        double fj;
-        if (xj <= 3.0) {
-            fj = (xj - 2.0) * (xj - 2.0);
-        } else {
-            double lg = 2.0 * log(xj - 2.0);
-            fj = lg + 1.0;
-        }
+        /* f_j = x_j <= 3 ? (x_j - 2)^2 : 2*log(x_j - 2) + 1: thirteen constants, tabulated with correctly rounded logs */
+        static const double P18_BASE[13] = MLE_P18_BASE_INIT;
+        double fj = P18_BASE[j];
         double t1 = p18_coef(idx[0], xj) * x13;
         double acc = fj + t1;
         if (ndims == 2) {
@@ -423,7 +491,7 @@ static int lognormal1d_eval(const orc_model *M, int level, const double *xi, int
         double g = 0.0;
         const double *row = Phi + (size_t)i * ld;
         for (int k = 0; k < m; ++k) g = fma(row[k], xi[k], g);
-        work[i] = exp(g);
+        work[i] = orc_exp(g);
     }
     double qf = tridiag_mid(work, 1, N);
     *Qf = qf;

@@ -18,7 +18,8 @@ def check_moments(got, want, smp_got=None, smp_want=None, rtol=RTOL):
     assert np.all(np.abs(got[..., 1] - want[..., 1]) <= rtol * scale)
     assert np.all(np.abs(got[..., 2] - want[..., 2]) <= rtol * np.abs(want[..., 2]) + 1e-300)
     if smp_got is not None:
-        assert np.allclose(smp_got, smp_want, rtol=1e-13, atol=1e-16)
+        # per-sample (dQ, Qf): same operations in the same order on both sides (including log/exp) -> bit-identical
+        assert np.array_equal(smp_got, smp_want)
 
 
 def expsum_setup(engine, oracle, s, m0=4):
@@ -86,8 +87,8 @@ def test_problem18_reference_test_function(engine, oracle, ndims, index, R, n):
     got, smp = engine.sample_batch(gm, lat, d, index, sh, 0, n, want_samples=True)
     want, smp_w = oracle.sample_batch(om, z, dl, index, sh, 0, n, want_samples=True)
     assert got.shape == (R, 13, 2, 3)
-    assert np.allclose(smp, smp_w, rtol=0, atol=4e-16)  # log() of a handful of constants may differ by an ulp
-    check_moments(got, want, rtol=1e-11)  # dQ of several QoI is ~1e-2 * xi^3 on O(1) values: absolute rounding dominates
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
 
 
 def test_problem18_mc(engine, oracle):
@@ -96,7 +97,7 @@ def test_problem18_mc(engine, oracle):
     om = oracle.Model(oracle.MODEL_PROBLEM18, 1)
     got = engine.sample_batch(gm, None, d, [1], None, 0, 5000, mc_seed=3)
     want = oracle.sample_batch(om, None, [(0, [-0.5, 0.5])], [1], None, 0, 5000, mc_seed=3)
-    check_moments(got, want, rtol=1e-11)
+    check_moments(got, want)
 
 
 def lognormal_setup(engine, oracle, m, levels, n0=16):
@@ -119,11 +120,10 @@ def test_lognormal1d_levels(engine, oracle, level, R, k0, n):
     sh = splitmix_uniforms(2024, R * 100).reshape(R, 100)
     got, smp = engine.sample_batch(gm, lat, d, [level], sh, k0, n, want_samples=True)
     want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, k0, n, want_samples=True)
-    # per-sample values: identical elimination order, exp() from a different libm -> a few 1e-16 relative on Qf
-    assert np.allclose(smp[:, 0, 1], smp_w[:, 0, 1], rtol=1e-13, atol=0)
-    assert np.allclose(smp[:, 0, 0], smp_w[:, 0, 0], rtol=0, atol=1e-15)
+    # per-sample values: identical KL accumulation order, identical exp, identical elimination order -> bit-identical
+    assert np.array_equal(smp, smp_w)
     if n > 1:
-        check_moments(got, want, rtol=1e-11 if level >= 4 else RTOL)
+        check_moments(got, want)
 
 
 def test_lognormal1d_small_kl_and_errors(engine, oracle):
