@@ -1,0 +1,401 @@
+#!/usr/bin/env python3
+"""bench.py -- fine+coarse samples/sec of the sampling hot path on N B200s, with roofline and CPU baseline.
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): MLQMC on the 1-D lognormal diffusion problem -- rank-1 lattice
+(first 100 entries of K_3600_32), R = 16 random shifts, 100 Normal(0,1) KL terms, levels 0..6 (grid 16 * 2^l cells).
+One STEP = one `parallel_sample!`-sized batch on every level l = 0..6 with n_l = 2^20 * 2^(-1.5 l) points per shift
+(the N_l ~ sqrt(V_l / C_l) allocation of an MLQMC run with beta = 2, gamma = 1), i.e. 25.9 M fine+coarse samples.
+Every sample runs the whole path: lattice point -> shift -> Phi^-1 -> KL field -> exp -> fine and coarse tridiagonal
+solves -> (dQ, Qf) -> per-(level, shift) moments.  Multi-GPU: each rank owns its own contiguous slice of point numbers
+for every shift (weak scaling: n_l per rank fixed) and one NCCL all-gather per step combines the moment triplets,
+merged in rank order with Chan's formula.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_KL = 100
+R_SHIFTS = 16
+LEVELS = list(range(7))
+N0_POINTS = 1 << 20
+SHIFT_SEED = 2024
+
+
+def points_per_shift(level, scale=1.0):
+    return max(1, int(round(N0_POINTS * scale * 2.0 ** (-1.5 * level))))
+
+
+def splitmix_uniforms(seed, count):
+    M = (1 << 64) - 1
+    s = int(seed)
+    out = np.empty(count)
+    for i in range(count):
+        s = (s + 0x9E3779B97F4A7C15) & M
+        z = s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        out[i] = (z >> 11) * 2.0 ** -53
+    return out
+
+
+def level_shifts():
+    """independent shift vectors per (level, shift) like the reference (src/internals.jl:138)"""
+    u = splitmix_uniforms(SHIFT_SEED, len(LEVELS) * R_SHIFTS * M_KL)
+    return u.reshape(len(LEVELS), R_SHIFTS, M_KL)
+
+
+def algorithmic_flops_per_sample(level):
+    """FP64 operations of the reference algorithm per sample (add/mul/div/sqrt = 1, fused multiply-add = 2), DESIGN.md"""
+    N = 16 << level
+    gen = M_KL * (3 + 0.75 * 31 + 0.1875 * 35 + 0.0625 * 72)
+    kl = 2.0 * (N + 1) * M_KL
+    ex = 34.0 * (N + 1)
+    solve = 8.0 * (N - 1) + (8.0 * (N // 2 - 1) if level > 0 else 0.0) + 12
+    return gen + kl + ex + solve
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.lines, self.index = None, [], str(index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", self.index], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def fp64_peak_tflops():
+    """live DFMA / DMMA pipe peak from tools/fp64_microbench (MEASURED_PEAKS.json carries no FP64 figure)"""
+    exe = os.path.join(ROOT, "tools", "bin", "fp64_microbench")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(scale, threads_note=True):
+    """the oracle run the reference's way (scalar per-sample path, OpenMP over the (shift, k) product) on every level;
+    returns (samples, seconds, cores)"""
+    from oracle import oracle as O
+    import mle_b200.kl as kl
+    O.build()
+    z = O.genvec("K_3600_32", M_KL)
+    dl = [(O.NORMAL, [0.0, 1.0])] * M_KL
+    om = O.Model(O.MODEL_LOGNORMAL1D, 1, [16.0])
+    for lev in LEVELS:
+        om.set_basis(lev, kl.kl_basis_1d(lev, m=M_KL))
+    sh = level_shifts()
+    O.sample_batch(om, z, dl, [0], sh[0], 0, 256)  # warm the thread pool
+    total, t0 = 0, time.perf_counter()
+    for lev in LEVELS:
+        n = points_per_shift(lev, scale)
+        O.sample_batch(om, z, dl, [lev], sh[lev], 0, n)
+        total += n * R_SHIFTS
+    return total, time.perf_counter() - t0, O.num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Julia is not installed here or on the GPU box and the reference is pure
+    Julia (no C sources to compile into oracle/_ref), so this arm times the C oracle port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scale = 1.0 / 16
+    for _ in range(args.warmup):
+        cpu_reference_run(scale / 8)
+    times, samples, cores = [], 0, 1
+    for _ in range(args.steps):
+        samples, dt, cores = cpu_reference_run(scale)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = samples / (ms * 1e-3)
+    sample = "every level 0..6 at 1/16 of the bench step's points per shift (%d samples per step)" % samples
+    line = {"impl": "reference", "metric": "fine+coarse samples/sec", "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "C2: MLQMC 1-D lognormal diffusion, rank-1 lattice K_3600_32[:100], 16 random shifts, 100-term KL, "
+                        "levels 0-6 (grid 16*2^l), n_l = 2^20 * 2^(-1.5 l) points per shift per GPU",
+            "levels": LEVELS, "shifts": R_SHIFTS, "kl_terms": M_KL,
+            "points_per_shift": [points_per_shift(lev) for lev in LEVELS],
+            "samples_per_step_per_gpu": sum(points_per_shift(lev) for lev in LEVELS) * R_SHIFTS,
+            "parallelism": "point ranges sharded over ranks, one NCCL all-gather of the moment triplets per step",
+            "l2": "inputs are a few hundred KB by construction (the KL basis is re-read from L2 by design); a 256 MiB "
+                  "buffer is rewritten between steps, outside the per-step event pairs"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import mle_b200
+    import mle_b200.kl as kl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmle_cuda has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = mle_b200.Engine(local)
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+    z = eng.genvec("K_3600_32")[:M_KL]
+    lat = eng.lattice(z, M_KL)
+    dists = eng.dists([(mle_b200.NORMAL, [0.0, 1.0])] * M_KL)
+    model = eng.model("lognormal1d", 1, [16])
+    for lev in LEVELS:
+        model.set_basis(lev, kl.kl_basis_1d(lev, m=M_KL))
+    sh_host = level_shifts()
+    n_l = [points_per_shift(lev) for lev in LEVELS]
+    samples_per_step = sum(n_l) * R_SHIFTS  # per rank
+    nmom = R_SHIFTS * 2 * 3
+
+    # ---- device-resident arm ("value"): shifts already in HBM, moments stay in HBM -------------------------------------
+    sh_dev = torch.from_numpy(sh_host).cuda()
+    mom_dev = torch.zeros(len(LEVELS), R_SHIFTS, 1, 2, 3, dtype=torch.float64, device="cuda")
+    gathered = torch.zeros(world, mom_dev.numel(), dtype=torch.float64, device="cuda") if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        for li, lev in enumerate(LEVELS):
+            k0 = rank * n_l[li]  # this rank's slice of point numbers
+            eng.sample_batch_dev(model, lat, dists, [lev], sh_dev[li].data_ptr(), R_SHIFTS, k0, n_l[li], M_KL,
+                                 mom_dev[li].data_ptr())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered.view(-1), mom_dev.view(-1))
+
+    def merged_moments():
+        if world == 1:
+            return mom_dev.cpu().numpy()
+        g = gathered.cpu().numpy().reshape(world, len(LEVELS), R_SHIFTS, 1, 2, 3)
+        acc = g[0].copy()
+        for r in range(1, world):
+            acc = mle_b200.moments_merge(acc, g[r])
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # evict L2 between steps (torch's stream)
+        torch.cuda.synchronize()
+        ev[i][0].record(stream)
+        step_device()
+        ev[i][1].record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_local = sum(ms_steps) / len(ms_steps)
+    ms_t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_t.item())
+    value = samples_per_step * world / (ms_step * 1e-3)
+    final = merged_moments()
+
+    # ---- per-kernel timing of the dominant kernel (level launches), CUDA events on the launching stream ----------------
+    lvl_ms = []
+    for li, lev in enumerate(LEVELS):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        a.record(stream)
+        for _ in range(reps):
+            eng.sample_batch_dev(model, lat, dists, [lev], sh_dev[li].data_ptr(), R_SHIFTS, rank * n_l[li], n_l[li], M_KL,
+                                 mom_dev[li].data_ptr())
+        b.record(stream)
+        torch.cuda.synchronize()
+        lvl_ms.append(a.elapsed_time(b) / reps)
+
+    # ---- end-to-end arm through the host-buffer C-ABI call (H2D of the shifts + D2H of the moments every call) -----------
+    sh_pinned = torch.from_numpy(sh_host.copy()).pin_memory()
+    sh_np = sh_pinned.numpy()
+
+    def step_e2e():
+        out = []
+        for li, lev in enumerate(LEVELS):
+            out.append(eng.sample_batch(model, lat, dists, [lev], sh_np[li], rank * n_l[li], n_l[li], M_KL))
+        mom = np.stack(out)
+        if world > 1:
+            t = torch.from_numpy(mom).cuda()
+            g = torch.empty(world, t.numel(), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(g.view(-1), t.view(-1))
+            g = g.cpu().numpy().reshape((world,) + mom.shape)
+            acc = g[0].copy()
+            for r in range(1, world):
+                acc = mle_b200.moments_merge(acc, g[r])
+            mom = acc
+        return mom
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        mom_e2e = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = samples_per_step * world / float(e2e_t.item())
+    assert np.allclose(mom_e2e[..., 1], final[..., 1], rtol=1e-12), "device-resident and host-buffer arms disagree"
+
+    if rank == 0:
+        peaks = measured_peaks()
+        fp64 = fp64_peak_tflops() if world == 1 else {}
+        flops_step = sum(algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS for li, lev in enumerate(LEVELS))
+        kernel_ms = sum(lvl_ms)
+        achieved_tf = flops_step / (kernel_ms * 1e-3) * 1e-12
+        peak_tf = fp64.get("dmma_m8n8k4_tflops")
+        roofline = {"kernel": "lognormal1d_kernel (7 launches per step, one per level)", "bound": "tensor",
+                    "pipe": "FP64: on B200 DMMA (mma.sync f64) and DFMA share one pipe (measured: 37.1 / 33.9 / 36.7 TFLOP/s "
+                            "alone / alone / mixed), so the FP64 tensor figure is the roof of the whole kernel",
+                    "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": (achieved_tf / peak_tf) if peak_tf else None,
+                    "peak_source": "measured live by tools/fp64_microbench (MEASURED_PEAKS.json has no FP64 figure)",
+                    "traffic": None,
+                    "per_level_ms": lvl_ms,
+                    "per_level_samples_per_s": [n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) for li in range(len(LEVELS))],
+                    "per_level_tflops": [algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) * 1e-12
+                                         for li, lev in enumerate(LEVELS)]}
+        # the HBM-bound stage on its own: points kernel (lattice -> shift -> Phi^-1 -> 8 B/coordinate stored)
+        hbm = None
+        if world == 1:
+            npts = 1 << 18
+            out = torch.empty(R_SHIFTS * npts * M_KL, dtype=torch.float64, device="cuda")
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(2):
+                eng.points_dev(lat, dists, sh_dev[0].data_ptr(), R_SHIFTS, 0, npts, M_KL, out.data_ptr())
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(5):
+                eng.points_dev(lat, dists, sh_dev[0].data_ptr(), R_SHIFTS, 0, npts, M_KL, out.data_ptr())
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 5
+            gbs = out.numel() * 8 / (ms * 1e-3) * 1e-9
+            hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+            hbm = {"kernel": "points_kernel (2^18 points x 100 dims x 16 shifts = 3.36 GB, larger than L2)", "bound": "hbm",
+                   "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                   "peak_source": "MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650 GB/s",
+                   "algorithmic_bytes_per_coordinate": 8, "traffic": None,
+                   "coordinates_per_s": out.numel() / (ms * 1e-3)}
+            del out
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            total, dt, cores = cpu_reference_run(0.5)
+            cpu = {"value": total / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": "one pass over levels 0..6 at 1/2 of the step's points per shift (%d samples, %.1f s)" % (total, dt)}
+        line = {"metric": "fine+coarse samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(sh_host.nbytes),
+                        "d2h_bytes_per_step": int(len(LEVELS) * nmom * 8), "ms_per_step": float(e2e_t.item()) * 1e3},
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
+                "fp64_microbench": fp64 or None,
+                "estimate": {"mean_dQ_per_level": [float(final[li, :, 0, 0, 1].mean()) for li in range(len(LEVELS))],
+                             "sum": float(sum(final[li, :, 0, 0, 1].mean() for li in range(len(LEVELS))))}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,17 @@
 
 using namespace mle;
 
+// kernel instantiations per input mode (raw points / all Normal(0,1) / general distribution mix)
+template <int MODE> static constexpr auto points_k = points_kernel<POINTS_THREADS, MODE>;
+template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_EXPSUM, 2, MODE>;
+template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
+#define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
+    do {                                                                                       \
+        if ((mode) == GEN_RAW) K<GEN_RAW><<<grid, block, smem, stream>>>(__VA_ARGS__);         \
+        else if ((mode) == GEN_STDNORMAL) K<GEN_STDNORMAL><<<grid, block, smem, stream>>>(__VA_ARGS__); \
+        else K<GEN_GENERAL><<<grid, block, smem, stream>>>(__VA_ARGS__);                       \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // handles
 // ---------------------------------------------------------------------------------------------------------------
@@ -137,10 +148,15 @@ extern "C" int mle_init(int device, mle_ctx *out) {
         return fail(nullptr, MLE_ERR_CUDA, "mle_init: stream / event creation failed");
     }
     // opt in to large dynamic shared memory once
-    cudaFuncSetAttribute(points_kernel<POINTS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(sample_simple_kernel<MODEL_EXPSUM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(sample_simple_kernel<MODEL_PROBLEM18, 26>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lognormal1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+#define MLE_SET_SMEM(K, BYTES)                                                                      \
+    cudaFuncSetAttribute(K<GEN_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);          \
+    cudaFuncSetAttribute(K<GEN_STDNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);    \
+    cudaFuncSetAttribute(K<GEN_GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
+    MLE_SET_SMEM(points_k, 200 * 1024);
+    MLE_SET_SMEM(expsum_k, 200 * 1024);
+    MLE_SET_SMEM(problem18_k, 200 * 1024);
+    MLE_SET_SMEM(lognormal1d_kernel, 220 * 1024);
+#undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     *out = ctx;
     return MLE_OK;
@@ -355,20 +371,23 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
     if (level < 0 || level >= MLE_MAX_LEVELS) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
     const long long N = (long long)M->n0 << level;
     if (rows != N + 1) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be n0*2^level + 1 (nodes of the level's grid)");
-    if (cols < 1 || cols > 4 * LN_RC) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 256");
+    if (cols < 1 || cols > 352) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 352 (the xi tile must fit in shared memory)");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     // Row r' = 2*i' + side: side 0 -> node i', side 1 -> mirrored node N - i' (i' = 0..N/2), so both elimination sweeps
-    // read rows in ascending order.  Stored chunked and k-major: [chunk][k][RC], zero padded.
+    // read rows in ascending order.  Stored in DMMA A-fragment order: [row tile rt][k step ks][lane] holds
+    // Phi'[8 rt + lane/4][4 ks + lane%4], zero padded in rows (to whole chunks) and in k (to a multiple of 4).
     const int Mh = (int)(N / 2);
     const int nrows = 2 * (Mh + 1);
     const int nchunks = (nrows + LN_RC - 1) / LN_RC;
     const int mpad = (cols + 3) & ~3;
-    std::vector<double> packed((size_t)nchunks * mpad * LN_RC, 0.0);
+    const int nks = mpad / 4, ntiles = nchunks * (LN_RC / 8);
+    std::vector<double> packed((size_t)ntiles * nks * 32, 0.0);
     for (int rp = 0; rp < nrows; ++rp) {
         const int ip = rp >> 1, side = rp & 1;
         const long long node = side ? N - ip : ip;
-        const int c = rp / LN_RC, rr = rp % LN_RC;
-        for (int k = 0; k < cols; ++k) packed[((size_t)c * mpad + k) * LN_RC + rr] = phi[(size_t)node * cols + k];
+        const int rt = rp / 8, lr = rp % 8;
+        for (int k = 0; k < cols; ++k)
+            packed[((size_t)rt * nks + k / 4) * 32 + lr * 4 + (k % 4)] = phi[(size_t)node * cols + k];
     }
     double *d = nullptr;
     if (cudaMalloc(&d, packed.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
@@ -461,10 +480,10 @@ extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, con
     const int P = POINTS_TILE_CAP / m > 0 ? POINTS_TILE_CAP / m : 1;
     const long long tps = (long long)((n + (uint64_t)P - 1) / (uint64_t)P);
     const long long ntiles = tps * R;
-    const size_t smem = 2 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + 16;
+    const size_t smem = 2 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + (POINTS_THREADS / 32) * 4;
     long long grid = (long long)ctx->sm_count * 3;
     if (grid > ntiles) grid = ntiles;
-    points_kernel<POINTS_THREADS><<<(unsigned)grid, POINTS_THREADS, smem, ctx->stream>>>(g, out_dev, P, tps, ntiles);
+    MLE_LAUNCH_BY_MODE(g.mode, points_k, (unsigned)grid, POINTS_THREADS, smem, ctx->stream, g, out_dev, P, tps, ntiles);
     ctx->launches += 1;
     CU_TRY(ctx, cudaGetLastError());
     return MLE_OK;
@@ -530,8 +549,8 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         ma.idx0 = index[0];
         ma.idx1 = d > 1 ? index[1] : 0;
         const int W = SIMPLE_THREADS / 32;
-        const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_LD * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Moment) +
-                            (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + 16;
+        const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_MC * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Moment) +
+                            (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + W * 4;
         dim3 grid((unsigned)gx, (unsigned)R);
         if (M->kind == MODEL_EXPSUM) {
             if (index[0] > 30) return fail(ctx, MLE_ERR_ARG, "expsum: level too large");
@@ -546,10 +565,10 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             }
             ma.ml = (int)ml;
             ma.mlc = (int)mlc;
-            sample_simple_kernel<MODEL_EXPSUM, 2><<<grid, SIMPLE_THREADS, smem, ctx->stream>>>(g, ma, ctx->d_partials, samples_dev, tps);
+            MLE_LAUNCH_BY_MODE(g.mode, expsum_k, grid, SIMPLE_THREADS, smem, ctx->stream, g, ma, ctx->d_partials, samples_dev, tps);
         } else {
             if (m < M->ndims) return fail(ctx, MLE_ERR_ARG, "problem18: needs one uncertainty per index dimension");
-            sample_simple_kernel<MODEL_PROBLEM18, 26><<<grid, SIMPLE_THREADS, smem, ctx->stream>>>(g, ma, ctx->d_partials, samples_dev, tps);
+            MLE_LAUNCH_BY_MODE(g.mode, problem18_k, grid, SIMPLE_THREADS, smem, ctx->stream, g, ma, ctx->d_partials, samples_dev, tps);
         }
     } else if (M->kind == MODEL_LOGNORMAL1D) {
         const int level = index[0];
@@ -560,6 +579,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.N = M->n0 << level;
         la.mpad = M->basis_mpad[level];
         la.nchunks = M->basis_nchunks[level];
+        la.nrows = la.N + 2;
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
@@ -568,10 +588,11 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
         if (rc) return rc;
         const int W = LN_THREADS / 32;
-        const size_t smem = (size_t)la.mpad * LN_BT * 8 + (size_t)2 * LN_KC * LN_RC * 8 + (size_t)LN_RC * LN_BT * 8 +
-                            (size_t)3 * 2 * W * 8 + 2 * sizeof(Moment) + (size_t)2 * LN_BT * sizeof(SweepState) + 16 + 16;
+        const int gen_dims = 64 * (LN_THREADS / LN_BT);
+        const size_t smem = (size_t)la.mpad * LN_LDX * 8 + (size_t)LN_RC * LN_LDF * 8 + (size_t)3 * 2 * W * 8 + 2 * sizeof(Moment) +
+                            (size_t)2 * LN_BT * sizeof(SweepState) + W * 4 + (size_t)LN_BT * (m < gen_dims ? m : gen_dims) * 2 + 16;
         dim3 grid((unsigned)gx, (unsigned)R);
-        lognormal1d_kernel<<<grid, LN_THREADS, smem, ctx->stream>>>(g, la, ctx->d_partials, samples_dev, tps);
+        MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kernel, grid, LN_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
     } else {
         return fail(ctx, MLE_ERR_ARG, "unknown model kind");
     }

@@ -61,7 +61,7 @@ __device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, uint
 constexpr int POINTS_THREADS = 256;
 constexpr int POINTS_TILE_CAP = 4096;  // elements per tile buffer (32 KB)
 
-template <int THREADS>
+template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__restrict__ out, int P,
                                                          long long tiles_per_shift, long long ntiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__re
     double *buf1 = buf0 + POINTS_TILE_CAP;
     GenScratch sc;
     sc.queue = reinterpret_cast<unsigned short *>(buf1 + POINTS_TILE_CAP);
-    sc.cnt = reinterpret_cast<int *>(sc.queue + POINTS_TILE_CAP);
+    sc.wtot = reinterpret_cast<unsigned *>(sc.queue + POINTS_TILE_CAP);
 
     const int m = g.m;
     int it = 0;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__re
         double *buf = (it & 1) ? buf1 : buf0;
         // the bulk store issued two iterations ago read this buffer: wait until at most one store is still reading
         if (threadIdx.x == 0) bulk_wait_read<1>();
-        gen_tile<THREADS, false>(buf, m, 1, Pt, 0, m, g.k0 + i0, g, r, sc);
+        gen_tile_dense<THREADS, MODE>(buf, Pt, m, g.k0 + i0, g, r, sc);
         double *dst = out + ((size_t)r * g.n + i0) * (size_t)m;
         const uint32_t bytes = (uint32_t)Pt * (uint32_t)m * 8u;
         const bool tma_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0;
@@ -112,9 +112,8 @@ struct SimpleModelArgs {
     int idx0, idx1;
 };
 
-constexpr int SIMPLE_THREADS = 128;
-constexpr int SIMPLE_MC = 64;             // dims per chunk
-constexpr int SIMPLE_LD = SIMPLE_MC + 1;  // odd stride: conflict-free per-thread row reads
+constexpr int SIMPLE_THREADS = 128;       // = points per tile: every thread owns one point
+constexpr int SIMPLE_MC = 64;             // dims per chunk; tile[jj][point] (point fastest: conflict-free)
 
 // problem_18                                                      test/regression.jl:17-36 (1-d), :69-103 (2-d)
 __device__ __forceinline__ double p18_coef(int l, double xj) {
@@ -182,7 +181,7 @@ __device__ __forceinline__ void block_moments_merge(const double (&x)[V], int cn
 
 // grid = (G, R).  CTA (g, r) handles point tiles g, g+G, ... of shift r, SIMPLE_THREADS points per tile, dims in chunks.
 // partials[(r*V + v)*G + g] = merged (n, mean, M2) of this CTA.  samples (optional): [(r*V + v)*n + i].
-template <int MODEL, int V>
+template <int MODEL, int V, int MODE>
 __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g, SimpleModelArgs ma,
                                                                        Moment *__restrict__ partials,
                                                                        double *__restrict__ samples,
@@ -190,12 +189,12 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g
     constexpr int THREADS = SIMPLE_THREADS;
     constexpr int W = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *tile = reinterpret_cast<double *>(smem_raw);                    // [THREADS][SIMPLE_LD]
-    double *red = tile + THREADS * SIMPLE_LD;                               // [3][V][W]
+    double *tile = reinterpret_cast<double *>(smem_raw);                    // [SIMPLE_MC][THREADS]
+    double *red = tile + THREADS * SIMPLE_MC;                               // [3][V][W]
     Moment *acc = reinterpret_cast<Moment *>(red + 3 * V * W);              // [V]
     GenScratch sc;
     sc.queue = reinterpret_cast<unsigned short *>(acc + V);                 // [THREADS*SIMPLE_MC]
-    sc.cnt = reinterpret_cast<int *>(sc.queue + THREADS * SIMPLE_MC);
+    sc.wtot = reinterpret_cast<unsigned *>(sc.queue + THREADS * SIMPLE_MC);
 
     const int r = blockIdx.y;
     const int tid = threadIdx.x;
@@ -211,21 +210,18 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g
         double xi0 = 0.0, xi1 = 0.0;
         for (int j0 = 0; j0 < g.m; j0 += SIMPLE_MC) {
             const int mc = min(SIMPLE_MC, g.m - j0);
-            gen_tile<THREADS, false>(tile, SIMPLE_LD, 1, Pt, j0, mc, g.k0 + i0, g, r, sc);
-            if (tid < Pt) {
-                const double *row = tile + tid * SIMPLE_LD;
-                if (MODEL == MODEL_EXPSUM) {
-                    for (int jj = 0; jj < mc; ++jj) {
-                        const int j = j0 + jj;
-                        if (j < ma.ml) s_acc = __fma_rn(__ldg(ma.weights + j), row[jj], s_acc);
-                        if (j == ma.mlc - 1) s_coarse = s_acc;
-                    }
-                } else {
-                    if (j0 == 0) { xi0 = row[0]; if (mc > 1) xi1 = row[1]; }
+            // always a full tile of points: surplus points (tid >= Pt) are masked out of the statistics
+            gen_tile_owned<THREADS, THREADS, MODE>(tile, j0, mc, g.k0 + i0, g, r, sc);
+            if (MODEL == MODEL_EXPSUM) {
+                for (int jj = 0; jj < mc; ++jj) {
+                    const int j = j0 + jj;
+                    if (j < ma.ml) s_acc = __fma_rn(__ldg(ma.weights + j), tile[jj * THREADS + tid], s_acc);
+                    if (j == ma.mlc - 1) s_coarse = s_acc;
                 }
+            } else {
+                if (j0 == 0) { xi0 = tile[tid]; if (mc > 1) xi1 = tile[THREADS + tid]; }
             }
-            // gen_tile starts with a barrier after resetting its counters, but the tile itself is overwritten in pass 1:
-            __syncthreads();
+            __syncthreads();  // the tile is overwritten by the next chunk
         }
         if (MODEL == MODEL_EXPSUM) {
             double qf = exp_det(s_acc);
@@ -291,33 +287,38 @@ __global__ void finalize_kernel(const Moment *__restrict__ partials, int G, int 
 }
 
 // ===================================================================================================================
-// 1-D lognormal diffusion, fully fused (see oracle/mle_oracle.c for the model definition)
+// 1-D lognormal diffusion, fully fused (model definition: see the header of include/mle_cuda.h and DESIGN.md)
 //
-//  per CTA tile: BT samples of one shift.
-//   A. xi tile [mpad][BT] (k-major, sample fastest) generated in shared memory (lattice -> shift -> Phi^-1).
-//   B. the field is produced in row chunks of RC rows; a "row" is (half-node i', side): side 0 = node i', side 1 = the
-//      mirrored node N-i', so that BOTH elimination sweeps of the two-sided Thomas solve consume rows in ascending order.
-//      G[row][sample] = sum_k A[row][k] xi[k][sample], k ascending with fused multiply-adds (bit-identical to the oracle);
-//      A arrives by TMA bulk loads in k-chunks [KC][RC] (double-buffered, mbarrier-tracked); every thread owns an
-//      8-row x 4-sample register tile.  Epilogue: a = exp(G) -> F[row][sample] in shared memory.
+//  per CTA tile: BT = 64 samples of one shift, 256 threads (8 warps), 2 CTAs per SM.
+//   A. xi tile [mpad][BT+4] (k-major, sample fastest) generated in shared memory: lattice -> shift -> Phi^-1.
+//   B. KL contraction on the FP64 tensor instruction: G[row][sample] = sum_k A[row][k] xi[k][sample] with
+//      mma.sync.m8n8k4.f64 (DMMA), accumulators chained over k.  On B200 one DMMA is bit-identical to four fused
+//      multiply-adds in ascending k (tools/dmma_order_test.cu: 262144/262144), so the field equals the oracle's
+//      sequential-FMA field bit for bit.  A "row" is (half-node i', side): side 0 = node i', side 1 = the mirrored node
+//      N-i', so BOTH elimination sweeps of the two-sided Thomas solve consume rows in ascending order.  Rows are
+//      processed in chunks of RC = 32 (4 row tiles x 8 sample tiles, each warp a 2x2 block of 8x8 tiles).  The basis is
+//      stored in HBM in fragment order, so an A fragment is one fully coalesced 256-byte load served by L1/L2; the B
+//      fragment comes from the xi tile (padded stride: conflict-free).  Epilogue: a = exp(G) -> F[row][sample] (smem).
 //   C. sweeps: thread (side, sample) advances the fine elimination by one row per half-node and the coarse one on every
 //      even half-node (coarse field = even nodes of the fine field, docs/src/example.md:120); only running scalars are
 //      kept -- the field never leaves the SM and nothing per-sample is written to HBM.
 //   D. the two sides meet at the mid node: Qf, Qc, dQ = Qf - Qc; corrected two-pass block moments; Chan merge.
 // ===================================================================================================================
 struct Lognormal1dArgs {
-    const double *basis;  // [nchunks][mpad][RC] permuted, chunked, k-major basis of this level
+    const double *basis;  // fragment-ordered basis of this level: [row tile][k step][lane] (see mle_model_set_basis)
     int N;                // fine cells
     int mpad;             // KL terms padded to a multiple of 4
-    int nchunks;          // row chunks
+    int nrows;            // N + 2 rows (both sides, mid node twice)
+    int nchunks;          // row chunks of LN_RC rows
     int level;
     double h2, h2c;       // 1/N^2, 1/(N/2)^2
 };
 
-constexpr int LN_THREADS = 128;
-constexpr int LN_BT = 64;   // samples per tile
-constexpr int LN_RC = 64;   // rows per chunk (32 half-nodes x 2 sides)
-constexpr int LN_KC = 20;   // k per A chunk
+constexpr int LN_THREADS = 256;
+constexpr int LN_BT = 64;          // samples per tile
+constexpr int LN_RC = 32;          // rows per chunk (16 half-nodes x 2 sides)
+constexpr int LN_LDX = LN_BT + 4;  // xi row stride: the 4 k-rows of a B fragment fall into different banks
+constexpr int LN_LDF = LN_BT + 8;  // F row stride: conflict-free 16-byte epilogue stores
 
 struct SweepState {
     double a_prev, k_prev, p, y;
@@ -354,122 +355,113 @@ __device__ __forceinline__ double sweep_combine(const SweepState &L, const Sweep
     return __ddiv_rn(num, den);
 }
 
-__global__ void __launch_bounds__(LN_THREADS) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la,
-                                                                 Moment *__restrict__ partials,
-                                                                 double *__restrict__ samples,
-                                                                 long long tiles_per_shift) {
-    constexpr int THREADS = LN_THREADS, BT = LN_BT, RC = LN_RC, KC = LN_KC, W = THREADS / 32;
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(LN_THREADS, 2) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la,
+                                                                    Moment *__restrict__ partials,
+                                                                    double *__restrict__ samples,
+                                                                    long long tiles_per_shift) {
+    constexpr int THREADS = LN_THREADS, BT = LN_BT, RC = LN_RC, LDX = LN_LDX, LDF = LN_LDF, W = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int mpad = la.mpad;
-    double *xi = reinterpret_cast<double *>(smem_raw);       // [mpad][BT]
-    double *As = xi + (size_t)mpad * BT;                     // [2][KC][RC]
-    double *F = As + 2 * KC * RC;                            // [RC][BT]   (aliased by the generator queue)
-    double *red = F + RC * BT;                               // [3][2][W]
-    Moment *acc = reinterpret_cast<Moment *>(red + 3 * 2 * W);  // [2]
-    SweepState *xch = reinterpret_cast<SweepState *>(acc + 2);  // [2][BT] right-side states (fine, coarse)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(xch + 2 * BT);  // [2]
+    double *xi = reinterpret_cast<double *>(smem_raw);           // [mpad][LDX]
+    double *F = xi + (size_t)mpad * LDX;                         // [RC][LDF]
+    double *red = F + RC * LDF;                                  // [3][2][W]
+    Moment *acc = reinterpret_cast<Moment *>(red + 3 * 2 * W);   // [2]
+    SweepState *xch = reinterpret_cast<SweepState *>(acc + 2);   // [2][BT] right-side states (fine, coarse)
     GenScratch sc;
-    sc.queue = reinterpret_cast<unsigned short *>(F);        // BT*mpad*2 bytes <= RC*BT*8 needs mpad <= 4*RC (host-checked)
-    sc.cnt = reinterpret_cast<int *>(bars + 2);
+    sc.wtot = reinterpret_cast<unsigned *>(xch + 2 * BT);        // [W]
+    sc.queue = reinterpret_cast<unsigned short *>(sc.wtot + W);  // [BT * 64*(THREADS/BT)] at most
 
-    const int tid = threadIdx.x, r = blockIdx.y;
-    const int ty = tid >> 4, tx = tid & 15;  // 8 row groups x 16 sample groups
-    const int M = la.N / 2;                  // mid node
-    const int nkc = (mpad + KC - 1) / KC;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
+    const int M = la.N / 2;  // mid node
+    const int nks = mpad >> 2;
+    // warp -> 2x2 block of 8x8 tiles inside the RC x BT chunk: row tiles {2*wr, 2*wr+1}, sample tiles {2*wc, 2*wc+1}
+    const int wr = warp >> 2, wc = warp & 3;
+    const int lr = lane >> 2, lk = lane & 3;
     if (tid < 2) acc[tid] = Moment{0.0, 0.0, 0.0};
-    // zero the k-padding rows of xi once (gen_tile never writes them)
-    for (int e = tid; e < (mpad - g.m) * BT; e += THREADS) xi[(size_t)g.m * BT + e] = 0.0;
+    for (int e = tid; e < (mpad - g.m) * LDX; e += THREADS) xi[(size_t)g.m * LDX + e] = 0.0;  // k padding rows
     __syncthreads();
-    uint32_t phase[2] = {0u, 0u};
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
         const unsigned long long i0 = (unsigned long long)ti * BT;
         const unsigned long long left = g.n - i0;
         const int Pt = left < (unsigned long long)BT ? (int)left : BT;
         // A. inputs (always a full tile: surplus points are masked out of the statistics)
-        gen_tile<THREADS, true>(xi, 1, BT, BT, 0, g.m, g.k0 + i0, g, r, sc);
+        constexpr int GEN_DIMS = 64 * (THREADS / BT);
+        for (int j0 = 0; j0 < g.m; j0 += GEN_DIMS)
+            gen_tile_owned<THREADS, BT, MODE, LDX>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc);
 
         SweepState sf{0, 0, 0, 0}, scs{0, 0, 0, 0};
-        const int side = tid / BT, b = tid - side * BT;
+        const int side = tid / BT, b = tid & (BT - 1);  // sweep role (threads 0 .. 2*BT-1)
 
-        // first A chunk of this tile
-        int it = 0;  // running (row chunk, k chunk) counter within the tile
-        if (tid == 0) {
-            const int kc0 = min(KC, mpad);
-            mbar_expect_tx(&bars[0], (uint32_t)(kc0 * RC * 8));
-            bulk_load_g2s(As, la.basis, (uint32_t)(kc0 * RC * 8), &bars[0]);
-        }
         for (int c = 0; c < la.nchunks; ++c) {
-            double accr[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int jx = 0; jx < 4; ++jx) accr[i][jx] = 0.0;
-            for (int kci = 0; kci < nkc; ++kci, ++it) {
-                const int st = it & 1;
-                const int kbeg = kci * KC, kc = min(KC, mpad - kbeg);
-                // prefetch the next (row chunk, k chunk) block into the other stage
-                if (tid == 0) {
-                    int nc = c, nk = kci + 1;
-                    if (nk == nkc) { nk = 0; ++nc; }
-                    if (nc < la.nchunks) {
-                        const int nkb = nk * KC, nkcnt = min(KC, mpad - nkb);
-                        const double *src = la.basis + ((size_t)nc * mpad + nkb) * RC;
-                        mbar_expect_tx(&bars[st ^ 1], (uint32_t)(nkcnt * RC * 8));
-                        bulk_load_g2s(As + (st ^ 1) * KC * RC, src, (uint32_t)(nkcnt * RC * 8), &bars[st ^ 1]);
+            // B. contraction for rows [c*RC, c*RC + RC): this warp's row tiles rt0, rt0+1 (global tile numbers)
+            const int rt0 = c * (RC / 8) + 2 * wr;
+            const int rows_left = la.nrows - rt0 * 8;  // > 0: first tile live; > 8: second tile live
+            double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
+            if (rows_left > 0) {
+                const bool two = rows_left > 8;
+                const double *A0 = la.basis + (size_t)rt0 * nks * 32 + lane;
+                const double *A1 = two ? A0 + (size_t)nks * 32 : A0;
+                const double *B0 = xi + lk * LDX + 16 * wc + lr;
+                double a0 = __ldg(A0), a1 = __ldg(A1);
+                double b0 = B0[0], b1 = B0[8];
+#pragma unroll 5
+                for (int ks = 0; ks < nks; ++ks) {
+                    const int kn = (ks + 1 < nks) ? ks + 1 : ks;  // prefetch the next k step's fragments
+                    const double na0 = __ldg(A0 + kn * 32), na1 = __ldg(A1 + kn * 32);
+                    const double nb0 = B0[kn * 4 * LDX], nb1 = B0[kn * 4 * LDX + 8];
+                    dmma_m8n8k4(c00a, c00b, a0, b0);
+                    dmma_m8n8k4(c01a, c01b, a0, b1);
+                    if (two) {
+                        dmma_m8n8k4(c10a, c10b, a1, b0);
+                        dmma_m8n8k4(c11a, c11b, a1, b1);
                     }
+                    a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
                 }
-                mbar_wait(&bars[st], phase[st]);
-                phase[st] ^= 1u;
-                const double *Ak = As + st * KC * RC + 8 * ty;
-                const double *Xk = xi + (size_t)kbeg * BT + 2 * tx;
-#pragma unroll 4
-                for (int k = 0; k < kc; ++k) {
-                    double a[8], x[4];
-                    const double2 *ap = reinterpret_cast<const double2 *>(Ak + k * RC);
-                    double2 a01 = ap[0], a23 = ap[1], a45 = ap[2], a67 = ap[3];
-                    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
-                    a[4] = a45.x; a[5] = a45.y; a[6] = a67.x; a[7] = a67.y;
-                    double2 x01 = *reinterpret_cast<const double2 *>(Xk + k * BT);
-                    double2 x23 = *reinterpret_cast<const double2 *>(Xk + k * BT + 32);
-                    x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int jx = 0; jx < 4; ++jx) accr[i][jx] = __fma_rn(a[i], x[jx], accr[i][jx]);
-                }
-                __syncthreads();  // everyone is done with stage st (refilled two iterations later) -- and with F
             }
-            // epilogue: a = exp(G) -> F[row][sample]; thread owns rows 8ty..8ty+7, samples {2tx, 2tx+1, 32+2tx, 32+2tx+1}
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double2 lo, hi;
-                lo.x = exp_det(accr[i][0]); lo.y = exp_det(accr[i][1]);
-                hi.x = exp_det(accr[i][2]); hi.y = exp_det(accr[i][3]);
-                double *frow = F + (8 * ty + i) * BT + 2 * tx;
-                *reinterpret_cast<double2 *>(frow) = lo;
-                *reinterpret_cast<double2 *>(frow + 32) = hi;
+            __syncthreads();  // the previous chunk's sweeps have finished reading F
+            // epilogue: a = exp(G) -> F[row in chunk][sample]; lane holds row lr, samples 2*lk, 2*lk+1 of each 8x8 tile
+            if (rows_left > 0) {
+                double *f0 = F + (16 * wr + lr) * LDF + 16 * wc + 2 * lk;
+                double2 v;
+                v.x = exp_det(c00a); v.y = exp_det(c00b);
+                *reinterpret_cast<double2 *>(f0) = v;
+                v.x = exp_det(c01a); v.y = exp_det(c01b);
+                *reinterpret_cast<double2 *>(f0 + 8) = v;
+                if (rows_left > 8) {
+                    v.x = exp_det(c10a); v.y = exp_det(c10b);
+                    *reinterpret_cast<double2 *>(f0 + 8 * LDF) = v;
+                    v.x = exp_det(c11a); v.y = exp_det(c11b);
+                    *reinterpret_cast<double2 *>(f0 + 8 * LDF + 8) = v;
+                }
             }
             __syncthreads();
-            // C. sweeps over the RC/2 half-nodes of this chunk
-            const int ip0 = c * (RC / 2);
+            // C. sweeps over the RC/2 half-nodes of this chunk (threads 0 .. 2*BT-1)
+            if (tid < 2 * BT) {
+                const int ip0 = c * (RC / 2);
 #pragma unroll 4
-            for (int q = 0; q < RC / 2; ++q) {
-                const int ip = ip0 + q;
-                if (ip <= M) {
-                    const double a = F[(2 * q + side) * BT + b];
-                    sweep_step(sf, ip, a, la.h2);
-                    if (la.level > 0 && (ip & 1) == 0) sweep_step(scs, ip >> 1, a, la.h2c);
+                for (int q = 0; q < RC / 2; ++q) {
+                    const int ip = ip0 + q;
+                    if (ip <= M) {
+                        const double a = F[(2 * q + side) * LDF + b];
+                        sweep_step(sf, ip, a, la.h2);
+                        if (la.level > 0 && (ip & 1) == 0) sweep_step(scs, ip >> 1, a, la.h2c);
+                    }
                 }
             }
-            // (the k-chunk barriers of the next row chunk order these reads before F is rewritten)
         }
         // D. meet in the middle
-        if (side == 1) { xch[b] = sf; xch[BT + b] = scs; }
+        if (tid < 2 * BT && side == 1) { xch[b] = sf; xch[BT + b] = scs; }
         __syncthreads();
         double val[2] = {0.0, 0.0};
-        if (side == 0) {
+        if (tid < BT) {
             const double qf = sweep_combine(sf, xch[b], M, la.h2);
             val[1] = qf;
             val[0] = qf;
@@ -479,7 +471,7 @@ __global__ void __launch_bounds__(LN_THREADS) lognormal1d_kernel(GenArgs g, Logn
                 samples[((size_t)r * 2 + 1) * g.n + i0 + b] = val[1];
             }
         }
-        block_moments_merge<THREADS, 2>(val, Pt, red, acc);  // valid threads: tid < Pt <= BT (side 0)
+        block_moments_merge<THREADS, 2>(val, Pt, red, acc);  // valid threads: tid < Pt <= BT
     }
     if (tid < 2) partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = acc[tid];
 }
