@@ -25,6 +25,17 @@ template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MOD
         else K<GEN_GENERAL><<<grid, block, smem, stream>>>(__VA_ARGS__);                       \
     } while (0)
 
+template <typename K>
+static int resident_ctas_per_sm(K kernel, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 1; }
+    return n;
+}
+#define MLE_OCC_BY_MODE(mode, K, threads, smem)                                             \
+    ((mode) == GEN_RAW ? resident_ctas_per_sm(K<GEN_RAW>, threads, smem)                    \
+                       : (mode) == GEN_STDNORMAL ? resident_ctas_per_sm(K<GEN_STDNORMAL>, threads, smem) \
+                                                 : resident_ctas_per_sm(K<GEN_GENERAL>, threads, smem))
+
 // ---------------------------------------------------------------------------------------------------------------
 // handles
 // ---------------------------------------------------------------------------------------------------------------
@@ -481,7 +492,7 @@ extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, con
     const long long tps = (long long)((n + (uint64_t)P - 1) / (uint64_t)P);
     const long long ntiles = tps * R;
     const size_t smem = 2 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + (POINTS_THREADS / 32) * 4;
-    long long grid = (long long)ctx->sm_count * 3;
+    long long grid = (long long)ctx->sm_count * MLE_OCC_BY_MODE(g.mode, points_k, POINTS_THREADS, smem);
     if (grid > ntiles) grid = ntiles;
     MLE_LAUNCH_BY_MODE(g.mode, points_k, (unsigned)grid, POINTS_THREADS, smem, ctx->stream, g, out_dev, P, tps, ntiles);
     ctx->launches += 1;
@@ -515,9 +526,10 @@ extern "C" int mle_points(mle_ctx ctx, mle_lattice lat, mle_dists dists, const d
 // the hot path
 // ---------------------------------------------------------------------------------------------------------------
 static long long grid_x_for(mle_ctx ctx, long long tiles_per_shift, int R, int ctas_per_sm) {
-    // persistent-style: about ctas_per_sm CTAs per SM in total, split evenly over the R shifts
+    // Persistent CTAs: never launch more CTAs than are resident at once (a second, nearly empty wave would double the
+    // run time), so the grid is the largest gx with gx * R <= SMs * ctas_per_sm.
     long long total = (long long)ctx->sm_count * ctas_per_sm;
-    long long gx = (total + R - 1) / R;
+    long long gx = total / R;
     if (gx < 1) gx = 1;
     if (gx > tiles_per_shift) gx = tiles_per_shift;
     return gx;
@@ -539,9 +551,6 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
     long long gx = 0;
     if (M->kind == MODEL_EXPSUM || M->kind == MODEL_PROBLEM18) {
         const long long tps = (long long)((n + SIMPLE_THREADS - 1) / SIMPLE_THREADS);
-        gx = grid_x_for(ctx, tps, R, 4);
-        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
-        if (rc) return rc;
         SimpleModelArgs ma{};
         ma.weights = M->d_weights;
         ma.nweights = M->nweights;
@@ -551,6 +560,11 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         const int W = SIMPLE_THREADS / 32;
         const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_MC * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Moment) +
                             (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + W * 4;
+        const int occ = M->kind == MODEL_EXPSUM ? MLE_OCC_BY_MODE(g.mode, expsum_k, SIMPLE_THREADS, smem)
+                                                : MLE_OCC_BY_MODE(g.mode, problem18_k, SIMPLE_THREADS, smem);
+        gx = grid_x_for(ctx, tps, R, occ);
+        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+        if (rc) return rc;
         dim3 grid((unsigned)gx, (unsigned)R);
         if (M->kind == MODEL_EXPSUM) {
             if (index[0] > 30) return fail(ctx, MLE_ERR_ARG, "expsum: level too large");
@@ -584,13 +598,13 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
         const long long tps = (long long)((n + LN_BT - 1) / LN_BT);
-        gx = grid_x_for(ctx, tps, R, 2);
-        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
-        if (rc) return rc;
         const int W = LN_THREADS / 32;
         const int gen_dims = 64 * (LN_THREADS / LN_BT);
         const size_t smem = (size_t)la.mpad * LN_LDX * 8 + (size_t)LN_RC * LN_LDF * 8 + (size_t)3 * 2 * W * 8 + 2 * sizeof(Moment) +
                             (size_t)2 * LN_BT * sizeof(SweepState) + W * 4 + (size_t)LN_BT * (m < gen_dims ? m : gen_dims) * 2 + 16;
+        gx = grid_x_for(ctx, tps, R, MLE_OCC_BY_MODE(g.mode, lognormal1d_kernel, LN_THREADS, smem));
+        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+        if (rc) return rc;
         dim3 grid((unsigned)gx, (unsigned)R);
         MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kernel, grid, LN_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
     } else {

@@ -119,6 +119,28 @@ __global__ void k_exp(double *out, int iters, double a) {
     if (s == 12345.678) out[0] = s;
 }
 
+// dependent-issue latency of DFMA / DMMA: one warp, one chain, clock64 around it
+__global__ void k_lat(double *out, long long *cyc, double a, double b) {
+    double x = threadIdx.x * 1e-9;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x = fma(x, a, b);
+    }
+    long long t1 = clock64();
+    double c0 = x, c1 = -x;
+    long long t2 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c0, c1, a, b);
+    }
+    long long t3 = clock64();
+    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t3 - t2; }
+    if (c0 + c1 + x == 12345.678) out[0] = x;
+}
+
 __global__ void k_store(double2 *out, size_t n2, double v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     double2 w = make_double2(v, v + 1);
@@ -168,6 +190,14 @@ int main() {
     printf(", \"ddiv_gops\": %.1f", 8.0 * (iters / 8) * nthreads / ms * 1e-6);
     ms = time_ms([&] { k_exp<<<blocks, threads>>>(d, iters / 8, 0.5); });
     printf(", \"exp_gops\": %.1f", 8.0 * (iters / 8) * nthreads / ms * 1e-6);
+    {
+        long long *cyc, h[2];
+        CK(cudaMalloc(&cyc, 16));
+        k_lat<<<1, 32>>>(d, cyc, 1.0000001, 1e-9);
+        k_lat<<<1, 32>>>(d, cyc, 1.0000001, 1e-9);
+        CK(cudaMemcpy(h, cyc, 16, cudaMemcpyDeviceToHost));
+        printf(", \"dfma_dependent_latency_cycles\": %.2f, \"dmma_dependent_latency_cycles\": %.2f", h[0] / 4096.0, h[1] / 4096.0);
+    }
     const size_t bytes = (size_t)4 << 30;
     double2 *a, *b; CK(cudaMalloc(&a, bytes)); CK(cudaMalloc(&b, bytes));
     ms = time_ms([&] { k_store<<<sms * 16, 512>>>(a, bytes / 16, 1.0); });
