@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -18,11 +19,19 @@ using namespace mle;
 template <int MODE> static constexpr auto points_k = points_kernel<POINTS_THREADS, MODE>;
 template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_EXPSUM, 2, MODE>;
 template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
+template <int MODE> static constexpr auto lognormal1d_k64 = lognormal1d_kernel<MODE, 64>;
+template <int MODE> static constexpr auto lognormal1d_k32 = lognormal1d_kernel<MODE, 32>;
+// mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
 #define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
     do {                                                                                       \
-        if ((mode) == GEN_RAW) K<GEN_RAW><<<grid, block, smem, stream>>>(__VA_ARGS__);         \
-        else if ((mode) == GEN_STDNORMAL) K<GEN_STDNORMAL><<<grid, block, smem, stream>>>(__VA_ARGS__); \
-        else K<GEN_GENERAL><<<grid, block, smem, stream>>>(__VA_ARGS__);                       \
+        switch (mode) {                                                                        \
+        case GEN_RAW: K<GEN_RAW><<<grid, block, smem, stream>>>(__VA_ARGS__); break;           \
+        case GEN_STDNORMAL: K<GEN_STDNORMAL><<<grid, block, smem, stream>>>(__VA_ARGS__); break; \
+        case GEN_GENERAL: K<GEN_GENERAL><<<grid, block, smem, stream>>>(__VA_ARGS__); break;   \
+        case GEN_RAW | GEN_MC: K<GEN_RAW | GEN_MC><<<grid, block, smem, stream>>>(__VA_ARGS__); break; \
+        case GEN_STDNORMAL | GEN_MC: K<GEN_STDNORMAL | GEN_MC><<<grid, block, smem, stream>>>(__VA_ARGS__); break; \
+        default: K<GEN_GENERAL | GEN_MC><<<grid, block, smem, stream>>>(__VA_ARGS__); break;   \
+        }                                                                                      \
     } while (0)
 
 template <typename K>
@@ -33,8 +42,11 @@ static int resident_ctas_per_sm(K kernel, int threads, size_t smem) {
 }
 #define MLE_OCC_BY_MODE(mode, K, threads, smem)                                             \
     ((mode) == GEN_RAW ? resident_ctas_per_sm(K<GEN_RAW>, threads, smem)                    \
-                       : (mode) == GEN_STDNORMAL ? resident_ctas_per_sm(K<GEN_STDNORMAL>, threads, smem) \
-                                                 : resident_ctas_per_sm(K<GEN_GENERAL>, threads, smem))
+     : (mode) == GEN_STDNORMAL ? resident_ctas_per_sm(K<GEN_STDNORMAL>, threads, smem)      \
+     : (mode) == GEN_GENERAL ? resident_ctas_per_sm(K<GEN_GENERAL>, threads, smem)          \
+     : (mode) == (GEN_RAW | GEN_MC) ? resident_ctas_per_sm(K<GEN_RAW | GEN_MC>, threads, smem) \
+     : (mode) == (GEN_STDNORMAL | GEN_MC) ? resident_ctas_per_sm(K<GEN_STDNORMAL | GEN_MC>, threads, smem) \
+                                          : resident_ctas_per_sm(K<GEN_GENERAL | GEN_MC>, threads, smem))
 
 // ---------------------------------------------------------------------------------------------------------------
 // handles
@@ -48,11 +60,14 @@ struct mle_ctx_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     uint64_t launches = 0;
+    int ln_bt_override = 0;  // MLE_LN_BT=32|64 in the environment: tuning knob for the lognormal1d tile width
     // reusable device / pinned scratch
     Moment *d_partials = nullptr;
     size_t partials_cap = 0;  // in Moments
     double *d_shifts = nullptr;
     size_t shifts_cap = 0;
+    double *d_zero = nullptr;  // a row of zeros standing in for the shift of an unshifted rule
+    size_t zero_cap = 0;
     double *d_moments = nullptr;
     size_t moments_cap = 0;
     double *h_pinned = nullptr;
@@ -162,13 +177,18 @@ extern "C" int mle_init(int device, mle_ctx *out) {
 #define MLE_SET_SMEM(K, BYTES)                                                                      \
     cudaFuncSetAttribute(K<GEN_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);          \
     cudaFuncSetAttribute(K<GEN_STDNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);    \
-    cudaFuncSetAttribute(K<GEN_GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
+    cudaFuncSetAttribute(K<GEN_GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);      \
+    cudaFuncSetAttribute(K<GEN_RAW | GEN_MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES); \
+    cudaFuncSetAttribute(K<GEN_STDNORMAL | GEN_MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES); \
+    cudaFuncSetAttribute(K<GEN_GENERAL | GEN_MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
     MLE_SET_SMEM(points_k, 200 * 1024);
     MLE_SET_SMEM(expsum_k, 200 * 1024);
     MLE_SET_SMEM(problem18_k, 200 * 1024);
-    MLE_SET_SMEM(lognormal1d_kernel, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_k64, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_k32, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
+    if (const char *e = getenv("MLE_LN_BT")) { int v = atoi(e); if (v == 32 || v == 64) ctx->ln_bt_override = v; }
     *out = ctx;
     return MLE_OK;
 }
@@ -179,6 +199,7 @@ extern "C" int mle_destroy(mle_ctx ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     if (ctx->d_shifts) cudaFree(ctx->d_shifts);
+    if (ctx->d_zero) cudaFree(ctx->d_zero);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0);
@@ -447,6 +468,16 @@ static int make_gen_args(mle_ctx ctx, mle_lattice lat, mle_dists dists, const do
         if (shifts_dev) return fail(ctx, MLE_ERR_ARG, "MC sampling takes no shifts");
     }
     if (dists && m > dists->m) return fail(ctx, MLE_ERR_ARG, "nb_of_uncertainties exceeds the number of distributions");
+    if (lat && !shifts_dev) {  // unshifted rule: a zero shift (x + 0.0 is exact) keeps the generator branch-free
+        if (ctx->zero_cap < (size_t)lat->s) {
+            if (ctx->d_zero) cudaFree(ctx->d_zero);
+            ctx->d_zero = nullptr; ctx->zero_cap = 0;
+            if (cudaMalloc(&ctx->d_zero, sizeof(double) * (size_t)lat->s) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(zero shift)"); }
+            if (cudaMemsetAsync(ctx->d_zero, 0, sizeof(double) * (size_t)lat->s, ctx->stream) != cudaSuccess) return fail(ctx, MLE_ERR_CUDA, "cudaMemsetAsync");
+            ctx->zero_cap = (size_t)lat->s;
+        }
+        shifts_dev = ctx->d_zero;
+    }
     g->zd = lat ? lat->d_z : nullptr;
     g->shifts = shifts_dev;
     g->kind = dists ? dists->d_kind : nullptr;
@@ -457,7 +488,7 @@ static int make_gen_args(mle_ctx ctx, mle_lattice lat, mle_dists dists, const do
     g->s = lat ? lat->s : 0;
     g->m = m;
     g->R = R;
-    g->mode = dists ? dists->mode : GEN_RAW;
+    g->mode = (dists ? dists->mode : GEN_RAW) | (lat ? 0 : GEN_MC);
     return MLE_OK;
 }
 
@@ -597,16 +628,22 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
-        const long long tps = (long long)((n + LN_BT - 1) / LN_BT);
-        const int W = LN_THREADS / 32;
-        const int gen_dims = 64 * (LN_THREADS / LN_BT);
-        const size_t smem = (size_t)la.mpad * LN_LDX * 8 + (size_t)LN_RC * LN_LDF * 8 + (size_t)3 * 2 * W * 8 + 2 * sizeof(Moment) +
-                            (size_t)2 * LN_BT * sizeof(SweepState) + W * 4 + (size_t)LN_BT * (m < gen_dims ? m : gen_dims) * 2 + 16;
-        gx = grid_x_for(ctx, tps, R, MLE_OCC_BY_MODE(g.mode, lognormal1d_kernel, LN_THREADS, smem));
+        // samples per tile: 32 (128 threads, up to 5 CTAs per SM: phases of different CTAs overlap) unless the xi tile
+        // of a 64-sample CTA is needed to amortise the basis traffic of the large levels
+        const int bt = ctx->ln_bt_override ? ctx->ln_bt_override : 32;
+        const long long tps = (long long)((n + bt - 1) / bt);
+        const int threads = ln_threads(bt), W = threads / 32;
+        const int qdims = m < 256 ? m : 256;
+        const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
+        const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)2 * bt * sizeof(SweepState) +
+                            (size_t)2 * bt * sizeof(Moment) + W * 4 + (qbytes <= fbytes ? 0 : qbytes) + 16;
+        const int occ = bt == 64 ? MLE_OCC_BY_MODE(g.mode, lognormal1d_k64, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal1d_k32, threads, smem);
+        gx = grid_x_for(ctx, tps, R, occ);
         rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
         if (rc) return rc;
         dim3 grid((unsigned)gx, (unsigned)R);
-        MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kernel, grid, LN_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
+        if (bt == 64) MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k64, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
+        else MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k32, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
     } else {
         return fail(ctx, MLE_ERR_ARG, "unknown model kind");
     }

@@ -314,11 +314,12 @@ struct Lognormal1dArgs {
     double h2, h2c;       // 1/N^2, 1/(N/2)^2
 };
 
-constexpr int LN_THREADS = 256;
-constexpr int LN_BT = 64;          // samples per tile
-constexpr int LN_RC = 32;          // rows per chunk (16 half-nodes x 2 sides)
-constexpr int LN_LDX = LN_BT + 4;  // xi row stride: the 4 k-rows of a B fragment fall into different banks
-constexpr int LN_LDF = LN_BT + 8;  // F row stride: conflict-free 16-byte epilogue stores
+constexpr int LN_RC = 32;  // rows per chunk (16 half-nodes x 2 sides)
+// samples per tile BT (32 or 64) is a template parameter; THREADS = 4*BT; xi row stride BT+4 (the 4 k-rows of a B fragment
+// fall into different banks); F row stride BT+8 (conflict-free 16-byte epilogue stores)
+__host__ __device__ constexpr int ln_threads(int bt) { return 4 * bt; }
+__host__ __device__ constexpr int ln_ldx(int bt) { return bt + 4; }
+__host__ __device__ constexpr int ln_ldf(int bt) { return bt + 8; }
 
 struct SweepState {
     double a_prev, k_prev, p, y;
@@ -361,39 +362,52 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(LN_THREADS, 2) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la,
-                                                                    Moment *__restrict__ partials,
-                                                                    double *__restrict__ samples,
-                                                                    long long tiles_per_shift) {
-    constexpr int THREADS = LN_THREADS, BT = LN_BT, RC = LN_RC, LDX = LN_LDX, LDF = LN_LDF, W = THREADS / 32;
+// per-thread running statistics (Welford): n is the same for every thread of a tile slot, so 1/n is computed once
+struct Welford {
+    double mean, m2;
+};
+__device__ __forceinline__ void welford_add(Welford &w, double x, double inv_n) {
+    const double d = x - w.mean;
+    w.mean += d * inv_n;
+    w.m2 += d * (x - w.mean);
+}
+
+template <int MODE, int BT>
+__global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la,
+                                                                                 Moment *__restrict__ partials,
+                                                                                 double *__restrict__ samples,
+                                                                                 long long tiles_per_shift) {
+    constexpr int THREADS = ln_threads(BT), RC = LN_RC, LDX = ln_ldx(BT), LDF = ln_ldf(BT), W = THREADS / 32;
+    constexpr int WC = BT / 16;  // warp grid: 2 (row-tile pairs) x WC (sample-tile pairs)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int mpad = la.mpad;
     double *xi = reinterpret_cast<double *>(smem_raw);           // [mpad][LDX]
     double *F = xi + (size_t)mpad * LDX;                         // [RC][LDF]
-    double *red = F + RC * LDF;                                  // [3][2][W]
-    Moment *acc = reinterpret_cast<Moment *>(red + 3 * 2 * W);   // [2]
-    SweepState *xch = reinterpret_cast<SweepState *>(acc + 2);   // [2][BT] right-side states (fine, coarse)
+    SweepState *xch = reinterpret_cast<SweepState *>(F + RC * LDF);  // [2][BT] right-side states (fine, coarse)
+    Moment *mred = reinterpret_cast<Moment *>(xch + 2 * BT);     // [2][BT] final per-thread moments
     GenScratch sc;
-    sc.wtot = reinterpret_cast<unsigned *>(xch + 2 * BT);        // [W]
-    sc.queue = reinterpret_cast<unsigned short *>(sc.wtot + W);  // [BT * 64*(THREADS/BT)] at most
+    sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * BT);       // [W]
+    // generator queue [BT * min(m, 256)]: lives inside F when it fits (F is idle while the inputs are generated)
+    const int qbytes = BT * min(g.m, 256) * 2;
+    sc.queue = qbytes <= RC * LDF * 8 ? reinterpret_cast<unsigned short *>(F) : reinterpret_cast<unsigned short *>(sc.wtot + W);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
     const int M = la.N / 2;  // mid node
     const int nks = mpad >> 2;
     // warp -> 2x2 block of 8x8 tiles inside the RC x BT chunk: row tiles {2*wr, 2*wr+1}, sample tiles {2*wc, 2*wc+1}
-    const int wr = warp >> 2, wc = warp & 3;
+    const int wr = warp / WC, wc = warp % WC;
     const int lr = lane >> 2, lk = lane & 3;
-    if (tid < 2) acc[tid] = Moment{0.0, 0.0, 0.0};
     for (int e = tid; e < (mpad - g.m) * LDX; e += THREADS) xi[(size_t)g.m * LDX + e] = 0.0;  // k padding rows
     __syncthreads();
+    Welford wdq{0.0, 0.0}, wqf{0.0, 0.0};  // threads tid < BT: running statistics of sample slot tid over this CTA's tiles
+    double ncount = 0.0;
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
         const unsigned long long i0 = (unsigned long long)ti * BT;
         const unsigned long long left = g.n - i0;
         const int Pt = left < (unsigned long long)BT ? (int)left : BT;
         // A. inputs (always a full tile: surplus points are masked out of the statistics)
-        constexpr int GEN_DIMS = 64 * (THREADS / BT);
+        constexpr int GEN_DIMS = 64 * (THREADS / BT);  // 64 iterations per thread fit the class masks
         for (int j0 = 0; j0 < g.m; j0 += GEN_DIMS)
             gen_tile_owned<THREADS, BT, MODE, LDX>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc);
 
@@ -460,20 +474,34 @@ __global__ void __launch_bounds__(LN_THREADS, 2) lognormal1d_kernel(GenArgs g, L
         // D. meet in the middle
         if (tid < 2 * BT && side == 1) { xch[b] = sf; xch[BT + b] = scs; }
         __syncthreads();
-        double val[2] = {0.0, 0.0};
         if (tid < BT) {
             const double qf = sweep_combine(sf, xch[b], M, la.h2);
-            val[1] = qf;
-            val[0] = qf;
-            if (la.level > 0) val[0] = __dsub_rn(qf, sweep_combine(scs, xch[BT + b], M / 2, la.h2c));
-            if (samples && b < Pt) {
-                samples[((size_t)r * 2 + 0) * g.n + i0 + b] = val[0];
-                samples[((size_t)r * 2 + 1) * g.n + i0 + b] = val[1];
+            double dq = qf;
+            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(scs, xch[BT + b], M / 2, la.h2c));
+            if (b < Pt) {
+                if (samples) {
+                    samples[((size_t)r * 2 + 0) * g.n + i0 + b] = dq;
+                    samples[((size_t)r * 2 + 1) * g.n + i0 + b] = qf;
+                }
+                ncount += 1.0;
+                const double inv_n = 1.0 / ncount;
+                welford_add(wdq, dq, inv_n);
+                welford_add(wqf, qf, inv_n);
             }
         }
-        block_moments_merge<THREADS, 2>(val, Pt, red, acc);  // valid threads: tid < Pt <= BT
+        // (the barriers of the next tile's generator order the xch reads above before xch is rewritten)
     }
-    if (tid < 2) partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = acc[tid];
+    // merge the BT per-thread statistics in a fixed order: slot b holds every BT-th sample of this CTA's tiles
+    if (tid < BT) {
+        mred[tid] = Moment{ncount, wdq.mean, wdq.m2};
+        mred[BT + tid] = Moment{ncount, wqf.mean, wqf.m2};
+    }
+    __syncthreads();
+    if (tid < 2) {
+        Moment a{0.0, 0.0, 0.0};
+        for (int i = 0; i < BT; ++i) a = moment_merge(a, mred[tid * BT + i]);
+        partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
+    }
 }
 
 }  // namespace mle
