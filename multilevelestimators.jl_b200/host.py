@@ -1,0 +1,565 @@
+"""Host-side mirror of the reference interface for the hot path: `Estimator(index_set, sample_method, sample_function,
+distributions; options...)`, `run(estimator, tol)` and the `History` it returns.
+
+This is the Python twin of the Julia glue in julia/MLECuda.jl (Julia is not installed in the build or GPU images, so the
+control loop is restated here to make `run` testable end to end).  It follows the reference line by line where the hot
+path is concerned:
+
+  sample! / update_samples      src/sample.jl:8-34      point numbers continue across calls (Istart = N + 1)
+  parallel_sample!              src/sample.jl:39-56, :79-102   -> ONE `sample_batch` call on the backend (libmle_cuda)
+  append_samples!               src/sample.jl:58-63, :104-111  -> Chan merge of (n, mean, M2) per (qoi, shift)
+  mean / var / varest / cost    src/methods.jl:44-68, :282
+  _run (SL / ML / multi-index)  src/run.jl:41-142
+  rates, regression, bias, MSE splitting, optimal_nb_of_samples   src/methods.jl:70-201
+  History keys                  src/history.jl:55-103
+
+Out of scope: AD and U index sets, HC / ZC index sets, printing, JLD2 output, `save_samples`.
+The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
+"""
+import math
+import time as _time
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# index sets (src/index_set.jl) and sample methods (src/sample_method.jl)
+# ---------------------------------------------------------------------------------------------------------------
+class SL:
+    ndims = 1
+
+    def get_index_set(self, sz):
+        return [(0,)]
+
+
+class ML:
+    ndims = 1
+
+    def get_index_set(self, sz):  # src/index_set.jl:49-55
+        return [(l,) for l in range(sz + 1)]
+
+
+class _Weighted:
+    def __init__(self, *weights):
+        if len(weights) == 1 and isinstance(weights[0], int):
+            weights = (1.0,) * weights[0]
+        if len(weights) < 2:
+            raise ValueError("to use %s, dimension must be greater than 1, got %d" % (type(self).__name__, len(weights)))
+        if any(w <= 0 or w > 1 for w in weights):
+            raise ValueError("weights must be in (0, 1]")
+        self.weights = tuple(float(w) for w in weights)
+        self.ndims = len(weights)
+
+    def get_index_set(self, sz):
+        import itertools
+        rng = [range(int(math.floor(sz / w + 1e-12)) + 1) for w in self.weights]
+        return [idx for idx in itertools.product(*rng) if self.filter(idx, sz)]
+
+
+class FT(_Weighted):  # full tensor, src/index_set.jl:81
+    def filter(self, idx, sz):
+        return all(w * i <= sz + 1e-12 for w, i in zip(self.weights, idx))
+
+
+class TD(_Weighted):  # total degree, src/index_set.jl:114
+    def filter(self, idx, sz):
+        return sum(w * i for w, i in zip(self.weights, idx)) <= sz + 1e-12
+
+
+class MC:
+    pass
+
+
+class QMC:
+    pass
+
+
+# distributions (src/distribution.jl): constructors with the reference's argument checks
+def Uniform(a=0.0, b=1.0):
+    if not (math.isfinite(a) and math.isfinite(b)) or not a < b:
+        raise ValueError("Uniform: a and b must be finite with a < b")
+    return (0, [float(a), float(b)])
+
+
+def Normal(mu=0.0, sigma=1.0):
+    if not (math.isfinite(mu) and math.isfinite(sigma)) or not sigma > 0:
+        raise ValueError("Normal: mu finite, sigma finite and > 0")
+    return (1, [float(mu), float(sigma)])
+
+
+def TruncatedNormal(mu=0.0, sigma=1.0, a=-2.0, b=2.0):
+    if not all(math.isfinite(v) for v in (mu, sigma, a, b)) or not sigma > 0 or not a < b:
+        raise ValueError("TruncatedNormal: finite parameters, sigma > 0, a < b")
+    return (2, [float(mu), float(sigma), float(a), float(b)])
+
+
+def Weibull(k=2.0, lam=math.sqrt(2.0)):
+    if not (math.isfinite(k) and math.isfinite(lam)) or not (k > 0 and lam > 0):
+        raise ValueError("Weibull: k and lambda finite and > 0")
+    return (3, [float(k), float(lam)])
+
+
+class ModelSpec:
+    """Device sample function: registry name, index dimension, parameters, KL bases per level (lognormal models)."""
+
+    def __init__(self, name, ndims=1, params=(), bases=None):
+        self.name, self.ndims, self.params, self.bases = name, ndims, list(params), dict(bases or {})
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backend: where `parallel_sample!` runs.  GpuBackend = libmle_cuda on one GPU; ShardedBackend = one rank of a
+# torch.distributed job (each rank takes a contiguous slice of the point numbers, one all-gather of the moments).
+# ---------------------------------------------------------------------------------------------------------------
+class GpuBackend:
+    def __init__(self, engine):
+        self.engine = engine
+
+    def lattice(self, z, s, nmax=2**32 - 1):
+        return self.engine.lattice(z, s, nmax)
+
+    def dists(self, dists):
+        return self.engine.dists(dists)
+
+    def model(self, spec):
+        m = self.engine.model(spec.name, spec.ndims, spec.params)
+        for level, phi in spec.bases.items():
+            m.set_basis(level, phi)
+        return m
+
+    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed):
+        mom, t = self.engine.sample_batch(model, lattice, dists, index, shifts, k0, n, m=m, mc_seed=mc_seed, want_time=True)
+        return mom, t
+
+
+def split_range(k0, n, world, rank):
+    """contiguous slice of the point numbers k0 .. k0+n-1 owned by `rank` (first n % world ranks get one more)"""
+    base, rem = divmod(n, world)
+    cnt = base + (1 if rank < rem else 0)
+    start = k0 + rank * base + min(rank, rem)
+    return start, cnt
+
+
+class ShardedBackend:
+    """One rank of a multi-GPU run: shards every `sample_batch` over the ranks of a torch.distributed group and combines the
+    per-rank moment triplets with ONE all-gather, merged in rank order (deterministic).  `inner` is the local backend."""
+
+    def __init__(self, inner, group=None, device=None, merge=None):
+        import torch.distributed as dist
+        self.inner, self.dist, self.group, self.device = inner, dist, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if merge is None:
+            from .engine import moments_merge as merge
+        self.merge = merge
+
+    def lattice(self, *a, **k):
+        return self.inner.lattice(*a, **k)
+
+    def dists(self, *a, **k):
+        return self.inner.dists(*a, **k)
+
+    def model(self, spec):
+        return self.inner.model(spec)
+
+    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed):
+        import torch
+        start, cnt = split_range(k0, n, self.world, self.rank)
+        R = 1 if shifts is None else len(shifts)
+        q = getattr(model, "nqoi", 1)
+        if cnt > 0:
+            mom, t = self.inner.sample_batch(model, lattice, dists, index, shifts, start, cnt, m, mc_seed)
+        else:
+            mom, t = np.zeros((R, q, 2, 3)), 0.0
+        payload = torch.from_numpy(np.concatenate([mom.reshape(-1), [t]]))
+        if self.device is not None:
+            payload = payload.to(self.device)
+        out = [torch.empty_like(payload) for _ in range(self.world)]
+        self.dist.all_gather(out, payload, group=self.group)
+        parts = [o.cpu().numpy() for o in out]
+        acc = parts[0][:-1].reshape(mom.shape).copy()
+        for p in parts[1:]:
+            acc = self.merge(acc, p[:-1].reshape(mom.shape))
+        return acc, max(float(p[-1]) for p in parts)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Estimator
+# ---------------------------------------------------------------------------------------------------------------
+_DEFAULTS = dict(nb_of_qoi=None, aggregation="max", qoi_with_max_var=1, continuate=True, nb_of_tols=10,
+                 continuation_mul_factor=1.3, min_splitting=0.5, max_splitting=0.99, robustify_bias_estimate=True,
+                 do_mse_splitting=True, do_regression=True, min_index_set_param=2, max_index_set_param=None,
+                 sample_mul_factor=1.2, nb_of_warm_up_samples=None, nb_of_shifts=10, nb_of_uncertainties=None,
+                 cost_model=None, point_generator=None, shifts=None, shift_seed=0, mc_seed=1, name="UntitledEstimator",
+                 verbose=False)
+
+
+class Estimator:
+    """Estimator(index_set, sample_method, sample_function, distributions; options...)  (src/estimator.jl:121)"""
+
+    def __init__(self, index_set, sample_method, sample_function, distributions, backend, **options):
+        if not isinstance(sample_function, ModelSpec):
+            raise TypeError("sample_function must be a ModelSpec naming a device model (arbitrary closures cannot run on the GPU)")
+        if isinstance(distributions, tuple):
+            distributions = [distributions]
+        unknown = set(options) - set(_DEFAULTS)
+        if unknown:
+            raise ValueError("in Estimator, invalid option %s" % sorted(unknown))  # src/estimator.jl:127-131
+        o = dict(_DEFAULTS)
+        o.update(options)
+        self.index_set, self.sample_method, self.spec, self.distributions, self.backend = (
+            index_set, sample_method, sample_function, list(distributions), backend)
+        self.qmc = isinstance(sample_method, QMC)
+        d = index_set.ndims
+        if o["max_index_set_param"] is None:
+            o["max_index_set_param"] = 10 * d                          # src/parse.jl:193-194
+        if o["nb_of_warm_up_samples"] is None:
+            o["nb_of_warm_up_samples"] = 1 if self.qmc else 20          # src/parse.jl:35-36
+        elif o["nb_of_warm_up_samples"] <= 1:
+            raise ValueError("in Estimator, optional key nb_of_warm_up_samples must be larger than 1")  # src/parse.jl:39
+        if not callable(o["nb_of_shifts"]):
+            if o["nb_of_shifts"] <= 1:
+                raise ValueError("in Estimator, optional key nb_of_shifts must be larger than 1")      # src/parse.jl:243
+            R = int(o["nb_of_shifts"])
+            o["nb_of_shifts"] = lambda index: R
+        if o["nb_of_uncertainties"] is None:
+            m_all = len(self.distributions)
+            o["nb_of_uncertainties"] = lambda index: m_all              # src/parse.jl:272-275
+        if o["aggregation"] not in ("max", "sum", "norm"):
+            raise ValueError("in Estimator, optional key aggregation must be 'sum', 'max' or 'norm'")
+        if not (0 < o["min_splitting"] <= o["max_splitting"] <= 1):
+            raise ValueError("in Estimator, min_splitting / max_splitting must satisfy 0 < min <= max <= 1")
+        self.options = o
+        self.model = backend.model(sample_function)
+        self.nqoi = o["nb_of_qoi"] or getattr(self.model, "nqoi", 1)
+        self.dists = backend.dists(self.distributions)
+        s = len(self.distributions)
+        self.lattice = None
+        if self.qmc:
+            z = o["point_generator"]  # a generating vector; None -> default LatticeRule32(s), src/parse.jl:251-254
+            self.lattice = backend.lattice(z, s)
+        # internals (src/internals.jl:35-54): per index cumulative moments [R, q, 2, 3], counters, and one shift per (index, r)
+        box = index_set.get_index_set(o["max_index_set_param"])
+        self.moments, self.nb_of_samples, self.total_work, self.total_time = {}, {}, {}, {}
+        self.shifts = {}
+        rng = np.random.default_rng(o["shift_seed"])
+        for index in sorted(box, key=lambda t: t[::-1]):  # column-major order of the index box, src/internals.jl:138
+            R = o["nb_of_shifts"](index) if self.qmc else 1
+            self.nb_of_samples[index], self.total_work[index], self.total_time[index] = 0, 0.0, 0.0
+            if self.qmc:
+                given = o["shifts"]
+                self.shifts[index] = np.asarray(given[index] if isinstance(given, dict) else given(index), dtype=np.float64) \
+                    if given is not None else rng.random((R, s))
+        self.current_index_set = set()
+        self.sz = self.max_sz = 0
+
+    def __getitem__(self, key):  # estimator[:key], src/options.jl:46
+        return self.options[key]
+
+    # ---- the hot path -----------------------------------------------------------------------------------------------
+    def sample(self, index, n):
+        """sample!(estimator, index, n), src/sample.jl:21-34"""
+        istart = self.nb_of_samples[index] + 1
+        m = self.options["nb_of_uncertainties"](index)
+        t0 = _time.perf_counter()
+        mom, _gpu_t = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
+                                                self.shifts.get(index), istart - 1, n, m, self.options["mc_seed"])
+        t = _time.perf_counter() - t0
+        if index in self.moments:
+            from .engine import moments_merge
+            self.moments[index] = moments_merge(self.moments[index], mom)
+        else:
+            self.moments[index] = np.array(mom, dtype=np.float64)
+        self.nb_of_samples[index] += n                                  # src/internals.jl:90
+        cm = self.options["cost_model"]
+        self.total_work[index] += 0.0 if cm is None else n * cm(index)  # src/internals.jl:98
+        self.total_time[index] += t                                     # src/internals.jl:106
+
+    def update_samples(self, n_opt):  # src/sample.jl:8-13
+        for index in n_opt:
+            n_due = n_opt[index] - self.nb_of_samples[index]
+            if n_due > 0:
+                self.sample(index, n_due)
+
+    def has_samples_at_index(self, index):
+        return self.nb_of_samples.get(index, 0) > 0
+
+    # ---- statistics (src/methods.jl:28-68, :282) -------------------------------------------------------------------------
+    def _aggregate(self, values):
+        a = self.options["aggregation"]
+        if a == "sum":
+            return float(np.sum(values))
+        if a == "norm":
+            return float(np.linalg.norm(values))
+        return float(values[self.options["qoi_with_max_var"] - 1])
+
+    def _per_qoi(self, index, X, f):
+        mom = self.moments[index][:, :, X, :]  # [R, q, 3]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if f == "mean":
+                per_shift = mom[..., 1]
+            else:
+                per_shift = mom[..., 2] / (mom[..., 0] - 1.0)  # corrected variance; NaN with one sample like the reference
+        return per_shift.mean(axis=0)  # MC: R == 1
+
+    def mean(self, index=None):
+        if index is None:
+            return sum(self.mean(i) for i in self.keys())
+        return self._aggregate(self._per_qoi(index, 0, "mean"))
+
+    def var(self, index):
+        return self._aggregate(self._per_qoi(index, 0, "var"))
+
+    def mean0(self, index):
+        return self._aggregate(self._per_qoi(index, 1, "mean"))
+
+    def var0(self, index):
+        return self._aggregate(self._per_qoi(index, 1, "var"))
+
+    def varest(self, index=None):
+        if index is None:
+            return sum(self.varest(i) for i in self.keys())
+        if not self.qmc:
+            return self.var(index) / self.nb_of_samples[index]          # src/methods.jl:66
+        means = self.moments[index][:, :, 0, 1]                         # per-shift means [R, q]
+        R = means.shape[0]
+        return self._aggregate(means.var(axis=0, ddof=1) / R)           # src/methods.jl:282
+
+    def cost(self, index):  # src/methods.jl:64
+        tot = self.total_time if self.options["cost_model"] is None else self.total_work
+        return tot[index] / self.nb_of_samples[index]
+
+    def time(self, index):
+        return self.total_time[index] / self.nb_of_samples[index]
+
+    def keys(self):
+        return sorted(self.current_index_set, key=lambda t: t[::-1])
+
+    def all_keys(self):
+        return sorted((i for i, n in self.nb_of_samples.items() if n > 0), key=lambda t: t[::-1])
+
+    # ---- rates and regression (src/methods.jl:70-163) -----------------------------------------------------------------------
+    @staticmethod
+    def _interp1(x, y):
+        A = np.column_stack([np.ones(len(x)), np.asarray(x, dtype=float)])
+        return np.linalg.lstsq(A, np.asarray(y, dtype=float), rcond=None)[0]
+
+    def _rates(self, g, idx, dir):
+        m = idx[dir] - 1
+        if m < 2:
+            return (float("nan"), float("nan"))
+        e = tuple(1 if i == dir else 0 for i in range(len(idx)))
+        xs, ys = [], []
+        for k in range(1, m + 1):
+            index = tuple(a - k * b for a, b in zip(idx, e))
+            y = g(index)
+            x = m - k + 1
+            if not (math.isnan(y) or y == 0):
+                xs.append(x)
+                ys.append(math.log2(abs(y)))
+        return tuple(self._interp1(xs, ys))
+
+    def _rate(self, g, sgn):
+        if isinstance(self.index_set, SL):
+            return None
+        out = []
+        for dir in range(self.index_set.ndims):
+            top = max(k[dir] for k in self.keys()) + 1
+            idx = tuple(top if i == dir else 0 for i in range(self.index_set.ndims))
+            out.append(sgn * self._rates(g, idx, dir)[1])
+        return out
+
+    def alpha(self):
+        return self._rate(self.mean, -1)
+
+    def beta(self):
+        return self._rate(self.var, -1)
+
+    def gamma(self):
+        return self._rate(self.cost, 1)
+
+    def _interp(self, f):
+        have = [i for i, n in self.nb_of_samples.items() if (n > 0 if self.qmc else n > 1)]
+        A = np.array([[1.0] + list(i) for i in have])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            y = np.array([math.log2(f(i)) if f(i) > 0 else float("-inf") for i in have])
+        ok = np.isfinite(y)
+        try:
+            return np.linalg.lstsq(A[ok], y[ok], rcond=None)[0]
+        except Exception:  # noqa: BLE001
+            return np.full(A.shape[1], float("nan"))
+
+    def _regress(self, g, index):
+        est = []
+        for dir in range(len(index)):
+            p = self._rates(g, index, dir)
+            est.append(2.0 ** (p[0] + index[dir] * p[1]))
+        est = [v for v in est if not math.isnan(v)]
+        if est:
+            return float(np.mean(est))
+        p = self._interp(g)
+        return 2.0 ** (p[0] + float(np.dot(p[1:], index)))
+
+    def regress_var(self, index):
+        return self._regress(self.var, index)
+
+    def regress_cost(self, index):
+        cm = self.options["cost_model"]
+        return self._regress(self.cost, index) if cm is None else cm(index)
+
+    def regress_nb_of_samples(self, index_set, eps, theta, L):  # src/methods.jl:134-163
+        warm = self.options["nb_of_warm_up_samples"]
+        if isinstance(self.index_set, SL):
+            return {(0,): warm}
+        if self.qmc or not (self.options["do_regression"] and L > 2):
+            return {i: warm for i in index_set}
+        vars_ = {i: self.regress_var(i) for i in index_set}
+        costs = {i: self.regress_cost(i) for i in index_set}
+        sig = self.Sigma() + sum(math.sqrt(vars_[i] * costs[i]) for i in index_set)
+        return {i: max(2, min(self._n_opt(eps, theta, vars_[i], costs[i], sig), warm)) for i in index_set}
+
+    # ---- MSE splitting, sample allocation, bias (src/methods.jl:165-201) ------------------------------------------------------
+    def Sigma(self):
+        return sum(math.sqrt(self.var(i) * self.cost(i)) for i in self.keys())
+
+    @staticmethod
+    def _n_opt(eps, theta, v, c, sig):
+        return int(math.ceil(1.0 / (theta * eps**2) * math.sqrt(v / c) * sig))
+
+    def optimal_nb_of_samples(self, index, eps, theta):
+        return self._n_opt(eps, theta, self.var(index), self.cost(index), self.Sigma())
+
+    def boundary(self, cntr):
+        prev = set(self.index_set.get_index_set(cntr - 1)) if cntr > 0 else set()
+        return [i for i in self.index_set.get_index_set(cntr) if i not in prev]
+
+    def bias(self, sz=None):
+        if isinstance(self.index_set, SL):
+            return 0.0
+        sz = self.sz if sz is None else sz
+        nxt = [i for i in self.boundary(sz + 1) if i in self.current_index_set]
+        if nxt and not self.options["robustify_bias_estimate"]:
+            return abs(sum(self.mean(i) for i in self.boundary(sz + 1)))
+        xs, ys = [], []
+        for x in range(max(1, sz - 2), sz + 1):
+            with np.errstate(divide="ignore"):
+                v = abs(sum(self.mean(i) for i in self.boundary(x)))
+                y = math.log2(v) if v > 0 else float("-inf")
+            if math.isfinite(y):
+                xs.append(x)
+                ys.append(y)
+        if not xs:
+            return float("nan")
+        p = self._interp1(xs, ys)
+        return 2.0 ** (p[0] + (sz + 1) * p[1])
+
+    def compute_splitting(self, eps):
+        b = self.bias(self.max_sz)
+        a, bmax = self.options["min_splitting"], self.options["max_splitting"]
+        s = 1 - b**2 / eps**2
+        return a if math.isnan(s) else min(bmax, max(a, s))
+
+    def mse(self):
+        return self.varest() + self.bias() ** 2
+
+    def rmse(self):
+        return math.sqrt(self.mse())
+
+    def converged(self, eps, theta):
+        return self.bias() ** 2 <= (1 - theta) * eps**2 or self.mse() <= eps**2
+
+    # ---- QMC sample growth (src/methods.jl:265-280) -----------------------------------------------------------------------------
+    def next_number_of_samples(self, index):
+        f, n = self.options["sample_mul_factor"], self.nb_of_samples[index]
+        if f == 2:
+            return {index: 1 << n.bit_length()}  # nextpow(2, n + 1)
+        if f <= 1:
+            return {index: n + 1}
+        return {index: int(math.ceil(n * f))}
+
+    def find_index_with_max_var_over_cost(self):
+        keys = self.keys()
+        vals = [self.varest(i) / self.cost(i) for i in keys]
+        return keys[int(np.argmax(vals))]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# run (src/run.jl:20-142) and History (src/history.jl)
+# ---------------------------------------------------------------------------------------------------------------
+class History:
+    def __init__(self):
+        self.data = []
+
+    def __getitem__(self, key):
+        return self.data[key] if isinstance(key, int) else self.data[-1][key]
+
+    def __len__(self):
+        return len(self.data)
+
+    def __contains__(self, key):
+        return key in self.data[-1]
+
+
+def get_tols(est, tol):  # src/methods.jl:15
+    if est["continuate"]:
+        n, p = est["nb_of_tols"], est["continuation_mul_factor"]
+        return [p ** (n - 1 - i) * tol for i in range(n)]
+    return [tol]
+
+
+def _run(est, eps):  # src/run.jl:41-142
+    sl = isinstance(est.index_set, SL)
+    L = 0
+    theta = 0.5 if sl else est["min_splitting"]
+    done = False
+    while not done:
+        index_set = est.boundary(L)
+        ns = est.regress_nb_of_samples(index_set, eps, theta, L)
+        for index in index_set:
+            if not est.has_samples_at_index(index):
+                est.sample(index, ns[index])
+        est.current_index_set.update(index_set)
+        est.sz, est.max_sz = L, max(L, est.max_sz)
+        theta = 0.5 if sl else (est.compute_splitting(eps) if est["do_mse_splitting"] else est["min_splitting"])
+        if not est.qmc:
+            n_opt = {i: est.optimal_nb_of_samples(i, eps, theta) for i in est.keys()}
+            est.update_samples(n_opt)
+        else:
+            while est.varest() > theta * eps**2:
+                est.update_samples(est.next_number_of_samples(est.find_index_with_max_var_over_cost()))
+                theta = 0.5 if sl else (est.compute_splitting(eps) if est["do_mse_splitting"] else est["min_splitting"])
+        if sl:
+            done = True
+        else:
+            done = L > est["min_index_set_param"] and est.converged(eps, theta)
+            if not done and est.sz >= est["max_index_set_param"]:
+                done = True
+            elif not done:
+                L += 1
+
+
+def update_history(history, est, tol, elapsed):  # src/history.jl:55-103
+    allk = est.all_keys()
+    h = {"type": "Estimator{%s, %s}" % (type(est.index_set).__name__, type(est.sample_method).__name__),
+         "ndims": est.index_set.ndims, "name": est["name"], "elapsed": elapsed, "tol": tol,
+         "current_index_set": est.keys(), "index_set": allk, "mse": est.mse(), "rmse": est.rmse(), "mean": est.mean(),
+         "varest": est.varest(), "bias": est.bias(),
+         "E": {i: est.mean0(i) for i in allk}, "V": {i: est.var0(i) for i in allk},
+         "dE": {i: est.mean(i) for i in allk}, "dV": {i: est.var(i) for i in allk},
+         "T": {i: est.time(i) for i in allk}, "alpha": est.alpha(), "beta": est.beta(), "gamma": est.gamma(),
+         "nb_of_samples": dict(est.nb_of_samples)}
+    if est["cost_model"] is not None:
+        h["W"] = {i: est.cost(i) for i in allk}
+    history.data.append(h)
+
+
+def run(est, tol):
+    """run(estimator, tol) -> History  (src/run.jl:20-38)"""
+    tols = list(tol) if isinstance(tol, (list, tuple, np.ndarray)) else get_tols(est, tol)
+    if any(t <= 0 for t in tols):
+        raise ValueError("in run, supplied tolerance(s) must be larger than 0")  # src/run.jl:23
+    history = History()
+    for t in tols:
+        est.current_index_set.clear()  # clear(estimator), src/internals.jl:116: samples persist across tolerances
+        t0 = _time.perf_counter()
+        _run(est, t)
+        update_history(history, est, t, _time.perf_counter() - t0)
+    return history

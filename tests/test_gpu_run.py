@@ -1,0 +1,77 @@
+"""GPU end-to-end: run(estimator, tol) through the host mirror on libmle_cuda against the same loop on the CPU oracle.
+Identical shifts and a fixed cost model make the adaptive loop deterministic, so both must take the same
+decisions (sample counts per level) and agree on estimates and per-level variances to 1e-12 relative (north star)."""
+import numpy as np
+import pytest
+
+from oracle_backend import OracleBackend
+
+pytestmark = pytest.mark.gpu
+
+
+def both(engine, make):
+    import mle_b200.host as H
+    g = make(H, H.GpuBackend(engine))
+    o = make(H, OracleBackend())
+    return H, g, o
+
+
+def compare(hg, ho, rtol=1e-12):
+    assert len(hg) == len(ho)
+    for i in range(len(hg)):
+        a, b = hg[i], ho[i]
+        assert a["nb_of_samples"] == b["nb_of_samples"], (i, a["nb_of_samples"], b["nb_of_samples"])
+        assert a["current_index_set"] == b["current_index_set"]
+        assert abs(a["mean"] - b["mean"]) <= rtol * abs(b["mean"])
+        assert abs(a["varest"] - b["varest"]) <= 1e-9 * abs(b["varest"])  # variance of 16 nearly equal shift means
+        for key in ("E", "dE", "V", "dV"):
+            for idx in b[key]:
+                x, y = a[key][idx], b[key][idx]
+                if np.isnan(y):
+                    assert np.isnan(x)
+                else:
+                    assert abs(x - y) <= rtol * abs(y), (key, idx, x, y)
+
+
+def test_mlqmc_lognormal1d_run_matches_oracle(engine):
+    """config C2 at test size: ML()/QMC(), 16 shifts, 100-term KL, levels up to 4"""
+    import mle_b200.kl as kl
+
+    def make(H, backend):
+        spec = H.ModelSpec("lognormal1d", 1, [16], {lev: kl.kl_basis_1d(lev, m=100) for lev in range(5)})
+        return H.Estimator(H.ML(), H.QMC(), spec, [H.Normal()] * 100, backend, nb_of_shifts=16, max_index_set_param=4,
+                           cost_model=lambda i: 2.0 ** i[0], shift_seed=7, nb_of_tols=4)
+
+    H, g, o = both(engine, make)
+    hg, ho = H.run(g, 2e-4), H.run(o, 2e-4)
+    compare(hg, ho)
+    assert hg["rmse"] <= 2e-4 * 1.5 or hg["current_index_set"][-1] == (4,)
+    assert len(hg["current_index_set"]) >= 3
+    assert 0.05 < hg["mean"] < 0.3
+
+
+def test_mlmc_expsum_run_matches_oracle(engine):
+    def make(H, backend):
+        w = [0.5 / (j + 1) for j in range(64)]
+        return H.Estimator(H.ML(), H.MC(), H.ModelSpec("expsum", 1, [4] + w), [H.Normal()] * 64, backend,
+                           max_index_set_param=4, cost_model=lambda i: 2.0 ** i[0], nb_of_tols=3)
+
+    H, g, o = both(engine, make)
+    compare(H.run(g, 5e-3), H.run(o, 5e-3))
+
+
+def test_problem18_regression_suite_on_gpu(engine):
+    """test/regression.jl on the device: ML x {MC, QMC} x {max, sum, norm} and TD(2)/FT(2) x QMC"""
+    for method in ("MC", "QMC"):
+        for agg, tol in (("max", 1e-2), ("sum", 1e-1), ("norm", 1e-1)):
+            def make(H, backend):
+                return H.Estimator(H.ML(), getattr(H, method)(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], backend,
+                                   nb_of_qoi=13, max_index_set_param=3, aggregation=agg, cost_model=lambda i: 2.0 ** i[0])
+            H, g, o = both(engine, make)
+            compare(H.run(g, tol), H.run(o, tol))
+    for iset in ("TD", "FT"):
+        def make(H, backend):
+            return H.Estimator(getattr(H, iset)(2), H.QMC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, backend,
+                               nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_shifts=8)
+        H, g, o = both(engine, make)
+        compare(H.run(g, 1e-2), H.run(o, 1e-2))

@@ -1,0 +1,146 @@
+"""CPU tests of the host-side mirror of the reference interface (Estimator / run / History) on the oracle backend, and of
+the multi-rank sharding logic with the gloo backend (world_size 2)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle_backend import OracleBackend
+
+
+def host():
+    import mle_b200.host as H
+    return H
+
+
+def test_index_sets_match_reference_cardinalities():
+    H = host()
+    # test/index_set.jl:22: 3-d, sz = 7: FT 512, TD 120;  weighted 2-d (1, 1/2), sz = 6 -> FT 28? (reference fixture order FT/TD)
+    assert len(H.FT(3).get_index_set(7)) == 512 and len(H.TD(3).get_index_set(7)) == 120
+    assert len(H.ML().get_index_set(4)) == 5 and H.SL().get_index_set(3) == [(0,)]
+    with pytest.raises(ValueError):
+        H.TD(1)
+
+
+def test_option_validation_mirrors_reference():
+    H = host()
+    spec = H.ModelSpec("problem18", 1)
+    be = OracleBackend()
+    with pytest.raises(ValueError):
+        H.Estimator(H.ML(), H.MC(), spec, [H.Uniform(-0.5, 0.5)], be, nb_of_warm_up_samples=1)   # test/estimator.jl
+    with pytest.raises(ValueError):
+        H.Estimator(H.ML(), H.QMC(), spec, [H.Uniform(-0.5, 0.5)], be, nb_of_shifts=1)
+    with pytest.raises(ValueError):
+        H.Estimator(H.ML(), H.MC(), spec, [H.Uniform(-0.5, 0.5)], be, aggregation="median")
+    with pytest.raises(ValueError):
+        H.Estimator(H.ML(), H.MC(), spec, [H.Uniform(-0.5, 0.5)], be, no_such_option=3)
+    with pytest.raises(TypeError):
+        H.Estimator(H.ML(), H.MC(), lambda l, x: (0, 0), [H.Uniform()], be)
+    with pytest.raises(ValueError):
+        H.Normal(0.0, -1.0)
+    with pytest.raises(ValueError):
+        H.Uniform(1.0, 0.0)
+    e = H.Estimator(H.ML(), H.QMC(), spec, [H.Uniform(-0.5, 0.5)], be)
+    assert e["nb_of_warm_up_samples"] == 1 and e["nb_of_shifts"]((0,)) == 10 and e["max_index_set_param"] == 10
+    assert e["continuation_mul_factor"] == 1.3 and e["sample_mul_factor"] == 1.2  # src/parse.jl:80, :216
+
+
+@pytest.mark.parametrize("method", ["MC", "QMC"])
+@pytest.mark.parametrize("aggregation,tol", [("max", 1e-2), ("sum", 1e-1), ("norm", 1e-1)])
+def test_regression_problem18_multilevel(method, aggregation, tol):
+    """test/regression.jl:49-66: run(Estimator(ML(), MC()/QMC(), problem_18, Uniform(-0.5,0.5); nb_of_qoi=13,
+    max_index_set_param=3, aggregation), tol) completes; here we also check the History"""
+    H = host()
+    est = H.Estimator(H.ML(), getattr(H, method)(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(),
+                      nb_of_qoi=13, max_index_set_param=3, aggregation=aggregation, cost_model=lambda i: 2.0 ** i[0])
+    h = H.run(est, tol)
+    assert len(h) == 10                                   # 10 tolerances, factor 1.3 apart (src/parse.jl:70-86)
+    assert abs(h[0]["tol"] / h[1]["tol"] - 1.3) < 1e-12 and abs(h["tol"] - tol) < 1e-15
+    for key in ("type", "ndims", "name", "elapsed", "tol", "current_index_set", "index_set", "mse", "rmse", "mean", "varest",
+                "bias", "E", "V", "dE", "dV", "T", "alpha", "beta", "gamma", "nb_of_samples", "W"):
+        assert key in h                                   # src/history.jl:57-84
+    assert h["rmse"] <= 2 * tol or h["current_index_set"][-1] == (3,)
+    ns = [h[i]["nb_of_samples"][(0,)] for i in range(len(h))]
+    assert ns == sorted(ns)                               # samples persist across tolerances
+    # exact value of the level-3 model: f_j + E[xi^3] = f_j (odd moment vanishes); QoI 1 is (0-2)^2 = 4
+    if aggregation == "max":
+        assert abs(h["mean"] - 4.0) < 5 * tol
+
+
+def test_multi_index_problem18_td():
+    H = host()
+    est = H.Estimator(H.TD(2), H.QMC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(),
+                      nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_shifts=8)
+    h = H.run(est, 1e-2)
+    assert h["ndims"] == 2 and (1, 1) in h["index_set"]
+    assert abs(h["mean"] - 4.0) < 0.05
+
+
+def test_single_level_mc_expsum_closed_form():
+    """config C1: SL()/MC() on 16 Normal() inputs, E[exp(sum a_j xi_j)] = exp(sum a_j^2 / 2)"""
+    H = host()
+    w = [0.5 / (j + 1) for j in range(16)]
+    est = H.Estimator(H.SL(), H.MC(), H.ModelSpec("expsum", 1, [16] + w), [H.Normal()] * 16, OracleBackend(),
+                      cost_model=lambda i: 1.0, nb_of_tols=4)
+    h = H.run(est, 4e-3)
+    exact = math.exp(0.5 * sum(a * a for a in w))
+    assert abs(h["mean"] - exact) < 4 * 4e-3
+    n = h["nb_of_samples"][(0,)]
+    assert abs(n - 2 * h["V"][(0,)] / 4e-3**2) / n < 0.2   # theta = 1/2 for SL: N = V / (theta eps^2), src/run.jl:50
+
+
+def test_qmc_growth_rule_and_nan_variance_with_one_sample():
+    H = host()
+    est = H.Estimator(H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                      cost_model=lambda i: 2.0 ** i[0])
+    est.sample((0,), 1)
+    assert math.isnan(est.var((0,)))                     # var of a 1-vector is NaN
+    assert est.varest((0,)) > 0                          # ... while the across-shift variance drives the loop
+    est.current_index_set.add((0,))
+    assert est.next_number_of_samples((0,)) == {(0,): 2}  # ceil(1 * 1.2)
+    est.sample((0,), 4)
+    assert est.nb_of_samples[(0,)] == 5 and est.next_number_of_samples((0,)) == {(0,): 6}
+    assert est.moments[(0,)].shape == (10, 13, 2, 3) and (est.moments[(0,)][..., 0] == 5).all()
+
+
+def test_split_range_covers_everything():
+    H = host()
+    for n, world in [(1, 2), (7, 2), (8, 8), (3, 8), (1000, 3)]:
+        got = []
+        for r in range(world):
+            s, c = H.split_range(5, n, world, r)
+            got += list(range(s, s + c))
+        assert got == list(range(5, 5 + n))
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import mle_b200.host as H
+    be = H.ShardedBackend(OracleBackend())
+    est = H.Estimator(H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], be, nb_of_qoi=13,
+                      max_index_set_param=3, cost_model=lambda i: 2.0 ** i[0], nb_of_shifts=4, nb_of_tols=3)
+    h = H.run(est, 2e-2)
+    if rank == 0:
+        np.save(out, np.array([h["mean"], h["varest"], float(sum(h["nb_of_samples"].values()))]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_single_rank(tmp_path):
+    """world_size-2 gloo run: every sample_batch is split over the ranks, one all-gather merges the moments"""
+    import torch.multiprocessing as mp
+    H = host()
+    est = H.Estimator(H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                      max_index_set_param=3, cost_model=lambda i: 2.0 ** i[0], nb_of_shifts=4, nb_of_tols=3)
+    h = H.run(est, 2e-2)
+    out = str(tmp_path / "r0.npy")
+    mp.spawn(_worker, args=(2, 29517, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert got[2] == float(sum(h["nb_of_samples"].values()))      # identical decisions
+    assert abs(got[0] - h["mean"]) <= 1e-12 * abs(h["mean"])
+    assert abs(got[1] - h["varest"]) <= 1e-9 * abs(h["varest"])

@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Turn the scratch ncu output under gpurun_out/ into the tracked summaries under profiles/.
+
+usage: python tools/summarize_profiles.py <round tag> <launches.csv> <full .ncu-rep>
+  profiles/<tag>_launches.csv        per-kernel totals of the `--metrics gpu__time_duration.sum` launch list
+  profiles/<tag>_kernels.csv         one row per profiled launch of the `--set full` capture (key metrics)
+"""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
+os.makedirs(root, exist_ok=True)
+
+rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
+hdr = rows[0]
+ik, iv, iu, ip = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Process Name")
+tot, cnt = collections.Counter(), collections.Counter()
+for r in rows[1:]:
+    scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[iu], 1e-6)
+    key = (r[ip], r[ik].split("(")[0])
+    tot[key] += float(r[iv].replace(",", "")) * scale
+    cnt[key] += 1
+ours = sum(v for (p, k), v in tot.items() if "mle::" in k)
+with open(os.path.join(root, tag + "_launches.csv"), "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow(["process", "kernel", "launches", "total_ms", "share_of_libmle_cuda_time_pct"])
+    for (p, k), v in tot.most_common():
+        w.writerow([p, k, cnt[(p, k)], "%.4f" % v, "%.2f" % (100 * v / ours) if "mle::" in k else ""])
+
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, data = rows[0], rows[1], rows[2:]
+want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "gpu__time_duration.sum",
+        "smsp__cycles_active.avg", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+cols = []
+for wname in want:
+    for i, h in enumerate(hdr):
+        if h.endswith(wname):
+            cols.append((wname + (" [" + units[i] + "]" if units[i] else ""), i))
+            break
+with open(os.path.join(root, tag + "_kernels.csv"), "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow([c for c, _ in cols])
+    for r in data:
+        w.writerow([r[i][:90] for _, i in cols])
+print("wrote profiles/%s_launches.csv and profiles/%s_kernels.csv" % (tag, tag))
