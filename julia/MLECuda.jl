@@ -1,0 +1,162 @@
+# MLECuda.jl -- the reference-side binding of libmle_cuda: what a MultilevelEstimators.jl maintainer adds so that
+# `Estimator(index_set, sample_method, sample_function, distributions; options...)` / `run(estimator, tol)` keep working
+# unchanged while `parallel_sample!` runs on a B200.
+#
+# NOTE: Julia is not installed in the build container or on the GPU image, so this file has never been executed; it is
+# deliberately thin and mechanical (one `ccall` per entry point of include/mle_cuda.h).  The same calls, in the same order,
+# are exercised by the Python twin (multilevelestimators.jl_b200/host.py + engine.py) in tests/.
+#
+# Hook: `sample_function` must be a `Function` (the field is declared `sample_function::Function`, src/estimator.jl:115),
+# so the device model handle is a callable struct (`struct DeviceModel <: Function`, precedent:
+# `struct EmptyFunction <: Function end`, src/parse.jl:178).  The field is NOT a type parameter of `Estimator`
+# (src/estimator.jl:113-119), so `parallel_sample!` cannot dispatch on it; the maintainer adds ONE line at the top of each
+# of the two methods in src/sample.jl (:39 MC, :79 QMC):
+#
+#     estimator.sample_function isa MLECuda.DeviceModel && return MLECuda.device_parallel_sample!(estimator, index, Istart, Iend)
+#
+# and the statistics accessors of src/methods.jl:44-57, :282 read the moment table below instead of the sample vectors
+# when the sample function is a DeviceModel (see `_mean`, `_var`, `_varest_qmc` at the end of this file).
+module MLECuda
+
+using MultilevelEstimators
+import MultilevelEstimators: Estimator, AbstractIndexSet, MC, QMC, Index, parallel_sample!, nb_of_samples, distributions,
+                             generator, Uniform, Normal, TruncatedNormal, Weibull
+
+const libmle = "libmle_cuda"   # multilevelestimators.jl_b200/lib/libmle_cuda.so on the library path
+
+struct MLEDist
+    kind::Int32
+    reserved::Int32
+    p::NTuple{4, Float64}
+end
+MLEDist(d::Uniform) = MLEDist(0, 0, (Float64(d.a), Float64(d.b), 0.0, 0.0))
+MLEDist(d::Normal) = MLEDist(1, 0, (Float64(d.μ), Float64(d.σ), 0.0, 0.0))
+MLEDist(d::TruncatedNormal) = MLEDist(2, 0, (Float64(d.μ), Float64(d.σ), Float64(d.a), Float64(d.b)))
+MLEDist(d::Weibull) = MLEDist(3, 0, (Float64(d.k), Float64(d.λ), 0.0, 0.0))
+
+function check(ctx, rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:mle_last_error, libmle), Cstring, (Ptr{Cvoid},), ctx))
+    # MLE_ERR_ARG (-1) and MLE_ERR_RANGE (-3) are the reference's ArgumentError (src/check_input.jl)
+    (rc == -1 || rc == -3) ? throw(ArgumentError(msg)) : error("libmle_cuda error $rc: $msg")
+end
+
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:mle_init, libmle), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ref)
+        rc == 0 || error(unsafe_string(ccall((:mle_last_error, libmle), Cstring, (Ptr{Cvoid},), C_NULL)))
+        ctx = new(ref[])
+        finalizer(c -> ccall((:mle_destroy, libmle), Cint, (Ptr{Cvoid},), c.ptr), ctx)
+        ctx
+    end
+end
+
+"""
+    DeviceModel(ctx, name, ndims, params; bases = Dict{Int, Matrix{Float64}}())
+
+A built-in CUDA sample function ("expsum", "problem18", "lognormal1d").  `bases[level]` is the KL basis of the level,
+`size = (nodes, terms)`; it is handed over row-major (`permutedims`).
+"""
+mutable struct DeviceModel <: Function
+    ctx::Context
+    ptr::Ptr{Cvoid}
+    nqoi::Int
+    lattice::Ptr{Cvoid}      # created lazily from the estimator's point generator
+    dists::Ptr{Cvoid}
+end
+
+function DeviceModel(ctx::Context, name::String, ndims::Integer, params::Vector{Float64} = Float64[];
+                     bases::Dict{Int, Matrix{Float64}} = Dict{Int, Matrix{Float64}}())
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.ptr, ccall((:mle_model_create, libmle), Cint, (Ptr{Cvoid}, Cstring, Cint, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
+                         ctx.ptr, name, ndims, params, length(params), ref))
+    for (level, Φ) in bases
+        rowmajor = permutedims(Φ)            # Julia is column-major; the ABI wants [nodes][terms] row-major
+        check(ctx.ptr, ccall((:mle_model_set_basis, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}),
+                             ctx.ptr, ref[], level, size(Φ, 1), size(Φ, 2), rowmajor))
+    end
+    q = Ref{Cint}(0)
+    ccall((:mle_model_nqoi, libmle), Cint, (Ptr{Cvoid}, Ref{Cint}), ref[], q)
+    m = DeviceModel(ctx, ref[], q[], C_NULL, C_NULL)
+    finalizer(x -> ccall((:mle_model_destroy, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.ptr, x.ptr), m)
+    m
+end
+
+# Calling the handle like the closure it replaces is an error: samples are taken in batches on the device.
+(m::DeviceModel)(index, ξ) = error("DeviceModel is evaluated by libmle_cuda inside parallel_sample!, not per sample")
+
+function ensure_handles!(m::DeviceModel, estimator)
+    if m.dists == C_NULL
+        d = MLEDist.(distributions(estimator))
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(m.ctx.ptr, ccall((:mle_dists_create, libmle), Cint, (Ptr{Cvoid}, Ptr{MLEDist}, Cint, Ref{Ptr{Cvoid}}),
+                               m.ctx.ptr, d, length(d), ref))
+        m.dists = ref[]
+    end
+end
+
+# Moment state replaces the stored sample vectors (src/internals.jl:44-45): one (n, mean, M2) triplet per
+# (X ∈ {dQ, Qf}, qoi, shift), merged across calls by mle_moments_merge.  Kept in a side table keyed by the estimator.
+const MOMENTS = IdDict{Any, Dict{Any, Array{Float64, 4}}}()
+moments(estimator, index) = get!(() -> Dict{Any, Array{Float64, 4}}(), MOMENTS, estimator)[index]
+
+function merge_moments!(estimator, index, part::Array{Float64, 4})
+    tab = get!(() -> Dict{Any, Array{Float64, 4}}(), MOMENTS, estimator)
+    if haskey(tab, index)
+        ccall((:mle_moments_merge, libmle), Cint, (Ptr{Float64}, Ptr{Float64}, Csize_t), tab[index], part, length(part) ÷ 3)
+    else
+        tab[index] = part
+    end
+end
+
+# ---- the hot path: one ccall per parallel_sample! (replaces the pmap of src/sample.jl:79-102) ----------------------------
+function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
+    model = estimator.sample_function
+    ensure_handles!(model, estimator)
+    m = estimator[:nb_of_uncertainties](index)
+    R = estimator[:nb_of_shifts](index)
+    gens = [generator(estimator, index, r) for r in 1:R]
+    rule = gens[1].lattice_rule
+    if model.lattice == C_NULL
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(model.ctx.ptr, ccall((:mle_lattice_create, libmle), Cint, (Ptr{Cvoid}, Ptr{UInt32}, Cint, UInt64, Ref{Ptr{Cvoid}}),
+                                   model.ctx.ptr, rule.z, length(rule.z), UInt64(rule.n), ref))
+        model.lattice = ref[]
+    end
+    shifts = reduce(hcat, [Vector{Float64}(g.shift) for g in gens])          # [s x R], shift r in column r
+    mom = Array{Float64}(undef, 3, 2, model.nqoi, R)
+    idx = Int32[index.I...]
+    t = Ref{Float64}(0.0)
+    GC.@preserve shifts mom idx check(model.ctx.ptr,
+        ccall((:mle_sample_batch, libmle), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
+               Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+              model.ctx.ptr, model.ptr, model.lattice, model.dists, idx, length(idx), shifts, R,
+              UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, UInt64(0), mom, C_NULL, t))
+    merge_moments!(estimator, index, mom)
+end
+
+function device_parallel_sample!(estimator::Estimator{I, <:MC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
+    model = estimator.sample_function
+    ensure_handles!(model, estimator)
+    m = estimator[:nb_of_uncertainties](index)
+    mom = Array{Float64}(undef, 3, 2, model.nqoi, 1)
+    idx = Int32[index.I...]
+    GC.@preserve mom idx check(model.ctx.ptr,
+        ccall((:mle_sample_batch, libmle), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
+               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              model.ctx.ptr, model.ptr, C_NULL, model.dists, idx, length(idx), C_NULL, 1,
+              UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, UInt64(1), mom, C_NULL, C_NULL))
+    merge_moments!(estimator, index, mom)
+end
+
+# ---- statistics from the moment state (replace src/methods.jl:44-57, :282 for DeviceModel estimators) ---------------------
+# mom[:, X, q, r] = (n, mean, M2);  X = 1: dQ (samples_diff), X = 2: Qf (samples)
+_mean(mom, X, q) = sum(mom[2, X, q, r] for r in axes(mom, 4)) / size(mom, 4)
+_var(mom, X, q) = sum(mom[3, X, q, r] / (mom[1, X, q, r] - 1) for r in axes(mom, 4)) / size(mom, 4)
+_varest_qmc(mom, q) = (R = size(mom, 4); μ = [mom[2, 1, q, r] for r in 1:R]; sum(abs2, μ .- sum(μ) / R) / (R - 1) / R)
+
+end # module
