@@ -158,6 +158,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     scale = 1.0 / 16
     for _ in range(args.warmup):
         cpu_reference_run(scale / 8)
@@ -201,6 +203,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: libmle_cuda has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
