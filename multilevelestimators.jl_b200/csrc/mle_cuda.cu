@@ -21,6 +21,7 @@ template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_
 template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
 template <int MODE> static constexpr auto lognormal1d_k64 = lognormal1d_kernel<MODE, 64>;
 template <int MODE> static constexpr auto lognormal1d_k32 = lognormal1d_kernel<MODE, 32>;
+template <int MODE> static constexpr auto lognormal1d_ws = lognormal1d_ws_kernel<MODE>;
 // mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
 #define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
     do {                                                                                       \
@@ -61,6 +62,7 @@ struct mle_ctx_s {
     std::string err;
     uint64_t launches = 0;
     int ln_bt_override = 0;  // MLE_LN_BT=32|64 in the environment: tuning knob for the lognormal1d tile width
+    int ln_ws = 0;           // MLE_LN_WS=1: warp-specialised lognormal1d kernel
     // reusable device / pinned scratch
     Moment *d_partials = nullptr;
     size_t partials_cap = 0;  // in Moments
@@ -186,9 +188,11 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(problem18_k, 200 * 1024);
     MLE_SET_SMEM(lognormal1d_k64, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_k32, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_ws, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     if (const char *e = getenv("MLE_LN_BT")) { int v = atoi(e); if (v == 32 || v == 64) ctx->ln_bt_override = v; }
+    if (const char *e = getenv("MLE_LN_WS")) ctx->ln_ws = atoi(e) != 0;
     *out = ctx;
     return MLE_OK;
 }
@@ -628,22 +632,34 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
-        // samples per tile: 32 (128 threads, up to 5 CTAs per SM: phases of different CTAs overlap) unless the xi tile
-        // of a 64-sample CTA is needed to amortise the basis traffic of the large levels
-        const int bt = ctx->ln_bt_override ? ctx->ln_bt_override : 32;
+        // Schedule: the phase-synchronous kernel with 32-sample tiles (measured fastest on the C2 step); MLE_LN_BT=64
+        // selects 64-sample tiles and MLE_LN_WS=1 the warp-specialised kernel (kept for A/B measurements).
+        const int bt = ctx->ln_ws ? LNW_BT : (ctx->ln_bt_override ? ctx->ln_bt_override : 32);
         const long long tps = (long long)((n + bt - 1) / bt);
-        const int threads = ln_threads(bt), W = threads / 32;
-        const int qdims = m < 256 ? m : 256;
-        const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
-        const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)2 * bt * sizeof(SweepState) +
-                            (size_t)2 * bt * sizeof(Moment) + W * 4 + (qbytes <= fbytes ? 0 : qbytes) + 16;
-        const int occ = bt == 64 ? MLE_OCC_BY_MODE(g.mode, lognormal1d_k64, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal1d_k32, threads, smem);
-        gx = grid_x_for(ctx, tps, R, occ);
-        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
-        if (rc) return rc;
-        dim3 grid((unsigned)gx, (unsigned)R);
-        if (bt == 64) MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k64, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
-        else MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k32, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
+        if (ctx->ln_ws) {
+            const int Gd = LNW_THREADS / LNW_BT;
+            const int qdims = m <= 32 * Gd ? ((m + Gd - 1) / Gd) * Gd : 64 * Gd;
+            const size_t smem = (size_t)la.mpad * LNW_LDX * 8 + (size_t)2 * LN_RC * LNW_LDF * 8 + (size_t)2 * LNW_BT * sizeof(Moment) +
+                                8 * 4 + (size_t)LNW_BT * qdims * 2 + 16;
+            gx = grid_x_for(ctx, tps, R, MLE_OCC_BY_MODE(g.mode, lognormal1d_ws, LNW_THREADS, smem));
+            rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+            if (rc) return rc;
+            dim3 grid((unsigned)gx, (unsigned)R);
+            MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_ws, grid, LNW_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
+        } else {
+            const int threads = ln_threads(bt), W = threads / 32;
+            const int qdims = m < 256 ? m : 256;
+            const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
+            const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)2 * bt * sizeof(SweepState) +
+                                (size_t)2 * bt * sizeof(Moment) + W * 4 + (qbytes <= fbytes ? 0 : qbytes) + 16;
+            const int occ = bt == 64 ? MLE_OCC_BY_MODE(g.mode, lognormal1d_k64, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal1d_k32, threads, smem);
+            gx = grid_x_for(ctx, tps, R, occ);
+            rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+            if (rc) return rc;
+            dim3 grid((unsigned)gx, (unsigned)R);
+            if (bt == 64) MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k64, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
+            else MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k32, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
+        }
     } else {
         return fail(ctx, MLE_ERR_ARG, "unknown model kind");
     }

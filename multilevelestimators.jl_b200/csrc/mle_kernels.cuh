@@ -315,6 +315,9 @@ struct Lognormal1dArgs {
 };
 
 constexpr int LN_RC = 32;  // rows per chunk (16 half-nodes x 2 sides)
+#ifndef LN_GEN_U
+#define LN_GEN_U 4  // coordinates a generator thread keeps in flight
+#endif
 // samples per tile BT (32 or 64) is a template parameter; THREADS = 4*BT; xi row stride BT+4 (the 4 k-rows of a B fragment
 // fall into different banks); F row stride BT+8 (conflict-free 16-byte epilogue stores)
 __host__ __device__ constexpr int ln_threads(int bt) { return 4 * bt; }
@@ -407,9 +410,13 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         const unsigned long long left = g.n - i0;
         const int Pt = left < (unsigned long long)BT ? (int)left : BT;
         // A. inputs (always a full tile: surplus points are masked out of the statistics)
-        constexpr int GEN_DIMS = 64 * (THREADS / BT);  // 64 iterations per thread fit the class masks
-        for (int j0 = 0; j0 < g.m; j0 += GEN_DIMS)
-            gen_tile_owned<THREADS, BT, MODE, LDX>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc);
+        if (g.m <= 32 * (THREADS / BT)) {  // at most 32 dims per thread: 32-bit class masks
+            gen_tile_owned<THREADS, BT, MODE, LDX, unsigned, LN_GEN_U>(xi, 0, g.m, g.k0 + i0, g, r, sc);
+        } else {
+            constexpr int GEN_DIMS = 64 * (THREADS / BT);  // 64 iterations per thread fit the 64-bit class masks
+            for (int j0 = 0; j0 < g.m; j0 += GEN_DIMS)
+                gen_tile_owned<THREADS, BT, MODE, LDX, unsigned long long, LN_GEN_U>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc);
+        }
 
         SweepState sf{0, 0, 0, 0}, scs{0, 0, 0, 0};
         const int side = tid / BT, b = tid & (BT - 1);  // sweep role (threads 0 .. 2*BT-1)
@@ -495,6 +502,157 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
     if (tid < BT) {
         mred[tid] = Moment{ncount, wdq.mean, wdq.m2};
         mred[BT + tid] = Moment{ncount, wqf.mean, wqf.m2};
+    }
+    __syncthreads();
+    if (tid < 2) {
+        Moment a{0.0, 0.0, 0.0};
+        for (int i = 0; i < BT; ++i) a = moment_merge(a, mred[tid * BT + i]);
+        partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
+    }
+}
+
+
+// ===================================================================================================================
+// 1-D lognormal diffusion, warp-specialised variant (MLE_LN_WS=1; an experiment kept for A/B runs -- measured 8 % slower
+// than the phase-synchronous kernel on the C2 step): same arithmetic as lognormal1d_kernel, different schedule.  ncu showed the fused kernel above spending 35-50 % of its non-generator time at the barrier that separates the
+// KL contraction from the elimination sweeps: the sweeps are a latency-bound dependent chain (one IEEE division per row) that
+// only 2 of 4 warps execute while the other two idle.  Here a CTA is 5 warps for a 32-sample tile:
+//   warps 0-3 (producers): KL contraction with DMMA + exp epilogue into a DOUBLE-BUFFERED field chunk F[2][32 rows][32];
+//   warp 4 (consumer): all four elimination chains of sample `lane` (fine/coarse x left/right -> 4-way ILP in one
+//                      thread), meeting in the middle without any shared-memory exchange, then Welford statistics.
+// Producers and consumer hand chunks over with named barriers (bar.arrive / bar.sync, ids 1-4), so the contraction of chunk
+// c+1 overlaps the sweeps of chunk c and nobody waits at a CTA-wide barrier inside the chunk loop.
+// ===================================================================================================================
+constexpr int LNW_BT = 32;
+constexpr int LNW_THREADS = 160;
+constexpr int LNW_LDX = LNW_BT + 4;
+constexpr int LNW_LDF = LNW_BT + 8;
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs g, Lognormal1dArgs la,
+                                                                         Moment *__restrict__ partials,
+                                                                         double *__restrict__ samples,
+                                                                         long long tiles_per_shift) {
+    constexpr int THREADS = LNW_THREADS, BT = LNW_BT, RC = LN_RC, LDX = LNW_LDX, LDF = LNW_LDF;
+    constexpr int G = THREADS / BT;  // 5 generator threads per point
+    constexpr int FULL0 = 1, EMPTY0 = 3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int mpad = la.mpad;
+    double *xi = reinterpret_cast<double *>(smem_raw);            // [mpad][LDX]
+    double *F = xi + (size_t)mpad * LDX;                          // [2][RC][LDF]
+    Moment *mred = reinterpret_cast<Moment *>(F + 2 * RC * LDF);  // [2][BT]
+    GenScratch sc;
+    sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * BT);        // [W]
+    sc.queue = reinterpret_cast<unsigned short *>(sc.wtot + 8);   // [BT * dims per call]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
+    const int M = la.N / 2;
+    const int nks = mpad >> 2;
+    const bool consumer = warp == 4;
+    const int wr = warp >> 1, wc = warp & 1;  // producers: row tiles {2wr, 2wr+1}, sample tiles {2wc, 2wc+1}
+    const int lr = lane >> 2, lk = lane & 3;
+    for (int e = tid; e < (mpad - g.m) * LDX; e += THREADS) xi[(size_t)g.m * LDX + e] = 0.0;  // k padding rows
+    Welford wdq{0.0, 0.0}, wqf{0.0, 0.0};  // consumer lanes: running statistics of sample slot `lane`
+    double ncount = 0.0;
+
+    for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
+        const unsigned long long i0 = (unsigned long long)ti * BT;
+        const unsigned long long left = g.n - i0;
+        const int Pt = left < (unsigned long long)BT ? (int)left : BT;
+        __syncthreads();  // previous tile fully consumed (xi, F), padding rows written
+        if (g.m <= 32 * G) {
+            gen_tile_owned<THREADS, BT, MODE, LDX, unsigned, LN_GEN_U>(xi, 0, g.m, g.k0 + i0, g, r, sc);
+        } else {
+            for (int j0 = 0; j0 < g.m; j0 += 64 * G)
+                gen_tile_owned<THREADS, BT, MODE, LDX, unsigned long long, LN_GEN_U>(xi + (size_t)j0 * LDX, j0, min(64 * G, g.m - j0), g.k0 + i0, g, r, sc);
+        }
+        // (gen_tile_owned ends with a CTA barrier: xi is complete)
+
+        if (!consumer) {
+            for (int c = 0; c < la.nchunks; ++c) {
+                const int rt0 = c * (RC / 8) + 2 * wr;
+                const int rows_left = la.nrows - rt0 * 8;
+                double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
+                if (rows_left > 0) {
+                    const bool two = rows_left > 8;
+                    const double *A0 = la.basis + (size_t)rt0 * nks * 32 + lane;
+                    const double *A1 = two ? A0 + (size_t)nks * 32 : A0;
+                    const double *B0 = xi + lk * LDX + 16 * wc + lr;
+                    double a0 = __ldg(A0), a1 = __ldg(A1);
+                    double b0 = B0[0], b1 = B0[8];
+#pragma unroll 5
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const int kn = (ks + 1 < nks) ? ks + 1 : ks;  // prefetch the next k step's fragments
+                        const double na0 = __ldg(A0 + kn * 32), na1 = __ldg(A1 + kn * 32);
+                        const double nb0 = B0[kn * 4 * LDX], nb1 = B0[kn * 4 * LDX + 8];
+                        dmma_m8n8k4(c00a, c00b, a0, b0);
+                        dmma_m8n8k4(c01a, c01b, a0, b1);
+                        if (two) {
+                            dmma_m8n8k4(c10a, c10b, a1, b0);
+                            dmma_m8n8k4(c11a, c11b, a1, b1);
+                        }
+                        a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+                    }
+                }
+                if (c >= 2) named_bar_sync(EMPTY0 + (c & 1), THREADS);  // the consumer has released this F buffer
+                if (rows_left > 0) {
+                    double *f0 = F + (c & 1) * RC * LDF + (16 * wr + lr) * LDF + 16 * wc + 2 * lk;
+                    double2 v;
+                    v.x = exp_det(c00a); v.y = exp_det(c00b);
+                    *reinterpret_cast<double2 *>(f0) = v;
+                    v.x = exp_det(c01a); v.y = exp_det(c01b);
+                    *reinterpret_cast<double2 *>(f0 + 8) = v;
+                    if (rows_left > 8) {
+                        v.x = exp_det(c10a); v.y = exp_det(c10b);
+                        *reinterpret_cast<double2 *>(f0 + 8 * LDF) = v;
+                        v.x = exp_det(c11a); v.y = exp_det(c11b);
+                        *reinterpret_cast<double2 *>(f0 + 8 * LDF + 8) = v;
+                    }
+                }
+                named_bar_arrive(FULL0 + (c & 1), THREADS);
+            }
+        } else {
+            SweepState fl{0, 0, 0, 0}, fr{0, 0, 0, 0}, cl{0, 0, 0, 0}, cr{0, 0, 0, 0};
+            for (int c = 0; c < la.nchunks; ++c) {
+                named_bar_sync(FULL0 + (c & 1), THREADS);
+                const double *Fc = F + (c & 1) * RC * LDF + lane;
+                const int ip0 = c * (RC / 2);
+#pragma unroll 2
+                for (int q = 0; q < RC / 2; ++q) {
+                    const int ip = ip0 + q;
+                    if (ip <= M) {
+                        const double al = Fc[(2 * q) * LDF], ar = Fc[(2 * q + 1) * LDF];
+                        sweep_step(fl, ip, al, la.h2);
+                        sweep_step(fr, ip, ar, la.h2);
+                        if (la.level > 0 && (ip & 1) == 0) {
+                            sweep_step(cl, ip >> 1, al, la.h2c);
+                            sweep_step(cr, ip >> 1, ar, la.h2c);
+                        }
+                    }
+                }
+                if (c + 2 < la.nchunks) named_bar_arrive(EMPTY0 + (c & 1), THREADS);
+            }
+            const double qf = sweep_combine(fl, fr, M, la.h2);
+            double dq = qf;
+            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(cl, cr, M / 2, la.h2c));
+            if (lane < Pt) {
+                if (samples) {
+                    samples[((size_t)r * 2 + 0) * g.n + i0 + lane] = dq;
+                    samples[((size_t)r * 2 + 1) * g.n + i0 + lane] = qf;
+                }
+                ncount += 1.0;
+                const double inv_n = 1.0 / ncount;
+                welford_add(wdq, dq, inv_n);
+                welford_add(wqf, qf, inv_n);
+            }
+        }
+    }
+    if (consumer) {
+        mred[lane] = Moment{ncount, wdq.mean, wdq.m2};
+        mred[BT + lane] = Moment{ncount, wqf.mean, wqf.m2};
     }
     __syncthreads();
     if (tid < 2) {
