@@ -224,9 +224,10 @@ class Engine:
 
 
 def moments_merge(acc, part):
-    """acc <- acc (+) part for arrays of (n, mean, M2) triplets (last axis 3); fixed-order Chan merge in libmle_cuda"""
+    """-> acc (+) part for arrays of (n, mean, M2) triplets (last axis 3); Chan merge in libmle_cuda; the inputs are not
+    modified"""
     lib = _lib.load()
-    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    acc = np.array(acc, dtype=np.float64, order="C", copy=True)
     part = np.ascontiguousarray(part, dtype=np.float64)
     assert acc.shape == part.shape and acc.shape[-1] == 3
     lib.mle_moments_merge(_as_dp(acc), _as_dp(part), acc.size // 3)

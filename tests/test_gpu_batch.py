@@ -146,3 +146,45 @@ def test_moments_are_deterministic(engine, oracle):
     a = engine.sample_batch(gm, lat, d, [2], sh, 0, 3000)
     b = engine.sample_batch(gm, lat, d, [2], sh, 0, 3000)
     assert np.array_equal(a, b)
+
+
+def test_full_size_sweep_properties(engine):
+    """BASELINE-size batch (config C5 shape: 2^20 lattice points x 100 Normal dims x 16 shifts, expsum integrand) checked
+    through size-independent properties: closed-form mean, additivity of the moments over point ranges, determinism."""
+    import mle_b200
+    s, R, n = 100, 16, 1 << 20
+    w = [0.5 / (j + 1) for j in range(s)]
+    lat = engine.lattice(None, s)
+    d = engine.dists([NORMAL01] * s)
+    gm = engine.model("expsum", 1, [s] + w)
+    sh = splitmix_uniforms(2024, R * s).reshape(R, s)
+    whole = engine.sample_batch(gm, lat, d, [0], sh, 0, n)
+    assert (whole[..., 0] == n).all()
+    exact = np.exp(0.5 * np.sum(np.square(w)))
+    shift_means = whole[:, 0, 1, 1]
+    est, se = shift_means.mean(), shift_means.std(ddof=1) / np.sqrt(R)
+    assert abs(est - exact) < 6 * se and se < 1e-4          # 16.8 M lattice points: QMC error well below MC's 3e-4
+    half_a = engine.sample_batch(gm, lat, d, [0], sh, 0, n // 2)
+    half_b = engine.sample_batch(gm, lat, d, [0], sh, n // 2, n // 2)
+    merged = mle_b200.moments_merge(half_a, half_b)
+    check_moments(merged, whole)
+    assert np.array_equal(whole, engine.sample_batch(gm, lat, d, [0], sh, 0, n))
+    # the second half of a 2^20-point lattice sequence refines the first: its per-shift means differ only slightly
+    assert np.max(np.abs(half_a[:, 0, 1, 1] - half_b[:, 0, 1, 1])) < 5e-3
+
+
+def test_full_size_lognormal_level_properties(engine, oracle):
+    """C2 level 0 at bench size (2^20 points x 16 shifts): moments are additive over point ranges and the first 4096 points
+    of every shift agree with the oracle bit for bit"""
+    import mle_b200
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 100, [0])
+    sh = splitmix_uniforms(2024, 16 * 100).reshape(16, 100)
+    n = 1 << 20
+    whole = engine.sample_batch(gm, lat, d, [0], sh, 0, n)
+    parts = [engine.sample_batch(gm, lat, d, [0], sh, k0, cnt) for k0, cnt in ((0, 4096), (4096, n // 2 - 4096), (n // 2, n // 2))]
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = mle_b200.moments_merge(acc, p)
+    check_moments(acc, whole)
+    check_moments(parts[0], oracle.sample_batch(om, z, dl, [0], sh, 0, 4096))
+    assert 0.1 < whole[:, 0, 1, 1].mean() < 0.14   # E[u(1/2)] a little below the a == 1 value 1/8 (Jensen)
