@@ -722,3 +722,13 @@ extern "C" int mle_moments_merge(double *acc, const double *part, size_t count) 
     }
     return MLE_OK;
 }
+
+#ifdef MLE_PHASE_TIMING
+// debug builds only (-DMLE_PHASE_TIMING): wall cycles thread 0 of every CTA spent per phase of lognormal1d_kernel
+extern "C" int mle_debug_phase_cycles(unsigned long long *out8, int reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, mle::g_phase_cycles, sizeof(z)) != cudaSuccess) return -2;
+    if (reset && cudaMemcpyToSymbol(mle::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -2;
+    return 0;
+}
+#endif

@@ -375,6 +375,17 @@ __device__ __forceinline__ void welford_add(Welford &w, double x, double inv_n) 
     w.m2 += d * (x - w.mean);
 }
 
+#ifdef MLE_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define MLE_PH_DECL long long ph_t = clock64(); long long ph_acc[6] = {0, 0, 0, 0, 0, 0};
+#define MLE_PH(i) do { long long ph_n = clock64(); ph_acc[i] += ph_n - ph_t; ph_t = ph_n; } while (0)
+#define MLE_PH_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_phase_cycles[i_], (unsigned long long)ph_acc[i_]); } while (0)
+#else
+#define MLE_PH_DECL
+#define MLE_PH(i)
+#define MLE_PH_FLUSH
+#endif
+
 template <int MODE, int BT>
 __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la,
                                                                                  Moment *__restrict__ partials,
@@ -404,11 +415,13 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
     __syncthreads();
     Welford wdq{0.0, 0.0}, wqf{0.0, 0.0};  // threads tid < BT: running statistics of sample slot tid over this CTA's tiles
     double ncount = 0.0;
+    MLE_PH_DECL
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
         const unsigned long long i0 = (unsigned long long)ti * BT;
         const unsigned long long left = g.n - i0;
         const int Pt = left < (unsigned long long)BT ? (int)left : BT;
+        MLE_PH(5);
         // A. inputs (always a full tile: surplus points are masked out of the statistics)
         if (g.m <= 32 * (THREADS / BT)) {  // at most 32 dims per thread: 32-bit class masks
             gen_tile_owned<THREADS, BT, MODE, LDX, unsigned, LN_GEN_U>(xi, 0, g.m, g.k0 + i0, g, r, sc);
@@ -418,6 +431,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
                 gen_tile_owned<THREADS, BT, MODE, LDX, unsigned long long, LN_GEN_U>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc);
         }
 
+        MLE_PH(0);
         SweepState sf{0, 0, 0, 0}, scs{0, 0, 0, 0};
         const int side = tid / BT, b = tid & (BT - 1);  // sweep role (threads 0 .. 2*BT-1)
 
@@ -447,7 +461,9 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
                     a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
                 }
             }
+            MLE_PH(1);
             __syncthreads();  // the previous chunk's sweeps have finished reading F
+            MLE_PH(2);
             // epilogue: a = exp(G) -> F[row in chunk][sample]; lane holds row lr, samples 2*lk, 2*lk+1 of each 8x8 tile
             if (rows_left > 0) {
                 double *f0 = F + (16 * wr + lr) * LDF + 16 * wc + 2 * lk;
@@ -464,6 +480,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
                 }
             }
             __syncthreads();
+            MLE_PH(3);
             // C. sweeps over the RC/2 half-nodes of this chunk (threads 0 .. 2*BT-1)
             if (tid < 2 * BT) {
                 const int ip0 = c * (RC / 2);
@@ -478,6 +495,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
                 }
             }
         }
+        MLE_PH(4);
         // D. meet in the middle
         if (tid < 2 * BT && side == 1) { xch[b] = sf; xch[BT + b] = scs; }
         __syncthreads();
@@ -498,6 +516,8 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         }
         // (the barriers of the next tile's generator order the xch reads above before xch is rewritten)
     }
+    MLE_PH(5);
+    MLE_PH_FLUSH;
     // merge the BT per-thread statistics in a fixed order: slot b holds every BT-th sample of this CTA's tiles
     if (tid < BT) {
         mred[tid] = Moment{ncount, wdq.mean, wdq.m2};

@@ -13,7 +13,7 @@ path is concerned:
   rates, regression, bias, MSE splitting, optimal_nb_of_samples   src/methods.jl:70-201
   History keys                  src/history.jl:55-103
 
-Out of scope: AD and U index sets, HC / ZC index sets, printing, JLD2 output, `save_samples`.
+Out of scope: AD and U index sets, printing, JLD2 output, `save_samples`.
 The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
 """
 import math
@@ -40,6 +40,8 @@ class ML:
 
 
 class _Weighted:
+    """weighted multi-index sets: candidate box 0..sz+1 per dimension, filtered (src/index_set.jl:257); weights in (0, 1]"""
+
     def __init__(self, *weights):
         if len(weights) == 1 and isinstance(weights[0], int):
             weights = (1.0,) * weights[0]
@@ -52,18 +54,46 @@ class _Weighted:
 
     def get_index_set(self, sz):
         import itertools
-        rng = [range(int(math.floor(sz / w + 1e-12)) + 1) for w in self.weights]
-        return [idx for idx in itertools.product(*rng) if self.filter(idx, sz)]
+        if sz < 0:
+            return []
+        box = itertools.product(*[range(sz + 2)] * self.ndims)
+        # CartesianIndices order: first dimension fastest
+        return sorted((idx for idx in box if self.filter(idx, sz)), key=lambda t: t[::-1])
 
 
 class FT(_Weighted):  # full tensor, src/index_set.jl:81
     def filter(self, idx, sz):
-        return all(w * i <= sz + 1e-12 for w, i in zip(self.weights, idx))
+        return all(i / w <= sz for w, i in zip(self.weights, idx))
 
 
 class TD(_Weighted):  # total degree, src/index_set.jl:114
     def filter(self, idx, sz):
-        return sum(w * i for w, i in zip(self.weights, idx)) <= sz + 1e-12
+        return sum(i / w for w, i in zip(self.weights, idx)) <= sz
+
+
+class HC(_Weighted):  # hyperbolic cross, src/index_set.jl:147
+    def filter(self, idx, sz):
+        return math.prod(i / w + 1 for w, i in zip(self.weights, idx)) - 1 <= sz
+
+
+class ZC(_Weighted):  # Zaremba cross, src/index_set.jl:180
+    def filter(self, idx, sz):
+        if sz == 0:
+            return all(i == 0 for i in idx)
+        return math.prod(max(1.0, i / w) for w, i in zip(self.weights, idx)) <= sz
+
+
+def is_admissable(index_set, index):
+    """src/index_set.jl:265-277: index not yet in the set and all its backward neighbours are"""
+    s = set(index_set)
+    if index in s or any(i < 0 for i in index):
+        return False
+    for k in range(len(index)):
+        if index[k] > 0:
+            nb = tuple(v - (1 if t == k else 0) for t, v in enumerate(index))
+            if nb not in s:
+                return False
+    return True
 
 
 class MC:

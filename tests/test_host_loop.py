@@ -15,12 +15,22 @@ def host():
 
 
 def test_index_sets_match_reference_cardinalities():
+    """test/index_set.jl:21-52: 3-d sets at sz = 7 and weighted 2-d sets (1, 3/5) at sz = 6"""
     H = host()
-    # test/index_set.jl:22: 3-d, sz = 7: FT 512, TD 120;  weighted 2-d (1, 1/2), sz = 6 -> FT 28? (reference fixture order FT/TD)
-    assert len(H.FT(3).get_index_set(7)) == 512 and len(H.TD(3).get_index_set(7)) == 120
+    for name, n3, n2 in (("FT", 512, 28), ("TD", 120, 17), ("HC", 38, 11), ("ZC", 98, 15)):
+        T = getattr(H, name)
+        s3 = T(3).get_index_set(7)
+        assert len(s3) == n3 and s3[0] == (0, 0, 0) and (1, 1, 1) in s3
+        assert (8, 0, 0) not in s3 and (0, 8, 0) not in s3 and (0, 0, 8) not in s3
+        assert H.is_admissable(s3, (8, 0, 0)) and not H.is_admissable(s3, (0, 0, 0)) and not H.is_admissable(s3, (0, 9, 0))
+        s2 = T(1 / 1, 3 / 5).get_index_set(6)
+        assert len(s2) == n2 and s2[0] == (0, 0) and (1, 1) in s2 and (0, 4) not in s2
+    assert H.TD(2).get_index_set(2) == [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (0, 2)]   # src/index_set.jl:246-255
     assert len(H.ML().get_index_set(4)) == 5 and H.SL().get_index_set(3) == [(0,)]
     with pytest.raises(ValueError):
         H.TD(1)
+    with pytest.raises(ValueError):
+        H.HC(1.0, 1.5)
 
 
 def test_option_validation_mirrors_reference():
