@@ -22,6 +22,8 @@ template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MOD
 template <int MODE> static constexpr auto lognormal1d_k64 = lognormal1d_kernel<MODE, 64>;
 template <int MODE> static constexpr auto lognormal1d_k32 = lognormal1d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal1d_ws = lognormal1d_ws_kernel<MODE>;
+template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
+template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 // mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
 #define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
     do {                                                                                       \
@@ -68,6 +70,8 @@ struct mle_ctx_s {
     size_t partials_cap = 0;  // in Moments
     double *d_shifts = nullptr;
     size_t shifts_cap = 0;
+    double *d_scratch = nullptr;  // lognormal2d: per-group field / centre blocks for the large grids
+    size_t scratch_cap = 0;
     double *d_zero = nullptr;  // a row of zeros standing in for the shift of an unshifted rule
     size_t zero_cap = 0;
     double *d_moments = nullptr;
@@ -189,6 +193,8 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(lognormal1d_k64, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_k32, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_ws, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     if (const char *e = getenv("MLE_LN_BT")) { int v = atoi(e); if (v == 32 || v == 64) ctx->ln_bt_override = v; }
@@ -204,6 +210,7 @@ extern "C" int mle_destroy(mle_ctx ctx) {
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     if (ctx->d_shifts) cudaFree(ctx->d_shifts);
     if (ctx->d_zero) cudaFree(ctx->d_zero);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0);
@@ -393,6 +400,11 @@ extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const 
         if (ndims != 1 || n0 < 4 || (n0 & 1)) { delete M; return fail(ctx, MLE_ERR_ARG, "lognormal1d: ndims = 1, params = {n0}, n0 even and >= 4"); }
         M->kind = MODEL_LOGNORMAL1D;
         M->n0 = n0;
+    } else if (!strcmp(name, "lognormal2d")) {
+        int n0 = (nparams > 0 && params) ? (int)params[0] : 4;
+        if (ndims != 1 || n0 < 2 || (n0 & 1)) { delete M; return fail(ctx, MLE_ERR_ARG, "lognormal2d: ndims = 1, params = {n0}, n0 even and >= 2"); }
+        M->kind = MODEL_LOGNORMAL2D;
+        M->n0 = n0;
     } else {
         delete M;
         return fail(ctx, MLE_ERR_ARG, std::string("unknown model '") + name + "'");
@@ -403,9 +415,32 @@ extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const 
 
 extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows, int cols, const double *phi) {
     if (!ctx || !M || !phi) return MLE_ERR_ARG;
-    if (M->kind != MODEL_LOGNORMAL1D) return fail(ctx, MLE_ERR_ARG, "set_basis: model takes no KL basis");
+    if (M->kind != MODEL_LOGNORMAL1D && M->kind != MODEL_LOGNORMAL2D) return fail(ctx, MLE_ERR_ARG, "set_basis: model takes no KL basis");
     if (level < 0 || level >= MLE_MAX_LEVELS) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
     const long long N = (long long)M->n0 << level;
+    if (M->kind == MODEL_LOGNORMAL2D) {
+        if (N > 128) return fail(ctx, MLE_ERR_ARG, "set_basis: lognormal2d supports grids up to 128 x 128 cells");
+        const long long nodes = (N + 1) * (N + 1);
+        if (rows != nodes) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be (n0*2^level + 1)^2 (nodes of the level's grid)");
+        if (cols < 1 || cols > 1024) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 1024");
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        const long long npad = (nodes + 31) & ~31ll;
+        std::vector<double> tr((size_t)cols * npad, 0.0);  // transposed [k][node]: thread-per-node reads are coalesced
+        for (long long nd = 0; nd < nodes; ++nd)
+            for (int k = 0; k < cols; ++k) tr[(size_t)k * npad + nd] = phi[(size_t)nd * cols + k];
+        double *d2 = nullptr;
+        if (cudaMalloc(&d2, tr.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
+        cudaError_t e2 = cudaMemcpyAsync(d2, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+        if (e2 != cudaSuccess) { cudaFree(d2); return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e2)); }
+        if (M->d_basis[level]) cudaFree(M->d_basis[level]);
+        M->d_basis[level] = d2;
+        M->basis_rows[level] = rows;
+        M->basis_cols[level] = cols;
+        M->basis_mpad[level] = (int)npad;
+        M->basis_nchunks[level] = 0;
+        return MLE_OK;
+    }
     if (rows != N + 1) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be n0*2^level + 1 (nodes of the level's grid)");
     if (cols < 1 || cols > 352) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 352 (the xi tile must fit in shared memory)");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -475,6 +510,7 @@ static int make_gen_args(mle_ctx ctx, mle_lattice lat, mle_dists dists, const do
     if (lat && !shifts_dev) {  // unshifted rule: a zero shift (x + 0.0 is exact) keeps the generator branch-free
         if (ctx->zero_cap < (size_t)lat->s) {
             if (ctx->d_zero) cudaFree(ctx->d_zero);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
             ctx->d_zero = nullptr; ctx->zero_cap = 0;
             if (cudaMalloc(&ctx->d_zero, sizeof(double) * (size_t)lat->s) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(zero shift)"); }
             if (cudaMemsetAsync(ctx->d_zero, 0, sizeof(double) * (size_t)lat->s, ctx->stream) != cudaSuccess) return fail(ctx, MLE_ERR_CUDA, "cudaMemsetAsync");
@@ -660,6 +696,36 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             if (bt == 64) MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k64, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
             else MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k32, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
         }
+    } else if (M->kind == MODEL_LOGNORMAL2D) {
+        const int level = index[0];
+        if (level >= MLE_MAX_LEVELS || !M->d_basis[level]) return fail(ctx, MLE_ERR_STATE, "lognormal2d: no KL basis set for this level (mle_model_set_basis)");
+        if (m != M->basis_cols[level]) return fail(ctx, MLE_ERR_ARG, "lognormal2d: nb_of_uncertainties must equal the number of KL terms of the level's basis");
+        Lognormal2dArgs la{};
+        la.basisT = M->d_basis[level];
+        la.N = M->n0 << level;
+        la.nodes_pad = M->basis_mpad[level];
+        la.level = level;
+        const int N = la.N, nn = N - 1, W = N, nodes = (N + 1) * (N + 1), mpad = (m + 3) & ~3;
+        const bool big = N >= 64;  // one CTA per sample, field and centre blocks in global scratch
+        const int threads = big ? 256 : 128, groups = big ? 1 : 4;
+        la.use_scratch = big ? 1 : 0;
+        la.scratch_per_group = 2ll * nn * nn + nodes;
+        const size_t per_group = (size_t)mpad + (size_t)W * W + 5 * (size_t)W + (big ? 0 : (size_t)la.scratch_per_group);
+        const size_t smem = per_group * groups * sizeof(double) + 2 * groups * sizeof(Moment) + 16;
+        if (smem > 220 * 1024) return fail(ctx, MLE_ERR_ARG, "lognormal2d: KL terms x grid do not fit in shared memory");
+        const long long tps = (long long)((n + groups - 1) / groups);
+        const int occ = big ? MLE_OCC_BY_MODE(g.mode, lognormal2d_c, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal2d_w, threads, smem);
+        gx = grid_x_for(ctx, tps, R, occ);
+        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+        if (rc) return rc;
+        if (big) {
+            rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, (size_t)gx * R * groups * (size_t)la.scratch_per_group);
+            if (rc) return rc;
+            la.scratch = ctx->d_scratch;
+        }
+        dim3 grid((unsigned)gx, (unsigned)R);
+        if (big) MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_c, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev);
+        else MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_w, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev);
     } else {
         return fail(ctx, MLE_ERR_ARG, "unknown model kind");
     }

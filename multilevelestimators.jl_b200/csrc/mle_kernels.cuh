@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__re
 // ===================================================================================================================
 // analytic sample functions (one sample per thread), fused with generation and moments
 // ===================================================================================================================
-enum : int { MODEL_EXPSUM = 0, MODEL_PROBLEM18 = 1, MODEL_LOGNORMAL1D = 2 };
+enum : int { MODEL_EXPSUM = 0, MODEL_PROBLEM18 = 1, MODEL_LOGNORMAL1D = 2, MODEL_LOGNORMAL2D = 3 };
 
 struct SimpleModelArgs {
     const double *weights;  // expsum: a_j
@@ -679,6 +679,245 @@ __global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs 
         Moment a{0.0, 0.0, 0.0};
         for (int i = 0; i < BT; ++i) a = moment_merge(a, mred[tid * BT + i]);
         partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
+    }
+}
+
+
+// ===================================================================================================================
+// 2-D lognormal diffusion (config C3/C4 shape; model definition in oracle/mle_oracle.c and DESIGN.md):
+//   -div(a grad u) = 1 on the unit square, u = 0 on the boundary, N = n0 * 2^l cells per direction, 5-point stencil with
+//   edge coefficients = mean of the two node values, QoI = u(1/2, 1/2), coarse problem = even nodes.
+// One GROUP of TG threads owns one sample (TG = 32: a warp, 4 samples per CTA, N <= 32;  TG = 256: the whole CTA, N >= 64):
+//   1. xi (m inverse normals) -> shared memory;
+//   2. field: thread-per-node dot products over the KL terms in ascending k (fused multiply-adds, the oracle's order) from the
+//      TRANSPOSED basis [k][node] (coalesced), then exp;
+//   3. frontal Gaussian elimination towards the centre node: two half sweeps (the second on the y-mirrored field) carrying a
+//      sliding (n+1)x(n+1) window in shared memory -- per pivot one phase that loads the entering unknown and forms
+//      v_q = M[q][p], l_q = v_q / d, and one phase of rank-1 updates M[q][r] = fma(-l_q, v_r, M[q][r]) -- followed by a dense
+//      two-sided elimination along the centre line.  There is no reduction anywhere, so the thread mapping cannot change a
+//      single bit of the result.
+// ===================================================================================================================
+struct Lognormal2dArgs {
+    const double *basisT;  // [m][nodes_pad]: transposed KL basis of this level
+    int N;                 // cells per direction
+    int nodes_pad;
+    int level;
+    int use_scratch;       // field / second centre block in global scratch (N >= 64) instead of shared memory
+    double *scratch;       // [groups in grid][scratch_per_group]
+    long long scratch_per_group;
+};
+
+template <int TG>
+__device__ __forceinline__ void group_sync() {
+    if (TG == 32) __syncwarp();
+    else __syncthreads();
+}
+
+struct Field2d {
+    const double *a;
+    int lda, st, N, mirror;
+    __device__ __forceinline__ double at(int i, int j) const {
+        const int jj = mirror ? N - j : j;
+        return a[(size_t)(jj * st) * lda + (size_t)i * st];
+    }
+    __device__ __forceinline__ double kx(int i, int j) const { return __dmul_rn(0.5, __dadd_rn(at(i, j), at(i + 1, j))); }
+    __device__ __forceinline__ double ky(int i, int j) const { return __dmul_rn(0.5, __dadd_rn(at(i, j), at(i, j + 1))); }
+    __device__ __forceinline__ double diag(int i, int j) const {
+        return __dadd_rn(__dadd_rn(__dadd_rn(kx(i - 1, j), kx(i, j)), ky(i, j - 1)), ky(i, j));
+    }
+};
+
+// rank-1 update of the cnt x cnt block of M whose rows/cols are the window slots of unknowns first .. first+cnt-1
+// (ld = row stride of M, mod = slot modulus: W for the sliding window, anything > first+cnt for a plain matrix)
+template <int TG>
+__device__ __forceinline__ void rank1_update(double *M, double *gv, const double *l, const double *v, double gp, int ld,
+                                             int mod, int first, int cnt, int t) {
+    if (TG == 32) {
+        if (t < cnt) {
+            const int sr = (first + t) % mod;
+            const double vr = v[sr];
+            for (int qo = 0; qo < cnt; ++qo) {
+                const int sq = (first + qo) % mod;
+                M[sq * ld + sr] = __fma_rn(-l[sq], vr, M[sq * ld + sr]);
+            }
+            gv[sr] = __fma_rn(-l[sr], gp, gv[sr]);
+        }
+    } else {
+        const int tx = t & 31, ty = t >> 5;
+        for (int qo = ty; qo < cnt; qo += TG / 32) {
+            const int sq = (first + qo) % mod;
+            const double lq = -l[sq];
+            for (int ro = tx; ro < cnt; ro += 32) {
+                const int sr = (first + ro) % mod;
+                M[(size_t)sq * ld + sr] = __fma_rn(lq, v[sr], M[(size_t)sq * ld + sr]);
+            }
+        }
+        for (int qo = t; qo < cnt; qo += TG) { const int sq = (first + qo) % mod; gv[sq] = __fma_rn(-l[sq], gp, gv[sq]); }
+    }
+}
+
+template <int TG>
+__device__ void frontal_half_dev(const Field2d &f, double h2, double *M, double *gv, double *l, double *v, double *S,
+                                 double *gs, int t) {
+    const int N = f.N, n = N - 1, c = N / 2, W = n + 1;
+    const int P = (c - 1) * n, last = P + n - 1;
+    // entering unknown e: row/column slot(e) of the window <- its original matrix entries (one phase, no read of M)
+    auto load = [&](int e) {
+        const int ie = e % n + 1, je = e / n + 1, se = e % W;
+        const bool own = !(je == c && f.mirror);
+        for (int u = t; u < W; u += TG) {
+            double val = 0.0;
+            if (u == se) val = own ? f.diag(ie, je) : 0.0;
+            else if (ie > 1 && own && u == (e - 1) % W) val = -f.kx(ie - 1, je);
+            else if (je > 1 && u == (e - n) % W) val = -f.ky(ie, je - 1);
+            M[se * W + u] = val;
+            M[u * W + se] = val;
+        }
+        if (t == 0) gv[se] = own ? h2 : 0.0;
+    };
+    for (int e = 0; e < n && e <= last; ++e) load(e);
+    group_sync<TG>();
+    for (int p = 0; p < P; ++p) {
+        const int sp = p % W;
+        const bool enter = p + n <= last;
+        const int hi = enter ? p + n : last;
+        const double d = M[sp * W + sp], gp = gv[sp];
+        // phase A: v_q = M[q][p], l_q = v_q / d for the window p+1..hi (the entering unknown's coupling to p is known
+        // directly), and the entering unknown's row/column (the slot of pivot p-1; disjoint from everything read here)
+        for (int qo = t; qo < hi - p; qo += TG) {
+            const int q = p + 1 + qo, sq = q % W;
+            double vq;
+            if (enter && q == p + n) { const int ie = q % n + 1, je = q / n + 1; vq = -f.ky(ie, je - 1); }
+            else vq = M[sq * W + sp];
+            v[sq] = vq;
+            l[sq] = __ddiv_rn(vq, d);
+        }
+        if (enter) load(p + n);
+        group_sync<TG>();
+        // phase B: rank-1 update of the window
+        rank1_update<TG>(M, gv, l, v, gp, W, W, p + 1, hi - p, t);
+        group_sync<TG>();
+    }
+    for (int e = t; e < n * n; e += TG) { const int q = e / n, r = e - q * n; S[e] = M[((P + q) % W) * W + (P + r) % W]; }
+    for (int q = t; q < n; q += TG) gs[q] = gv[(P + q) % W];
+    group_sync<TG>();
+}
+
+template <int TG>
+__device__ double frontal_mid_dev(const double *a, int lda, int st, int N, double *M, double *gv, double *l, double *v,
+                                  double *S, double *gs, double *S2, double *gs2, int t) {
+    const int n = N - 1, c = N / 2, tc = c - 1;
+    const double h2 = 1.0 / ((double)N * (double)N);
+    Field2d f{a, lda, st, N, 1};
+    frontal_half_dev<TG>(f, h2, M, gv, l, v, S2, gs2, t);  // upper half first (y-mirrored field)
+    f.mirror = 0;
+    frontal_half_dev<TG>(f, h2, M, gv, l, v, S, gs, t);    // lower half
+    for (int e = t; e < n * n; e += TG) S[e] = __dadd_rn(S[e], S2[e]);
+    for (int q = t; q < n; q += TG) gs[q] = __dadd_rn(gs[q], gs2[q]);
+    group_sync<TG>();
+    // dense two-sided elimination along the centre line (row-major S, W = n)
+    for (int tt = 0; tt < tc; ++tt) {
+        const double d = S[tt * n + tt], gp = gs[tt];
+        for (int q = tt + 1 + t; q < n; q += TG) { v[q] = S[q * n + tt]; l[q] = __ddiv_rn(v[q], d); }
+        group_sync<TG>();
+        rank1_update<TG>(S, gs, l, v, gp, n, 1 << 30, tt + 1, n - tt - 1, t);
+        group_sync<TG>();
+    }
+    for (int tt = n - 1; tt > tc; --tt) {
+        const double d = S[tt * n + tt], gp = gs[tt];
+        for (int q = tc + t; q < tt; q += TG) { v[q] = S[q * n + tt]; l[q] = __ddiv_rn(v[q], d); }
+        group_sync<TG>();
+        rank1_update<TG>(S, gs, l, v, gp, n, 1 << 30, tc, tt - tc, t);
+        group_sync<TG>();
+    }
+    return __ddiv_rn(gs[tc], S[tc * n + tc]);
+}
+
+template <int MODE, int TG>
+__global__ void __launch_bounds__(TG == 32 ? 128 : 256) lognormal2d_kernel(GenArgs g, Lognormal2dArgs la,
+                                                                           Moment *__restrict__ partials,
+                                                                           double *__restrict__ samples) {
+    constexpr int THREADS = TG == 32 ? 128 : 256, GROUPS = THREADS / TG;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = la.N, n = N - 1, W = n + 1, nodes = (N + 1) * (N + 1);
+    const int t = threadIdx.x % TG, grp = threadIdx.x / TG, r = blockIdx.y;
+    // per-group shared memory: xi[mpad] | M[W*W] | gv[W] | l[W] | v[W] | gs[W] gs2[W] and, unless they live in the global
+    // scratch (N >= 64): S[n*n] | S2[n*n] | field[(N+1)^2]
+    const int mpad = (g.m + 3) & ~3;
+    const size_t per_group = (size_t)mpad + (size_t)W * W + 5 * (size_t)W + (la.use_scratch ? 0 : 2 * (size_t)n * n + (size_t)nodes);
+    double *base = reinterpret_cast<double *>(smem_raw) + (size_t)grp * per_group;
+    double *xi = base, *M = xi + mpad, *gv = M + (size_t)W * W, *l = gv + W, *v = l + W, *gs = v + W, *gs2 = gs + W;
+    double *S, *S2, *A;
+    if (la.use_scratch) {
+        S = la.scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * GROUPS + grp) * la.scratch_per_group;
+    } else {
+        S = gs2 + W;
+    }
+    S2 = S + (size_t)n * n;
+    A = S2 + (size_t)n * n;
+    Moment *mred = reinterpret_cast<Moment *>(reinterpret_cast<double *>(smem_raw) + (size_t)GROUPS * per_group);  // [2][GROUPS]
+    constexpr bool lattice = (MODE & GEN_MC) == 0;
+    const double *shift_r = lattice ? g.shifts + (size_t)r * g.s : nullptr;
+    Welford wdq{0.0, 0.0}, wqf{0.0, 0.0};
+    double ncount = 0.0;
+
+    // GROUPS samples per CTA iteration; every group runs the same number of iterations (barriers are CTA-wide for TG = 256)
+    for (unsigned long long i = (unsigned long long)blockIdx.x * GROUPS + grp;; i += (unsigned long long)gridDim.x * GROUPS) {
+        const bool active = i < g.n;
+        if (TG != 32) { if (!active) break; }         // one group per CTA: uniform exit
+        else if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            const unsigned long long k = g.k0 + i;
+            // 1. inputs
+            const double tphi = phi_to_unit(radical_phi((uint32_t)k));
+            for (int j = t; j < g.m; j += TG) {
+                const double x = lattice ? lattice_coord(tphi, __ldg(g.zd + j), __ldg(shift_r + j))
+                                         : mc_uniform(g.seed, k, (uint32_t)g.m, (uint32_t)j);
+                int cls;
+                double val = elem_first<MODE>(x, j, g, cls);
+                if (cls == 2) val = elem_finish<MODE, 2>(val, j, g);
+                else if (cls == 3) val = elem_finish<MODE, 3>(val, j, g);
+                xi[j] = val;
+            }
+            group_sync<TG>();
+            // 2. field
+            for (int node = t; node < nodes; node += TG) {
+                const double *col = la.basisT + node;
+                double acc = 0.0;
+                for (int kk = 0; kk < g.m; ++kk) acc = __fma_rn(__ldg(col + (size_t)kk * la.nodes_pad), xi[kk], acc);
+                A[node] = exp_det(acc);
+            }
+            group_sync<TG>();
+            // 3. solves
+            const double qf = frontal_mid_dev<TG>(A, N + 1, 1, N, M, gv, l, v, S, gs, S2, gs2, t);
+            double dq = qf;
+            if (la.level > 0) {
+                group_sync<TG>();
+                dq = __dsub_rn(qf, frontal_mid_dev<TG>(A, N + 1, 2, N / 2, M, gv, l, v, S, gs, S2, gs2, t));
+            }
+            if (t == 0) {
+                if (samples) {
+                    samples[((size_t)r * 2 + 0) * g.n + i] = dq;
+                    samples[((size_t)r * 2 + 1) * g.n + i] = qf;
+                }
+                ncount += 1.0;
+                const double inv_n = 1.0 / ncount;
+                welford_add(wdq, dq, inv_n);
+                welford_add(wqf, qf, inv_n);
+            }
+            group_sync<TG>();
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        mred[grp] = Moment{ncount, wdq.mean, wdq.m2};
+        mred[GROUPS + grp] = Moment{ncount, wqf.mean, wqf.m2};
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        Moment a{0.0, 0.0, 0.0};
+        for (int q = 0; q < GROUPS; ++q) a = moment_merge(a, mred[threadIdx.x * GROUPS + q]);
+        partials[((size_t)r * 2 + threadIdx.x) * gridDim.x + blockIdx.x] = a;
     }
 }
 

@@ -15,3 +15,24 @@ def kl_basis_1d(level, m=100, n0=16, sigma=0.5, decay=1.5):
     x = np.arange(N + 1, dtype=np.float64) / N
     k = np.arange(1, m + 1, dtype=np.float64)
     return np.ascontiguousarray(sigma * np.sqrt(2.0) * k**(-decay) * np.cos(np.pi * np.outer(x, k)))
+
+
+def kl_basis_2d(level, m=400, n0=4, sigma=0.5, decay=1.5):
+    """-> float64[(N+1)^2, m] for the level's grid of N = n0 * 2^level cells per direction on [0,1]^2; node (i, j) is row
+    j*(N+1) + i.  Separable cosine modes cos(pi p x) cos(pi q y) ordered by p + q (then p), amplitude
+    sigma * c_p c_q * (1 + p + q)^(-decay) with c_0 = 1, c_p = sqrt(2)."""
+    N = n0 << level
+    x = np.arange(N + 1, dtype=np.float64) / N
+    modes, t = [], 0
+    while len(modes) < m:
+        for p in range(t + 1):
+            modes.append((p, t - p))
+        t += 1
+    modes = modes[1:m + 1]  # skip the constant mode (0, 0)
+    cols = []
+    for p, q in modes:
+        cp = 1.0 if p == 0 else np.sqrt(2.0)
+        cq = 1.0 if q == 0 else np.sqrt(2.0)
+        amp = sigma * cp * cq * (1.0 + p + q) ** (-decay)
+        cols.append(amp * np.outer(np.cos(np.pi * q * x), np.cos(np.pi * p * x)).reshape(-1))  # [j][i] -> j*(N+1)+i
+    return np.ascontiguousarray(np.stack(cols, axis=1))

@@ -334,7 +334,7 @@ ORC_API orc_model *orc_model_create(int kind, int ndims, const double *params, i
     } else if (kind == ORC_MODEL_PROBLEM18) {
         M->nqoi = 13;
     } else { /* lognormal: params = {n0} */
-        M->n0 = nparams > 0 ? (int)params[0] : 16;
+        M->n0 = nparams > 0 ? (int)params[0] : (kind == ORC_MODEL_LOGNORMAL2D ? 4 : 16);
     }
     return M;
 }
@@ -503,6 +503,128 @@ static int lognormal1d_eval(const orc_model *M, int level, const double *xi, int
     return 0;
 }
 
+/* --- lognormal diffusion, 2-D:  -div(a grad u) = 1 on (0,1)^2, u = 0 on the boundary ---------------------------------
+ * level l: N = n0 * 2^l cells per direction, nodes (i,j), i,j = 0..N (node number j*(N+1) + i); log a at a node =
+ * sum_k Phi_l[node][k] xi_k (k ascending, fused); edge coefficients = arithmetic mean of the two node values; 5-point
+ * stencil; QoI = u at the centre node (N/2, N/2); the coarse problem uses the even nodes (docs/src/example.md:120:
+ * `view(af, 2:2:end, 2:2:end)`).  The centre value comes from a FRONTAL (banded, fill-in carrying) Gaussian elimination in
+ * two independent half sweeps -- lines 1..N/2-1 upwards and, on the y-mirrored field, lines N-1..N/2+1 downwards --
+ * followed by a dense two-sided elimination along the centre line.  Only a sliding (n+1)x(n+1) window is ever stored
+ * (n = N-1); every entry is updated by fma(-l_q, v_r, M[q][r]) in pivot order, so there is no reduction whose order a
+ * parallel implementation could change: the CUDA kernel reproduces the result bit for bit. */
+typedef struct {
+    const double *a; /* node values */
+    int lda, st, N, mirror;
+} field2d;
+static inline double F2(const field2d *f, int i, int j) {
+    int jj = f->mirror ? f->N - j : j;
+    return f->a[(size_t)(jj * f->st) * f->lda + (size_t)i * f->st];
+}
+static inline double KX(const field2d *f, int i, int j) { return 0.5 * (F2(f, i, j) + F2(f, i + 1, j)); } /* (i,j)-(i+1,j) */
+static inline double KY(const field2d *f, int i, int j) { return 0.5 * (F2(f, i, j) + F2(f, i, j + 1)); } /* (i,j)-(i,j+1) */
+static inline double DIAG2(const field2d *f, int i, int j) {
+    return ((KX(f, i - 1, j) + KX(f, i, j)) + KY(f, i, j - 1)) + KY(f, i, j);
+}
+
+/* one half sweep; on return S[n*n], gs[n] hold this half's centre-line block (row-major, unknowns i = 1..n) */
+static void frontal_half(const field2d *f, double h2, double *M, double *g, double *l, double *v, double *S, double *gs) {
+    const int N = f->N, n = N - 1, c = N / 2, W = n + 1;
+    const int P = (c - 1) * n;     /* pivots of this half */
+    const int last = P + n - 1;    /* last unknown (end of the centre line) */
+#define SLOT(e) ((e) % W)
+#define LOAD_UNKNOWN(e)                                                                          \
+    do {                                                                                         \
+        int ie_ = (e) % n + 1, je_ = (e) / n + 1, se_ = SLOT(e);                                 \
+        int centre_ = (je_ == c);                                                                \
+        int own_ = !(centre_ && f->mirror); /* the centre line's own entries are loaded once */  \
+        for (int t_ = 0; t_ < W; ++t_) { M[se_ * W + t_] = 0.0; M[t_ * W + se_] = 0.0; }         \
+        M[se_ * W + se_] = own_ ? DIAG2(f, ie_, je_) : 0.0;                                      \
+        g[se_] = own_ ? h2 : 0.0;                                                                \
+        if (ie_ > 1 && own_) { double k_ = -KX(f, ie_ - 1, je_); M[se_ * W + SLOT((e)-1)] = k_; M[SLOT((e)-1) * W + se_] = k_; } \
+        if (je_ > 1) { double k_ = -KY(f, ie_, je_ - 1); M[se_ * W + SLOT((e)-n)] = k_; M[SLOT((e)-n) * W + se_] = k_; }         \
+    } while (0)
+    for (int e = 0; e < n && e <= last; ++e) LOAD_UNKNOWN(e);
+    for (int p = 0; p < P; ++p) {
+        if (p + n <= last) LOAD_UNKNOWN(p + n);
+        const int sp = SLOT(p);
+        const int hi = (p + n <= last) ? p + n : last;
+        const double d = M[sp * W + sp], gp = g[sp];
+        for (int q = p + 1; q <= hi; ++q) { v[SLOT(q)] = M[SLOT(q) * W + sp]; l[SLOT(q)] = v[SLOT(q)] / d; }
+        for (int q = p + 1; q <= hi; ++q) {
+            const int sq = SLOT(q);
+            const double lq = l[sq];
+            g[sq] = fma(-lq, gp, g[sq]);
+            for (int r = p + 1; r <= hi; ++r) M[sq * W + SLOT(r)] = fma(-lq, v[SLOT(r)], M[sq * W + SLOT(r)]);
+        }
+    }
+    for (int q = 0; q < n; ++q) {
+        gs[q] = g[SLOT(P + q)];
+        for (int r = 0; r < n; ++r) S[q * n + r] = M[SLOT(P + q) * W + SLOT(P + r)];
+    }
+#undef LOAD_UNKNOWN
+#undef SLOT
+}
+
+static double frontal_mid(const double *a, int lda, int st, int N) {
+    const int n = N - 1, c = N / 2, W = n + 1, tc = c - 1;
+    const double h2 = 1.0 / ((double)N * (double)N);
+    double *M = (double *)malloc(sizeof(double) * (size_t)W * W), *g = (double *)malloc(sizeof(double) * (size_t)W);
+    double *l = (double *)malloc(sizeof(double) * (size_t)W), *v = (double *)malloc(sizeof(double) * (size_t)W);
+    double *S = (double *)malloc(sizeof(double) * (size_t)n * n), *gs = (double *)malloc(sizeof(double) * (size_t)n);
+    double *S2 = (double *)malloc(sizeof(double) * (size_t)n * n), *gs2 = (double *)malloc(sizeof(double) * (size_t)n);
+    field2d f = {a, lda, st, N, 1};
+    frontal_half(&f, h2, M, g, l, v, S2, gs2); /* upper half first (y-mirrored field) */
+    f.mirror = 0;
+    frontal_half(&f, h2, M, g, l, v, S, gs);   /* lower half */
+    for (int q = 0; q < n; ++q) {
+        gs[q] = gs[q] + gs2[q];
+        for (int r = 0; r < n; ++r) S[q * n + r] = S[q * n + r] + S2[q * n + r];
+    }
+    /* dense two-sided elimination along the centre line: t = 0..tc-1 ascending, then t = n-1..tc+1 descending */
+    for (int t = 0; t < tc; ++t) {
+        const double d = S[t * n + t], gp = gs[t];
+        for (int q = t + 1; q < n; ++q) { v[q] = S[q * n + t]; l[q] = v[q] / d; }
+        for (int q = t + 1; q < n; ++q) {
+            gs[q] = fma(-l[q], gp, gs[q]);
+            for (int r = t + 1; r < n; ++r) S[q * n + r] = fma(-l[q], v[r], S[q * n + r]);
+        }
+    }
+    for (int t = n - 1; t > tc; --t) {
+        const double d = S[t * n + t], gp = gs[t];
+        for (int q = tc; q < t; ++q) { v[q] = S[q * n + t]; l[q] = v[q] / d; }
+        for (int q = tc; q < t; ++q) {
+            gs[q] = fma(-l[q], gp, gs[q]);
+            for (int r = tc; r < t; ++r) S[q * n + r] = fma(-l[q], v[r], S[q * n + r]);
+        }
+    }
+    const double u = gs[tc] / S[tc * n + tc];
+    free(M); free(g); free(l); free(v); free(S); free(gs); free(S2); free(gs2);
+    return u;
+}
+
+ORC_API double orc_frontal_mid(const double *a, int lda, int st, int N) { return frontal_mid(a, lda, st, N); }
+
+static int lognormal2d_eval(const orc_model *M, int level, const double *xi, int m, double *dQ, double *Qf) {
+    const double *Phi = M->basis[level];
+    if (!Phi) return -3;
+    const int N = M->n0 << level, nodes = (N + 1) * (N + 1);
+    if (M->basis_rows[level] != nodes || M->basis_cols[level] < m) return -3;
+    const int ld = M->basis_cols[level];
+    double *a = (double *)malloc(sizeof(double) * (size_t)nodes);
+    for (int i = 0; i < nodes; ++i) {
+        double gsum = 0.0;
+        const double *row = Phi + (size_t)i * ld;
+        for (int k = 0; k < m; ++k) gsum = fma(row[k], xi[k], gsum);
+        a[i] = orc_exp(gsum);
+    }
+    const double qf = frontal_mid(a, N + 1, 1, N);
+    *Qf = qf;
+    *dQ = qf;
+    if (level > 0) *dQ = qf - frontal_mid(a, N + 1, 2, N / 2);
+    free(a);
+    return 0;
+}
+
 /* f(index, xi) -> (dQ[nqoi], Qf[nqoi]).   dQ = Qf + sum_{(kappa, +-1) in diff(index)} +- Q_kappa  (src/index.jl:49-58) */
 ORC_API int orc_model_eval(const orc_model *M, const int *index, const double *xi, int m, double *dQ, double *Qf) {
     switch (M->kind) {
@@ -543,6 +665,8 @@ ORC_API int orc_model_eval(const orc_model *M, const int *index, const double *x
         free(work);
         return rc;
     }
+    case ORC_MODEL_LOGNORMAL2D:
+        return lognormal2d_eval(M, index[0], xi, m, dQ, Qf);
     default:
         return -4;
     }

@@ -64,6 +64,8 @@ def lib():
         L.orc_model_eval.argtypes = [C.c_void_p, ip, dp, C.c_int, dp, dp]
         L.orc_tridiag_mid.restype = C.c_double
         L.orc_tridiag_mid.argtypes = [dp, C.c_int, C.c_int]
+        L.orc_frontal_mid.restype = C.c_double
+        L.orc_frontal_mid.argtypes = [dp, C.c_int, C.c_int, C.c_int]
         L.orc_tridiag_mid_full.restype = C.c_double
         L.orc_tridiag_mid_full.argtypes = [dp, C.c_int]
         L.orc_sample_batch.restype = C.c_int

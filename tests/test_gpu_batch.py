@@ -188,3 +188,37 @@ def test_full_size_lognormal_level_properties(engine, oracle):
     check_moments(acc, whole)
     check_moments(parts[0], oracle.sample_batch(om, z, dl, [0], sh, 0, 4096))
     assert 0.1 < whole[:, 0, 1, 1].mean() < 0.14   # E[u(1/2)] a little below the a == 1 value 1/8 (Jensen)
+
+
+def lognormal2d_setup(engine, oracle, m, levels, n0=4):
+    import mle_b200.kl as kl
+    z = oracle.genvec("K_3600_32", m)
+    gm = engine.model("lognormal2d", 1, [n0])
+    om = oracle.Model(oracle.MODEL_LOGNORMAL2D, 1, [float(n0)])
+    for lev in levels:
+        phi = kl.kl_basis_2d(lev, m=m, n0=n0)
+        gm.set_basis(lev, phi)
+        om.set_basis(lev, phi)
+    return z, engine.lattice(z, m), [NORMAL01] * m, engine.dists([NORMAL01] * m), gm, om
+
+
+@pytest.mark.parametrize("level,R,k0,n,m", [(0, 3, 0, 1, 40), (0, 2, 5, 130, 40), (1, 4, 0, 37, 40), (2, 2, 0, 50, 40), (3, 2, 0, 17, 40),
+                                            (4, 2, 0, 5, 40), (5, 1, 0, 2, 24), (1, 2, 0, 20, 400)])
+def test_lognormal2d_levels(engine, oracle, level, R, k0, n, m):
+    """configs C3/C4 shape: 2-D lognormal diffusion, grid 4*2^l per direction (warp-per-sample path up to 32x32, CTA-per-sample
+    path for 64x64 and 128x128), lattice inputs; per-sample (dQ, Qf) bit-identical to the oracle's frontal elimination"""
+    z, lat, dl, d, gm, om = lognormal2d_setup(engine, oracle, m, [level])
+    sh = splitmix_uniforms(2024, R * m).reshape(R, m)
+    got, smp = engine.sample_batch(gm, lat, d, [level], sh, k0, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, k0, n, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    if n > 1:
+        check_moments(got, want)
+
+
+def test_lognormal2d_mc(engine, oracle):
+    """config C3: ML()/MC() on the 2-D problem (counter-based uniforms instead of lattice points)"""
+    z, lat, dl, d, gm, om = lognormal2d_setup(engine, oracle, 40, [2])
+    got = engine.sample_batch(gm, None, d, [2], None, 0, 300, mc_seed=9)
+    want = oracle.sample_batch(om, None, dl, [2], None, 0, 300, mc_seed=9)
+    check_moments(got, want)

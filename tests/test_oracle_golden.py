@@ -200,3 +200,49 @@ def test_lognormal1d_oracle_model(oracle):
     # discretisation error decays: |dQ| shrinks with the level
     dq2, _ = M.eval([2], xi)
     assert abs(dq2[0]) < abs(dq1[0])
+
+
+def test_frontal_elimination_matches_dense_solve(oracle):
+    """2-D model: the frontal two-half elimination returns the centre value of the 5-point system"""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    L = oracle.lib()
+
+    def dense_mid(a, N):
+        n = N - 1
+        idx = lambda i, j: (j - 1) * n + (i - 1)
+        A = np.zeros((n * n, n * n))
+        kx = lambda i, j: 0.5 * (a[j, i] + a[j, i + 1])
+        ky = lambda i, j: 0.5 * (a[j, i] + a[j + 1, i])
+        for j in range(1, N):
+            for i in range(1, N):
+                p = idx(i, j)
+                A[p, p] = kx(i - 1, j) + kx(i, j) + ky(i, j - 1) + ky(i, j)
+                if i > 1: A[p, idx(i - 1, j)] = -kx(i - 1, j)
+                if i < n: A[p, idx(i + 1, j)] = -kx(i, j)
+                if j > 1: A[p, idx(i, j - 1)] = -ky(i, j - 1)
+                if j < n: A[p, idx(i, j + 1)] = -ky(i, j)
+        return np.linalg.solve(A, np.full(n * n, 1.0 / N**2))[idx(N // 2, N // 2)]
+
+    for N in (2, 4, 8, 16):
+        a = np.exp(0.7 * rng.normal(size=(N + 1, N + 1)))
+        got = L.orc_frontal_mid(a.ctypes.data_as(C.POINTER(C.c_double)), N + 1, 1, N)
+        assert abs(got - dense_mid(a, N)) <= 1e-13 * abs(got)
+    a = np.exp(0.5 * rng.normal(size=(17, 17)))
+    coarse = L.orc_frontal_mid(a.ctypes.data_as(C.POINTER(C.c_double)), 17, 2, 8)
+    assert abs(coarse - dense_mid(np.ascontiguousarray(a[::2, ::2]), 8)) <= 1e-13 * abs(coarse)
+    one = np.ones((33, 33))
+    mid = L.orc_frontal_mid(one.ctypes.data_as(C.POINTER(C.c_double)), 33, 1, 32)
+    assert abs(mid - 0.0736713) < 2e-4  # u(1/2,1/2) of -lap u = 1 on the unit square, O(h^2) discretisation error
+
+
+def test_lognormal2d_oracle_model(oracle):
+    import mle_b200.kl as kl
+    M = oracle.Model(oracle.MODEL_LOGNORMAL2D, 1, [4.0])
+    for lev in range(4):
+        M.set_basis(lev, kl.kl_basis_2d(lev, m=30))
+    xi = np.random.default_rng(4).normal(size=30)
+    d = [M.eval([lev], xi) for lev in range(4)]
+    assert d[0][0][0] == d[0][1][0]
+    assert abs(d[2][0][0]) < abs(d[1][0][0]) and abs(d[3][0][0]) < abs(d[2][0][0])   # |dQ| decays with the level
+    assert abs(sum(x[0][0] for x in d) - d[3][1][0]) < 1e-15                       # telescoping sum = finest Qf
