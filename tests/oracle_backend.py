@@ -7,7 +7,7 @@ from oracle import oracle as O
 
 class _OModel:
     def __init__(self, spec):
-        kind = {"expsum": O.MODEL_EXPSUM, "problem18": O.MODEL_PROBLEM18, "lognormal1d": O.MODEL_LOGNORMAL1D}[spec.name]
+        kind = {"expsum": O.MODEL_EXPSUM, "problem18": O.MODEL_PROBLEM18, "lognormal1d": O.MODEL_LOGNORMAL1D, "lognormal2d": O.MODEL_LOGNORMAL2D}[spec.name]
         self.m = O.Model(kind, spec.ndims, [float(p) for p in spec.params])
         for level, phi in spec.bases.items():
             self.m.set_basis(level, phi)

@@ -75,3 +75,18 @@ def test_problem18_regression_suite_on_gpu(engine):
                                nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_shifts=8)
         H, g, o = both(engine, make)
         compare(H.run(g, 1e-2), H.run(o, 1e-2))
+
+
+def test_mlmc_lognormal2d_run_matches_oracle(engine):
+    """config C3 at test size: ML()/MC() on the 2-D lognormal diffusion problem, levels up to 3 (32 x 32 cells)"""
+    import mle_b200.kl as kl
+
+    def make(H, backend):
+        spec = H.ModelSpec("lognormal2d", 1, [4], {lev: kl.kl_basis_2d(lev, m=60) for lev in range(4)})
+        return H.Estimator(H.ML(), H.MC(), spec, [H.Normal()] * 60, backend, max_index_set_param=3,
+                           cost_model=lambda i: 4.0 ** i[0], nb_of_tols=3, mc_seed=5)
+
+    H, g, o = both(engine, make)
+    hg, ho = H.run(g, 2e-3), H.run(o, 2e-3)
+    compare(hg, ho)
+    assert 0.05 < hg["mean"] < 0.09
