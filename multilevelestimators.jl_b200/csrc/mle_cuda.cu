@@ -108,6 +108,32 @@ struct mle_model_s {
 
 static thread_local std::string g_init_err;
 
+// MLE_DEBUG=1: report on stderr which entry point leaves a CUDA error pending (an unchecked runtime call), and log every
+// device allocation and release
+static bool mle_debug() { static const bool on = getenv("MLE_DEBUG") != nullptr; return on; }
+struct ApiScope {
+    const char *fn;
+    explicit ApiScope(const char *f) : fn(f) {
+        if (mle_debug()) { cudaError_t e = cudaPeekAtLastError(); if (e != cudaSuccess) fprintf(stderr, "[mle] %s entered with pending CUDA error: %s\n", fn, cudaGetErrorString(e)); }
+    }
+    ~ApiScope() {
+        if (mle_debug()) { cudaError_t e = cudaPeekAtLastError(); if (e != cudaSuccess) fprintf(stderr, "[mle] %s left CUDA error: %s\n", fn, cudaGetErrorString(e)); }
+    }
+};
+#define MLE_API_SCOPE ApiScope api_scope_(__func__)
+static cudaError_t mle_free_(void *p, int line) {
+    cudaError_t e = cudaFree(p);
+    if (p && mle_debug()) fprintf(stderr, "[mle] free %p @%d -> %s\n", p, line, cudaGetErrorString(e));
+    return e;
+}
+static cudaError_t mle_malloc_(void **p, size_t bytes, int line) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (mle_debug()) fprintf(stderr, "[mle] malloc %zu @%d -> %p %s\n", bytes, line, *p, cudaGetErrorString(e));
+    return e;
+}
+#define cudaFree(p) mle_free_((void *)(p), __LINE__)
+#define MLE_MALLOC(pp, bytes) mle_malloc_(reinterpret_cast<void **>(pp), (bytes), __LINE__)
+
 static int fail(mle_ctx ctx, int code, const std::string &msg) {
     if (ctx) ctx->err = msg; else g_init_err = msg;
     return code;
@@ -128,7 +154,7 @@ static int ensure_dev(mle_ctx ctx, T **p, size_t *cap, size_t need) {
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
     size_t want = need + need / 2 + 64;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), want * sizeof(T));
+    cudaError_t e = MLE_MALLOC(p, want * sizeof(T));
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc failed (scratch)"); }
     *cap = want;
     return MLE_OK;
@@ -148,9 +174,11 @@ static int ensure_pinned(mle_ctx ctx, size_t need) {
 // ---------------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int mle_abi_version(void) { return MLE_ABI_VERSION; }
+extern "C" int mle_abi_version(void) {
+    MLE_API_SCOPE; return MLE_ABI_VERSION; }
 
 extern "C" int mle_init(int device, mle_ctx *out) {
+    MLE_API_SCOPE;
     if (!out) return fail(nullptr, MLE_ERR_ARG, "mle_init: ctx is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -204,6 +232,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
 }
 
 extern "C" int mle_destroy(mle_ctx ctx) {
+    MLE_API_SCOPE;
     if (!ctx) return MLE_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -220,9 +249,11 @@ extern "C" int mle_destroy(mle_ctx ctx) {
     return MLE_OK;
 }
 
-extern "C" const char *mle_last_error(mle_ctx ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+extern "C" const char *mle_last_error(mle_ctx ctx) {
+    MLE_API_SCOPE; return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
 
 extern "C" int mle_device_info(mle_ctx ctx, int *sm_count, size_t *hbm_bytes, int *cc) {
+    MLE_API_SCOPE;
     if (!ctx) return MLE_ERR_ARG;
     if (sm_count) *sm_count = ctx->sm_count;
     if (hbm_bytes) *hbm_bytes = ctx->hbm;
@@ -231,18 +262,21 @@ extern "C" int mle_device_info(mle_ctx ctx, int *sm_count, size_t *hbm_bytes, in
 }
 
 extern "C" int mle_stream(mle_ctx ctx, void **stream) {
+    MLE_API_SCOPE;
     if (!ctx || !stream) return MLE_ERR_ARG;
     *stream = reinterpret_cast<void *>(ctx->stream);
     return MLE_OK;
 }
 
 extern "C" int mle_launch_count(mle_ctx ctx, uint64_t *count) {
+    MLE_API_SCOPE;
     if (!ctx || !count) return MLE_ERR_ARG;
     *count = ctx->launches;
     return MLE_OK;
 }
 
 extern "C" int mle_sync(mle_ctx ctx) {
+    MLE_API_SCOPE;
     if (!ctx) return MLE_ERR_ARG;
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return MLE_OK;
@@ -252,6 +286,7 @@ extern "C" int mle_sync(mle_ctx ctx) {
 // lattice rule
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int mle_genvec(const char *name, const uint32_t **z, int *len) {
+    MLE_API_SCOPE;
     if (!name || !z || !len) return MLE_ERR_ARG;
     if (!strcmp(name, "K_3600_32")) { *z = MLE_GENVEC_K3600; *len = MLE_GENVEC_K3600_LEN; return MLE_OK; }
     if (!strcmp(name, "CKN_250_20")) { *z = MLE_GENVEC_CKN250; *len = MLE_GENVEC_CKN250_LEN; return MLE_OK; }
@@ -259,6 +294,7 @@ extern "C" int mle_genvec(const char *name, const uint32_t **z, int *len) {
 }
 
 extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_t nmax, mle_lattice *out) {
+    MLE_API_SCOPE;
     if (!ctx || !out) return MLE_ERR_ARG;
     *out = nullptr;
     // check_args, src/lattice.jl:181-185: s > 0, s <= length(z) (caller's contract), n <= 2^32
@@ -276,7 +312,7 @@ extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_
     L->nmax = nmax;
     std::vector<double> zd((size_t)s);
     for (int j = 0; j < s; ++j) zd[(size_t)j] = (double)z[j];
-    if (cudaMalloc(&L->d_z, sizeof(double) * (size_t)s) != cudaSuccess) { delete L; (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(z)"); }
+    if (MLE_MALLOC(&L->d_z, sizeof(double) * (size_t)s) != cudaSuccess) { delete L; (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(z)"); }
     cudaError_t e = cudaMemcpyAsync(L->d_z, zd.data(), sizeof(double) * (size_t)s, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(L->d_z); delete L; return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e)); }
@@ -285,6 +321,7 @@ extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_
 }
 
 extern "C" int mle_lattice_destroy(mle_ctx ctx, mle_lattice lat) {
+    MLE_API_SCOPE;
     if (!lat) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(lat->d_z);
@@ -302,6 +339,7 @@ static double host_normcdf(double x) {  // Phi(x) = 1/2*(1 + erf(x/sqrt(2)))    
 }
 
 extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists *out) {
+    MLE_API_SCOPE;
     if (!ctx || !out) return MLE_ERR_ARG;
     *out = nullptr;
     if (!d || m <= 0) return fail(ctx, MLE_ERR_ARG, "distributions: need at least one distribution");
@@ -349,8 +387,8 @@ extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists
     if (!S) return fail(ctx, MLE_ERR_NOMEM, "out of host memory");
     S->m = m;
     S->mode = all_std ? GEN_STDNORMAL : GEN_GENERAL;
-    cudaError_t e = cudaMalloc(&S->d_kind, sizeof(int) * (size_t)m);
-    if (e == cudaSuccess) e = cudaMalloc(&S->d_par, sizeof(double) * (size_t)m * 6);
+    cudaError_t e = MLE_MALLOC(&S->d_kind, sizeof(int) * (size_t)m);
+    if (e == cudaSuccess) e = MLE_MALLOC(&S->d_par, sizeof(double) * (size_t)m * 6);
     if (e == cudaSuccess) e = cudaMemcpyAsync(S->d_kind, kind.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(S->d_par, par.data(), sizeof(double) * (size_t)m * 6, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -364,6 +402,7 @@ extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists
 }
 
 extern "C" int mle_dists_destroy(mle_ctx ctx, mle_dists dists) {
+    MLE_API_SCOPE;
     if (!dists) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(dists->d_kind);
@@ -376,6 +415,7 @@ extern "C" int mle_dists_destroy(mle_ctx ctx, mle_dists dists) {
 // model registry
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *out) {
+    MLE_API_SCOPE;
     if (!ctx || !out || !name) return MLE_ERR_ARG;
     *out = nullptr;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -387,7 +427,7 @@ extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const 
         M->kind = MODEL_EXPSUM;
         M->n0 = (int)params[0];
         M->nweights = nparams - 1;
-        cudaError_t e = cudaMalloc(&M->d_weights, sizeof(double) * (size_t)M->nweights);
+        cudaError_t e = MLE_MALLOC(&M->d_weights, sizeof(double) * (size_t)M->nweights);
         if (e == cudaSuccess) e = cudaMemcpyAsync(M->d_weights, params + 1, sizeof(double) * (size_t)M->nweights, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(M->d_weights); delete M; return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e)); }
@@ -414,6 +454,7 @@ extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const 
 }
 
 extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows, int cols, const double *phi) {
+    MLE_API_SCOPE;
     if (!ctx || !M || !phi) return MLE_ERR_ARG;
     if (M->kind != MODEL_LOGNORMAL1D && M->kind != MODEL_LOGNORMAL2D) return fail(ctx, MLE_ERR_ARG, "set_basis: model takes no KL basis");
     if (level < 0 || level >= MLE_MAX_LEVELS) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
@@ -429,7 +470,7 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
         for (long long nd = 0; nd < nodes; ++nd)
             for (int k = 0; k < cols; ++k) tr[(size_t)k * npad + nd] = phi[(size_t)nd * cols + k];
         double *d2 = nullptr;
-        if (cudaMalloc(&d2, tr.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
+        if (MLE_MALLOC(&d2, tr.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
         cudaError_t e2 = cudaMemcpyAsync(d2, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
         if (e2 != cudaSuccess) { cudaFree(d2); return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e2)); }
@@ -461,7 +502,7 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
             packed[((size_t)rt * nks + k / 4) * 32 + lr * 4 + (k % 4)] = phi[(size_t)node * cols + k];
     }
     double *d = nullptr;
-    if (cudaMalloc(&d, packed.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
+    if (MLE_MALLOC(&d, packed.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
     cudaError_t e = cudaMemcpyAsync(d, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(d); return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e)); }
@@ -475,12 +516,14 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
 }
 
 extern "C" int mle_model_nqoi(mle_model M, int *nqoi) {
+    MLE_API_SCOPE;
     if (!M || !nqoi) return MLE_ERR_ARG;
     *nqoi = M->nqoi;
     return MLE_OK;
 }
 
 extern "C" int mle_model_destroy(mle_ctx ctx, mle_model M) {
+    MLE_API_SCOPE;
     if (!M) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(M->d_weights);
@@ -510,9 +553,8 @@ static int make_gen_args(mle_ctx ctx, mle_lattice lat, mle_dists dists, const do
     if (lat && !shifts_dev) {  // unshifted rule: a zero shift (x + 0.0 is exact) keeps the generator branch-free
         if (ctx->zero_cap < (size_t)lat->s) {
             if (ctx->d_zero) cudaFree(ctx->d_zero);
-    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
             ctx->d_zero = nullptr; ctx->zero_cap = 0;
-            if (cudaMalloc(&ctx->d_zero, sizeof(double) * (size_t)lat->s) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(zero shift)"); }
+            if (MLE_MALLOC(&ctx->d_zero, sizeof(double) * (size_t)lat->s) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(zero shift)"); }
             if (cudaMemsetAsync(ctx->d_zero, 0, sizeof(double) * (size_t)lat->s, ctx->stream) != cudaSuccess) return fail(ctx, MLE_ERR_CUDA, "cudaMemsetAsync");
             ctx->zero_cap = (size_t)lat->s;
         }
@@ -552,6 +594,7 @@ static int upload_shifts(mle_ctx ctx, mle_lattice lat, const double *shifts, int
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts_dev, int R, uint64_t k0,
                               uint64_t n, int m, uint64_t mc_seed, double *out_dev) {
+    MLE_API_SCOPE;
     if (!ctx || !out_dev) return MLE_ERR_ARG;
     GenArgs g;
     int rc = make_gen_args(ctx, lat, dists, shifts_dev, R, k0, n, m, mc_seed, &g);
@@ -573,6 +616,7 @@ extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, con
 
 extern "C" int mle_points(mle_ctx ctx, mle_lattice lat, mle_dists dists, const double *shifts, int R, uint64_t k0, uint64_t n,
                           int m, uint64_t mc_seed, double *out) {
+    MLE_API_SCOPE;
     if (!ctx || !out) return MLE_ERR_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (R < 1 || m < 1) return fail(ctx, MLE_ERR_ARG, "R and m must be positive");
@@ -582,7 +626,7 @@ extern "C" int mle_points(mle_ctx ctx, mle_lattice lat, mle_dists dists, const d
     if (n == 0) return MLE_OK;
     const size_t cnt = (size_t)R * n * (size_t)m;
     double *d_out = nullptr;
-    if (cudaMalloc(&d_out, cnt * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "mle_points: cudaMalloc(out)"); }
+    if (MLE_MALLOC(&d_out, cnt * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "mle_points: cudaMalloc(out)"); }
     rc = mle_points_dev(ctx, lat, dists, sh_dev, R, k0, n, m, mc_seed, d_out);
     if (rc == MLE_OK) {
         cudaError_t e = cudaMemcpyAsync(out, d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
@@ -609,12 +653,17 @@ static long long grid_x_for(mle_ctx ctx, long long tiles_per_shift, int R, int c
 extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
                                     const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
                                     double *moments_dev, double *samples_dev) {
+    MLE_API_SCOPE;
     if (!ctx || !M || !index || !moments_dev) return MLE_ERR_ARG;
     if (d != M->ndims) return fail(ctx, MLE_ERR_ARG, "index dimension does not match the model");
     for (int t = 0; t < d; ++t)
         if (index[t] < 0) return fail(ctx, MLE_ERR_ARG, "index must be non-negative");
     if (n == 0) return fail(ctx, MLE_ERR_ARG, "sample!: number of samples must be positive");
     GenArgs g;
+    {   // an error left behind by an earlier unchecked failure must not be blamed on this launch
+        cudaError_t stale = cudaGetLastError();
+        if (stale != cudaSuccess) return fail(ctx, MLE_ERR_CUDA, std::string("CUDA error pending before mle_sample_batch: ") + cudaGetErrorString(stale));
+    }
     int rc = make_gen_args(ctx, lat, dists, shifts_dev, R, k0, n, m, mc_seed, &g);
     if (rc) return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -742,6 +791,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
 extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
                                 const double *shifts, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed, double *moments,
                                 double *samples, double *gpu_seconds) {
+    MLE_API_SCOPE;
     if (!ctx || !M || !moments) return MLE_ERR_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (R < 1) return fail(ctx, MLE_ERR_ARG, "number of shifts must be at least 1");
@@ -754,7 +804,7 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     double *d_samples = nullptr;
     const size_t ns = samples ? (size_t)R * 2 * (size_t)M->nqoi * n : 0;
     if (samples && ns) {
-        if (cudaMalloc(&d_samples, ns * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(samples)"); }
+        if (MLE_MALLOC(&d_samples, ns * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(samples)"); }
     }
     cudaEventRecord(ctx->ev0, ctx->stream);
     rc = mle_sample_batch_dev(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, ctx->d_moments, d_samples);
@@ -780,6 +830,7 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
 // host-side moment algebra
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int mle_moments_merge(double *acc, const double *part, size_t count) {
+    MLE_API_SCOPE;
     if (!acc || !part) return MLE_ERR_ARG;
     for (size_t i = 0; i < count; ++i) {
         Moment a{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]}, b{part[3 * i], part[3 * i + 1], part[3 * i + 2]};
@@ -792,6 +843,7 @@ extern "C" int mle_moments_merge(double *acc, const double *part, size_t count) 
 #ifdef MLE_PHASE_TIMING
 // debug builds only (-DMLE_PHASE_TIMING): wall cycles thread 0 of every CTA spent per phase of lognormal1d_kernel
 extern "C" int mle_debug_phase_cycles(unsigned long long *out8, int reset) {
+    MLE_API_SCOPE;
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyFromSymbol(out8, mle::g_phase_cycles, sizeof(z)) != cudaSuccess) return -2;
     if (reset && cudaMemcpyToSymbol(mle::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -2;
