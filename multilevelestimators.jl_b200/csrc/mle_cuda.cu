@@ -714,6 +714,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.mpad = M->basis_mpad[level];
         la.nchunks = M->basis_nchunks[level];
         la.nrows = la.N + 2;
+        if (const char *e = getenv("MLE_SKIP")) la.skip = atoi(e);  // debug: timing experiments only
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
@@ -733,7 +734,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_ws, grid, LNW_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
         } else {
             const int threads = ln_threads(bt), W = threads / 32;
-            const int qdims = m < 256 ? m : 256;
+            const int qdims = m < 256 ? ((m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims
             const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
             const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)2 * bt * sizeof(SweepState) +
                                 (size_t)2 * bt * sizeof(Moment) + W * 4 + (qbytes <= fbytes ? 0 : qbytes) + 16;

@@ -311,6 +311,7 @@ struct Lognormal1dArgs {
     int nrows;            // N + 2 rows (both sides, mid node twice)
     int nchunks;          // row chunks of LN_RC rows
     int level;
+    int skip;             // debug (MLE_SKIP env): 1 = generator, 2 = contraction, 4 = exp, 8 = sweeps; results invalid when set
     double h2, h2c;       // 1/N^2, 1/(N/2)^2
 };
 
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
     GenScratch sc;
     sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * BT);       // [W]
     // generator queue [BT * min(m, 256)]: lives inside F when it fits (F is idle while the inputs are generated)
-    const int qbytes = BT * min(g.m, 256) * 2;
+    const int qbytes = BT * (g.m < 256 ? ((g.m + 3) & ~3) : 256) * 2;
     sc.queue = qbytes <= RC * LDF * 8 ? reinterpret_cast<unsigned short *>(F) : reinterpret_cast<unsigned short *>(sc.wtot + W);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         const int Pt = left < (unsigned long long)BT ? (int)left : BT;
         MLE_PH(5);
         // A. inputs (always a full tile: surplus points are masked out of the statistics)
-        if (g.m <= 32 * (THREADS / BT)) {  // at most 32 dims per thread: 32-bit class masks
+        if (la.skip & 1) {
+        } else if (g.m <= 32 * (THREADS / BT)) {  // at most 32 dims per thread: 32-bit class masks
             gen_tile_owned<THREADS, BT, MODE, LDX, unsigned, LN_GEN_U>(xi, 0, g.m, g.k0 + i0, g, r, sc);
         } else {
             constexpr int GEN_DIMS = 64 * (THREADS / BT);  // 64 iterations per thread fit the 64-bit class masks
@@ -436,53 +438,80 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         const int side = tid / BT, b = tid & (BT - 1);  // sweep role (threads 0 .. 2*BT-1)
 
         for (int c = 0; c < la.nchunks; ++c) {
-            // B. contraction for rows [c*RC, c*RC + RC): this warp's row tiles rt0, rt0+1 (global tile numbers)
+            // B. contraction for rows [c*RC, c*RC + RC).  A full chunk (4 live row tiles) is split 2x2 per warp: row tiles
+            // {2wr, 2wr+1} x sample tiles {2wc, 2wc+1}.  A partial chunk (the only chunk of the coarse levels, the last chunk
+            // of the others) would leave half the warps idle that way, so there warp w owns sample tile w and ALL live row tiles.
+            const int live = min(RC / 8, (la.nrows - c * RC + 7) / 8);
+            const bool full = live == RC / 8;
             const int rt0 = c * (RC / 8) + 2 * wr;
-            const int rows_left = la.nrows - rt0 * 8;  // > 0: first tile live; > 8: second tile live
             double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
-            if (rows_left > 0) {
-                const bool two = rows_left > 8;
-                const double *A0 = la.basis + (size_t)rt0 * nks * 32 + lane;
-                const double *A1 = two ? A0 + (size_t)nks * 32 : A0;
-                const double *B0 = xi + lk * LDX + 16 * wc + lr;
-                double a0 = __ldg(A0), a1 = __ldg(A1);
-                double b0 = B0[0], b1 = B0[8];
+            if (!(la.skip & 2)) {
+                if (full) {
+                    const double *A0 = la.basis + (size_t)rt0 * nks * 32 + lane;
+                    const double *A1 = A0 + (size_t)nks * 32;
+                    const double *B0 = xi + lk * LDX + 16 * wc + lr;
+                    double a0 = __ldg(A0), a1 = __ldg(A1);
+                    double b0 = B0[0], b1 = B0[8];
 #pragma unroll 5
-                for (int ks = 0; ks < nks; ++ks) {
-                    const int kn = (ks + 1 < nks) ? ks + 1 : ks;  // prefetch the next k step's fragments
-                    const double na0 = __ldg(A0 + kn * 32), na1 = __ldg(A1 + kn * 32);
-                    const double nb0 = B0[kn * 4 * LDX], nb1 = B0[kn * 4 * LDX + 8];
-                    dmma_m8n8k4(c00a, c00b, a0, b0);
-                    dmma_m8n8k4(c01a, c01b, a0, b1);
-                    if (two) {
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const int kn = (ks + 1 < nks) ? ks + 1 : ks;  // prefetch the next k step's fragments
+                        const double na0 = __ldg(A0 + kn * 32), na1 = __ldg(A1 + kn * 32);
+                        const double nb0 = B0[kn * 4 * LDX], nb1 = B0[kn * 4 * LDX + 8];
+                        dmma_m8n8k4(c00a, c00b, a0, b0);
+                        dmma_m8n8k4(c01a, c01b, a0, b1);
                         dmma_m8n8k4(c10a, c10b, a1, b0);
                         dmma_m8n8k4(c11a, c11b, a1, b1);
+                        a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
                     }
-                    a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+                } else {
+                    // accumulators: (c00), (c01), (c10) = row tiles 0, 1, 2 of the chunk for sample tile `warp`
+                    const double *Ab = la.basis + (size_t)(c * (RC / 8)) * nks * 32 + lane;
+                    const double *Bp = xi + lk * LDX + 8 * warp + lr;
+                    const size_t ts = (size_t)nks * 32;
+                    double a0 = __ldg(Ab), a1 = live > 1 ? __ldg(Ab + ts) : 0.0, a2 = live > 2 ? __ldg(Ab + 2 * ts) : 0.0;
+                    double b0 = Bp[0];
+#pragma unroll 5
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const int kn = (ks + 1 < nks) ? ks + 1 : ks;
+                        const double na0 = __ldg(Ab + kn * 32);
+                        const double na1 = live > 1 ? __ldg(Ab + ts + kn * 32) : 0.0;
+                        const double na2 = live > 2 ? __ldg(Ab + 2 * ts + kn * 32) : 0.0;
+                        const double nb0 = Bp[kn * 4 * LDX];
+                        dmma_m8n8k4(c00a, c00b, a0, b0);
+                        if (live > 1) dmma_m8n8k4(c01a, c01b, a1, b0);
+                        if (live > 2) dmma_m8n8k4(c10a, c10b, a2, b0);
+                        a0 = na0; a1 = na1; a2 = na2; b0 = nb0;
+                    }
                 }
             }
             MLE_PH(1);
             __syncthreads();  // the previous chunk's sweeps have finished reading F
             MLE_PH(2);
             // epilogue: a = exp(G) -> F[row in chunk][sample]; lane holds row lr, samples 2*lk, 2*lk+1 of each 8x8 tile
-            if (rows_left > 0) {
+            if (la.skip & 4) { c00a = c00b = c01a = c01b = c10a = c10b = c11a = c11b = -1e300; }
+            if (full) {
                 double *f0 = F + (16 * wr + lr) * LDF + 16 * wc + 2 * lk;
                 double2 v;
                 v.x = exp_det(c00a); v.y = exp_det(c00b);
                 *reinterpret_cast<double2 *>(f0) = v;
                 v.x = exp_det(c01a); v.y = exp_det(c01b);
                 *reinterpret_cast<double2 *>(f0 + 8) = v;
-                if (rows_left > 8) {
-                    v.x = exp_det(c10a); v.y = exp_det(c10b);
-                    *reinterpret_cast<double2 *>(f0 + 8 * LDF) = v;
-                    v.x = exp_det(c11a); v.y = exp_det(c11b);
-                    *reinterpret_cast<double2 *>(f0 + 8 * LDF + 8) = v;
-                }
+                v.x = exp_det(c10a); v.y = exp_det(c10b);
+                *reinterpret_cast<double2 *>(f0 + 8 * LDF) = v;
+                v.x = exp_det(c11a); v.y = exp_det(c11b);
+                *reinterpret_cast<double2 *>(f0 + 8 * LDF + 8) = v;
+            } else {
+                double *f0 = F + lr * LDF + 8 * warp + 2 * lk;
+                double2 v;
+                v.x = exp_det(c00a); v.y = exp_det(c00b);
+                *reinterpret_cast<double2 *>(f0) = v;
+                if (live > 1) { v.x = exp_det(c01a); v.y = exp_det(c01b); *reinterpret_cast<double2 *>(f0 + 8 * LDF) = v; }
+                if (live > 2) { v.x = exp_det(c10a); v.y = exp_det(c10b); *reinterpret_cast<double2 *>(f0 + 16 * LDF) = v; }
             }
             __syncthreads();
             MLE_PH(3);
             // C. sweeps over the RC/2 half-nodes of this chunk (threads 0 .. 2*BT-1)
-            if (tid < 2 * BT) {
+            if (tid < 2 * BT && !(la.skip & 8)) {
                 const int ip0 = c * (RC / 2);
 #pragma unroll 4
                 for (int q = 0; q < RC / 2; ++q) {
