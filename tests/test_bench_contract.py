@@ -1,0 +1,45 @@
+"""CPU test of the driver-facing bench.py contract: the reference arm runs without a GPU, prints exactly one JSON line with
+the required keys, and non-zero ranks of a torchrun launch exit quietly."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def run_bench(extra_env, *args):
+    env = dict(os.environ, **extra_env)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, env=env,
+                          timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = run_bench({"RANK": "0", "WORLD_SIZE": "1"}, "--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 1e4
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    r = run_bench({"RANK": "1", "WORLD_SIZE": "2"}, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_workload_definition_matches_baseline_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.M_KL == 100 and bench.R_SHIFTS == 16 and bench.LEVELS == list(range(7))   # BASELINE.json configs[1]
+    assert [16 << l for l in bench.LEVELS][-1] == 1024                                      # grid 2^(l+4)
+    assert bench.points_per_shift(0) == 1 << 20 and bench.points_per_shift(6) == 2048
+    sh = bench.level_shifts()
+    assert sh.shape == (7, 16, 100) and (sh >= 0).all() and (sh < 1).all()

@@ -222,3 +222,14 @@ def test_lognormal2d_mc(engine, oracle):
     got = engine.sample_batch(gm, None, d, [2], None, 0, 300, mc_seed=9)
     want = oracle.sample_batch(om, None, dl, [2], None, 0, 300, mc_seed=9)
     check_moments(got, want)
+
+
+@pytest.mark.parametrize("m,level", [(200, 1), (300, 0), (129, 2)])
+def test_lognormal1d_many_kl_terms(engine, oracle, m, level):
+    """more than 128 KL terms: the generator switches to 64-bit class masks and multiple passes over the dimensions"""
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, m, [level])
+    sh = splitmix_uniforms(77, 3 * m).reshape(3, m)
+    got, smp = engine.sample_batch(gm, lat, d, [level], sh, 11, 150, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, 11, 150, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
