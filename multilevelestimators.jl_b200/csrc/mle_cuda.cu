@@ -21,7 +21,9 @@ template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_
 template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
 template <int MODE> static constexpr auto lognormal1d_k64 = lognormal1d_kernel<MODE, 64>;
 template <int MODE> static constexpr auto lognormal1d_k32 = lognormal1d_kernel<MODE, 32>;
+#ifdef MLE_WITH_WS
 template <int MODE> static constexpr auto lognormal1d_ws = lognormal1d_ws_kernel<MODE>;
+#endif
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 // mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
@@ -220,7 +222,9 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(problem18_k, 200 * 1024);
     MLE_SET_SMEM(lognormal1d_k64, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_k32, 220 * 1024);
+#ifdef MLE_WITH_WS
     MLE_SET_SMEM(lognormal1d_ws, 220 * 1024);
+#endif
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
 #undef MLE_SET_SMEM
@@ -720,8 +724,13 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
         // Schedule: the phase-synchronous kernel with 32-sample tiles (measured fastest on the C2 step); MLE_LN_BT=64
         // selects 64-sample tiles and MLE_LN_WS=1 the warp-specialised kernel (kept for A/B measurements).
+#ifdef MLE_WITH_WS
         const int bt = ctx->ln_ws ? LNW_BT : (ctx->ln_bt_override ? ctx->ln_bt_override : 32);
+#else
+        const int bt = ctx->ln_bt_override ? ctx->ln_bt_override : 32;
+#endif
         const long long tps = (long long)((n + bt - 1) / bt);
+#ifdef MLE_WITH_WS
         if (ctx->ln_ws) {
             const int Gd = LNW_THREADS / LNW_BT;
             const int qdims = m <= 32 * Gd ? ((m + Gd - 1) / Gd) * Gd : 64 * Gd;
@@ -732,7 +741,9 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             if (rc) return rc;
             dim3 grid((unsigned)gx, (unsigned)R);
             MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_ws, grid, LNW_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
-        } else {
+        } else
+#endif
+        {
             const int threads = ln_threads(bt), W = threads / 32;
             const int qdims = m < 256 ? ((m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims
             const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;

@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
 }
 
 
+#ifdef MLE_WITH_WS  // experiment, off by default: make EXTRA=-DMLE_WITH_WS, then MLE_LN_WS=1 at run time
 // ===================================================================================================================
 // 1-D lognormal diffusion, warp-specialised variant (MLE_LN_WS=1; an experiment kept for A/B runs -- measured 8 % slower
 // than the phase-synchronous kernel on the C2 step): same arithmetic as lognormal1d_kernel, different schedule.  ncu showed the fused kernel above spending 35-50 % of its non-generator time at the barrier that separates the
@@ -711,6 +712,8 @@ __global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs 
     }
 }
 
+
+#endif  // MLE_WITH_WS
 
 // ===================================================================================================================
 // 2-D lognormal diffusion (config C3/C4 shape; model definition in oracle/mle_oracle.c and DESIGN.md):
