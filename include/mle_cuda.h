@@ -92,13 +92,17 @@ int mle_dists_destroy(mle_ctx ctx, mle_dists dists);
  *   "lognormal1d"  -(a u')' = 1 on (0,1), u(0)=u(1)=0, log a = KL expansion; level l has n0 2^l cells; params = {n0};
  *                  structure of docs/src/example.md:106-128 (coarse field = even nodes of the fine field, QoI = u(1/2));
  *                  needs mle_model_set_basis for every level used; 1 QoI; ndims = 1
- *   "lognormal2d"  -div(a grad u) = 1 on the unit square, u = 0 on the boundary; level l has n0 2^l cells per direction
- *                  (params = {n0}, default 4, grids up to 128 x 128); basis rows = nodes (i,j) -> j*(N+1) + i;
- *                  QoI = u(1/2,1/2); coarse field = even nodes; frontal elimination; 1 QoI; ndims = 1
+ *   "lognormal2d"  -div(a grad u) = 1 on the unit square, u = 0 on the boundary, QoI = u(1/2,1/2); params = {n0} (default 4);
+ *                  ndims = 1 (multilevel): level l has n0 2^l cells per direction, coarse field = even nodes;
+ *                  ndims = 2 (multi-index, docs/src/example.md:221-243): index (lx, ly) has n0 2^lx x n0 2^ly cells and
+ *                  dQ is the mixed difference over diff(index) (src/index.jl:49-58), every coarse solve a strided view
+ *                  of the one fine field; up to 128 cells in x; basis rows = nodes (i,j) -> j*(Nx+1) + i;
+ *                  frontal elimination; 1 QoI
  * Every model returns (dQ, Qf) per sample exactly like the reference's sample functions. */
 int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *model);
 /* KL basis of one level: phi[cols x rows] = row-major [rows = nodes][cols = KL terms], log a(node i) = sum_k phi[i][k] xi_k
- * (lognormal1d: rows = n0 2^level + 1 nodes; lognormal2d: rows = (n0 2^level + 1)^2 nodes) */
+ * (lognormal1d: rows = n0 2^level + 1 nodes; lognormal2d: rows = (n0 2^level + 1)^2 nodes; lognormal2d with ndims = 2:
+ * `level` carries the multi-index packed as lx + 16*ly and rows = (n0 2^lx + 1)(n0 2^ly + 1)) */
 int mle_model_set_basis(mle_ctx ctx, mle_model model, int level, int rows, int cols, const double *phi);
 int mle_model_nqoi(mle_model model, int *nqoi);
 int mle_model_destroy(mle_ctx ctx, mle_model model);

@@ -95,7 +95,7 @@ struct mle_dists_s {
     double *d_par = nullptr;  // [m][6]
 };
 
-static const int MLE_MAX_LEVELS = 16;
+static const int MLE_MAX_LEVELS = 256;  // levels, or packed multi-indices lx + 16*ly (lognormal2d with ndims = 2)
 struct mle_model_s {
     int kind = 0, ndims = 1, nqoi = 1, n0 = 0;
     int nweights = 0;
@@ -446,7 +446,7 @@ extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const 
         M->n0 = n0;
     } else if (!strcmp(name, "lognormal2d")) {
         int n0 = (nparams > 0 && params) ? (int)params[0] : 4;
-        if (ndims != 1 || n0 < 2 || (n0 & 1)) { delete M; return fail(ctx, MLE_ERR_ARG, "lognormal2d: ndims = 1, params = {n0}, n0 even and >= 2"); }
+        if ((ndims != 1 && ndims != 2) || n0 < 2 || (n0 & 1)) { delete M; return fail(ctx, MLE_ERR_ARG, "lognormal2d: ndims = 1 (multilevel) or 2 (multi-index), params = {n0}, n0 even and >= 2"); }
         M->kind = MODEL_LOGNORMAL2D;
         M->n0 = n0;
     } else {
@@ -462,11 +462,14 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
     if (!ctx || !M || !phi) return MLE_ERR_ARG;
     if (M->kind != MODEL_LOGNORMAL1D && M->kind != MODEL_LOGNORMAL2D) return fail(ctx, MLE_ERR_ARG, "set_basis: model takes no KL basis");
     if (level < 0 || level >= MLE_MAX_LEVELS) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
-    const long long N = (long long)M->n0 << level;
     if (M->kind == MODEL_LOGNORMAL2D) {
-        if (N > 128) return fail(ctx, MLE_ERR_ARG, "set_basis: lognormal2d supports grids up to 128 x 128 cells");
-        const long long nodes = (N + 1) * (N + 1);
-        if (rows != nodes) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be (n0*2^level + 1)^2 (nodes of the level's grid)");
+        // multilevel: level l (Nx = Ny = n0 2^l); multi-index: level = lx + 16*ly
+        const int lx = M->ndims == 2 ? (level & 15) : level, ly = M->ndims == 2 ? (level >> 4) : level;
+        if (lx > 12 || ly > 12) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
+        const long long Nx = (long long)M->n0 << lx, Ny = (long long)M->n0 << ly;
+        if (Nx > 128 || Ny > 4096) return fail(ctx, MLE_ERR_ARG, "set_basis: lognormal2d supports grids up to 128 cells in x");
+        const long long nodes = (Nx + 1) * (Ny + 1);
+        if (rows != nodes) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be (n0*2^lx + 1)*(n0*2^ly + 1) (nodes of the index's grid)");
         if (cols < 1 || cols > 1024) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 1024");
         CU_TRY(ctx, cudaSetDevice(ctx->device));
         const long long npad = (nodes + 31) & ~31ll;
@@ -486,6 +489,8 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
         M->basis_nchunks[level] = 0;
         return MLE_OK;
     }
+    if (level > 20) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
+    const long long N = (long long)M->n0 << level;
     if (rows != N + 1) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be n0*2^level + 1 (nodes of the level's grid)");
     if (cols < 1 || cols > 352) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 352 (the xi tile must fit in shared memory)");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -758,19 +763,27 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             else MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k32, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
         }
     } else if (M->kind == MODEL_LOGNORMAL2D) {
-        const int level = index[0];
-        if (level >= MLE_MAX_LEVELS || !M->d_basis[level]) return fail(ctx, MLE_ERR_STATE, "lognormal2d: no KL basis set for this level (mle_model_set_basis)");
-        if (m != M->basis_cols[level]) return fail(ctx, MLE_ERR_ARG, "lognormal2d: nb_of_uncertainties must equal the number of KL terms of the level's basis");
+        const int lx = index[0], ly = d == 2 ? index[1] : index[0];
+        if (lx > 12 || ly > 12) return fail(ctx, MLE_ERR_ARG, "lognormal2d: index out of range");
+        const int key = d == 2 ? lx + 16 * ly : lx;
+        if (key >= MLE_MAX_LEVELS || !M->d_basis[key]) return fail(ctx, MLE_ERR_STATE, "lognormal2d: no KL basis set for this index (mle_model_set_basis)");
+        if (m != M->basis_cols[key]) return fail(ctx, MLE_ERR_ARG, "lognormal2d: nb_of_uncertainties must equal the number of KL terms of the index's basis");
         Lognormal2dArgs la{};
-        la.basisT = M->d_basis[level];
-        la.N = M->n0 << level;
-        la.nodes_pad = M->basis_mpad[level];
-        la.level = level;
-        const int N = la.N, nn = N - 1, W = N, nodes = (N + 1) * (N + 1), mpad = (m + 3) & ~3;
-        const bool big = N >= 64;  // one CTA per sample, field and centre blocks in global scratch
+        la.basisT = M->d_basis[key];
+        la.Nx = M->n0 << lx;
+        la.Ny = M->n0 << ly;
+        la.nodes_pad = M->basis_mpad[key];
+        la.ndims = d;
+        la.lx = lx;
+        la.ly = ly;
+        const int nn = la.Nx - 1, W = la.Nx, nodes = (la.Nx + 1) * (la.Ny + 1), mpad = (m + 3) & ~3;
+        la.scratch_per_group = 2ll * nn * nn + nodes;
+        // a warp per sample while window, centre blocks and field of 4 samples fit in shared memory; else a CTA per sample
+        // with the centre blocks and the field in (L2-resident) global scratch
+        const size_t warp_smem = ((size_t)mpad + (size_t)W * W + 5 * (size_t)W + (size_t)la.scratch_per_group) * 4 * sizeof(double);
+        const bool big = la.Nx > 32 || warp_smem > 200 * 1024;
         const int threads = big ? 256 : 128, groups = big ? 1 : 4;
         la.use_scratch = big ? 1 : 0;
-        la.scratch_per_group = 2ll * nn * nn + nodes;
         const size_t per_group = (size_t)mpad + (size_t)W * W + 5 * (size_t)W + (big ? 0 : (size_t)la.scratch_per_group);
         const size_t smem = per_group * groups * sizeof(double) + 2 * groups * sizeof(Moment) + 16;
         if (smem > 220 * 1024) return fail(ctx, MLE_ERR_ARG, "lognormal2d: KL terms x grid do not fit in shared memory");

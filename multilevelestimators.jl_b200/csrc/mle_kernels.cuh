@@ -717,8 +717,9 @@ __global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs 
 
 // ===================================================================================================================
 // 2-D lognormal diffusion (config C3/C4 shape; model definition in oracle/mle_oracle.c and DESIGN.md):
-//   -div(a grad u) = 1 on the unit square, u = 0 on the boundary, N = n0 * 2^l cells per direction, 5-point stencil with
-//   edge coefficients = mean of the two node values, QoI = u(1/2, 1/2), coarse problem = even nodes.
+//   -div(a grad u) = 1 on the unit square, u = 0 on the boundary, Nx x Ny = n0 2^lx x n0 2^ly cells (multilevel: lx = ly = l;
+//   multi-index: anisotropic, mixed differences over diff(index) with strided coarse fields, docs/src/example.md:221-243),
+//   5-point stencil with edge coefficients = mean of the two node values scaled by 1/h^2, QoI = u(1/2, 1/2).
 // One GROUP of TG threads owns one sample (TG = 32: a warp, 4 samples per CTA, N <= 32;  TG = 256: the whole CTA, N >= 64):
 //   1. xi (m inverse normals) -> shared memory;
 //   2. field: thread-per-node dot products over the KL terms in ascending k (fused multiply-adds, the oracle's order) from the
@@ -730,11 +731,12 @@ __global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs 
 //      single bit of the result.
 // ===================================================================================================================
 struct Lognormal2dArgs {
-    const double *basisT;  // [m][nodes_pad]: transposed KL basis of this level
-    int N;                 // cells per direction
+    const double *basisT;  // [m][nodes_pad]: transposed KL basis of this index
+    int Nx, Ny;            // cells per direction (Nx = n0 2^lx, Ny = n0 2^ly; multilevel model: lx = ly)
     int nodes_pad;
-    int level;
-    int use_scratch;       // field / second centre block in global scratch (N >= 64) instead of shared memory
+    int ndims;             // 1: multilevel (one coarse solve), 2: multi-index (mixed differences, src/index.jl:49-58)
+    int lx, ly;
+    int use_scratch;       // field / centre blocks in global scratch (Nx >= 64) instead of shared memory
     double *scratch;       // [groups in grid][scratch_per_group]
     long long scratch_per_group;
 };
@@ -745,15 +747,17 @@ __device__ __forceinline__ void group_sync() {
     else __syncthreads();
 }
 
+// node values a[(j*sty)*lda + i*stx] of an Nx x Ny-cell grid (optionally y-mirrored) and its scaled edge coefficients
 struct Field2d {
     const double *a;
-    int lda, st, N, mirror;
+    int lda, stx, sty, Nx, Ny, mirror;
+    double wx, wy;  // 1/hx^2 = Nx^2, 1/hy^2 = Ny^2
     __device__ __forceinline__ double at(int i, int j) const {
-        const int jj = mirror ? N - j : j;
-        return a[(size_t)(jj * st) * lda + (size_t)i * st];
+        const int jj = mirror ? Ny - j : j;
+        return a[(size_t)(jj * sty) * lda + (size_t)i * stx];
     }
-    __device__ __forceinline__ double kx(int i, int j) const { return __dmul_rn(0.5, __dadd_rn(at(i, j), at(i + 1, j))); }
-    __device__ __forceinline__ double ky(int i, int j) const { return __dmul_rn(0.5, __dadd_rn(at(i, j), at(i, j + 1))); }
+    __device__ __forceinline__ double kx(int i, int j) const { return __dmul_rn(wx, __dmul_rn(0.5, __dadd_rn(at(i, j), at(i + 1, j)))); }
+    __device__ __forceinline__ double ky(int i, int j) const { return __dmul_rn(wy, __dmul_rn(0.5, __dadd_rn(at(i, j), at(i, j + 1)))); }
     __device__ __forceinline__ double diag(int i, int j) const {
         return __dadd_rn(__dadd_rn(__dadd_rn(kx(i - 1, j), kx(i, j)), ky(i, j - 1)), ky(i, j));
     }
@@ -789,9 +793,8 @@ __device__ __forceinline__ void rank1_update(double *M, double *gv, const double
 }
 
 template <int TG>
-__device__ void frontal_half_dev(const Field2d &f, double h2, double *M, double *gv, double *l, double *v, double *S,
-                                 double *gs, int t) {
-    const int N = f.N, n = N - 1, c = N / 2, W = n + 1;
+__device__ void frontal_half_dev(const Field2d &f, double *M, double *gv, double *l, double *v, double *S, double *gs, int t) {
+    const int n = f.Nx - 1, c = f.Ny / 2, W = n + 1;
     const int P = (c - 1) * n, last = P + n - 1;
     // entering unknown e: row/column slot(e) of the window <- its original matrix entries (one phase, no read of M)
     auto load = [&](int e) {
@@ -805,7 +808,7 @@ __device__ void frontal_half_dev(const Field2d &f, double h2, double *M, double 
             M[se * W + u] = val;
             M[u * W + se] = val;
         }
-        if (t == 0) gv[se] = own ? h2 : 0.0;
+        if (t == 0) gv[se] = own ? 1.0 : 0.0;
     };
     for (int e = 0; e < n && e <= last; ++e) load(e);
     group_sync<TG>();
@@ -835,19 +838,19 @@ __device__ void frontal_half_dev(const Field2d &f, double h2, double *M, double 
     group_sync<TG>();
 }
 
+// u at the centre node (Nx/2, Ny/2)
 template <int TG>
-__device__ double frontal_mid_dev(const double *a, int lda, int st, int N, double *M, double *gv, double *l, double *v,
-                                  double *S, double *gs, double *S2, double *gs2, int t) {
-    const int n = N - 1, c = N / 2, tc = c - 1;
-    const double h2 = 1.0 / ((double)N * (double)N);
-    Field2d f{a, lda, st, N, 1};
-    frontal_half_dev<TG>(f, h2, M, gv, l, v, S2, gs2, t);  // upper half first (y-mirrored field)
+__device__ double frontal_mid_dev(const double *a, int lda, int stx, int sty, int Nx, int Ny, double *M, double *gv,
+                                  double *l, double *v, double *S, double *gs, double *S2, double *gs2, int t) {
+    const int n = Nx - 1, tc = Nx / 2 - 1;
+    Field2d f{a, lda, stx, sty, Nx, Ny, 1, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
+    frontal_half_dev<TG>(f, M, gv, l, v, S2, gs2, t);  // upper half first (y-mirrored field)
     f.mirror = 0;
-    frontal_half_dev<TG>(f, h2, M, gv, l, v, S, gs, t);    // lower half
+    frontal_half_dev<TG>(f, M, gv, l, v, S, gs, t);    // lower half
     for (int e = t; e < n * n; e += TG) S[e] = __dadd_rn(S[e], S2[e]);
     for (int q = t; q < n; q += TG) gs[q] = __dadd_rn(gs[q], gs2[q]);
     group_sync<TG>();
-    // dense two-sided elimination along the centre line (row-major S, W = n)
+    // dense two-sided elimination along the centre line (row-major S)
     for (int tt = 0; tt < tc; ++tt) {
         const double d = S[tt * n + tt], gp = gs[tt];
         for (int q = tt + 1 + t; q < n; q += TG) { v[q] = S[q * n + tt]; l[q] = __ddiv_rn(v[q], d); }
@@ -862,7 +865,9 @@ __device__ double frontal_mid_dev(const double *a, int lda, int st, int N, doubl
         rank1_update<TG>(S, gs, l, v, gp, n, 1 << 30, tc, tt - tc, t);
         group_sync<TG>();
     }
-    return __ddiv_rn(gs[tc], S[tc * n + tc]);
+    const double u = __ddiv_rn(gs[tc], S[tc * n + tc]);
+    group_sync<TG>();  // the buffers are reused by the next solve
+    return u;
 }
 
 template <int MODE, int TG>
@@ -871,10 +876,10 @@ __global__ void __launch_bounds__(TG == 32 ? 128 : 256) lognormal2d_kernel(GenAr
                                                                            double *__restrict__ samples) {
     constexpr int THREADS = TG == 32 ? 128 : 256, GROUPS = THREADS / TG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int N = la.N, n = N - 1, W = n + 1, nodes = (N + 1) * (N + 1);
+    const int Nx = la.Nx, Ny = la.Ny, n = Nx - 1, W = n + 1, nodes = (Nx + 1) * (Ny + 1);
     const int t = threadIdx.x % TG, grp = threadIdx.x / TG, r = blockIdx.y;
     // per-group shared memory: xi[mpad] | M[W*W] | gv[W] | l[W] | v[W] | gs[W] gs2[W] and, unless they live in the global
-    // scratch (N >= 64): S[n*n] | S2[n*n] | field[(N+1)^2]
+    // scratch (Nx >= 64): S[n*n] | S2[n*n] | field[(Nx+1)(Ny+1)]
     const int mpad = (g.m + 3) & ~3;
     const size_t per_group = (size_t)mpad + (size_t)W * W + 5 * (size_t)W + (la.use_scratch ? 0 : 2 * (size_t)n * n + (size_t)nodes);
     double *base = reinterpret_cast<double *>(smem_raw) + (size_t)grp * per_group;
@@ -920,12 +925,15 @@ __global__ void __launch_bounds__(TG == 32 ? 128 : 256) lognormal2d_kernel(GenAr
                 A[node] = exp_det(acc);
             }
             group_sync<TG>();
-            // 3. solves
-            const double qf = frontal_mid_dev<TG>(A, N + 1, 1, N, M, gv, l, v, S, gs, S2, gs2, t);
+            // 3. solves: Qf and the coarse terms of diff(index), added in the order (lx-1,ly-1), (lx,ly-1), (lx-1,ly)
+            const double qf = frontal_mid_dev<TG>(A, Nx + 1, 1, 1, Nx, Ny, M, gv, l, v, S, gs, S2, gs2, t);
             double dq = qf;
-            if (la.level > 0) {
-                group_sync<TG>();
-                dq = __dsub_rn(qf, frontal_mid_dev<TG>(A, N + 1, 2, N / 2, M, gv, l, v, S, gs, S2, gs2, t));
+            if (la.ndims == 1) {
+                if (la.lx > 0) dq = __dsub_rn(qf, frontal_mid_dev<TG>(A, Nx + 1, 2, 2, Nx / 2, Ny / 2, M, gv, l, v, S, gs, S2, gs2, t));
+            } else {
+                if (la.lx > 0 && la.ly > 0) dq = __dadd_rn(dq, frontal_mid_dev<TG>(A, Nx + 1, 2, 2, Nx / 2, Ny / 2, M, gv, l, v, S, gs, S2, gs2, t));
+                if (la.ly > 0) dq = __dsub_rn(dq, frontal_mid_dev<TG>(A, Nx + 1, 1, 2, Nx, Ny / 2, M, gv, l, v, S, gs, S2, gs2, t));
+                if (la.lx > 0) dq = __dsub_rn(dq, frontal_mid_dev<TG>(A, Nx + 1, 2, 1, Nx / 2, Ny, M, gv, l, v, S, gs, S2, gs2, t));
             }
             if (t == 0) {
                 if (samples) {

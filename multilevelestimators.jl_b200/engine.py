@@ -58,6 +58,9 @@ class DeviceModel(_Handle):
     nqoi = 1
 
     def set_basis(self, level, phi):
+        """level: int, or the multi-index (lx, ly) of the 2-D multi-index model (packed as lx + 16*ly for the C ABI)"""
+        if not isinstance(level, (int, np.integer)):
+            level = int(level[0]) + 16 * int(level[1]) if len(level) == 2 else int(level[0])
         phi = np.ascontiguousarray(phi, dtype=np.float64)
         self.engine._check(self.engine.lib.mle_model_set_basis(self.engine.ctx, self.handle, int(level), phi.shape[0],
                                                                phi.shape[1], _as_dp(phi)))

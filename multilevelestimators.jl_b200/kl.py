@@ -18,11 +18,13 @@ def kl_basis_1d(level, m=100, n0=16, sigma=0.5, decay=1.5):
 
 
 def kl_basis_2d(level, m=400, n0=4, sigma=0.5, decay=1.5):
-    """-> float64[(N+1)^2, m] for the level's grid of N = n0 * 2^level cells per direction on [0,1]^2; node (i, j) is row
-    j*(N+1) + i.  Separable cosine modes cos(pi p x) cos(pi q y) ordered by p + q (then p), amplitude
-    sigma * c_p c_q * (1 + p + q)^(-decay) with c_0 = 1, c_p = sqrt(2)."""
-    N = n0 << level
-    x = np.arange(N + 1, dtype=np.float64) / N
+    """-> float64[(Nx+1)(Ny+1), m] for the grid of Nx x Ny cells on [0,1]^2, Nx = n0 * 2^lx, Ny = n0 * 2^ly with
+    level = l (lx = ly = l) or level = (lx, ly); node (i, j) is row j*(Nx+1) + i.  Separable cosine modes
+    cos(pi p x) cos(pi q y) ordered by p + q (then p), amplitude sigma * c_p c_q * (1 + p + q)^(-decay), c_0 = 1, c_p = sqrt(2)."""
+    lx, ly = (level, level) if isinstance(level, (int, np.integer)) else level
+    Nx, Ny = n0 << lx, n0 << ly
+    x = np.arange(Nx + 1, dtype=np.float64) / Nx
+    y = np.arange(Ny + 1, dtype=np.float64) / Ny
     modes, t = [], 0
     while len(modes) < m:
         for p in range(t + 1):
@@ -34,5 +36,5 @@ def kl_basis_2d(level, m=400, n0=4, sigma=0.5, decay=1.5):
         cp = 1.0 if p == 0 else np.sqrt(2.0)
         cq = 1.0 if q == 0 else np.sqrt(2.0)
         amp = sigma * cp * cq * (1.0 + p + q) ** (-decay)
-        cols.append(amp * np.outer(np.cos(np.pi * q * x), np.cos(np.pi * p * x)).reshape(-1))  # [j][i] -> j*(N+1)+i
+        cols.append(amp * np.outer(np.cos(np.pi * q * y), np.cos(np.pi * p * x)).reshape(-1))  # [j][i] -> j*(Nx+1)+i
     return np.ascontiguousarray(np.stack(cols, axis=1))

@@ -307,7 +307,7 @@ ORC_API int orc_points(const uint32_t *z, int s, uint64_t nmax, const int *kinds
 /* ------------------------------------------------------------------------------------------------ */
 enum { ORC_MODEL_EXPSUM = 0, ORC_MODEL_PROBLEM18 = 1, ORC_MODEL_LOGNORMAL1D = 2, ORC_MODEL_LOGNORMAL2D = 3 };
 
-#define ORC_MAX_LEVELS 16
+#define ORC_MAX_LEVELS 256 /* levels, or packed multi-indices lx + 16*ly */
 typedef struct {
     int kind;
     int nqoi;
@@ -513,22 +513,25 @@ static int lognormal1d_eval(const orc_model *M, int level, const double *xi, int
  * (n = N-1); every entry is updated by fma(-l_q, v_r, M[q][r]) in pivot order, so there is no reduction whose order a
  * parallel implementation could change: the CUDA kernel reproduces the result bit for bit. */
 typedef struct {
-    const double *a; /* node values */
-    int lda, st, N, mirror;
+    const double *a; /* node values, row j (y) has stride lda */
+    int lda, stx, sty, Nx, Ny, mirror;
+    double wx, wy; /* 1/hx^2 = Nx^2, 1/hy^2 = Ny^2 */
 } field2d;
 static inline double F2(const field2d *f, int i, int j) {
-    int jj = f->mirror ? f->N - j : j;
-    return f->a[(size_t)(jj * f->st) * f->lda + (size_t)i * f->st];
+    int jj = f->mirror ? f->Ny - j : j;
+    return f->a[(size_t)(jj * f->sty) * f->lda + (size_t)i * f->stx];
 }
-static inline double KX(const field2d *f, int i, int j) { return 0.5 * (F2(f, i, j) + F2(f, i + 1, j)); } /* (i,j)-(i+1,j) */
-static inline double KY(const field2d *f, int i, int j) { return 0.5 * (F2(f, i, j) + F2(f, i, j + 1)); } /* (i,j)-(i,j+1) */
+/* scaled edge coefficients: x-edge (i,j)-(i+1,j) and y-edge (i,j)-(i,j+1); every product and sum rounded on its own */
+static inline double KX(const field2d *f, int i, int j) { double k = 0.5 * (F2(f, i, j) + F2(f, i + 1, j)); return f->wx * k; }
+static inline double KY(const field2d *f, int i, int j) { double k = 0.5 * (F2(f, i, j) + F2(f, i, j + 1)); return f->wy * k; }
 static inline double DIAG2(const field2d *f, int i, int j) {
     return ((KX(f, i - 1, j) + KX(f, i, j)) + KY(f, i, j - 1)) + KY(f, i, j);
 }
 
-/* one half sweep; on return S[n*n], gs[n] hold this half's centre-line block (row-major, unknowns i = 1..n) */
-static void frontal_half(const field2d *f, double h2, double *M, double *g, double *l, double *v, double *S, double *gs) {
-    const int N = f->N, n = N - 1, c = N / 2, W = n + 1;
+/* one half sweep over the lines 1..c-1 (c = Ny/2); on return S[n*n], gs[n] hold this half's centre-line block
+ * (row-major, unknowns i = 1..n, n = Nx-1) */
+static void frontal_half(const field2d *f, double *M, double *g, double *l, double *v, double *S, double *gs) {
+    const int n = f->Nx - 1, c = f->Ny / 2, W = n + 1;
     const int P = (c - 1) * n;     /* pivots of this half */
     const int last = P + n - 1;    /* last unknown (end of the centre line) */
 #define SLOT(e) ((e) % W)
@@ -539,7 +542,7 @@ static void frontal_half(const field2d *f, double h2, double *M, double *g, doub
         int own_ = !(centre_ && f->mirror); /* the centre line's own entries are loaded once */  \
         for (int t_ = 0; t_ < W; ++t_) { M[se_ * W + t_] = 0.0; M[t_ * W + se_] = 0.0; }         \
         M[se_ * W + se_] = own_ ? DIAG2(f, ie_, je_) : 0.0;                                      \
-        g[se_] = own_ ? h2 : 0.0;                                                                \
+        g[se_] = own_ ? 1.0 : 0.0;                                                               \
         if (ie_ > 1 && own_) { double k_ = -KX(f, ie_ - 1, je_); M[se_ * W + SLOT((e)-1)] = k_; M[SLOT((e)-1) * W + se_] = k_; } \
         if (je_ > 1) { double k_ = -KY(f, ie_, je_ - 1); M[se_ * W + SLOT((e)-n)] = k_; M[SLOT((e)-n) * W + se_] = k_; }         \
     } while (0)
@@ -565,17 +568,17 @@ static void frontal_half(const field2d *f, double h2, double *M, double *g, doub
 #undef SLOT
 }
 
-static double frontal_mid(const double *a, int lda, int st, int N) {
-    const int n = N - 1, c = N / 2, W = n + 1, tc = c - 1;
-    const double h2 = 1.0 / ((double)N * (double)N);
+/* u at the centre node (Nx/2, Ny/2) of the Nx x Ny-cell grid whose node values are a[(j*sty)*lda + i*stx] */
+static double frontal_mid(const double *a, int lda, int stx, int sty, int Nx, int Ny) {
+    const int n = Nx - 1, W = n + 1, tc = Nx / 2 - 1;
     double *M = (double *)malloc(sizeof(double) * (size_t)W * W), *g = (double *)malloc(sizeof(double) * (size_t)W);
     double *l = (double *)malloc(sizeof(double) * (size_t)W), *v = (double *)malloc(sizeof(double) * (size_t)W);
     double *S = (double *)malloc(sizeof(double) * (size_t)n * n), *gs = (double *)malloc(sizeof(double) * (size_t)n);
     double *S2 = (double *)malloc(sizeof(double) * (size_t)n * n), *gs2 = (double *)malloc(sizeof(double) * (size_t)n);
-    field2d f = {a, lda, st, N, 1};
-    frontal_half(&f, h2, M, g, l, v, S2, gs2); /* upper half first (y-mirrored field) */
+    field2d f = {a, lda, stx, sty, Nx, Ny, 1, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
+    frontal_half(&f, M, g, l, v, S2, gs2); /* upper half first (y-mirrored field) */
     f.mirror = 0;
-    frontal_half(&f, h2, M, g, l, v, S, gs);   /* lower half */
+    frontal_half(&f, M, g, l, v, S, gs);   /* lower half */
     for (int q = 0; q < n; ++q) {
         gs[q] = gs[q] + gs2[q];
         for (int r = 0; r < n; ++r) S[q * n + r] = S[q * n + r] + S2[q * n + r];
@@ -602,14 +605,24 @@ static double frontal_mid(const double *a, int lda, int st, int N) {
     return u;
 }
 
-ORC_API double orc_frontal_mid(const double *a, int lda, int st, int N) { return frontal_mid(a, lda, st, N); }
+ORC_API double orc_frontal_mid(const double *a, int lda, int st, int N) { return frontal_mid(a, lda, st, st, N, N); }
+ORC_API double orc_frontal_mid_rect(const double *a, int lda, int stx, int sty, int Nx, int Ny) {
+    return frontal_mid(a, lda, stx, sty, Nx, Ny);
+}
 
-static int lognormal2d_eval(const orc_model *M, int level, const double *xi, int m, double *dQ, double *Qf) {
-    const double *Phi = M->basis[level];
+/* index = (l) for the multilevel model (Nx = Ny = n0 2^l) or (lx, ly) for the multi-index model (Nx = n0 2^lx,
+ * Ny = n0 2^ly, anisotropic coarsening as in docs/src/example.md:221-243); the KL basis of an index is stored under the key
+ * lx + 16*ly.  dQ = Qf + sum over diff(index) of +-Q_kappa, coarse fields = strided views of the fine field
+ * (`step = (index - key).I .+ 1`), added in the order (lx-1, ly-1), (lx, ly-1), (lx-1, ly). */
+static int lognormal2d_eval(const orc_model *M, const int *index, const double *xi, int m, double *dQ, double *Qf) {
+    const int lx = index[0], ly = M->ndims == 2 ? index[1] : index[0];
+    const int key = M->ndims == 2 ? lx + 16 * ly : lx;
+    if (key < 0 || key >= ORC_MAX_LEVELS) return -3;
+    const double *Phi = M->basis[key];
     if (!Phi) return -3;
-    const int N = M->n0 << level, nodes = (N + 1) * (N + 1);
-    if (M->basis_rows[level] != nodes || M->basis_cols[level] < m) return -3;
-    const int ld = M->basis_cols[level];
+    const int Nx = M->n0 << lx, Ny = M->n0 << ly, nodes = (Nx + 1) * (Ny + 1);
+    if (M->basis_rows[key] != nodes || M->basis_cols[key] < m) return -3;
+    const int ld = M->basis_cols[key];
     double *a = (double *)malloc(sizeof(double) * (size_t)nodes);
     for (int i = 0; i < nodes; ++i) {
         double gsum = 0.0;
@@ -617,10 +630,17 @@ static int lognormal2d_eval(const orc_model *M, int level, const double *xi, int
         for (int k = 0; k < m; ++k) gsum = fma(row[k], xi[k], gsum);
         a[i] = orc_exp(gsum);
     }
-    const double qf = frontal_mid(a, N + 1, 1, N);
+    const double qf = frontal_mid(a, Nx + 1, 1, 1, Nx, Ny);
     *Qf = qf;
-    *dQ = qf;
-    if (level > 0) *dQ = qf - frontal_mid(a, N + 1, 2, N / 2);
+    double dq = qf;
+    if (M->ndims == 1) {
+        if (lx > 0) dq = qf - frontal_mid(a, Nx + 1, 2, 2, Nx / 2, Ny / 2);
+    } else {
+        if (lx > 0 && ly > 0) dq = dq + frontal_mid(a, Nx + 1, 2, 2, Nx / 2, Ny / 2);
+        if (ly > 0) dq = dq - frontal_mid(a, Nx + 1, 1, 2, Nx, Ny / 2);
+        if (lx > 0) dq = dq - frontal_mid(a, Nx + 1, 2, 1, Nx / 2, Ny);
+    }
+    *dQ = dq;
     free(a);
     return 0;
 }
@@ -666,7 +686,7 @@ ORC_API int orc_model_eval(const orc_model *M, const int *index, const double *x
         return rc;
     }
     case ORC_MODEL_LOGNORMAL2D:
-        return lognormal2d_eval(M, index[0], xi, m, dQ, Qf);
+        return lognormal2d_eval(M, index, xi, m, dQ, Qf);
     default:
         return -4;
     }

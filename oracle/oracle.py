@@ -66,6 +66,8 @@ def lib():
         L.orc_tridiag_mid.argtypes = [dp, C.c_int, C.c_int]
         L.orc_frontal_mid.restype = C.c_double
         L.orc_frontal_mid.argtypes = [dp, C.c_int, C.c_int, C.c_int]
+        L.orc_frontal_mid_rect.restype = C.c_double
+        L.orc_frontal_mid_rect.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_tridiag_mid_full.restype = C.c_double
         L.orc_tridiag_mid_full.argtypes = [dp, C.c_int]
         L.orc_sample_batch.restype = C.c_int
@@ -161,6 +163,9 @@ class Model:
         self.nqoi = lib().orc_model_nqoi(self.h)
 
     def set_basis(self, level, phi):
+        """level: int, or (lx, ly) for the multi-index 2-D model (stored under lx + 16*ly)"""
+        if not isinstance(level, (int, np.integer)):
+            level = int(level[0]) + 16 * int(level[1])
         phi = np.ascontiguousarray(phi, dtype=np.float64)
         rc = lib().orc_model_set_basis(self.h, level, phi.shape[0], phi.shape[1], _dp(phi))
         assert rc == 0

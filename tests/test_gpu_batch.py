@@ -224,6 +224,71 @@ def test_lognormal2d_mc(engine, oracle):
     check_moments(got, want)
 
 
+def lognormal2d_mi_setup(engine, oracle, m, index, n0=4):
+    """multi-index 2-D model: bases for the index and the coarser grids of diff(index)"""
+    import mle_b200.kl as kl
+    z = oracle.genvec("K_3600_32", m)
+    gm = engine.model("lognormal2d", 2, [n0])
+    om = oracle.Model(oracle.MODEL_LOGNORMAL2D, 2, [float(n0)])
+    phi = kl.kl_basis_2d(tuple(index), m=m, n0=n0)
+    gm.set_basis(tuple(index), phi)
+    om.set_basis(tuple(index), phi)
+    return z, engine.lattice(z, m), [NORMAL01] * m, engine.dists([NORMAL01] * m), gm, om
+
+
+@pytest.mark.parametrize("index,R,n,m", [((0, 0), 2, 33, 40), ((1, 0), 2, 40, 40), ((0, 1), 3, 40, 40), ((1, 1), 2, 40, 40), ((2, 1), 2, 21, 40),
+                                         ((0, 3), 2, 9, 40), ((3, 0), 2, 9, 40), ((2, 3), 1, 7, 32), ((4, 1), 1, 3, 24), ((1, 4), 1, 3, 24),
+                                         ((5, 0), 1, 2, 16), ((0, 6), 1, 2, 16)])
+def test_lognormal2d_multi_index(engine, oracle, index, R, n, m):
+    """config C4 shape: anisotropic grids 4*2^lx x 4*2^ly, mixed differences over diff(index) (src/index.jl:49-58) from
+    strided views of the one fine field; per-sample (dQ, Qf) bit-identical to the oracle"""
+    z, lat, dl, d, gm, om = lognormal2d_mi_setup(engine, oracle, m, index)
+    sh = splitmix_uniforms(404, R * m).reshape(R, m)
+    got, smp = engine.sample_batch(gm, lat, d, list(index), sh, 3, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, list(index), sh, 3, n, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
+
+
+def test_lognormal2d_multi_index_telescopes(engine, oracle):
+    """sum of dQ over the full tensor index set {0..2}^2 equals Qf of the finest index, sample by sample (same inputs, nested
+    grids): the defining property of the multi-index difference"""
+    import mle_b200.kl as kl
+    m, n = 24, 16
+    z = oracle.genvec("K_3600_32", m)
+    gm = engine.model("lognormal2d", 2, [4])
+    lat, d = engine.lattice(z, m), engine.dists([NORMAL01] * m)
+    sh = splitmix_uniforms(5, m).reshape(1, m)
+    fine = kl.kl_basis_2d((2, 2), m=m, n0=4).reshape(17, 17, m)
+    total = np.zeros(n)
+    for lx in range(3):
+        for ly in range(3):
+            # nested bases: the coarse grid's nodes are a strided subset of the finest grid's
+            phi = fine[:: 2 ** (2 - ly), :: 2 ** (2 - lx), :].reshape(-1, m)
+            gm.set_basis((lx, ly), phi)
+            _, smp = engine.sample_batch(gm, lat, d, [lx, ly], sh, 0, n, want_samples=True)
+            total += smp[0, 0, 0]
+            if (lx, ly) == (2, 2):
+                qf = smp[0, 0, 1].copy()
+    assert np.allclose(total, qf, rtol=1e-12, atol=0)
+
+
+def test_lognormal2d_argument_errors(engine):
+    import mle_b200
+    import mle_b200.kl as kl
+    gm = engine.model("lognormal2d", 2, [4])
+    with pytest.raises(mle_b200.MLEArgumentError):
+        gm.set_basis((1, 0), np.zeros((5 * 5, 8)))       # rows must be 9 x 5 nodes
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.model("lognormal2d", 3, [4])
+    gm.set_basis((1, 0), kl.kl_basis_2d((1, 0), m=8))
+    lat, d = engine.lattice(None, 8), engine.dists([NORMAL01] * 8)
+    with pytest.raises(mle_b200.MLEError):
+        engine.sample_batch(gm, lat, d, [0, 1], np.zeros((1, 8)), 0, 4)   # no basis for (0, 1)
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.sample_batch(gm, lat, d, [1], np.zeros((1, 8)), 0, 4)      # index dimension mismatch
+
+
 @pytest.mark.parametrize("m,level", [(200, 1), (300, 0), (129, 2)])
 def test_lognormal1d_many_kl_terms(engine, oracle, m, level):
     """more than 128 KL terms: the generator switches to 64-bit class masks and multiple passes over the dimensions"""

@@ -1,0 +1,15 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import mle_b200, mle_b200.kl as kl
+eng = mle_b200.Engine(0)
+m = 400
+d = eng.dists([(1, [0.0, 1.0])] * m)
+gm = eng.model("lognormal2d", 1, [4])
+mom = torch.zeros(6, dtype=torch.float64, device="cuda")
+for lev, n in ((0, 1 << 17), (2, 1 << 14)):
+    gm.set_basis(lev, kl.kl_basis_2d(lev, m=m))
+    for rep in range(2):
+        eng.sample_batch_dev(gm, None, d, [lev], None, 1, 0, n, m, mom.data_ptr(), mc_seed=1)
+    eng.sync()
+print("ok")
