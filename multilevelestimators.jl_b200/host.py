@@ -17,6 +17,7 @@ Out of scope: AD and U index sets, printing, JLD2 output, `sav
 The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
 """
 import math
+import random as _random
 import time as _time
 
 import numpy as np
@@ -81,6 +82,19 @@ class ZC(_Weighted):  # Zaremba cross, src/index_set.jl:180
         if sz == 0:
             return all(i == 0 for i in idx)
         return math.prod(max(1.0, i / w) for w, i in zip(self.weights, idx)) <= sz
+
+
+class AD:
+    """adaptive index set AD(d), src/index_set.jl:195-210: no a-priori shape; grown one index at a time by profit
+    (src/methods.jl:206-251) inside `max_search_space` at size `max_index_set_param`"""
+
+    def __init__(self, d):
+        if d <= 1:
+            raise ValueError("to use AD, dimension must be greater than 1, got %d" % d)
+        self.ndims = int(d)
+
+    def get_index_set(self, sz):
+        raise NotImplementedError("get_index_set not implemented for index sets of type AD")  # src/index_set.jl:259
 
 
 def is_admissable(index_set, index):
@@ -219,7 +233,8 @@ _DEFAULTS = dict(nb_of_qoi=None, aggregation="max", qoi_with_max_var=1, continua
                  do_mse_splitting=True, do_regression=True, min_index_set_param=2, max_index_set_param=None,
                  sample_mul_factor=1.2, nb_of_warm_up_samples=None, nb_of_shifts=10, nb_of_uncertainties=None,
                  cost_model=None, point_generator=None, shifts=None, shift_seed=0, mc_seed=1, name="UntitledEstimator",
-                 verbose=False)
+                 verbose=False, max_search_space=None, penalization=0.5, acceptance_rate=1.0)
+_AD_ONLY = ("max_search_space", "penalization", "acceptance_rate")  # src/options.jl:36
 
 
 class Estimator:
@@ -233,6 +248,9 @@ class Estimator:
         unknown = set(options) - set(_DEFAULTS)
         if unknown:
             raise ValueError("in Estimator, invalid option %s" % sorted(unknown))  # src/estimator.jl:127-131
+        self.adaptive = isinstance(index_set, AD)
+        if not self.adaptive and any(k in options for k in _AD_ONLY):
+            raise ValueError("in Estimator, invalid option %s" % sorted(set(options) & set(_AD_ONLY)))
         o = dict(_DEFAULTS)
         o.update(options)
         self.index_set, self.sample_method, self.spec, self.distributions, self.backend = (
@@ -257,6 +275,14 @@ class Estimator:
             raise ValueError("in Estimator, optional key aggregation must be 'sum', 'max' or 'norm'")
         if not (0 < o["min_splitting"] <= o["max_splitting"] <= 1):
             raise ValueError("in Estimator, min_splitting / max_splitting must satisfy 0 < min <= max <= 1")
+        if self.adaptive:
+            if o["max_search_space"] is None:
+                o["max_search_space"] = TD(d)                           # src/parse.jl:263-264
+            if getattr(o["max_search_space"], "ndims", None) != d:
+                raise ValueError("in Estimator, dimensions of max_search_space must be equal to %d" % d)  # src/parse.jl:267
+            for key in ("penalization", "acceptance_rate"):
+                if not (math.isfinite(o[key]) and 0 <= o[key] <= 1):
+                    raise ValueError("in Estimator, optional key %s must be in [0, 1]" % key)  # src/parse.jl:277-297
         self.options = o
         self.model = backend.model(sample_function)
         self.nqoi = o["nb_of_qoi"] or getattr(self.model, "nqoi", 1)
@@ -267,7 +293,13 @@ class Estimator:
             z = o["point_generator"]  # a generating vector; None -> default LatticeRule32(s), src/parse.jl:251-254
             self.lattice = backend.lattice(z, s)
         # internals (src/internals.jl:35-54): per index cumulative moments [R, q, 2, 3], counters, and one shift per (index, r)
-        box = index_set.get_index_set(o["max_index_set_param"])
+        space = o["max_search_space"] if self.adaptive else index_set   # src/internals.jl:36,133
+        box = space.get_index_set(o["max_index_set_param"])
+        self.search_space = set(box)
+        # ADInternals, src/internals.jl:150-171
+        self.old_set, self.active_set, self.max_index_set, self.logbook = set(), set(), set(), []
+        self.ad_boundary = {(0,) * d}
+        self._ad_rng = _random.Random(o["shift_seed"])
         self.moments, self.nb_of_samples, self.total_work, self.total_time = {}, {}, {}, {}
         self.shifts = {}
         rng = np.random.default_rng(o["shift_seed"])
@@ -457,6 +489,61 @@ class Estimator:
     def optimal_nb_of_samples(self, index, eps, theta):
         return self._n_opt(eps, theta, self.var(index), self.cost(index), self.Sigma())
 
+    # ---- adaptivity (src/methods.jl:206-261) -------------------------------------------------------------------------------
+    def profit(self, index):
+        return abs(self.mean(index)) / math.sqrt(self.var(index) * self.cost(index)) ** self.options["penalization"]
+
+    def find_index_with_max_profit(self):
+        indices = sorted(self.active_set, key=lambda t: t[::-1])
+        profits = [self.profit(i) for i in indices]
+        best = int(np.argmax(profits))
+        if self._ad_rng.random() < self.options["acceptance_rate"] or len(profits) == 1:
+            return indices[best]
+        return indices[self._ad_rng.choice([t for t in range(len(profits)) if t != best])]
+
+    def new_index_set(self, sz):
+        """the indices entering at iteration sz: the boundary of the a-priori set, or, for AD, the index with the largest
+        profit moves from the active to the old set and its admissable forward neighbours become active"""
+        if not self.adaptive:
+            return self.boundary(sz)
+        d = self.index_set.ndims
+        if not self.active_set:
+            max_index = (0,) * d
+            self.active_set.add(max_index)
+            new = [max_index]
+        else:
+            max_index = self.find_index_with_max_profit()
+            self.old_set.add(max_index)
+            self.active_set.discard(max_index)
+            new = [max_index]
+            for k in range(d):
+                nb = tuple(v + (1 if t == k else 0) for t, v in enumerate(max_index))
+                if is_admissable(self.old_set, nb):
+                    if nb in self.search_space:
+                        self.active_set.add(nb)
+                        new.append(nb)
+                    else:
+                        self.max_index_set.add(nb)  # outside the search space: ignored (src/print.jl:247)
+        self.logbook.append((set(self.old_set), set(self.active_set), max_index))
+        return new
+
+    def set_sz(self, n):  # src/internals.jl:256-262
+        if self.adaptive and n > self.max_sz:
+            self.ad_boundary = set(self.active_set)
+        self.sz, self.max_sz = n, max(n, self.max_sz)
+
+    def max_level_exceeded(self):  # src/methods.jl:208, :203
+        if self.adaptive:
+            return not (self.search_space - self.current_index_set)
+        return self.sz >= self.options["max_index_set_param"]
+
+    def clear(self):  # src/internals.jl:116, :200-206: samples persist across tolerances, the index sets do not
+        self.current_index_set.clear()
+        self.active_set.clear()
+        self.old_set.clear()
+        self.max_index_set.clear()
+        self.logbook.clear()
+
     def boundary(self, cntr):
         prev = set(self.index_set.get_index_set(cntr - 1)) if cntr > 0 else set()
         return [i for i in self.index_set.get_index_set(cntr) if i not in prev]
@@ -465,6 +552,9 @@ class Estimator:
         if isinstance(self.index_set, SL):
             return 0.0
         sz = self.sz if sz is None else sz
+        if self.adaptive:  # src/methods.jl:253-260
+            b = lambda indices: abs(sum(self.mean(i) for i in sorted(indices, key=lambda t: t[::-1])))
+            return b(self.active_set) if sz != self.max_sz else min(b(self.active_set), b(self.ad_boundary))
         nxt = [i for i in self.boundary(sz + 1) if i in self.current_index_set]
         if nxt and not self.options["robustify_bias_estimate"]:
             return abs(sum(self.mean(i) for i in self.boundary(sz + 1)))
@@ -541,13 +631,13 @@ def _run(est, eps):  # src/run.jl:41-142
     theta = 0.5 if sl else est["min_splitting"]
     done = False
     while not done:
-        index_set = est.boundary(L)
+        index_set = est.new_index_set(L)
         ns = est.regress_nb_of_samples(index_set, eps, theta, L)
         for index in index_set:
             if not est.has_samples_at_index(index):
                 est.sample(index, ns[index])
         est.current_index_set.update(index_set)
-        est.sz, est.max_sz = L, max(L, est.max_sz)
+        est.set_sz(L)
         theta = 0.5 if sl else (est.compute_splitting(eps) if est["do_mse_splitting"] else est["min_splitting"])
         if not est.qmc:
             n_opt = {i: est.optimal_nb_of_samples(i, eps, theta) for i in est.keys()}
@@ -560,10 +650,12 @@ def _run(est, eps):  # src/run.jl:41-142
             done = True
         else:
             done = L > est["min_index_set_param"] and est.converged(eps, theta)
-            if not done and est.sz >= est["max_index_set_param"]:
+            if not done and est.max_level_exceeded():
                 done = True
             elif not done:
                 L += 1
+    if est.adaptive:
+        est.ad_boundary = set(est.active_set)  # update_boundary, src/run.jl:138
 
 
 def update_history(history, est, tol, elapsed):  # src/history.jl:55-103
@@ -578,6 +670,8 @@ def update_history(history, est, tol, elapsed):  # src/history.jl:55-103
          "nb_of_samples": dict(est.nb_of_samples)}
     if est["cost_model"] is not None:
         h["W"] = {i: est.cost(i) for i in allk}
+    if est.adaptive:
+        h["logbook"] = list(est.logbook)  # src/history.jl:87
     history.data.append(h)
 
 
@@ -588,7 +682,7 @@ def run(est, tol):
         raise ValueError("in run, supplied tolerance(s) must be larger than 0")  # src/run.jl:23
     history = History()
     for t in tols:
-        est.current_index_set.clear()  # clear(estimator), src/internals.jl:116: samples persist across tolerances
+        est.clear()
         t0 = _time.perf_counter()
         _run(est, t)
         update_history(history, est, t, _time.perf_counter() - t0)

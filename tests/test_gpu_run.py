@@ -90,3 +90,21 @@ def test_mlmc_lognormal2d_run_matches_oracle(engine):
     hg, ho = H.run(g, 2e-3), H.run(o, 2e-3)
     compare(hg, ho)
     assert 0.05 < hg["mean"] < 0.09
+
+
+def test_adaptive_multi_index_lognormal2d_run_matches_oracle(engine):
+    """config C4 at test size: AD(2)/QMC, 2-D lognormal diffusion with anisotropic multi-index differences; the adaptive
+    index-set construction on the device follows the oracle's step for step (same profits -> same logbook)"""
+    import mle_b200.kl as kl
+
+    def make(H, backend):
+        bases = {i: kl.kl_basis_2d(i, m=40) for i in H.TD(2).get_index_set(3)}
+        spec = H.ModelSpec("lognormal2d", 2, [4], bases)
+        return H.Estimator(H.AD(2), H.QMC(), spec, [H.Normal()] * 40, backend, max_index_set_param=3, nb_of_shifts=8,
+                           nb_of_warm_up_samples=8, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3, min_index_set_param=1)
+
+    H, g, o = both(engine, make)
+    hg, ho = H.run(g, 2e-3), H.run(o, 2e-3)
+    compare(hg, ho)
+    assert hg["logbook"] == ho["logbook"]
+    assert 0.05 < hg["mean"] < 0.09

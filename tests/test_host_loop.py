@@ -154,3 +154,73 @@ def test_two_rank_sharding_matches_single_rank(tmp_path):
     assert got[2] == float(sum(h["nb_of_samples"].values()))      # identical decisions
     assert abs(got[0] - h["mean"]) <= 1e-12 * abs(h["mean"])
     assert abs(got[1] - h["varest"]) <= 1e-9 * abs(h["varest"])
+
+
+def test_adaptive_index_set_mechanics():
+    """src/methods.jl:223-251 and test/index_set.jl:54-60: AD starts from the root index, moves the index with the largest
+    profit into the old set, activates its admissable forward neighbours inside max_search_space, and logs every step"""
+    H = host()
+    with pytest.raises(ValueError):
+        H.AD(1)
+    with pytest.raises(NotImplementedError):
+        H.AD(2).get_index_set(3)
+    spec = H.ModelSpec("problem18", 2)
+    be = OracleBackend()
+    with pytest.raises(ValueError):
+        H.Estimator(H.TD(2), H.MC(), spec, [H.Uniform(-0.5, 0.5)] * 2, be, penalization=0.5)     # AD-only key, src/options.jl:36
+    with pytest.raises(ValueError):
+        H.Estimator(H.AD(2), H.MC(), spec, [H.Uniform(-0.5, 0.5)] * 2, be, max_search_space=H.TD(3))
+    with pytest.raises(ValueError):
+        H.Estimator(H.AD(2), H.MC(), spec, [H.Uniform(-0.5, 0.5)] * 2, be, acceptance_rate=1.5)
+    est = H.Estimator(H.AD(2), H.MC(), spec, [H.Uniform(-0.5, 0.5)] * 2, be, nb_of_qoi=13, max_index_set_param=3,
+                      cost_model=lambda i: 2.0 ** sum(i))
+    assert isinstance(est["max_search_space"], H.TD) and est["penalization"] == 0.5 and est["acceptance_rate"] == 1.0
+    first = est.new_index_set(0)
+    assert first == [(0, 0)] and est.active_set == {(0, 0)} and not est.old_set
+    est.sample((0, 0), 20)
+    est.current_index_set.update(first)
+    second = est.new_index_set(1)
+    assert second[0] == (0, 0) and set(second[1:]) == {(1, 0), (0, 1)}
+    assert est.old_set == {(0, 0)} and est.active_set == {(1, 0), (0, 1)}
+    assert est.logbook[-1][2] == (0, 0) and len(est.logbook) == 2
+    for i in second[1:]:
+        est.sample(i, 20)
+    est.current_index_set.update(second)
+    third = est.new_index_set(2)
+    # (1, 1) is not admissable until both (1, 0) and (0, 1) are old
+    assert (1, 1) not in third and len(est.old_set) == 2
+
+
+@pytest.mark.parametrize("method", ["MC", "QMC"])
+def test_regression_problem18_adaptive(method):
+    """test/regression.jl:105-121 shape: run(Estimator(AD(2), MC()/QMC(), problem_18, ...; max_index_set_param = 3)) completes
+    with a downward-closed index set inside the TD search space and a logbook in the History"""
+    H = host()
+    est = H.Estimator(H.AD(2), getattr(H, method)(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(),
+                      nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=4)
+    h = H.run(est, 1e-2)
+    assert len(h) == 4 and "logbook" in h and h["type"] == "Estimator{AD, %s}" % method
+    cur = set(h["current_index_set"])
+    space = set(H.TD(2).get_index_set(3))
+    assert (0, 0) in cur and cur <= space
+    for idx in cur:                                       # downward closed
+        for k in range(2):
+            if idx[k] > 0:
+                assert tuple(v - (t == k) for t, v in enumerate(idx)) in cur
+    old, active, _ = h["logbook"][-1]
+    assert old | active == cur and not (old & active)
+    assert h["rmse"] <= 2e-2 or cur == space
+
+
+def test_adaptive_lognormal2d_multi_index_run():
+    """config C4 at test size: AD(2)/QMC on the anisotropic 2-D lognormal problem (multi-index differences), oracle backend"""
+    import mle_b200.kl as kl
+    H = host()
+    m = 20
+    bases = {i: kl.kl_basis_2d(i, m=m) for i in H.TD(2).get_index_set(2)}
+    spec = H.ModelSpec("lognormal2d", 2, [4], bases)
+    est = H.Estimator(H.AD(2), H.QMC(), spec, [H.Normal()] * m, OracleBackend(), max_index_set_param=2, nb_of_shifts=4,
+                      nb_of_warm_up_samples=4, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=2, min_index_set_param=1)
+    h = H.run(est, 5e-3)
+    assert 0.05 < h["mean"] < 0.09 and h["ndims"] == 2
+    assert all(abs(h["dE"][i]) < abs(h["dE"][(0, 0)]) for i in h["index_set"] if i != (0, 0))
