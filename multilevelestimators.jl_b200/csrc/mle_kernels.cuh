@@ -113,7 +113,8 @@ struct SimpleModelArgs {
 };
 
 constexpr int SIMPLE_THREADS = 128;       // = points per tile: every thread owns one point
-constexpr int SIMPLE_MC = 64;             // dims per chunk; tile[jj][point] (point fastest: conflict-free)
+constexpr int SIMPLE_MC = 32;             // dims per chunk; tile[jj][point] (point fastest: conflict-free); 32 dims =
+                                          // one 32-bit class mask per thread and 40 KB per CTA (5 CTAs per SM)
 
 // problem_18                                                      test/regression.jl:17-36 (1-d), :69-103 (2-d)
 __device__ __forceinline__ double p18_coef(int l, double xj) {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g
         for (int j0 = 0; j0 < g.m; j0 += SIMPLE_MC) {
             const int mc = min(SIMPLE_MC, g.m - j0);
             // always a full tile of points: surplus points (tid >= Pt) are masked out of the statistics
-            gen_tile_owned<THREADS, THREADS, MODE>(tile, j0, mc, g.k0 + i0, g, r, sc);
+            gen_tile_owned<THREADS, THREADS, MODE, THREADS, unsigned, 4>(tile, j0, mc, g.k0 + i0, g, r, sc);
             if (MODEL == MODEL_EXPSUM) {
                 for (int jj = 0; jj < mc; ++jj) {
                     const int j = j0 + jj;
@@ -404,9 +405,14 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
     sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * BT);       // [W]
     // generator queue [BT * min(m, 256)]: lives inside F when it fits (F is idle while the inputs are generated)
     const int qbytes = BT * (g.m < 256 ? ((g.m + 3) & ~3) : 256) * 2;
-    sc.queue = qbytes <= RC * LDF * 8 ? reinterpret_cast<unsigned short *>(F) : reinterpret_cast<unsigned short *>(sc.wtot + W);
+    // {z_j, shift_j} of this CTA's shift (lattice modes), 16-byte aligned behind wtot; then the queue when it does not fit in F
+    double2 *zs = reinterpret_cast<double2 *>(sc.wtot + ((W + 3) & ~3));
+    constexpr bool lattice = (MODE & GEN_MC) == 0;
+    unsigned short *qtail = reinterpret_cast<unsigned short *>(zs + (lattice ? g.m : 0));
+    sc.queue = qbytes <= RC * LDF * 8 ? reinterpret_cast<unsigned short *>(F) : qtail;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
+    if (lattice) stage_lattice_row<THREADS>(zs, g, r);
     const int M = la.N / 2;  // mid node
     const int nks = mpad >> 2;
     // warp -> 2x2 block of 8x8 tiles inside the RC x BT chunk: row tiles {2*wr, 2*wr+1}, sample tiles {2*wc, 2*wc+1}
@@ -426,11 +432,11 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         // A. inputs (always a full tile: surplus points are masked out of the statistics)
         if (la.skip & 1) {
         } else if (g.m <= 32 * (THREADS / BT)) {  // at most 32 dims per thread: 32-bit class masks
-            gen_tile_owned<THREADS, BT, MODE, LDX, unsigned, LN_GEN_U>(xi, 0, g.m, g.k0 + i0, g, r, sc);
+            gen_tile_owned<THREADS, BT, MODE, LDX, unsigned, LN_GEN_U, lattice>(xi, 0, g.m, g.k0 + i0, g, r, sc, zs);
         } else {
             constexpr int GEN_DIMS = 64 * (THREADS / BT);  // 64 iterations per thread fit the 64-bit class masks
             for (int j0 = 0; j0 < g.m; j0 += GEN_DIMS)
-                gen_tile_owned<THREADS, BT, MODE, LDX, unsigned long long, LN_GEN_U>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc);
+                gen_tile_owned<THREADS, BT, MODE, LDX, unsigned long long, LN_GEN_U, lattice>(xi + (size_t)j0 * LDX, j0, min(GEN_DIMS, g.m - j0), g.k0 + i0, g, r, sc, zs);
         }
 
         MLE_PH(0);
