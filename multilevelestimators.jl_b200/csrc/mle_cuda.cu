@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "mle_kernels.cuh"
+#include "mle_kernels2d.cuh"
 #include "../../include/mle_genvec_data.inc"
 
 using namespace mle;
@@ -26,6 +27,11 @@ template <int MODE> static constexpr auto lognormal1d_ws = lognormal1d_ws_kernel
 #endif
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
+template <int MODE> static constexpr auto lognormal2d_r4 = lognormal2d_rows_kernel<MODE, 4>;
+template <int MODE> static constexpr auto lognormal2d_r8 = lognormal2d_rows_kernel<MODE, 8>;
+template <int MODE> static constexpr auto lognormal2d_r16 = lognormal2d_rows_kernel<MODE, 16>;
+template <int MODE> static constexpr auto lognormal2d_r32 = lognormal2d_rows_kernel<MODE, 32>;
+template <int MODE> static constexpr auto lognormal2d_r64 = lognormal2d_rows_kernel<MODE, 64>;
 // mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
 #define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
     do {                                                                                       \
@@ -67,6 +73,7 @@ struct mle_ctx_s {
     uint64_t launches = 0;
     int ln_bt_override = 0;  // MLE_LN_BT=32|64 in the environment: tuning knob for the lognormal1d tile width
     int ln_ws = 0;           // MLE_LN_WS=1: warp-specialised lognormal1d kernel
+    int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
     // reusable device / pinned scratch
     Moment *d_partials = nullptr;
     size_t partials_cap = 0;  // in Moments
@@ -106,6 +113,10 @@ struct mle_model_s {
     int basis_cols[MLE_MAX_LEVELS] = {};
     int basis_mpad[MLE_MAX_LEVELS] = {};
     int basis_nchunks[MLE_MAX_LEVELS] = {};
+    // lognormal2d, power-of-two Nx <= 64: the basis in DMMA A-fragment order [node tile][k step][lane]
+    double *d_frag[MLE_MAX_LEVELS] = {};
+    int frag_tiles[MLE_MAX_LEVELS] = {};
+    int frag_mpad[MLE_MAX_LEVELS] = {};
 };
 
 static thread_local std::string g_init_err;
@@ -227,10 +238,16 @@ extern "C" int mle_init(int device, mle_ctx *out) {
 #endif
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_r4, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_r8, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_r16, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_r32, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_r64, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     if (const char *e = getenv("MLE_LN_BT")) { int v = atoi(e); if (v == 32 || v == 64) ctx->ln_bt_override = v; }
     if (const char *e = getenv("MLE_LN_WS")) ctx->ln_ws = atoi(e) != 0;
+    if (const char *e = getenv("MLE_2D_WINDOW_SMEM")) ctx->ln2d_old = atoi(e) != 0;
     *out = ctx;
     return MLE_OK;
 }
@@ -487,6 +504,22 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
         M->basis_cols[level] = cols;
         M->basis_mpad[level] = (int)npad;
         M->basis_nchunks[level] = 0;
+        if (M->d_frag[level]) { cudaFree(M->d_frag[level]); M->d_frag[level] = nullptr; }
+        if (Nx >= 4 && Nx <= 64 && (Nx & (Nx - 1)) == 0) {  // register-window kernel: fragment-ordered copy
+            const int mpad = (cols + 3) & ~3, nks = mpad / 4, ntiles = (int)((nodes + 7) / 8);
+            std::vector<double> packed((size_t)ntiles * nks * 32, 0.0);
+            for (long long nd = 0; nd < nodes; ++nd)
+                for (int k = 0; k < cols; ++k)
+                    packed[((size_t)(nd / 8) * nks + k / 4) * 32 + (nd % 8) * 4 + (k % 4)] = phi[(size_t)nd * cols + k];
+            double *d3 = nullptr;
+            if (MLE_MALLOC(&d3, packed.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
+            cudaError_t e3 = cudaMemcpyAsync(d3, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+            if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(ctx->stream);
+            if (e3 != cudaSuccess) { cudaFree(d3); return fail(ctx, MLE_ERR_CUDA, cudaGetErrorString(e3)); }
+            M->d_frag[level] = d3;
+            M->frag_tiles[level] = ntiles;
+            M->frag_mpad[level] = mpad;
+        }
         return MLE_OK;
     }
     if (level > 20) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
@@ -536,7 +569,7 @@ extern "C" int mle_model_destroy(mle_ctx ctx, mle_model M) {
     if (!M) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(M->d_weights);
-    for (int l = 0; l < MLE_MAX_LEVELS; ++l) cudaFree(M->d_basis[l]);
+    for (int l = 0; l < MLE_MAX_LEVELS; ++l) { cudaFree(M->d_basis[l]); cudaFree(M->d_frag[l]); }
     delete M;
     return MLE_OK;
 }
@@ -688,7 +721,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         ma.idx1 = d > 1 ? index[1] : 0;
         const int W = SIMPLE_THREADS / 32;
         const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_MC * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Moment) +
-                            (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + W * 4;
+                            (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + ((W + 3) & ~3) * 4 + 2 * SIMPLE_MC * 16;
         const int occ = M->kind == MODEL_EXPSUM ? MLE_OCC_BY_MODE(g.mode, expsum_k, SIMPLE_THREADS, smem)
                                                 : MLE_OCC_BY_MODE(g.mode, problem18_k, SIMPLE_THREADS, smem);
         gx = grid_x_for(ctx, tps, R, occ);
@@ -769,6 +802,50 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         const int key = d == 2 ? lx + 16 * ly : lx;
         if (key >= MLE_MAX_LEVELS || !M->d_basis[key]) return fail(ctx, MLE_ERR_STATE, "lognormal2d: no KL basis set for this index (mle_model_set_basis)");
         if (m != M->basis_cols[key]) return fail(ctx, MLE_ERR_ARG, "lognormal2d: nb_of_uncertainties must equal the number of KL terms of the index's basis");
+        // register-window kernel (power-of-two Nx <= 64) when its shared memory fits; else the shared-memory-window kernel
+        bool rows_done = false;
+        if (M->d_frag[key] && !ctx->ln2d_old) {
+            const int Nx = M->n0 << lx, Ny = M->n0 << ly;
+            int rows_rc = -1;
+#define MLE_ROWS_CASE(WW, KK)                                                                                          \
+            case WW: {                                                                                                 \
+                using Cfg = Rows2dCfg<WW>;                                                                             \
+                Lognormal2dRowsArgs ra{};                                                                              \
+                ra.basis = M->d_frag[key]; ra.Nx = Nx; ra.Ny = Ny; ra.ndims = d; ra.lx = lx; ra.ly = ly;               \
+                ra.mpad = M->frag_mpad[key]; ra.ntiles = M->frag_tiles[key];                                           \
+                const size_t fbytes = (size_t)ra.ntiles * 8 * Cfg::LDF * 8, qbytes = (size_t)32 * Cfg::THREADS * 2;    \
+                const size_t fixed = (size_t)ra.mpad * Cfg::LDX * 8 + (size_t)Cfg::CS * rows_sh_doubles(WW) * 8 +     \
+                                     (size_t)2 * Cfg::S * 8 + (size_t)2 * Cfg::S * sizeof(Moment) +                    \
+                                     (((Cfg::THREADS / 32) + 3) & ~3) * 4 + 128;                                       \
+                ra.use_scratch = (fixed + fbytes + (qbytes > fbytes ? qbytes : 0) > 200 * 1024) ? 1 : 0;               \
+                const size_t smem = fixed + (ra.use_scratch ? qbytes : fbytes + (qbytes > fbytes ? qbytes : 0));       \
+                if (smem > 220 * 1024) break;                                                                          \
+                const long long tps = (long long)((n + Cfg::S - 1) / Cfg::S);                                          \
+                const int occ = MLE_OCC_BY_MODE(g.mode, KK, Cfg::THREADS, smem);                                       \
+                gx = grid_x_for(ctx, tps, R, occ);                                                                     \
+                rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);                \
+                if (rc) return rc;                                                                                     \
+                if (ra.use_scratch) {                                                                                  \
+                    rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, (size_t)gx * R * (fbytes / 8));           \
+                    if (rc) return rc;                                                                                 \
+                    ra.scratch = ctx->d_scratch;                                                                       \
+                }                                                                                                      \
+                dim3 grid((unsigned)gx, (unsigned)R);                                                                  \
+                MLE_LAUNCH_BY_MODE(g.mode, KK, grid, Cfg::THREADS, smem, ctx->stream, g, ra, ctx->d_partials, samples_dev, tps); \
+                rows_rc = 0;                                                                                           \
+            } break;
+            switch (Nx) {
+                MLE_ROWS_CASE(4, lognormal2d_r4)
+                MLE_ROWS_CASE(8, lognormal2d_r8)
+                MLE_ROWS_CASE(16, lognormal2d_r16)
+                MLE_ROWS_CASE(32, lognormal2d_r32)
+                MLE_ROWS_CASE(64, lognormal2d_r64)
+                default: break;
+            }
+#undef MLE_ROWS_CASE
+            rows_done = rows_rc == 0;
+        }
+        if (!rows_done) {
         Lognormal2dArgs la{};
         la.basisT = M->d_basis[key];
         la.Nx = M->n0 << lx;
@@ -801,6 +878,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         dim3 grid((unsigned)gx, (unsigned)R);
         if (big) MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_c, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev);
         else MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_w, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev);
+        }
     } else {
         return fail(ctx, MLE_ERR_ARG, "unknown model kind");
     }

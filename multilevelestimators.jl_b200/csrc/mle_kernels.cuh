@@ -196,10 +196,20 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g
     GenScratch sc;
     sc.queue = reinterpret_cast<unsigned short *>(acc + V);                 // [THREADS*SIMPLE_MC]
     sc.wtot = reinterpret_cast<unsigned *>(sc.queue + THREADS * SIMPLE_MC);
+    // {z_j, shift_j} of the current and the next chunk of dims (lattice modes): staged while the previous chunk is consumed
+    double2 *zsbuf = reinterpret_cast<double2 *>(sc.wtot + ((W + 3) & ~3));  // [2][SIMPLE_MC]
+    constexpr bool lattice = (MODE & GEN_MC) == 0;
 
     const int r = blockIdx.y;
     const int tid = threadIdx.x;
+    const double *shift_r = lattice ? g.shifts + (size_t)r * g.s : nullptr;
+    auto stage = [&](int buf, int j0) {
+        if (lattice && tid < SIMPLE_MC && j0 + tid < g.m)
+            zsbuf[buf * SIMPLE_MC + tid] = make_double2(__ldg(g.zd + j0 + tid), __ldg(shift_r + j0 + tid));
+    };
+    int cb = 0;
     if (tid < V) acc[tid] = Moment{0.0, 0.0, 0.0};
+    stage(0, 0);
     __syncthreads();
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
@@ -212,7 +222,10 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) sample_simple_kernel(GenArgs g
         for (int j0 = 0; j0 < g.m; j0 += SIMPLE_MC) {
             const int mc = min(SIMPLE_MC, g.m - j0);
             // always a full tile of points: surplus points (tid >= Pt) are masked out of the statistics
-            gen_tile_owned<THREADS, THREADS, MODE, THREADS, unsigned, 4>(tile, j0, mc, g.k0 + i0, g, r, sc);
+            gen_tile_owned<THREADS, THREADS, MODE, THREADS, unsigned, 4, lattice>(tile, j0, mc, g.k0 + i0, g, r, sc,
+                                                                                  zsbuf + cb * SIMPLE_MC - j0);
+            stage(cb ^ 1, j0 + SIMPLE_MC < g.m ? j0 + SIMPLE_MC : 0);  // next chunk (or chunk 0 of the next tile)
+            cb ^= 1;
             if (MODEL == MODEL_EXPSUM) {
                 for (int jj = 0; jj < mc; ++jj) {
                     const int j = j0 + jj;
@@ -822,7 +835,7 @@ __device__ void frontal_half_dev(const Field2d &f, double *M, double *gv, double
         const int sp = p % W;
         const bool enter = p + n <= last;
         const int hi = enter ? p + n : last;
-        const double d = M[sp * W + sp], gp = gv[sp];
+        const double rd = __ddiv_rn(1.0, M[sp * W + sp]), gp = gv[sp];  // multipliers l = v * (1/d)
         // phase A: v_q = M[q][p], l_q = v_q / d for the window p+1..hi (the entering unknown's coupling to p is known
         // directly), and the entering unknown's row/column (the slot of pivot p-1; disjoint from everything read here)
         for (int qo = t; qo < hi - p; qo += TG) {
@@ -831,7 +844,7 @@ __device__ void frontal_half_dev(const Field2d &f, double *M, double *gv, double
             if (enter && q == p + n) { const int ie = q % n + 1, je = q / n + 1; vq = -f.ky(ie, je - 1); }
             else vq = M[sq * W + sp];
             v[sq] = vq;
-            l[sq] = __ddiv_rn(vq, d);
+            l[sq] = __dmul_rn(vq, rd);
         }
         if (enter) load(p + n);
         group_sync<TG>();
@@ -858,15 +871,15 @@ __device__ double frontal_mid_dev(const double *a, int lda, int stx, int sty, in
     group_sync<TG>();
     // dense two-sided elimination along the centre line (row-major S)
     for (int tt = 0; tt < tc; ++tt) {
-        const double d = S[tt * n + tt], gp = gs[tt];
-        for (int q = tt + 1 + t; q < n; q += TG) { v[q] = S[q * n + tt]; l[q] = __ddiv_rn(v[q], d); }
+        const double rd = __ddiv_rn(1.0, S[tt * n + tt]), gp = gs[tt];
+        for (int q = tt + 1 + t; q < n; q += TG) { v[q] = S[q * n + tt]; l[q] = __dmul_rn(v[q], rd); }
         group_sync<TG>();
         rank1_update<TG>(S, gs, l, v, gp, n, 1 << 30, tt + 1, n - tt - 1, t);
         group_sync<TG>();
     }
     for (int tt = n - 1; tt > tc; --tt) {
-        const double d = S[tt * n + tt], gp = gs[tt];
-        for (int q = tc + t; q < tt; q += TG) { v[q] = S[q * n + tt]; l[q] = __ddiv_rn(v[q], d); }
+        const double rd = __ddiv_rn(1.0, S[tt * n + tt]), gp = gs[tt];
+        for (int q = tc + t; q < tt; q += TG) { v[q] = S[q * n + tt]; l[q] = __dmul_rn(v[q], rd); }
         group_sync<TG>();
         rank1_update<TG>(S, gs, l, v, gp, n, 1 << 30, tc, tt - tc, t);
         group_sync<TG>();

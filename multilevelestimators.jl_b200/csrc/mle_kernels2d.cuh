@@ -1,0 +1,345 @@
+// mle_kernels2d.cuh -- register-resident frontal solver for the 2-D lognormal model (configs C3 / C4).
+//
+// Same arithmetic as frontal_half_dev / frontal_mid_dev in mle_kernels.cuh (and as oracle/mle_oracle.c:frontal_mid): every
+// window entry receives fma(-l_q, v_r, M[q][r]) in pivot order with l_q = v_q * (1/d), so the result is bit-identical for
+// any thread mapping.  What changes is WHERE the sliding window lives:
+//
+//   * row q of the window belongs to LPR adjacent lanes (row group q % NW); each lane keeps C = NW / LPR consecutive window
+//     columns in REGISTERS, indexed by position = column - pivot.  One elimination step is
+//         reg[pos - 1] = fma(-l_q, v[pos - 1], reg[pos])          (static register indices: the shift by one position IS the
+//                                                                   advance of the window)
+//     with l_q from the lane's own position-0 entry and the column vector v (every row's position-0 entry) broadcast through
+//     shared memory: C FMAs against C/2 16-byte LDS per lane and step, ONE barrier per pivot (double-buffered v).
+//   * the reciprocal of the next pivot is computed by its row right after that row's update, off the critical path.
+//   * stencil coefficients are computed a grid line at a time by all lanes (lane i: unknown i+1 of the line) and handed to
+//     the entering row through the same shared-memory exchange.
+//   * both half sweeps run in the same registers (the upper half's centre block is parked in a second register set); the
+//     two-sided centre-line elimination continues in place: top-down with the same step, bottom-up with the mirrored shift.
+//
+// Kernel: one CTA iteration = S samples.  A: inputs (gen_tile_owned) -> xi[m][S] in shared memory.  B: field = exp(Phi xi)
+// with mma.sync.m8n8k4.f64 over node tiles (basis in HBM/L2 in A-fragment order) -> F[node][S] (shared memory, or an
+// L2-resident global scratch for the large grids).  C: CS = THREADS / (NW*LPR) samples are solved concurrently, S / CS
+// rounds; fine solve + the coarse solves of diff(index) on strided views of F.  D: per-slot Welford, fixed-order merge.
+#pragma once
+#include "mle_kernels.cuh"
+
+namespace mle {
+
+struct Lognormal2dRowsArgs {
+    const double *basis;  // fragment order [node tile][k step][lane]
+    int Nx, Ny, ndims, lx, ly;
+    int mpad;             // KL terms padded to a multiple of 4
+    int ntiles;           // node tiles of 8 rows
+    int use_scratch;      // F in global scratch instead of shared memory
+    double *scratch;      // [CTAs in grid][ntiles*8*LDF]
+};
+
+// node values a[((j*sty)*lda + i*stx) * ns] of an Nx x Ny-cell grid (optionally y-mirrored); ns = distance between nodes
+struct FieldView {
+    const double *a;
+    int ns, lda, stx, sty, Nx, Ny, mirror;
+    double wx, wy;
+    __device__ __forceinline__ double at(int i, int j) const {
+        const int jj = mirror ? Ny - j : j;
+        return a[(size_t)((jj * sty) * lda + i * stx) * ns];
+    }
+    __device__ __forceinline__ double kx(int i, int j) const { return __dmul_rn(wx, __dmul_rn(0.5, __dadd_rn(at(i, j), at(i + 1, j)))); }
+    __device__ __forceinline__ double ky(int i, int j) const { return __dmul_rn(wy, __dmul_rn(0.5, __dadd_rn(at(i, j), at(i, j + 1)))); }
+    __device__ __forceinline__ double diag(int i, int j) const {
+        return __dadd_rn(__dadd_rn(__dadd_rn(kx(i - 1, j), kx(i, j)), ky(i, j - 1)), ky(i, j));
+    }
+};
+
+template <int GT>
+__device__ __forceinline__ void rows_sync(int barid) {
+    if (GT <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(barid), "n"(GT) : "memory");
+}
+
+__host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * w + 8; }
+
+// u at the centre node (Nx/2, Ny/2) of the NW x Ny-cell grid.  Called by all GT threads of the sample's group
+// (tg = 0 .. GT-1, GT = 32 stands for "some lanes of one warp"); lanes with tg >= NW*LPR idle (coarse solves run on the fine
+// solve's group).  sh: rows_sh_doubles(NW) doubles of group-private shared memory, 16-byte aligned.
+template <int NW, int LPR, int GT>
+__device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg, int barid) {
+    constexpr int C = NW / LPR, n = NW - 1, tc = NW / 2 - 1, L = NW / 2 - 1;  // L = n - 1 - tc: position of the last pivot column
+    static_assert(C >= 2 && C * LPR == NW && (C % 2) == 0, "NW / LPR even and >= 2");
+    const int q = tg / LPR, s = tg % LPR;
+    const bool lane_on = q < NW;
+    double *vs = sh;            // [2][NW]: column vector v of the current pivot (slot = row - p - 1)
+    double *piv = sh + 2 * NW;  // [2][4]: 1/d, g_p, -kx and diagonal of the entering unknown
+    const int c = f.Ny / 2, P = (c - 1) * n, last = P + n - 1;
+    double reg[C], s2[C], g = 0.0, g2 = 0.0, rcp = 0.0;
+    int row = -1, step = 0;  // step: running parity of the exchange buffers
+#pragma unroll
+    for (int j = 0; j < C; ++j) { reg[j] = 0.0; s2[j] = 0.0; }
+
+    // shift-left elimination step on pivot row p: rows (p, ..] get reg[pos-1] = fma(-l, v[pos-1], reg[pos]).
+    // enter: unknown e = p + n joins the window in row group `se`; its coefficients are published by the lane that holds them
+    // (group ie - 1).  top_kx / top_dg: what the last window column (position n) holds for row e-1 / row e.
+    auto eliminate = [&](int p, bool enter, int e, int se, int ie, double cdg, double ckx, double cky, double gv) {
+        const int buf = step & 1;
+        ++step;
+        double *vb = vs + buf * NW, *pb = piv + buf * 4;
+        if (lane_on && s == 0) {
+            if (row > p) vb[row - p - 1] = reg[0];
+            else if (row == p) { pb[0] = rcp; pb[1] = g; }
+            if (enter && q == ie - 1) { vb[n - 1] = cky; pb[2] = ckx; pb[3] = cdg; }
+        }
+        rows_sync<GT>(barid);
+        if (enter && lane_on && q == se) {  // the freed row group takes the entering unknown
+            row = e;
+#pragma unroll
+            for (int j = 0; j < C; ++j) reg[j] = 0.0;
+            if (s == LPR - 1) { reg[C - 1] = pb[3]; reg[C - 2] = pb[2]; }
+            if (s == 0) reg[0] = vb[n - 1];
+            g = gv;
+        }
+        double nb = 0.0;
+        if (LPR > 1) nb = __shfl_down_sync(0xffffffffu, reg[0], 1);  // position (s+1)*C lives in the next lane of the row
+        if (row > p) {
+            const double v = LPR == 1 ? reg[0] : vb[row - p - 1];
+            const double l = __dmul_rn(v, pb[0]);
+            g = __fma_rn(-l, pb[1], g);
+            if (s == LPR - 1 && !(enter && row == e)) reg[C - 1] = (enter && row == e - 1) ? pb[2] : 0.0;
+            const double2 *vv = reinterpret_cast<const double2 *>(vb + s * C);
+            double w[C];
+#pragma unroll
+            for (int j2 = 0; j2 < C / 2; ++j2) { const double2 t = vv[j2]; w[2 * j2] = t.x; w[2 * j2 + 1] = t.y; }
+            reg[0] = __fma_rn(-l, w[0], reg[1]);
+            if (s == 0 && row == p + 1) rcp = __ddiv_rn(1.0, reg[0]);  // the next pivot: its division overlaps the FMAs below
+#pragma unroll
+            for (int j = 2; j < C; ++j) reg[j - 1] = __fma_rn(-l, w[j - 1], reg[j]);
+            if (LPR > 1 && s < LPR - 1) reg[C - 1] = __fma_rn(-l, w[C - 1], nb);
+        } else if (row == p) {
+            row = -1;
+        }
+    };
+
+    double cdg = 0.0, ckx = 0.0, cky = 0.0;  // coefficients of unknown (q+1, line) held by row group q
+    for (int half = 0; half < 2; ++half) {
+        f.mirror = half == 0;  // upper half first (y-mirrored field)
+        // line 1: unknowns 0 .. n-1 are rows 0 .. n-1
+        const bool own1 = !(c == 1 && f.mirror);
+        row = (lane_on && q < n) ? q : -1;
+        {
+            double dg = 0.0, kl = 0.0, kr = 0.0;
+            if (row >= 0 && own1) {
+                dg = f.diag(q + 1, 1);
+                if (q > 0) kl = -f.kx(q, 1);
+                if (q + 1 < n) kr = -f.kx(q + 1, 1);
+            }
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const int pos = s * C + j;
+                reg[j] = pos == q ? dg : pos == q - 1 ? kl : pos == q + 1 ? kr : 0.0;
+            }
+            g = (row >= 0 && own1) ? 1.0 : 0.0;
+            if (s == 0 && row == 0) rcp = __ddiv_rn(1.0, reg[0]);
+        }
+        int ie = 1, je = 2, se = n;  // (ie, je), row group of the entering unknown e = p + n
+        for (int p = 0; p < P; ++p) {
+            const int e = p + n;
+            const bool enter = e <= last;
+            const bool own = !(je == c && f.mirror);
+            if (enter && ie == 1) {  // a new line starts entering: every row group computes the coefficients of "its" unknown
+                cdg = 0.0; ckx = 0.0; cky = 0.0;
+                if (lane_on && q < n) {
+                    if (own) { cdg = f.diag(q + 1, je); if (q > 0) ckx = -f.kx(q, je); }
+                    cky = -f.ky(q + 1, je - 1);
+                }
+            }
+            eliminate(p, enter, e, se, ie, cdg, ckx, cky, own ? 1.0 : 0.0);
+            if (++ie > n) { ie = 1; ++je; }
+            if (++se == NW) se = 0;
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) s2[j] = reg[j];
+            g2 = g;
+            rows_sync<GT>(barid);  // the exchange buffers are re-initialised by the second half
+        }
+    }
+    // centre line: rows P .. last hold S (lower) in reg and S2 (upper) in s2, columns P .. last at positions 0 .. n-1
+#pragma unroll
+    for (int j = 0; j < C; ++j) reg[j] = __dadd_rn(reg[j], s2[j]);
+    g = __dadd_rn(g, g2);
+    if (s == 0 && row == P) rcp = __ddiv_rn(1.0, reg[0]);
+    // top-down: pivots P .. P+tc-1 with the same shift-left step
+    for (int t = 0; t < tc; ++t) eliminate(P + t, false, 0, 0, 0, 0.0, 0.0, 0.0, 0.0);
+    // bottom-up: pivots last .. P+tc+1; the pivot column stays at position L, everything shifts right by one per step
+    constexpr int sL = L / C, jL = L % C;
+    const int rtc = P + tc;
+    if (s == sL && row == last && last > rtc) rcp = __ddiv_rn(1.0, reg[jL]);
+    for (int k = 0; k < n - 1 - tc; ++k) {
+        const int rowt = last - k;
+        const int buf = step & 1;
+        ++step;
+        double *vb = vs + buf * NW, *pb = piv + buf * 4;
+        if (lane_on && s == sL) {
+            if (row >= rtc && row < rowt) vb[row - rtc + k] = reg[jL];
+            else if (row == rowt) { pb[0] = rcp; pb[1] = g; }
+        }
+        rows_sync<GT>(barid);
+        double pv[LPR > 1 ? C : 1];
+        if (LPR > 1) {  // position s*C - 1 lives in the previous lane of the row
+            pv[0] = __shfl_up_sync(0xffffffffu, reg[C - 1], 1);
+        }
+        if (row >= rtc && row < rowt) {
+            const double l = __dmul_rn(vb[row - rtc + k], pb[0]);
+            g = __fma_rn(-l, pb[1], g);
+            // new[pos + 1] = fma(-l, v[pos], old[pos]) for pos = 0 .. L-1, descending so nothing is overwritten early
+#pragma unroll
+            for (int j = C - 1; j >= 1; --j) {
+                const int pos = s * C + j - 1;  // source position
+                if (pos < L) reg[j] = __fma_rn(-l, vb[pos], reg[j - 1]);
+            }
+            if (LPR > 1 && s > 0 && s * C - 1 < L) reg[0] = __fma_rn(-l, vb[s * C - 1], pv[0]);
+            if (s == sL && row == rowt - 1 && rowt - 1 > rtc) rcp = __ddiv_rn(1.0, reg[jL]);
+        } else if (row == rowt) {
+            row = -1;
+        }
+    }
+    // u = gs[tc] / S[tc][tc]
+    {
+        const int buf = step & 1;
+        ++step;
+        if (lane_on && s == sL && row == rtc) piv[buf * 4] = __ddiv_rn(g, reg[jL]);
+        rows_sync<GT>(barid);
+        const double u = piv[buf * 4];
+        rows_sync<GT>(barid);  // the buffers are reused by the next solve
+        return u;
+    }
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------------------------
+template <int W> struct Rows2dCfg {
+    static constexpr int LPR = W > 32 ? W / 32 : 1;
+    static constexpr int TGS = W * LPR;                       // threads per sample
+    static constexpr int THREADS = W >= 8 ? 256 : 32 * W;
+    static constexpr int CS = THREADS / TGS;                  // samples solved concurrently
+    static constexpr int S = CS < 8 ? 8 : CS;                 // samples per CTA iteration (a multiple of the DMMA tile)
+    static constexpr int LDX = S + 4, LDF = S == 8 ? 8 : S + 8;
+    static constexpr int GT = TGS <= 32 ? 32 : TGS;
+    static constexpr int GEN_DIMS = 32 * (THREADS / S);       // dims per generator call (32-bit class masks)
+};
+
+template <int MODE, int W>
+__global__ void __launch_bounds__(Rows2dCfg<W>::THREADS) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la,
+                                                                                Moment *__restrict__ partials,
+                                                                                double *__restrict__ samples,
+                                                                                long long tiles_per_shift) {
+    static_assert(W >= 4, "the coarse solve needs W / 2 >= 2");
+    using Cfg = Rows2dCfg<W>;
+    constexpr int THREADS = Cfg::THREADS, S = Cfg::S, LDX = Cfg::LDX, LDF = Cfg::LDF, TGS = Cfg::TGS, CS = Cfg::CS;
+    constexpr int LPR = Cfg::LPR, GT = Cfg::GT, NWARP = THREADS / 32, ST = S / 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int mpad = la.mpad, nks = mpad >> 2;
+    double *xi = reinterpret_cast<double *>(smem_raw);                       // [mpad][LDX]
+    double *gsh = xi + (size_t)mpad * LDX;                                   // [CS][rows_sh_doubles(W)]
+    double *res = gsh + CS * rows_sh_doubles(W);                             // [S][2]
+    Moment *mred = reinterpret_cast<Moment *>(res + 2 * S);                  // [2][S]
+    GenScratch sc;
+    sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * S);                    // [NWARP]
+    double *tail = reinterpret_cast<double *>(sc.wtot + ((NWARP + 3) & ~3));
+    const size_t fdoubles = (size_t)la.ntiles * 8 * LDF;
+    double *F = la.use_scratch ? la.scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * fdoubles : tail;  // [ntiles*8][LDF]
+    // generator queue: inside F while it is idle, else behind it
+    const size_t qbytes = (size_t)32 * THREADS * 2;
+    sc.queue = (!la.use_scratch && qbytes <= fdoubles * 8) ? reinterpret_cast<unsigned short *>(F)
+               : reinterpret_cast<unsigned short *>(la.use_scratch ? tail : tail + fdoubles);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
+    const int lr = lane >> 2, lk = lane & 3;
+    for (int e = tid; e < (mpad - g.m) * LDX; e += THREADS) xi[(size_t)g.m * LDX + e] = 0.0;  // k padding rows
+    __syncthreads();
+    Welford wdq{0.0, 0.0}, wqf{0.0, 0.0};
+    double ncount = 0.0;
+    const int Nx = la.Nx, Ny = la.Ny;
+
+    for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
+        const unsigned long long i0 = (unsigned long long)ti * S;
+        const unsigned long long left = g.n - i0;
+        const int Pt = left < (unsigned long long)S ? (int)left : S;
+        // A. inputs (always a full tile: surplus points are masked out of the statistics)
+        for (int j0 = 0; j0 < g.m; j0 += Cfg::GEN_DIMS)
+            gen_tile_owned<THREADS, S, MODE, LDX, unsigned, 4>(xi + (size_t)j0 * LDX, j0, min(Cfg::GEN_DIMS, g.m - j0),
+                                                              g.k0 + i0, g, r, sc);
+        // B. field: F[node][sample] = exp(sum_k Phi[node][k] xi[k][sample]), ascending k (DMMA = 4 sequential FMAs)
+        for (int rt = warp; rt < la.ntiles; rt += NWARP) {
+            double acc[ST][2];
+#pragma unroll
+            for (int st = 0; st < ST; ++st) { acc[st][0] = 0.0; acc[st][1] = 0.0; }
+            const double *A = la.basis + (size_t)rt * nks * 32 + lane;
+            const double *B = xi + lk * LDX + lr;
+            double a = __ldg(A);
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) {
+                const double na = __ldg(A + (ks + 1 < nks ? ks + 1 : ks) * 32);
+#pragma unroll
+                for (int st = 0; st < ST; ++st) dmma_m8n8k4(acc[st][0], acc[st][1], a, B[ks * 4 * LDX + 8 * st]);
+                a = na;
+            }
+            double *f0 = F + (size_t)(8 * rt + lr) * LDF + 2 * lk;
+#pragma unroll
+            for (int st = 0; st < ST; ++st) {
+                double2 v;
+                v.x = exp_det(acc[st][0]);
+                v.y = exp_det(acc[st][1]);
+                *reinterpret_cast<double2 *>(f0 + 8 * st) = v;
+            }
+        }
+        __syncthreads();
+        // C. solves: CS samples at a time
+        for (int rd = 0; rd < S / CS; ++rd) {
+            const int grp = tid / TGS, tg = tid % TGS, sigma = rd * CS + grp;
+            double *sh = gsh + grp * rows_sh_doubles(W);
+            FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
+            const double qf = frontal_mid_rows<W, LPR, GT>(fv, sh, tg, 1 + grp);
+            double dq = qf;
+            // coarse terms of diff(index), added in the order (lx-1,ly-1), (lx,ly-1), (lx-1,ly); multilevel: one coarse solve
+            auto coarse = [&](int stx, int sty) {
+                FieldView cv = fv;
+                cv.stx = stx; cv.sty = sty; cv.Nx = Nx / stx; cv.Ny = Ny / sty;
+                cv.wx = (double)cv.Nx * (double)cv.Nx; cv.wy = (double)cv.Ny * (double)cv.Ny;
+                if (stx == 2) return frontal_mid_rows<W / 2, (W / 2 / LPR >= 2 ? LPR : 1), GT>(cv, sh, tg, 1 + grp);
+                return frontal_mid_rows<W, LPR, GT>(cv, sh, tg, 1 + grp);
+            };
+            if (la.ndims == 1) {
+                if (la.lx > 0) dq = __dsub_rn(qf, coarse(2, 2));
+            } else {
+                if (la.lx > 0 && la.ly > 0) dq = __dadd_rn(dq, coarse(2, 2));
+                if (la.ly > 0) dq = __dsub_rn(dq, coarse(1, 2));
+                if (la.lx > 0) dq = __dsub_rn(dq, coarse(2, 1));
+            }
+            if (tg == 0) { res[2 * sigma] = dq; res[2 * sigma + 1] = qf; }
+        }
+        __syncthreads();
+        // D. statistics: slot tid < S
+        if (tid < Pt) {
+            const double dq = res[2 * tid], qf = res[2 * tid + 1];
+            if (samples) {
+                samples[((size_t)r * 2 + 0) * g.n + i0 + tid] = dq;
+                samples[((size_t)r * 2 + 1) * g.n + i0 + tid] = qf;
+            }
+            ncount += 1.0;
+            const double inv_n = 1.0 / ncount;
+            welford_add(wdq, dq, inv_n);
+            welford_add(wqf, qf, inv_n);
+        }
+        // (the barriers of the next tile's generator order the res reads above before res is rewritten)
+    }
+    if (tid < S) {
+        mred[tid] = Moment{ncount, wdq.mean, wdq.m2};
+        mred[S + tid] = Moment{ncount, wqf.mean, wqf.m2};
+    }
+    __syncthreads();
+    if (tid < 2) {
+        Moment a{0.0, 0.0, 0.0};
+        for (int i = 0; i < S; ++i) a = moment_merge(a, mred[tid * S + i]);
+        partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
+    }
+}
+
+}  // namespace mle

@@ -551,8 +551,8 @@ static void frontal_half(const field2d *f, double *M, double *g, double *l, doub
         if (p + n <= last) LOAD_UNKNOWN(p + n);
         const int sp = SLOT(p);
         const int hi = (p + n <= last) ? p + n : last;
-        const double d = M[sp * W + sp], gp = g[sp];
-        for (int q = p + 1; q <= hi; ++q) { v[SLOT(q)] = M[SLOT(q) * W + sp]; l[SLOT(q)] = v[SLOT(q)] / d; }
+        const double rd = 1.0 / M[sp * W + sp], gp = g[sp]; /* multipliers l = v * (1/d): one division per pivot */
+        for (int q = p + 1; q <= hi; ++q) { v[SLOT(q)] = M[SLOT(q) * W + sp]; l[SLOT(q)] = v[SLOT(q)] * rd; }
         for (int q = p + 1; q <= hi; ++q) {
             const int sq = SLOT(q);
             const double lq = l[sq];
@@ -585,16 +585,16 @@ static double frontal_mid(const double *a, int lda, int stx, int sty, int Nx, in
     }
     /* dense two-sided elimination along the centre line: t = 0..tc-1 ascending, then t = n-1..tc+1 descending */
     for (int t = 0; t < tc; ++t) {
-        const double d = S[t * n + t], gp = gs[t];
-        for (int q = t + 1; q < n; ++q) { v[q] = S[q * n + t]; l[q] = v[q] / d; }
+        const double rd = 1.0 / S[t * n + t], gp = gs[t];
+        for (int q = t + 1; q < n; ++q) { v[q] = S[q * n + t]; l[q] = v[q] * rd; }
         for (int q = t + 1; q < n; ++q) {
             gs[q] = fma(-l[q], gp, gs[q]);
             for (int r = t + 1; r < n; ++r) S[q * n + r] = fma(-l[q], v[r], S[q * n + r]);
         }
     }
     for (int t = n - 1; t > tc; --t) {
-        const double d = S[t * n + t], gp = gs[t];
-        for (int q = tc; q < t; ++q) { v[q] = S[q * n + t]; l[q] = v[q] / d; }
+        const double rd = 1.0 / S[t * n + t], gp = gs[t];
+        for (int q = tc; q < t; ++q) { v[q] = S[q * n + t]; l[q] = v[q] * rd; }
         for (int q = tc; q < t; ++q) {
             gs[q] = fma(-l[q], gp, gs[q]);
             for (int r = tc; r < t; ++r) S[q * n + r] = fma(-l[q], v[r], S[q * n + r]);
