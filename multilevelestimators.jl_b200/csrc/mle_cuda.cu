@@ -32,6 +32,7 @@ template <int MODE> static constexpr auto lognormal2d_r8 = lognormal2d_rows_kern
 template <int MODE> static constexpr auto lognormal2d_r16 = lognormal2d_rows_kernel<MODE, 16>;
 template <int MODE> static constexpr auto lognormal2d_r32 = lognormal2d_rows_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_r64 = lognormal2d_rows_kernel<MODE, 64>;
+template <int MODE> static constexpr auto lognormal2d_r128 = lognormal2d_rows_kernel<MODE, 128>;
 // mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
 #define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
     do {                                                                                       \
@@ -243,6 +244,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(lognormal2d_r16, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r32, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r64, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_r128, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     if (const char *e = getenv("MLE_LN_BT")) { int v = atoi(e); if (v == 32 || v == 64) ctx->ln_bt_override = v; }
@@ -505,7 +507,7 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
         M->basis_mpad[level] = (int)npad;
         M->basis_nchunks[level] = 0;
         if (M->d_frag[level]) { cudaFree(M->d_frag[level]); M->d_frag[level] = nullptr; }
-        if (Nx >= 4 && Nx <= 64 && (Nx & (Nx - 1)) == 0) {  // register-window kernel: fragment-ordered copy
+        if (Nx >= 4 && Nx <= 128 && (Nx & (Nx - 1)) == 0) {  // register-window kernel: fragment-ordered copy
             const int mpad = (cols + 3) & ~3, nks = mpad / 4, ntiles = (int)((nodes + 7) / 8);
             std::vector<double> packed((size_t)ntiles * nks * 32, 0.0);
             for (long long nd = 0; nd < nodes; ++nd)
@@ -825,10 +827,12 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                 gx = grid_x_for(ctx, tps, R, occ);                                                                     \
                 rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);                \
                 if (rc) return rc;                                                                                     \
-                if (ra.use_scratch) {                                                                                  \
-                    rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, (size_t)gx * R * (fbytes / 8));           \
+                {                                                                                                      \
+                    const size_t park = (size_t)gx * R * 32 * Cfg::THREADS;                                            \
+                    rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, park + (ra.use_scratch ? (size_t)gx * R * (fbytes / 8) : 0)); \
                     if (rc) return rc;                                                                                 \
-                    ra.scratch = ctx->d_scratch;                                                                       \
+                    ra.park = ctx->d_scratch;                                                                          \
+                    ra.scratch = ctx->d_scratch + park;                                                                \
                 }                                                                                                      \
                 dim3 grid((unsigned)gx, (unsigned)R);                                                                  \
                 MLE_LAUNCH_BY_MODE(g.mode, KK, grid, Cfg::THREADS, smem, ctx->stream, g, ra, ctx->d_partials, samples_dev, tps); \
@@ -840,6 +844,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                 MLE_ROWS_CASE(16, lognormal2d_r16)
                 MLE_ROWS_CASE(32, lognormal2d_r32)
                 MLE_ROWS_CASE(64, lognormal2d_r64)
+                MLE_ROWS_CASE(128, lognormal2d_r128)
                 default: break;
             }
 #undef MLE_ROWS_CASE

@@ -21,6 +21,8 @@
 // L2-resident global scratch for the large grids).  C: CS = THREADS / (NW*LPR) samples are solved concurrently, S / CS
 // rounds; fine solve + the coarse solves of diff(index) on strided views of F.  D: per-slot Welford, fixed-order merge.
 #pragma once
+#include <cuda/std/type_traits>
+
 #include "mle_kernels.cuh"
 
 namespace mle {
@@ -32,6 +34,7 @@ struct Lognormal2dRowsArgs {
     int ntiles;           // node tiles of 8 rows
     int use_scratch;      // F in global scratch instead of shared memory
     double *scratch;      // [CTAs in grid][ntiles*8*LDF]
+    double *park;         // [CTAs in grid][32][THREADS]: the upper half's centre block of every thread
 };
 
 // node values a[((j*sty)*lda + i*stx) * ns] of an Nx x Ny-cell grid (optionally y-mirrored); ns = distance between nodes
@@ -60,9 +63,10 @@ __host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * w + 8; }
 
 // u at the centre node (Nx/2, Ny/2) of the NW x Ny-cell grid.  Called by all GT threads of the sample's group
 // (tg = 0 .. GT-1, GT = 32 stands for "some lanes of one warp"); lanes with tg >= NW*LPR idle (coarse solves run on the fine
-// solve's group).  sh: rows_sh_doubles(NW) doubles of group-private shared memory, 16-byte aligned.
+// solve's group).  sh: rows_sh_doubles(NW) doubles of group-private shared memory, 16-byte aligned.  park: this thread's
+// column of a global scratch [C][pstride] that holds the upper half's centre block while the lower half is eliminated.
 template <int NW, int LPR, int GT>
-__device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg, int barid) {
+__device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double *park, int pstride, int tg, int barid) {
     constexpr int C = NW / LPR, n = NW - 1, tc = NW / 2 - 1, L = NW / 2 - 1;  // L = n - 1 - tc: position of the last pivot column
     static_assert(C >= 2 && C * LPR == NW && (C % 2) == 0, "NW / LPR even and >= 2");
     const int q = tg / LPR, s = tg % LPR;
@@ -70,54 +74,69 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg,
     double *vs = sh;            // [2][NW]: column vector v of the current pivot (slot = row - p - 1)
     double *piv = sh + 2 * NW;  // [2][4]: 1/d, g_p, -kx and diagonal of the entering unknown
     const int c = f.Ny / 2, P = (c - 1) * n, last = P + n - 1;
-    double reg[C], s2[C], g = 0.0, g2 = 0.0, rcp = 0.0;
+    double reg[C], g = 0.0, g2 = 0.0, rcp = 0.0;
     int row = -1, step = 0;  // step: running parity of the exchange buffers
 #pragma unroll
-    for (int j = 0; j < C; ++j) { reg[j] = 0.0; s2[j] = 0.0; }
+    for (int j = 0; j < C; ++j) reg[j] = 0.0;
 
-    // shift-left elimination step on pivot row p: rows (p, ..] get reg[pos-1] = fma(-l, v[pos-1], reg[pos]).
-    // enter: unknown e = p + n joins the window in row group `se`; its coefficients are published by the lane that holds them
-    // (group ie - 1).  top_kx / top_dg: what the last window column (position n) holds for row e-1 / row e.
-    auto eliminate = [&](int p, bool enter, int e, int se, int ie, double cdg, double ckx, double cky, double gv) {
+    // One shift-left elimination step on pivot row p, written branch-free: rows (p, ..] get
+    // reg[pos-1] = fma(-l, v[pos-1], reg[pos]); every other lane runs the same FMAs with l = 0 (its registers are dead).
+    // ENTER: unknown e = p + n joins the window in row group `se` (the one freed by pivot p - 1) with coefficients published
+    // by the group that holds them (ie - 1); its registers are cleared by predicated moves inside the same basic block.
+    auto eliminate = [&](auto enter_tag, int p, int e, int se, int ie, double cdg, double ckx, double cky, double gv) {
+        constexpr bool ENTER = decltype(enter_tag)::value;
         const int buf = step & 1;
         ++step;
         double *vb = vs + buf * NW, *pb = piv + buf * 4;
         if (lane_on && s == 0) {
             if (row > p) vb[row - p - 1] = reg[0];
-            else if (row == p) { pb[0] = rcp; pb[1] = g; }
-            if (enter && q == ie - 1) { vb[n - 1] = cky; pb[2] = ckx; pb[3] = cdg; }
+            if (row == p) *reinterpret_cast<double2 *>(pb) = make_double2(rcp, g);
+            if (ENTER && q == ie - 1) { vb[n - 1] = cky; *reinterpret_cast<double2 *>(pb + 2) = make_double2(ckx, cdg); }
         }
         rows_sync<GT>(barid);
-        if (enter && lane_on && q == se) {  // the freed row group takes the entering unknown
-            row = e;
+        const double2 pg = *reinterpret_cast<const double2 *>(pb);  // 1/d, g_p
+        double top = 0.0;                                            // what position n holds for this row
+        if (ENTER) {
+            const double2 ent = *reinterpret_cast<const double2 *>(pb + 2);  // -kx, diagonal of the entering unknown
+            const bool me = lane_on && q == se;
+            if (me) {
+                row = e;
+                g = gv;
 #pragma unroll
-            for (int j = 0; j < C; ++j) reg[j] = 0.0;
-            if (s == LPR - 1) { reg[C - 1] = pb[3]; reg[C - 2] = pb[2]; }
-            if (s == 0) reg[0] = vb[n - 1];
-            g = gv;
+                for (int j = 0; j < C; ++j) reg[j] = 0.0;
+                if (s == LPR - 1) reg[C - 2] = ent.x;
+                if (s == 0) reg[0] = vb[n - 1];
+            }
+            top = me ? ent.y : (row == e - 1 ? ent.x : 0.0);
         }
+        if (s == LPR - 1) reg[C - 1] = top;
         double nb = 0.0;
         if (LPR > 1) nb = __shfl_down_sync(0xffffffffu, reg[0], 1);  // position (s+1)*C lives in the next lane of the row
-        if (row > p) {
-            const double v = LPR == 1 ? reg[0] : vb[row - p - 1];
-            const double l = __dmul_rn(v, pb[0]);
-            g = __fma_rn(-l, pb[1], g);
-            if (s == LPR - 1 && !(enter && row == e)) reg[C - 1] = (enter && row == e - 1) ? pb[2] : 0.0;
-            const double2 *vv = reinterpret_cast<const double2 *>(vb + s * C);
-            double w[C];
-#pragma unroll
-            for (int j2 = 0; j2 < C / 2; ++j2) { const double2 t = vv[j2]; w[2 * j2] = t.x; w[2 * j2 + 1] = t.y; }
-            reg[0] = __fma_rn(-l, w[0], reg[1]);
-            if (s == 0 && row == p + 1) rcp = __ddiv_rn(1.0, reg[0]);  // the next pivot: its division overlaps the FMAs below
-#pragma unroll
-            for (int j = 2; j < C; ++j) reg[j - 1] = __fma_rn(-l, w[j - 1], reg[j]);
-            if (LPR > 1 && s < LPR - 1) reg[C - 1] = __fma_rn(-l, w[C - 1], nb);
-        } else if (row == p) {
-            row = -1;
+        const bool active = row > p;
+        const double v = LPR == 1 ? reg[0] : vb[active ? row - p - 1 : 0];
+        const double l = active ? __dmul_rn(v, pg.x) : 0.0;
+        g = __fma_rn(-l, pg.y, g);
+        const double2 *vv = reinterpret_cast<const double2 *>(vb + s * C);
+        {
+            const double2 t = vv[0];
+            reg[0] = __fma_rn(-l, t.x, reg[1]);
+            const double r1 = __ddiv_rn(1.0, reg[0]);  // the next pivot's reciprocal: overlaps the FMAs below
+            rcp = (s == 0 && row == p + 1) ? r1 : rcp;
+            if (C > 2) reg[1] = __fma_rn(-l, t.y, reg[2]);
+            else if (LPR > 1 && s < LPR - 1) reg[1] = __fma_rn(-l, t.y, nb);
         }
+#pragma unroll
+        for (int j2 = 1; j2 < C / 2; ++j2) {
+            const double2 t = vv[j2];
+            reg[2 * j2] = __fma_rn(-l, t.x, reg[2 * j2 + 1]);
+            if (2 * j2 + 2 < C) reg[2 * j2 + 1] = __fma_rn(-l, t.y, reg[2 * j2 + 2]);
+            else if (LPR > 1 && s < LPR - 1) reg[2 * j2 + 1] = __fma_rn(-l, t.y, nb);
+        }
+        row = row == p ? -1 : row;
     };
+    using with_enter = cuda::std::true_type;
+    using no_enter = cuda::std::false_type;
 
-    double cdg = 0.0, ckx = 0.0, cky = 0.0;  // coefficients of unknown (q+1, line) held by row group q
     for (int half = 0; half < 2; ++half) {
         f.mirror = half == 0;  // upper half first (y-mirrored field)
         // line 1: unknowns 0 .. n-1 are rows 0 .. n-1
@@ -138,36 +157,35 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg,
             g = (row >= 0 && own1) ? 1.0 : 0.0;
             if (s == 0 && row == 0) rcp = __ddiv_rn(1.0, reg[0]);
         }
-        int ie = 1, je = 2, se = n;  // (ie, je), row group of the entering unknown e = p + n
-        for (int p = 0; p < P; ++p) {
-            const int e = p + n;
-            const bool enter = e <= last;
-            const bool own = !(je == c && f.mirror);
-            if (enter && ie == 1) {  // a new line starts entering: every row group computes the coefficients of "its" unknown
-                cdg = 0.0; ckx = 0.0; cky = 0.0;
-                if (lane_on && q < n) {
-                    if (own) { cdg = f.diag(q + 1, je); if (q > 0) ckx = -f.kx(q, je); }
-                    cky = -f.ky(q + 1, je - 1);
-                }
+        // lines 2 .. c enter one unknown per pivot: line je during pivots (je-2)*n .. (je-1)*n - 1
+        int p = 0, se = n;
+        for (int je = 2; je <= c; ++je) {
+            const bool own = !(je == c && f.mirror);  // the centre line's own entries are loaded once (lower half)
+            double cdg = 0.0, ckx = 0.0, cky = 0.0;   // coefficients of unknown (q+1, je), held by row group q
+            if (lane_on && q < n) {
+                if (own) { cdg = f.diag(q + 1, je); if (q > 0) ckx = -f.kx(q, je); }
+                cky = -f.ky(q + 1, je - 1);
             }
-            eliminate(p, enter, e, se, ie, cdg, ckx, cky, own ? 1.0 : 0.0);
-            if (++ie > n) { ie = 1; ++je; }
-            if (++se == NW) se = 0;
+            const double gv = own ? 1.0 : 0.0;
+            for (int ie = 1; ie <= n; ++ie, ++p) {
+                eliminate(with_enter{}, p, p + n, se, ie, cdg, ckx, cky, gv);
+                if (++se == NW) se = 0;
+            }
         }
         if (half == 0) {
 #pragma unroll
-            for (int j = 0; j < C; ++j) s2[j] = reg[j];
+            for (int j = 0; j < C; ++j) park[(size_t)j * pstride] = reg[j];
             g2 = g;
             rows_sync<GT>(barid);  // the exchange buffers are re-initialised by the second half
         }
     }
-    // centre line: rows P .. last hold S (lower) in reg and S2 (upper) in s2, columns P .. last at positions 0 .. n-1
+    // centre line: rows P .. last hold S (lower) in reg and S2 (upper) in the park, columns P .. last at positions 0 .. n-1
 #pragma unroll
-    for (int j = 0; j < C; ++j) reg[j] = __dadd_rn(reg[j], s2[j]);
+    for (int j = 0; j < C; ++j) reg[j] = __dadd_rn(reg[j], park[(size_t)j * pstride]);
     g = __dadd_rn(g, g2);
     if (s == 0 && row == P) rcp = __ddiv_rn(1.0, reg[0]);
     // top-down: pivots P .. P+tc-1 with the same shift-left step
-    for (int t = 0; t < tc; ++t) eliminate(P + t, false, 0, 0, 0, 0.0, 0.0, 0.0, 0.0);
+    for (int t = 0; t < tc; ++t) eliminate(no_enter{}, P + t, 0, 0, 0, 0.0, 0.0, 0.0, 0.0);
     // bottom-up: pivots last .. P+tc+1; the pivot column stays at position L, everything shifts right by one per step
     constexpr int sL = L / C, jL = L % C;
     const int rtc = P + tc;
@@ -182,10 +200,8 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg,
             else if (row == rowt) { pb[0] = rcp; pb[1] = g; }
         }
         rows_sync<GT>(barid);
-        double pv[LPR > 1 ? C : 1];
-        if (LPR > 1) {  // position s*C - 1 lives in the previous lane of the row
-            pv[0] = __shfl_up_sync(0xffffffffu, reg[C - 1], 1);
-        }
+        double pv = 0.0;
+        if (LPR > 1) pv = __shfl_up_sync(0xffffffffu, reg[C - 1], 1);  // position s*C - 1 lives in the previous lane of the row
         if (row >= rtc && row < rowt) {
             const double l = __dmul_rn(vb[row - rtc + k], pb[0]);
             g = __fma_rn(-l, pb[1], g);
@@ -195,7 +211,7 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg,
                 const int pos = s * C + j - 1;  // source position
                 if (pos < L) reg[j] = __fma_rn(-l, vb[pos], reg[j - 1]);
             }
-            if (LPR > 1 && s > 0 && s * C - 1 < L) reg[0] = __fma_rn(-l, vb[s * C - 1], pv[0]);
+            if (LPR > 1 && s > 0 && s * C - 1 < L) reg[0] = __fma_rn(-l, vb[s * C - 1], pv);
             if (s == sL && row == rowt - 1 && rowt - 1 > rtc) rcp = __ddiv_rn(1.0, reg[jL]);
         } else if (row == rowt) {
             row = -1;
@@ -217,7 +233,8 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, int tg,
 template <int W> struct Rows2dCfg {
     static constexpr int LPR = W > 32 ? W / 32 : 1;
     static constexpr int TGS = W * LPR;                       // threads per sample
-    static constexpr int THREADS = W >= 8 ? 256 : 32 * W;
+    static constexpr int THREADS = W >= 128 ? 512 : W >= 8 ? 256 : 32 * W;
+    static constexpr int MINB = W >= 128 ? 1 : W >= 32 ? 2 : 1;  // resident CTAs the register budget is sized for
     static constexpr int CS = THREADS / TGS;                  // samples solved concurrently
     static constexpr int S = CS < 8 ? 8 : CS;                 // samples per CTA iteration (a multiple of the DMMA tile)
     static constexpr int LDX = S + 4, LDF = S == 8 ? 8 : S + 8;
@@ -226,7 +243,7 @@ template <int W> struct Rows2dCfg {
 };
 
 template <int MODE, int W>
-__global__ void __launch_bounds__(Rows2dCfg<W>::THREADS) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la,
+__global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la,
                                                                                 Moment *__restrict__ partials,
                                                                                 double *__restrict__ samples,
                                                                                 long long tiles_per_shift) {
@@ -296,15 +313,16 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS) lognormal2d_rows_kernel
             const int grp = tid / TGS, tg = tid % TGS, sigma = rd * CS + grp;
             double *sh = gsh + grp * rows_sh_doubles(W);
             FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
-            const double qf = frontal_mid_rows<W, LPR, GT>(fv, sh, tg, 1 + grp);
+            double *park = la.park + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 * THREADS + tid;
+            const double qf = frontal_mid_rows<W, LPR, GT>(fv, sh, park, THREADS, tg, 1 + grp);
             double dq = qf;
             // coarse terms of diff(index), added in the order (lx-1,ly-1), (lx,ly-1), (lx-1,ly); multilevel: one coarse solve
             auto coarse = [&](int stx, int sty) {
                 FieldView cv = fv;
                 cv.stx = stx; cv.sty = sty; cv.Nx = Nx / stx; cv.Ny = Ny / sty;
                 cv.wx = (double)cv.Nx * (double)cv.Nx; cv.wy = (double)cv.Ny * (double)cv.Ny;
-                if (stx == 2) return frontal_mid_rows<W / 2, (W / 2 / LPR >= 2 ? LPR : 1), GT>(cv, sh, tg, 1 + grp);
-                return frontal_mid_rows<W, LPR, GT>(cv, sh, tg, 1 + grp);
+                if (stx == 2) return frontal_mid_rows<W / 2, (W / 2 / LPR >= 2 ? LPR : 1), GT>(cv, sh, park, THREADS, tg, 1 + grp);
+                return frontal_mid_rows<W, LPR, GT>(cv, sh, park, THREADS, tg, 1 + grp);
             };
             if (la.ndims == 1) {
                 if (la.lx > 0) dq = __dsub_rn(qf, coarse(2, 2));

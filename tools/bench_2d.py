@@ -9,7 +9,7 @@ d = eng.dists([(1, [0.0, 1.0])] * m)
 gm = eng.model("lognormal2d", 1, [4])
 mom = torch.zeros(6, dtype=torch.float64, device="cuda")
 stream = torch.cuda.ExternalStream(eng.stream)
-for lev, n in ((0, 1 << 18), (1, 1 << 17), (2, 1 << 16), (3, 1 << 14), (4, 1 << 11), (5, 296)):
+for lev, n in ((0, 1 << 18), (1, 1 << 17), (2, 1 << 16), (3, 1 << 14), (4, 1 << 11), (5, 1184)):
     gm.set_basis(lev, kl.kl_basis_2d(lev, m=m))
     eng.sample_batch_dev(gm, None, d, [lev], None, 1, 0, n, m, mom.data_ptr(), mc_seed=1); eng.sync()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

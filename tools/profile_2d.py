@@ -7,7 +7,8 @@ m = 400
 d = eng.dists([(1, [0.0, 1.0])] * m)
 gm = eng.model("lognormal2d", 1, [4])
 mom = torch.zeros(6, dtype=torch.float64, device="cuda")
-for lev, n in ((0, 1 << 17), (2, 1 << 14)):
+levels = [int(x) for x in os.environ.get('P2D_LEVELS', '0,2').split(',')]
+for lev, n in [(l, max(296 * 8, (1 << 17) >> (3 * l))) for l in levels]:
     gm.set_basis(lev, kl.kl_basis_2d(lev, m=m))
     for rep in range(2):
         eng.sample_batch_dev(gm, None, d, [lev], None, 1, 0, n, m, mom.data_ptr(), mc_seed=1)
