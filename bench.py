@@ -366,7 +366,23 @@ def run_ours(args):
                    "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                    "peak_source": "MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650 GB/s",
                    "algorithmic_bytes_per_coordinate": 8, "traffic": None,
-                   "coordinates_per_s": out.numel() / (ms * 1e-3)}
+                   "coordinates_per_s": out.numel() / (ms * 1e-3),
+                   "note": "with the Normal inverse CDF (about 45 FP64 instructions per coordinate) this stage is bound by the "
+                           "FP64 pipe, not by HBM: 8 B x (FP64 issue rate / 45) = 3.3 TB/s is its ceiling; `raw` below is "
+                           "the same kernel without the transform (lattice point + shift only), which IS store-bound"}
+            # the same kernel without the inverse CDF: shifted lattice points only (stage 1 alone)
+            for _ in range(2):
+                eng.points_dev(lat, None, sh_dev[0].data_ptr(), R_SHIFTS, 0, npts, M_KL, out.data_ptr())
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(5):
+                eng.points_dev(lat, None, sh_dev[0].data_ptr(), R_SHIFTS, 0, npts, M_KL, out.data_ptr())
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms_raw = a.elapsed_time(b) / 5
+            gbs_raw = out.numel() * 8 / (ms_raw * 1e-3) * 1e-9
+            hbm["raw"] = {"achieved": gbs_raw, "frac": gbs_raw / hbm_peak, "unit": "GB/s",
+                          "coordinates_per_s": out.numel() / (ms_raw * 1e-3)}
             del out
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
