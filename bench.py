@@ -339,8 +339,8 @@ def run_ours(args):
                     "frac": (achieved_tf / peak_tf) if peak_tf else None,
                     "peak_source": "measured live by tools/fp64_microbench (MEASURED_PEAKS.json has no FP64 figure)",
                     # dram__bytes_read.sum + dram__bytes_write.sum of the 7 launches of one step, from the ncu --set full capture
-                    # of this command (profiles/r01_final_kernels.csv): 0.10+0.12+0.14+0.19+0.29+0.50+0.91 MB read, 0 B written
-                    "traffic": 2.25e6, "traffic_unit": "bytes per step (all 7 launches); algorithmic HBM bytes per sample: 0",
+                    # of this command (profiles/r01_final_kernels.csv): 0.11+0.12+0.15+0.20+0.30+0.51+0.92 MB read, 0 B written
+                    "traffic": 2.30e6, "traffic_unit": "bytes per step (all 7 launches); algorithmic HBM bytes per sample: 0",
                     "per_level_ms": lvl_ms,
                     "per_level_samples_per_s": [n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) for li in range(len(LEVELS))],
                     "per_level_tflops": [algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) * 1e-12

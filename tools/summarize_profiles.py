@@ -38,6 +38,8 @@ want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "gpu__time_duration.sum",
         "smsp__cycles_active.avg", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -48,9 +50,12 @@ for wname in want:
         if h.endswith(wname):
             cols.append((wname + (" [" + units[i] + "]" if units[i] else ""), i))
             break
+stall = [i for i, h in enumerate(hdr) if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
 with open(os.path.join(root, tag + "_kernels.csv"), "w", newline="") as f:
     w = csv.writer(f)
-    w.writerow([c for c, _ in cols])
+    w.writerow([c for c, _ in cols] + ["top warp stall reasons (% of samples)"])
     for r in data:
-        w.writerow([r[i][:90] for _, i in cols])
+        tot_s = sum(float(r[i] or 0) for i in stall) or 1.0
+        top = sorted(((float(r[i] or 0) / tot_s * 100, hdr[i].split("issue_stalled_")[-1]) for i in stall), reverse=True)[:5]
+        w.writerow([r[i][:90] for _, i in cols] + [" ".join("%s=%.1f" % (n, v) for v, n in top)])
 print("wrote profiles/%s_launches.csv and profiles/%s_kernels.csv" % (tag, tag))
