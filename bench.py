@@ -33,6 +33,19 @@ N0_POINTS = 1 << 20
 SHIFT_SEED = 2024
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the one JSON line, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def points_per_shift(level, scale=1.0):
     return max(1, int(round(N0_POINTS * scale * 2.0 ** (-1.5 * level))))
 
@@ -176,7 +189,7 @@ def run_reference(args):
             "config": workload_config(),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config():
@@ -203,9 +216,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: libmle_cuda has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -399,7 +409,7 @@ def run_ours(args):
                 "fp64_microbench": fp64 or None,
                 "estimate": {"mean_dQ_per_level": [float(final[li, :, 0, 0, 1].mean()) for li in range(len(LEVELS))],
                              "sum": float(sum(final[li, :, 0, 0, 1].mean() for li in range(len(LEVELS))))}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -414,6 +424,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: native libraries (the NCCL version banner, for one) write to file descriptor 1
+    # directly, so fd 1 is pointed at stderr for the run and the JSON line goes to a private duplicate of the real stdout
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
