@@ -289,6 +289,48 @@ def test_lognormal2d_argument_errors(engine):
         engine.sample_batch(gm, lat, d, [1], np.zeros((1, 8)), 0, 4)      # index dimension mismatch
 
 
+@pytest.mark.parametrize("n0,ndims,index,n", [(6, 1, (0,), 40), (6, 1, (1,), 24), (6, 1, (2,), 9), (6, 2, (1, 0), 20), (6, 2, (0, 2), 12),
+                                              (2, 1, (0,), 50), (2, 1, (1,), 50), (2, 2, (0, 1), 30), (2, 2, (1, 1), 30), (10, 1, (1,), 7)])
+def test_lognormal2d_other_base_grids(engine, oracle, n0, ndims, index, n):
+    """base grids that are not 4 * 2^l: Nx = 6, 12, 24, 20 (not a power of two) and Nx = 2 run on the shared-memory-window
+    kernel, Nx = 4 with a 2-cell coarse grid on the register-window kernel; all bit-identical to the oracle"""
+    import mle_b200.kl as kl
+    m = 24
+    z = oracle.genvec("K_3600_32", m)
+    gm = engine.model("lognormal2d", ndims, [n0])
+    om = oracle.Model(oracle.MODEL_LOGNORMAL2D, ndims, [float(n0)])
+    key = index[0] if ndims == 1 else tuple(index)
+    phi = kl.kl_basis_2d(key, m=m, n0=n0)
+    gm.set_basis(key, phi)
+    om.set_basis(key, phi)
+    lat, d = engine.lattice(z, m), engine.dists([NORMAL01] * m)
+    sh = splitmix_uniforms(99, 2 * m).reshape(2, m)
+    got, smp = engine.sample_batch(gm, lat, d, list(index), sh, 1, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, [NORMAL01] * m, list(index), sh, 1, n, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
+
+
+def test_lognormal2d_both_kernels_agree(engine, oracle, monkeypatch):
+    """MLE_2D_WINDOW_SMEM=1 forces the shared-memory-window kernel: same bits as the register-window kernel"""
+    import mle_b200
+    import mle_b200.kl as kl
+    m = 32
+    phi = kl.kl_basis_2d(2, m=m)
+    sh = splitmix_uniforms(3, 2 * m).reshape(2, m)
+    out = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("MLE_2D_WINDOW_SMEM", force)
+        eng = mle_b200.Engine(0)
+        gm = eng.model("lognormal2d", 1, [4])
+        gm.set_basis(2, phi)
+        _, smp = eng.sample_batch(gm, eng.lattice(None, m), eng.dists([NORMAL01] * m), [2], sh, 0, 40, want_samples=True)
+        out.append(smp)
+        gm.close()
+        eng.close()
+    assert np.array_equal(out[0], out[1])
+
+
 @pytest.mark.parametrize("m,level", [(200, 1), (300, 0), (129, 2)])
 def test_lognormal1d_many_kl_terms(engine, oracle, m, level):
     """more than 128 KL terms: the generator switches to 64-bit class masks and multiple passes over the dimensions"""
