@@ -67,15 +67,21 @@ mutable struct DeviceModel <: Function
     dists::Ptr{Cvoid}
 end
 
+# `bases`: KL basis per level (key = level) or, for the multi-index 2-D model (name "lognormal2d", ndims = 2), per multi-index:
+# the C ABI packs the zero-based index (lx, ly) into one Int as lx + 16*ly (see `basis_key`).
+basis_key(level::Integer) = Int(level)
+basis_key(index::NTuple{2, <:Integer}) = Int(index[1]) + 16 * Int(index[2])
+basis_key(index::Index{2}) = basis_key(index.I)
+
 function DeviceModel(ctx::Context, name::String, ndims::Integer, params::Vector{Float64} = Float64[];
-                     bases::Dict{Int, Matrix{Float64}} = Dict{Int, Matrix{Float64}}())
+                     bases::Dict = Dict{Int, Matrix{Float64}}())
     ref = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx.ptr, ccall((:mle_model_create, libmle), Cint, (Ptr{Cvoid}, Cstring, Cint, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
                          ctx.ptr, name, ndims, params, length(params), ref))
     for (level, Φ) in bases
         rowmajor = permutedims(Φ)            # Julia is column-major; the ABI wants [nodes][terms] row-major
         check(ctx.ptr, ccall((:mle_model_set_basis, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}),
-                             ctx.ptr, ref[], level, size(Φ, 1), size(Φ, 2), rowmajor))
+                             ctx.ptr, ref[], basis_key(level), size(Φ, 1), size(Φ, 2), rowmajor))
     end
     q = Ref{Cint}(0)
     ccall((:mle_model_nqoi, libmle), Cint, (Ptr{Cvoid}, Ref{Cint}), ref[], q)

@@ -170,9 +170,14 @@ class GpuBackend:
             m.set_basis(level, phi)
         return m
 
-    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed):
-        mom, t = self.engine.sample_batch(model, lattice, dists, index, shifts, k0, n, m=m, mc_seed=mc_seed, want_time=True)
-        return mom, t
+    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
+        """-> (moments, seconds) or, with want_samples (the `save_samples` option), (moments, seconds, samples[R, q, 2, n])"""
+        out = self.engine.sample_batch(model, lattice, dists, index, shifts, k0, n, m=m, mc_seed=mc_seed, want_time=True,
+                                       want_samples=want_samples)
+        if want_samples:
+            mom, smp, t = out
+            return mom, t, smp
+        return out
 
 
 def split_range(k0, n, world, rank):
@@ -204,8 +209,10 @@ class ShardedBackend:
     def model(self, spec):
         return self.inner.model(spec)
 
-    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed):
+    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         import torch
+        if want_samples:
+            raise NotImplementedError("save_samples is a single-rank option: the raw samples of a sharded run stay on their ranks")
         start, cnt = split_range(k0, n, self.world, self.rank)
         R = 1 if shifts is None else len(shifts)
         q = getattr(model, "nqoi", 1)
@@ -233,7 +240,7 @@ _DEFAULTS = dict(nb_of_qoi=None, aggregation="max", qoi_with_max_var=1, continua
                  do_mse_splitting=True, do_regression=True, min_index_set_param=2, max_index_set_param=None,
                  sample_mul_factor=1.2, nb_of_warm_up_samples=None, nb_of_shifts=10, nb_of_uncertainties=None,
                  cost_model=None, point_generator=None, shifts=None, shift_seed=0, mc_seed=1, name="UntitledEstimator",
-                 verbose=False, max_search_space=None, penalization=0.5, acceptance_rate=1.0)
+                 verbose=False, max_search_space=None, penalization=0.5, acceptance_rate=1.0, save_samples=False)
 _AD_ONLY = ("max_search_space", "penalization", "acceptance_rate")  # src/options.jl:36
 
 
@@ -301,6 +308,7 @@ class Estimator:
         self.ad_boundary = {(0,) * d}
         self._ad_rng = _random.Random(o["shift_seed"])
         self.moments, self.nb_of_samples, self.total_work, self.total_time = {}, {}, {}, {}
+        self.samples = {}  # save_samples: index -> list of [R, q, 2, n] blocks (X = 0: differences, 1: fine values)
         self.shifts = {}
         rng = np.random.default_rng(o["shift_seed"])
         for index in sorted(box, key=lambda t: t[::-1]):  # column-major order of the index box, src/internals.jl:138
@@ -322,8 +330,14 @@ class Estimator:
         istart = self.nb_of_samples[index] + 1
         m = self.options["nb_of_uncertainties"](index)
         t0 = _time.perf_counter()
-        mom, _gpu_t = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
-                                                self.shifts.get(index), istart - 1, n, m, self.options["mc_seed"])
+        if self.options["save_samples"]:  # src/history.jl:92-95: keep the raw samples as well (single-rank backends)
+            mom, _gpu_t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
+                                                         self.shifts.get(index), istart - 1, n, m, self.options["mc_seed"],
+                                                         want_samples=True)
+            self.samples.setdefault(index, []).append(np.array(smp))
+        else:
+            mom, _gpu_t = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
+                                                    self.shifts.get(index), istart - 1, n, m, self.options["mc_seed"])
         t = _time.perf_counter() - t0
         if index in self.moments:
             from .engine import moments_merge
@@ -672,6 +686,10 @@ def update_history(history, est, tol, elapsed):  # src/history.jl:55-103
         h["W"] = {i: est.cost(i) for i in allk}
     if est.adaptive:
         h["logbook"] = list(est.logbook)  # src/history.jl:87
+    if est["save_samples"]:  # src/history.jl:92-95; arrays [R, q, n] per index
+        cat = {i: np.concatenate(b, axis=-1) for i, b in est.samples.items()}
+        h["samples"] = {i: a[:, :, 1, :] for i, a in cat.items()}
+        h["samples_diff"] = {i: a[:, :, 0, :] for i, a in cat.items()}
     history.data.append(h)
 
 

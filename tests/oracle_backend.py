@@ -25,7 +25,10 @@ class OracleBackend:
     def model(self, spec):
         return _OModel(spec)
 
-    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed):
+    def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         z, nmax = lattice if lattice is not None else (None, 2**32 - 1)
+        if want_samples:
+            mom, smp = O.sample_batch(model.m, z, dists, index, shifts, k0, n, m=m, nmax=nmax, mc_seed=mc_seed, want_samples=True)
+            return mom, 0.0, smp
         mom = O.sample_batch(model.m, z, dists, index, shifts, k0, n, m=m, nmax=nmax, mc_seed=mc_seed)
         return mom, 0.0

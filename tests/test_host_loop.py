@@ -224,3 +224,18 @@ def test_adaptive_lognormal2d_multi_index_run():
     h = H.run(est, 5e-3)
     assert 0.05 < h["mean"] < 0.09 and h["ndims"] == 2
     assert all(abs(h["dE"][i]) < abs(h["dE"][(0, 0)]) for i in h["index_set"] if i != (0, 0))
+
+
+def test_save_samples_history_keys():
+    """src/history.jl:92-95: with save_samples the History carries the raw samples; mean / var recomputed from them the
+    reference's way (src/methods.jl:48-57) agree with the moment-based statistics"""
+    H = host()
+    est = H.Estimator(H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                      max_index_set_param=2, cost_model=lambda i: 2.0 ** i[0], nb_of_tols=2, nb_of_shifts=4, save_samples=True)
+    h = H.run(est, 5e-2)
+    assert "samples" in h and "samples_diff" in h
+    for idx in h["index_set"]:
+        sd = h["samples_diff"][idx]                        # [R, q, n]
+        assert sd.shape[0] == 4 and sd.shape[1] == 13 and sd.shape[2] == h["nb_of_samples"][idx]
+        assert abs(sd[:, 0, :].mean(axis=1).mean() - h["dE"][idx]) <= 1e-12 * max(1.0, abs(h["dE"][idx]))
+        assert abs(h["samples"][idx][:, 0, :].mean(axis=1).mean() - h["E"][idx]) <= 1e-12 * max(1.0, abs(h["E"][idx]))
