@@ -59,7 +59,8 @@ __device__ __forceinline__ void rows_sync(int barid) {
     else asm volatile("bar.sync %0, %1;" ::"r"(barid), "n"(GT) : "memory");
 }
 
-__host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * w + 8; }
+// 2 v buffers (skewed by 2 doubles per chunk when a row spans several lanes, i.e. from 64 cells up) + 8 for the pivot exchange
+__host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * (w + (w > 32 ? 16 : 0)) + 8; }
 
 // u at the centre node (Nx/2, Ny/2) of the NW x Ny-cell grid.  Called by all GT threads of the sample's group
 // (tg = 0 .. GT-1, GT = 32 stands for "some lanes of one warp"); lanes with tg >= NW*LPR idle (coarse solves run on the fine
@@ -71,8 +72,12 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
     static_assert(C >= 2 && C * LPR == NW && (C % 2) == 0, "NW / LPR even and >= 2");
     const int q = tg / LPR, s = tg % LPR;
     const bool lane_on = q < NW;
-    double *vs = sh;            // [2][NW]: column vector v of the current pivot (slot = row - p - 1)
-    double *piv = sh + 2 * NW;  // [2][4]: 1/d, g_p, -kx and diagonal of the entering unknown
+    // v buffers: chunk s (the C slots one lane reads) starts 2 doubles later than s*C, so that the 16-byte loads of the LPR
+    // lanes of a row (and of a quarter warp) fall into different banks (C*8 bytes is a multiple of the 128-byte bank row)
+    constexpr int VS = NW + (LPR > 1 ? 16 : 0);
+    auto vi = [](int slot) { return LPR == 1 ? slot : slot + 2 * (slot / C); };
+    double *vs = sh;            // [2][VS]: column vector v of the current pivot (slot = row - p - 1)
+    double *piv = sh + 2 * VS;  // [2][4]: 1/d, g_p, -kx and diagonal of the entering unknown
     const int c = f.Ny / 2, P = (c - 1) * n, last = P + n - 1;
     double reg[C], g = 0.0, g2 = 0.0, rcp = 0.0;
     int row = -1, step = 0;  // step: running parity of the exchange buffers
@@ -87,11 +92,11 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
         constexpr bool ENTER = decltype(enter_tag)::value;
         const int buf = step & 1;
         ++step;
-        double *vb = vs + buf * NW, *pb = piv + buf * 4;
+        double *vb = vs + buf * VS, *pb = piv + buf * 4;
         if (lane_on && s == 0) {
-            if (row > p) vb[row - p - 1] = reg[0];
+            if (row > p) vb[vi(row - p - 1)] = reg[0];
             if (row == p) *reinterpret_cast<double2 *>(pb) = make_double2(rcp, g);
-            if (ENTER && q == ie - 1) { vb[n - 1] = cky; *reinterpret_cast<double2 *>(pb + 2) = make_double2(ckx, cdg); }
+            if (ENTER && q == ie - 1) { vb[vi(n - 1)] = cky; *reinterpret_cast<double2 *>(pb + 2) = make_double2(ckx, cdg); }
         }
         rows_sync<GT>(barid);
         const double2 pg = *reinterpret_cast<const double2 *>(pb);  // 1/d, g_p
@@ -105,7 +110,7 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
 #pragma unroll
                 for (int j = 0; j < C; ++j) reg[j] = 0.0;
                 if (s == LPR - 1) reg[C - 2] = ent.x;
-                if (s == 0) reg[0] = vb[n - 1];
+                if (s == 0) reg[0] = vb[vi(n - 1)];
             }
             top = me ? ent.y : (row == e - 1 ? ent.x : 0.0);
         }
@@ -113,10 +118,10 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
         double nb = 0.0;
         if (LPR > 1) nb = __shfl_down_sync(0xffffffffu, reg[0], 1);  // position (s+1)*C lives in the next lane of the row
         const bool active = row > p;
-        const double v = LPR == 1 ? reg[0] : vb[active ? row - p - 1 : 0];
+        const double v = LPR == 1 ? reg[0] : vb[active ? vi(row - p - 1) : 0];
         const double l = active ? __dmul_rn(v, pg.x) : 0.0;
         g = __fma_rn(-l, pg.y, g);
-        const double2 *vv = reinterpret_cast<const double2 *>(vb + s * C);
+        const double2 *vv = reinterpret_cast<const double2 *>(vb + vi(s * C));
         {
             const double2 t = vv[0];
             reg[0] = __fma_rn(-l, t.x, reg[1]);
@@ -194,24 +199,24 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
         const int rowt = last - k;
         const int buf = step & 1;
         ++step;
-        double *vb = vs + buf * NW, *pb = piv + buf * 4;
+        double *vb = vs + buf * VS, *pb = piv + buf * 4;
         if (lane_on && s == sL) {
-            if (row >= rtc && row < rowt) vb[row - rtc + k] = reg[jL];
+            if (row >= rtc && row < rowt) vb[vi(row - rtc + k)] = reg[jL];
             else if (row == rowt) { pb[0] = rcp; pb[1] = g; }
         }
         rows_sync<GT>(barid);
         double pv = 0.0;
         if (LPR > 1) pv = __shfl_up_sync(0xffffffffu, reg[C - 1], 1);  // position s*C - 1 lives in the previous lane of the row
         if (row >= rtc && row < rowt) {
-            const double l = __dmul_rn(vb[row - rtc + k], pb[0]);
+            const double l = __dmul_rn(vb[vi(row - rtc + k)], pb[0]);
             g = __fma_rn(-l, pb[1], g);
             // new[pos + 1] = fma(-l, v[pos], old[pos]) for pos = 0 .. L-1, descending so nothing is overwritten early
 #pragma unroll
             for (int j = C - 1; j >= 1; --j) {
                 const int pos = s * C + j - 1;  // source position
-                if (pos < L) reg[j] = __fma_rn(-l, vb[pos], reg[j - 1]);
+                if (pos < L) reg[j] = __fma_rn(-l, vb[vi(pos)], reg[j - 1]);
             }
-            if (LPR > 1 && s > 0 && s * C - 1 < L) reg[0] = __fma_rn(-l, vb[s * C - 1], pv);
+            if (LPR > 1 && s > 0 && s * C - 1 < L) reg[0] = __fma_rn(-l, vb[vi(s * C - 1)], pv);
             if (s == sL && row == rowt - 1 && rowt - 1 > rtc) rcp = __ddiv_rn(1.0, reg[jL]);
         } else if (row == rowt) {
             row = -1;
