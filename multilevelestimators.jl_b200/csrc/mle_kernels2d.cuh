@@ -59,8 +59,9 @@ __device__ __forceinline__ void rows_sync(int barid) {
     else asm volatile("bar.sync %0, %1;" ::"r"(barid), "n"(GT) : "memory");
 }
 
-// 2 v buffers (skewed by 2 doubles per chunk when a row spans several lanes, i.e. from 64 cells up) + 8 for the pivot exchange
-__host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * (w + (w > 32 ? 16 : 0)) + 8; }
+// 2 v buffers + 8 for the pivot exchange + (rows spanning LPR = w/32 lanes, from 64 cells up) 2 x (LPR-1) x w for the
+// window entries that cross a chunk boundary
+__host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * w + 8 + (w > 32 ? 2 * (w / 32 - 1) * w : 0); }
 
 // u at the centre node (Nx/2, Ny/2) of the NW x Ny-cell grid.  Called by all GT threads of the sample's group
 // (tg = 0 .. GT-1, GT = 32 stands for "some lanes of one warp"); lanes with tg >= NW*LPR idle (coarse solves run on the fine
@@ -70,14 +71,15 @@ template <int NW, int LPR, int GT>
 __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double *park, int pstride, int tg, int barid) {
     constexpr int C = NW / LPR, n = NW - 1, tc = NW / 2 - 1, L = NW / 2 - 1;  // L = n - 1 - tc: position of the last pivot column
     static_assert(C >= 2 && C * LPR == NW && (C % 2) == 0, "NW / LPR even and >= 2");
-    const int q = tg / LPR, s = tg % LPR;
-    const bool lane_on = q < NW;
-    // v buffers: chunk s (the C slots one lane reads) starts 2 doubles later than s*C, so that the 16-byte loads of the LPR
-    // lanes of a row (and of a quarter warp) fall into different banks (C*8 bytes is a multiple of the 128-byte bank row)
-    constexpr int VS = NW + (LPR > 1 ? 16 : 0);
-    auto vi = [](int slot) { return LPR == 1 ? slot : slot + 2 * (slot / C); };
+    // row group q, chunk s: with several lanes per row, chunk s of all rows sits in consecutive threads, so the lanes of a
+    // warp read the same v entries (broadcast) and the entry that crosses a chunk boundary travels through shared memory
+    const int q = LPR == 1 ? tg : tg % NW, s = LPR == 1 ? 0 : tg / NW;
+    const bool lane_on = tg < NW * LPR;
+    constexpr int VS = NW;
+    auto vi = [](int slot) { return slot; };
     double *vs = sh;            // [2][VS]: column vector v of the current pivot (slot = row - p - 1)
     double *piv = sh + 2 * VS;  // [2][4]: 1/d, g_p, -kx and diagonal of the entering unknown
+    double *xch = piv + 8;      // [2][LPR-1][NW]: position s*C of row q before the step, for the lane that holds chunk s-1
     const int c = f.Ny / 2, P = (c - 1) * n, last = P + n - 1;
     double reg[C], g = 0.0, g2 = 0.0, rcp = 0.0;
     int row = -1, step = 0;  // step: running parity of the exchange buffers
@@ -98,12 +100,14 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
             if (row == p) *reinterpret_cast<double2 *>(pb) = make_double2(rcp, g);
             if (ENTER && q == ie - 1) { vb[vi(n - 1)] = cky; *reinterpret_cast<double2 *>(pb + 2) = make_double2(ckx, cdg); }
         }
+        if (LPR > 1 && lane_on && s > 0) xch[(buf * (LPR - 1) + s - 1) * NW + q] = reg[0];
         rows_sync<GT>(barid);
         const double2 pg = *reinterpret_cast<const double2 *>(pb);  // 1/d, g_p
         double top = 0.0;                                            // what position n holds for this row
+        bool me = false;
         if (ENTER) {
             const double2 ent = *reinterpret_cast<const double2 *>(pb + 2);  // -kx, diagonal of the entering unknown
-            const bool me = lane_on && q == se;
+            me = lane_on && q == se;
             if (me) {
                 row = e;
                 g = gv;
@@ -115,8 +119,8 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
             top = me ? ent.y : (row == e - 1 ? ent.x : 0.0);
         }
         if (s == LPR - 1) reg[C - 1] = top;
-        double nb = 0.0;
-        if (LPR > 1) nb = __shfl_down_sync(0xffffffffu, reg[0], 1);  // position (s+1)*C lives in the next lane of the row
+        double nb = 0.0;  // position (s+1)*C lives in the lane that holds the next chunk of the row
+        if (LPR > 1 && lane_on && s < LPR - 1 && !me) nb = xch[(buf * (LPR - 1) + s) * NW + q];
         const bool active = row > p;
         const double v = LPR == 1 ? reg[0] : vb[active ? vi(row - p - 1) : 0];
         const double l = active ? __dmul_rn(v, pg.x) : 0.0;
@@ -204,9 +208,10 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
             if (row >= rtc && row < rowt) vb[vi(row - rtc + k)] = reg[jL];
             else if (row == rowt) { pb[0] = rcp; pb[1] = g; }
         }
+        if (LPR > 1 && lane_on && s < LPR - 1) xch[(buf * (LPR - 1) + s) * NW + q] = reg[C - 1];
         rows_sync<GT>(barid);
-        double pv = 0.0;
-        if (LPR > 1) pv = __shfl_up_sync(0xffffffffu, reg[C - 1], 1);  // position s*C - 1 lives in the previous lane of the row
+        double pv = 0.0;  // position s*C - 1 lives in the lane that holds the previous chunk of the row
+        if (LPR > 1 && lane_on && s > 0) pv = xch[(buf * (LPR - 1) + s - 1) * NW + q];
         if (row >= rtc && row < rowt) {
             const double l = __dmul_rn(vb[vi(row - rtc + k)], pb[0]);
             g = __fma_rn(-l, pb[1], g);
