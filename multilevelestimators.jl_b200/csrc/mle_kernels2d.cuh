@@ -125,21 +125,31 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
         const double v = LPR == 1 ? reg[0] : vb[active ? vi(row - p - 1) : 0];
         const double l = active ? __dmul_rn(v, pg.x) : 0.0;
         g = __fma_rn(-l, pg.y, g);
-        const double2 *vv = reinterpret_cast<const double2 *>(vb + vi(s * C));
-        {
-            const double2 t = vv[0];
-            reg[0] = __fma_rn(-l, t.x, reg[1]);
-            const double r1 = __ddiv_rn(1.0, reg[0]);  // the next pivot's reciprocal: overlaps the FMAs below
-            rcp = (s == 0 && row == p + 1) ? r1 : rcp;
-            if (C > 2) reg[1] = __fma_rn(-l, t.y, reg[2]);
-            else if (LPR > 1 && s < LPR - 1) reg[1] = __fma_rn(-l, t.y, nb);
-        }
+        // v is read in groups of PF 16-byte loads issued ahead of the FMAs that consume them (volatile: the order is kept,
+        // so PF loads are in flight instead of one)
+        constexpr int PF = C >= 16 ? 4 : C / 2, NG = (C / 2) / PF;
+        const uint32_t va = smem_u32(vb + vi(s * C));
+        double w[2][2 * PF];
+        auto load_group = [&](int gi, double *dst) {
 #pragma unroll
-        for (int j2 = 1; j2 < C / 2; ++j2) {
-            const double2 t = vv[j2];
-            reg[2 * j2] = __fma_rn(-l, t.x, reg[2 * j2 + 1]);
-            if (2 * j2 + 2 < C) reg[2 * j2 + 1] = __fma_rn(-l, t.y, reg[2 * j2 + 2]);
-            else if (LPR > 1 && s < LPR - 1) reg[2 * j2 + 1] = __fma_rn(-l, t.y, nb);
+            for (int t = 0; t < PF; ++t)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(dst[2 * t]), "=d"(dst[2 * t + 1]) : "r"(va + 16 * (gi * PF + t)));
+        };
+        load_group(0, w[0]);
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            if (gi + 1 < NG) load_group(gi + 1, w[(gi + 1) & 1]);
+            const double *wg = w[gi & 1];
+#pragma unroll
+            for (int t = 0; t < 2 * PF; ++t) {
+                const int i = gi * 2 * PF + t;  // reg[i] = fma(-l, v[i], reg[i + 1])
+                if (i + 1 < C) reg[i] = __fma_rn(-l, wg[t], reg[i + 1]);
+                else if (LPR > 1 && s < LPR - 1) reg[i] = __fma_rn(-l, wg[t], nb);
+                if (i == 0) {
+                    const double r1 = __ddiv_rn(1.0, reg[0]);  // the next pivot's reciprocal: overlaps the FMAs below
+                    rcp = (s == 0 && row == p + 1) ? r1 : rcp;
+                }
+            }
         }
         row = row == p ? -1 : row;
     };
