@@ -108,3 +108,20 @@ def test_adaptive_multi_index_lognormal2d_run_matches_oracle(engine):
     compare(hg, ho)
     assert hg["logbook"] == ho["logbook"]
     assert 0.05 < hg["mean"] < 0.09
+
+
+def test_single_level_mc_c1_run_matches_oracle(engine):
+    """config C1 on the device: SL()/MC(), 16 Normal() inputs, run(estimator, 1e-3); closed form E = exp(sum a_j^2 / 2)"""
+    import math
+    w = [0.5 / (j + 1) for j in range(16)]
+
+    def make(H, backend):
+        return H.Estimator(H.SL(), H.MC(), H.ModelSpec("expsum", 1, [16] + w), [H.Normal()] * 16, backend,
+                           cost_model=lambda i: 1.0, nb_of_tols=4)
+
+    H, g, o = both(engine, make)
+    hg, ho = H.run(g, 1e-3), H.run(o, 1e-3)
+    compare(hg, ho)
+    exact = math.exp(0.5 * sum(a * a for a in w))
+    assert abs(hg["mean"] - exact) < 4e-3 and hg["rmse"] <= 1e-3 * 1.01
+    assert hg["nb_of_samples"][(0,)] > 100000     # theta = 0.5: N = 2 V / eps^2
