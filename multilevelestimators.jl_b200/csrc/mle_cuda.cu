@@ -828,7 +828,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                 rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);                \
                 if (rc) return rc;                                                                                     \
                 {                                                                                                      \
-                    const size_t park = (size_t)gx * R * 32 * Cfg::THREADS;                                            \
+                    const size_t park = (size_t)gx * R * ROWS_PARK * Cfg::THREADS;                                            \
                     rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, park + (ra.use_scratch ? (size_t)gx * R * (fbytes / 8) : 0)); \
                     if (rc) return rc;                                                                                 \
                     ra.park = ctx->d_scratch;                                                                          \

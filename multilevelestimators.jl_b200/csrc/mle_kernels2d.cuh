@@ -34,7 +34,7 @@ struct Lognormal2dRowsArgs {
     int ntiles;           // node tiles of 8 rows
     int use_scratch;      // F in global scratch instead of shared memory
     double *scratch;      // [CTAs in grid][ntiles*8*LDF]
-    double *park;         // [CTAs in grid][32][THREADS]: the upper half's centre block of every thread
+    double *park;         // [CTAs in grid][ROWS_PARK][THREADS]: the upper half's centre block of every thread
 };
 
 // node values a[((j*sty)*lda + i*stx) * ns] of an Nx x Ny-cell grid (optionally y-mirrored); ns = distance between nodes
@@ -53,6 +53,8 @@ struct FieldView {
     }
 };
 
+constexpr int ROWS_PARK = 64;  // window columns a lane can hold
+
 template <int GT>
 __device__ __forceinline__ void rows_sync(int barid) {
     if (GT <= 32) __syncwarp();
@@ -70,7 +72,7 @@ __host__ __device__ constexpr int rows_sh_doubles(int w) { return 2 * w + 8 + (w
 template <int NW, int LPR, int GT>
 __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double *park, int pstride, int tg, int barid) {
     constexpr int C = NW / LPR, n = NW - 1, tc = NW / 2 - 1, L = NW / 2 - 1;  // L = n - 1 - tc: position of the last pivot column
-    static_assert(C >= 2 && C * LPR == NW && (C % 2) == 0, "NW / LPR even and >= 2");
+    static_assert(C >= 2 && C <= ROWS_PARK && C * LPR == NW && (C % 2) == 0, "NW / LPR even, >= 2, <= ROWS_PARK");
     // row group q, chunk s: with several lanes per row, chunk s of all rows sits in consecutive threads, so the lanes of a
     // warp read the same v entries (broadcast) and the entry that crosses a chunk boundary travels through shared memory
     const int q = LPR == 1 ? tg : tg % NW, s = LPR == 1 ? 0 : tg / NW;
@@ -251,10 +253,13 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
 
 // ---- kernel ---------------------------------------------------------------------------------------------------------
 template <int W> struct Rows2dCfg {
-    static constexpr int LPR = W > 32 ? W / 32 : 1;
+#ifndef MLE_ROWS_FAT
+#define MLE_ROWS_FAT 1  // 1: 64 window columns per lane from 64 cells up (255 registers, one resident CTA); 0: 32 (two CTAs)
+#endif
+    static constexpr int LPR = MLE_ROWS_FAT ? (W > 64 ? W / 64 : 1) : (W > 32 ? W / 32 : 1);
     static constexpr int TGS = W * LPR;                       // threads per sample
-    static constexpr int THREADS = W >= 128 ? 512 : W >= 8 ? 256 : 32 * W;
-    static constexpr int MINB = W >= 128 ? 1 : W >= 32 ? 2 : 1;  // resident CTAs the register budget is sized for
+    static constexpr int THREADS = (W >= 128 && !MLE_ROWS_FAT) ? 512 : W >= 8 ? 256 : 32 * W;
+    static constexpr int MINB = (W >= 64 && MLE_ROWS_FAT) ? 1 : W >= 128 ? 1 : W >= 32 ? 2 : 1;  // resident CTAs the register budget is sized for
     static constexpr int CS = THREADS / TGS;                  // samples solved concurrently
     static constexpr int S = CS < 8 ? 8 : CS;                 // samples per CTA iteration (a multiple of the DMMA tile)
     static constexpr int LDX = S + 4, LDF = S == 8 ? 8 : S + 8;
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
             const int grp = tid / TGS, tg = tid % TGS, sigma = rd * CS + grp;
             double *sh = gsh + grp * rows_sh_doubles(W);
             FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
-            double *park = la.park + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 * THREADS + tid;
+            double *park = la.park + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ROWS_PARK * THREADS + tid;
             const double qf = frontal_mid_rows<W, LPR, GT>(fv, sh, park, THREADS, tg, 1 + grp);
             double dq = qf;
             // coarse terms of diff(index), added in the order (lx-1,ly-1), (lx,ly-1), (lx-1,ly); multilevel: one coarse solve
