@@ -337,7 +337,7 @@ def run_ours(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        fp64 = fp64_peak_tflops() if world == 1 else {}
+        fp64 = fp64_peak_tflops()  # a subprocess on device 0 = rank 0's GPU, after the timed regions
         flops_step = sum(algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS for li, lev in enumerate(LEVELS))
         kernel_ms = sum(lvl_ms)
         achieved_tf = flops_step / (kernel_ms * 1e-3) * 1e-12
