@@ -46,10 +46,18 @@ template <int MODE> static constexpr auto lognormal2d_r128 = lognormal2d_rows_ke
         }                                                                                      \
     } while (0)
 
+// resident CTAs per SM of (kernel, block size, dynamic shared memory); the query costs a few microseconds, so the answers are
+// remembered (one calling thread per context, see include/mle_cuda.h)
 template <typename K>
 static int resident_ctas_per_sm(K kernel, int threads, size_t smem) {
+    struct Entry { const void *fn; int threads; size_t smem; int n; };
+    static std::vector<Entry> cache;
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    for (const Entry &e : cache)
+        if (e.fn == fn && e.threads == threads && e.smem == smem) return e.n;
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 1; }
+    if (cache.size() < 256) cache.push_back(Entry{fn, threads, smem, n});
     return n;
 }
 #define MLE_OCC_BY_MODE(mode, K, threads, smem)                                             \
@@ -80,6 +88,7 @@ struct mle_ctx_s {
     size_t partials_cap = 0;  // in Moments
     double *d_shifts = nullptr;
     size_t shifts_cap = 0;
+    size_t shifts_staged = 0;  // doubles of h_pinned[0..] that mirror d_shifts (0: nothing valid)
     double *d_scratch = nullptr;  // lognormal2d: per-group field / centre blocks for the large grids
     size_t scratch_cap = 0;
     double *d_zero = nullptr;  // a row of zeros standing in for the shift of an unshifted rule
@@ -176,8 +185,9 @@ static int ensure_dev(mle_ctx ctx, T **p, size_t *cap, size_t need) {
 
 static int ensure_pinned(mle_ctx ctx, size_t need) {
     if (ctx->pinned_cap >= need) return MLE_OK;
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_pinned); }  // copies from it may be in flight
     ctx->h_pinned = nullptr; ctx->pinned_cap = 0;
+    ctx->shifts_staged = 0;
     size_t want = need + need / 2 + 64;
     cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_pinned), want * sizeof(double));
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMallocHost failed"); }
@@ -623,12 +633,20 @@ static int upload_shifts(mle_ctx ctx, mle_lattice lat, const double *shifts, int
     if (!shifts) return MLE_OK;
     if (!lat) return fail(ctx, MLE_ERR_ARG, "MC sampling takes no shifts");
     const size_t cnt = (size_t)R * (size_t)lat->s;
+    const double *before = ctx->d_shifts;
     int rc = ensure_dev(ctx, &ctx->d_shifts, &ctx->shifts_cap, cnt);
     if (rc) return rc;
+    if (ctx->d_shifts != before) ctx->shifts_staged = 0;
     rc = ensure_pinned(ctx, cnt + 4096);
     if (rc) return rc;
-    memcpy(ctx->h_pinned, shifts, cnt * sizeof(double));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_shifts, ctx->h_pinned, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // the adaptive loop calls again and again with the same shifts of an index (src/internals.jl:138: one shift vector per
+    // (index, shift) for the whole run): skip the copy when the staged image is still what the device holds
+    if (ctx->shifts_staged != cnt || memcmp(ctx->h_pinned, shifts, cnt * sizeof(double)) != 0) {
+        memcpy(ctx->h_pinned, shifts, cnt * sizeof(double));
+        ctx->shifts_staged = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_shifts, ctx->h_pinned, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->shifts_staged = cnt;
+    }
     *dev = ctx->d_shifts;
     return MLE_OK;
 }
@@ -910,19 +928,30 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     const size_t nm = (size_t)R * 2 * (size_t)M->nqoi * 3;
     rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, nm);
     if (rc) return rc;
+    const size_t mom_off = (shifts && lat) ? (size_t)R * (size_t)lat->s : 0;  // staging for the moments: behind the shifts image
+    if (mom_off + nm > ctx->pinned_cap) {
+        ctx->shifts_staged = 0;  // growing the staging area discards the shifts image (re-uploaded by the next call)
+        rc = ensure_pinned(ctx, mom_off + nm + 4096);
+        if (rc) return rc;
+        if (mom_off) { sh_dev = nullptr; rc = upload_shifts(ctx, lat, shifts, R, &sh_dev); if (rc) return rc; }
+    }
     double *d_samples = nullptr;
     const size_t ns = samples ? (size_t)R * 2 * (size_t)M->nqoi * n : 0;
     if (samples && ns) {
         if (MLE_MALLOC(&d_samples, ns * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(samples)"); }
     }
-    cudaEventRecord(ctx->ev0, ctx->stream);
+    if (gpu_seconds) cudaEventRecord(ctx->ev0, ctx->stream);  // timing is optional: two event records cost ~4 us per call
     rc = mle_sample_batch_dev(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, ctx->d_moments, d_samples);
-    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (gpu_seconds) cudaEventRecord(ctx->ev1, ctx->stream);
     if (rc == MLE_OK) {
-        cudaError_t e = cudaMemcpyAsync(moments, ctx->d_moments, nm * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        // the moment table comes back through the pinned staging area (behind the shifts image): a pageable destination
+        // would make the copy synchronous inside the driver
+        double *stage = (ctx->h_pinned && mom_off + nm <= ctx->pinned_cap) ? ctx->h_pinned + mom_off : nullptr;
+        cudaError_t e = cudaMemcpyAsync(stage ? stage : moments, ctx->d_moments, nm * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess && d_samples) e = cudaMemcpyAsync(samples, d_samples, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_batch: ") + cudaGetErrorString(e)); }
+        else if (stage) memcpy(moments, stage, nm * sizeof(double));
         if (rc == MLE_OK && gpu_seconds) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);

@@ -208,7 +208,7 @@ class Engine:
         self._check(self.lib.mle_sample_batch(self.ctx, model.handle, lattice.handle if lattice else None,
                                               dists.handle if dists else None, idx.ctypes.data_as(C.POINTER(C.c_int32)),
                                               len(idx), _as_dp(shifts), R, int(k0), int(n), int(m), int(mc_seed),
-                                              _as_dp(mom), _as_dp(smp), C.byref(t)))
+                                              _as_dp(mom), _as_dp(smp), C.byref(t) if want_time else None))
         out = (mom,)
         if want_samples:
             out += (smp,)
