@@ -26,7 +26,7 @@ def kl_basis_2d(level, m=400, n0=4, sigma=0.5, decay=1.5):
     x = np.arange(Nx + 1, dtype=np.float64) / Nx
     y = np.arange(Ny + 1, dtype=np.float64) / Ny
     modes, t = [], 0
-    while len(modes) < m:
+    while len(modes) < m + 1:  # + the constant mode that is dropped below
         for p in range(t + 1):
             modes.append((p, t - p))
         t += 1

@@ -331,6 +331,42 @@ def test_lognormal2d_both_kernels_agree(engine, oracle, monkeypatch):
     assert np.array_equal(out[0], out[1])
 
 
+MIXED = [(2, [0.0, 1.0, -2.0, 2.0]), (0, [-1.0, 1.0]), (1, [0.1, 0.7])]   # TruncatedNormal, Uniform, Normal(mu, sigma)
+
+
+@pytest.mark.parametrize("model,ndims,index,n0,mc", [("expsum", 1, (1,), 0, False), ("lognormal1d", 1, (2,), 16, False),
+                                                     ("lognormal1d", 1, (1,), 16, True), ("lognormal2d", 1, (2,), 4, False),
+                                                     ("lognormal2d", 2, (1, 2), 4, True), ("lognormal2d", 1, (1,), 6, False)])
+def test_general_distribution_mix_through_every_kernel(engine, oracle, model, ndims, index, n0, mc):
+    """heterogeneous `distributions` (src/estimator.jl:116: one object per dimension): the general inverse-CDF path
+    (TruncatedNormal, Uniform, Normal(mu, sigma) interleaved; Weibull's log/pow come from the platform libm and are covered
+    to 4 ulp in test_gpu_points.py) inside every fused kernel, lattice and MC inputs"""
+    import mle_b200.kl as kl
+    m = 36
+    dl = [MIXED[j % 3] for j in range(m)]
+    z = oracle.genvec("K_3600_32", m)
+    if model == "expsum":
+        w = [0.3 / (j + 1) for j in range(m)]
+        gm, om = engine.model("expsum", 1, [4] + w), oracle.Model(oracle.MODEL_EXPSUM, 1, [4] + w)
+    else:
+        kind = oracle.MODEL_LOGNORMAL1D if model == "lognormal1d" else oracle.MODEL_LOGNORMAL2D
+        gm, om = engine.model(model, ndims, [n0]), oracle.Model(kind, ndims, [float(n0)])
+        key = index[0] if ndims == 1 else tuple(index)
+        phi = 0.3 * (kl.kl_basis_1d(key, m=m, n0=n0) if model == "lognormal1d" else kl.kl_basis_2d(key, m=m, n0=n0))
+        gm.set_basis(key, phi)
+        om.set_basis(key, phi)
+    d = engine.dists(dl)
+    if mc:
+        got, smp = engine.sample_batch(gm, None, d, list(index), None, 0, 90, m=m, mc_seed=17, want_samples=True)
+        want, smp_w = oracle.sample_batch(om, None, dl, list(index), None, 0, 90, m=m, mc_seed=17, want_samples=True)
+    else:
+        sh = splitmix_uniforms(8, 3 * m).reshape(3, m)
+        got, smp = engine.sample_batch(gm, engine.lattice(z, m), d, list(index), sh, 2, 70, want_samples=True)
+        want, smp_w = oracle.sample_batch(om, z, dl, list(index), sh, 2, 70, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
+
+
 @pytest.mark.parametrize("m,level", [(200, 1), (300, 0), (129, 2)])
 def test_lognormal1d_many_kl_terms(engine, oracle, m, level):
     """more than 128 KL terms: the generator switches to 64-bit class masks and multiple passes over the dimensions"""
