@@ -331,6 +331,40 @@ def test_lognormal2d_both_kernels_agree(engine, oracle, monkeypatch):
     assert np.array_equal(out[0], out[1])
 
 
+@pytest.mark.parametrize("level,n,m", [(0, 70000, 24), (2, 12000, 24), (3, 6000, 24), (4, 1500, 16), (0, 300, 400)])
+def test_lognormal2d_many_tiles_per_cta(engine, oracle, level, n, m):
+    """more samples than the persistent grid holds at once (several CTA iterations, a ragged last tile, the L2 scratch field from
+    64x64 up, 400 KL terms generated in several chunks): every per-sample value still bit-identical"""
+    z, lat, dl, d, gm, om = lognormal2d_setup(engine, oracle, m, [level])
+    got, smp = engine.sample_batch(gm, None, d, [level], None, 5, n, mc_seed=3, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, None, dl, [level], None, 5, n, mc_seed=3, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
+
+
+@pytest.mark.parametrize("model", ["expsum", "problem18", "lognormal1d", "lognormal2d"])
+def test_empty_and_single_sample_batches(engine, oracle, model):
+    """n = 0 is refused (update_samples never asks for it: `n_due > 0 && sample!`, src/sample.jl:11) and n = 1 per shift works
+    (the QMC warm-up, src/parse.jl:36: the variance of one sample is NaN in the reference, M2 = 0 here)"""
+    import mle_b200
+    import mle_b200.kl as kl
+    m = 16
+    if model == "expsum":
+        gm = engine.model("expsum", 1, [4] + [0.1] * m)
+    elif model == "problem18":
+        gm, m = engine.model("problem18", 1), 1
+    else:
+        gm = engine.model(model, 1, [16 if model == "lognormal1d" else 4])
+        gm.set_basis(0, kl.kl_basis_1d(0, m=m) if model == "lognormal1d" else kl.kl_basis_2d(0, m=m))
+    dist = (0, [-0.5, 0.5]) if model == "problem18" else NORMAL01
+    lat, d = engine.lattice(None, m), engine.dists([dist] * m)
+    sh = splitmix_uniforms(4, 3 * m).reshape(3, m)
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.sample_batch(gm, lat, d, [0], sh, 0, 0)
+    mom1, smp = engine.sample_batch(gm, lat, d, [0], sh, 7, 1, want_samples=True)
+    assert np.all(mom1[..., 0] == 1) and np.all(mom1[..., 2] == 0) and np.array_equal(mom1[..., 1], smp[..., 0])
+
+
 MIXED = [(2, [0.0, 1.0, -2.0, 2.0]), (0, [-1.0, 1.0]), (1, [0.1, 0.7])]   # TruncatedNormal, Uniform, Normal(mu, sigma)
 
 
