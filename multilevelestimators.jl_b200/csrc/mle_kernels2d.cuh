@@ -251,15 +251,213 @@ __device__ __noinline__ double frontal_mid_rows(FieldView f, double *sh, double 
     }
 }
 
+// The same solver with RPL window rows per lane (NW <= 32): a sample occupies NW / RPL lanes of one warp, so the v loads and
+// all of the step's control flow are shared by RPL rows (2x the FMAs per issued instruction of overhead).  Row r of the
+// window lives in lane (r % NW) % TL, register set (r % NW) / TL, TL = NW / RPL.  Same arithmetic, same order.
+template <int NW, int RPL>
+__device__ __noinline__ double frontal_mid_rpl(FieldView f, double *sh, double *park, int pstride, int tg) {
+    constexpr int C = NW, n = NW - 1, tc = NW / 2 - 1, L = NW / 2 - 1, TL = NW / RPL;
+    static_assert(NW >= 4 && NW <= 32 && TL * RPL == NW && RPL * C <= ROWS_PARK, "window of at most 32 rows, RPL rows per lane");
+    const bool lane_on = tg < TL;
+    double *vs = sh;            // [2][NW]
+    double *piv = sh + 2 * NW;  // [2][4]
+    const int c = f.Ny / 2, P = (c - 1) * n, last = P + n - 1;
+    double reg[RPL][C], g[RPL], g2[RPL], rcp = 0.0;
+    int row[RPL], step = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        g[k] = 0.0; g2[k] = 0.0; row[k] = -1;
+#pragma unroll
+        for (int j = 0; j < C; ++j) reg[k][j] = 0.0;
+    }
+
+    auto eliminate = [&](auto enter_tag, int p, int e, int se, int ie, const double (&cdg)[RPL], const double (&ckx)[RPL],
+                         const double (&cky)[RPL], double gv) {
+        constexpr bool ENTER = decltype(enter_tag)::value;
+        const int buf = step & 1;
+        ++step;
+        double *vb = vs + buf * NW, *pb = piv + buf * 4;
+        if (lane_on) {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                if (row[k] > p) vb[row[k] - p - 1] = reg[k][0];
+                if (row[k] == p) *reinterpret_cast<double2 *>(pb) = make_double2(rcp, g[k]);
+                if (ENTER && k * TL + tg == ie - 1) { vb[n - 1] = cky[k]; *reinterpret_cast<double2 *>(pb + 2) = make_double2(ckx[k], cdg[k]); }
+            }
+        }
+        __syncwarp();
+        const double2 pg = *reinterpret_cast<const double2 *>(pb);  // 1/d, g_p
+        double l[RPL];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            double top = 0.0;
+            if (ENTER) {
+                const double2 ent = *reinterpret_cast<const double2 *>(pb + 2);  // -kx, diagonal of the entering unknown
+                const bool me = lane_on && k * TL + tg == se;
+                if (me) {
+                    row[k] = e;
+                    g[k] = gv;
+#pragma unroll
+                    for (int j = 0; j < C; ++j) reg[k][j] = 0.0;
+                    reg[k][C - 2] = ent.x;
+                    reg[k][0] = vb[n - 1];
+                }
+                top = me ? ent.y : (row[k] == e - 1 ? ent.x : 0.0);
+            }
+            reg[k][C - 1] = top;
+            l[k] = row[k] > p ? __dmul_rn(reg[k][0], pg.x) : 0.0;
+            g[k] = __fma_rn(-l[k], pg.y, g[k]);
+        }
+        constexpr int PF = C >= 16 ? 4 : C / 2, NG = (C / 2) / PF;
+        const uint32_t va = smem_u32(vb);
+        double w[2][2 * PF];
+        auto load_group = [&](int gi, double *dst) {
+#pragma unroll
+            for (int t = 0; t < PF; ++t)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(dst[2 * t]), "=d"(dst[2 * t + 1]) : "r"(va + 16 * (gi * PF + t)));
+        };
+        load_group(0, w[0]);
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            if (gi + 1 < NG) load_group(gi + 1, w[(gi + 1) & 1]);
+            const double *wg = w[gi & 1];
+#pragma unroll
+            for (int t = 0; t < 2 * PF; ++t) {
+                const int i = gi * 2 * PF + t;  // reg[i] = fma(-l, v[i], reg[i + 1])
+                if (i + 1 < C) {
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) reg[k][i] = __fma_rn(-l[k], wg[t], reg[k][i + 1]);
+                }
+                if (i == 0) {  // the next pivot's reciprocal: overlaps the FMAs below
+                    double x = reg[0][0];
+                    bool mine = row[0] == p + 1;
+#pragma unroll
+                    for (int k = 1; k < RPL; ++k) { if (row[k] == p + 1) { x = reg[k][0]; mine = true; } }
+                    const double r1 = __ddiv_rn(1.0, x);
+                    rcp = mine ? r1 : rcp;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) row[k] = row[k] == p ? -1 : row[k];
+    };
+    using with_enter = cuda::std::true_type;
+    using no_enter = cuda::std::false_type;
+    const double zero3[RPL] = {};
+
+    for (int half = 0; half < 2; ++half) {
+        f.mirror = half == 0;  // upper half first (y-mirrored field)
+        const bool own1 = !(c == 1 && f.mirror);
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int r = k * TL + tg;
+            row[k] = (lane_on && r < n) ? r : -1;
+            double dg = 0.0, kl = 0.0, kr = 0.0;
+            if (row[k] >= 0 && own1) {
+                dg = f.diag(r + 1, 1);
+                if (r > 0) kl = -f.kx(r, 1);
+                if (r + 1 < n) kr = -f.kx(r + 1, 1);
+            }
+#pragma unroll
+            for (int j = 0; j < C; ++j) reg[k][j] = j == r ? dg : j == r - 1 ? kl : j == r + 1 ? kr : 0.0;
+            g[k] = (row[k] >= 0 && own1) ? 1.0 : 0.0;
+            if (row[k] == 0) rcp = __ddiv_rn(1.0, reg[k][0]);
+        }
+        int p = 0, se = n;
+        for (int je = 2; je <= c; ++je) {
+            const bool own = !(je == c && f.mirror);
+            double cdg[RPL], ckx[RPL], cky[RPL];  // coefficients of unknown (q+1, je), q = k*TL + tg
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const int q = k * TL + tg;
+                cdg[k] = 0.0; ckx[k] = 0.0; cky[k] = 0.0;
+                if (lane_on && q < n) {
+                    if (own) { cdg[k] = f.diag(q + 1, je); if (q > 0) ckx[k] = -f.kx(q, je); }
+                    cky[k] = -f.ky(q + 1, je - 1);
+                }
+            }
+            const double gv = own ? 1.0 : 0.0;
+            for (int ie = 1; ie <= n; ++ie, ++p) {
+                eliminate(with_enter{}, p, p + n, se, ie, cdg, ckx, cky, gv);
+                if (++se == NW) se = 0;
+            }
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) park[(size_t)(k * C + j) * pstride] = reg[k][j];
+                g2[k] = g[k];
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) reg[k][j] = __dadd_rn(reg[k][j], park[(size_t)(k * C + j) * pstride]);
+        g[k] = __dadd_rn(g[k], g2[k]);
+        if (row[k] == P) rcp = __ddiv_rn(1.0, reg[k][0]);
+    }
+    for (int t = 0; t < tc; ++t) eliminate(no_enter{}, P + t, 0, 0, 0, zero3, zero3, zero3, 0.0);
+    const int rtc = P + tc;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k)
+        if (row[k] == last && last > rtc) rcp = __ddiv_rn(1.0, reg[k][L]);
+    for (int kk = 0; kk < n - 1 - tc; ++kk) {
+        const int rowt = last - kk;
+        const int buf = step & 1;
+        ++step;
+        double *vb = vs + buf * NW, *pb = piv + buf * 4;
+        if (lane_on) {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                if (row[k] >= rtc && row[k] < rowt) vb[row[k] - rtc + kk] = reg[k][L];
+                else if (row[k] == rowt) { pb[0] = rcp; pb[1] = g[k]; }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            if (row[k] >= rtc && row[k] < rowt) {
+                const double lk = __dmul_rn(vb[row[k] - rtc + kk], pb[0]);
+                g[k] = __fma_rn(-lk, pb[1], g[k]);
+#pragma unroll
+                for (int j = C - 1; j >= 1; --j)
+                    if (j - 1 < L) reg[k][j] = __fma_rn(-lk, vb[j - 1], reg[k][j - 1]);
+                if (row[k] == rowt - 1 && rowt - 1 > rtc) rcp = __ddiv_rn(1.0, reg[k][L]);
+            } else if (row[k] == rowt) {
+                row[k] = -1;
+            }
+        }
+    }
+    {
+        const int buf = step & 1;
+        ++step;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k)
+            if (lane_on && row[k] == rtc) piv[buf * 4] = __ddiv_rn(g[k], reg[k][L]);
+        __syncwarp();
+        const double u = piv[buf * 4];
+        __syncwarp();
+        return u;
+    }
+}
+
 // ---- kernel ---------------------------------------------------------------------------------------------------------
 template <int W> struct Rows2dCfg {
 #ifndef MLE_ROWS_FAT
 #define MLE_ROWS_FAT 1  // 1: 64 window columns per lane from 64 cells up (255 registers, one resident CTA); 0: 32 (two CTAs)
 #endif
     static constexpr int LPR = MLE_ROWS_FAT ? (W > 64 ? W / 64 : 1) : (W > 32 ? W / 32 : 1);
-    static constexpr int TGS = W * LPR;                       // threads per sample
+#ifndef MLE_ROWS_RPL
+#define MLE_ROWS_RPL 2  // window rows per lane for the 16-cell window (1: one row per lane)
+#endif
+    // measured: two rows per lane is +37 % at 16 cells; at 32 cells its 255 registers cost the second resident CTA and the gain
+    static constexpr int RPL = W == 16 ? MLE_ROWS_RPL : 1;
+    static constexpr int TGS = W * LPR / RPL;                 // threads per sample
     static constexpr int THREADS = (W >= 128 && !MLE_ROWS_FAT) ? 512 : W >= 8 ? 256 : 32 * W;
-    static constexpr int MINB = (W >= 64 && MLE_ROWS_FAT) ? 1 : W >= 128 ? 1 : W >= 32 ? 2 : 1;  // resident CTAs the register budget is sized for
+    static constexpr int MINB = (W >= 64 && MLE_ROWS_FAT) ? 1 : W >= 128 ? 1 : (W >= 32 && RPL == 1) ? 2 : 1;  // resident CTAs the register budget is sized for
     static constexpr int CS = THREADS / TGS;                  // samples solved concurrently
     static constexpr int S = CS < 8 ? 8 : CS;                 // samples per CTA iteration (a multiple of the DMMA tile)
     static constexpr int LDX = S + 4, LDF = S == 8 ? 8 : S + 8;
@@ -275,7 +473,7 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
     static_assert(W >= 4, "the coarse solve needs W / 2 >= 2");
     using Cfg = Rows2dCfg<W>;
     constexpr int THREADS = Cfg::THREADS, S = Cfg::S, LDX = Cfg::LDX, LDF = Cfg::LDF, TGS = Cfg::TGS, CS = Cfg::CS;
-    constexpr int LPR = Cfg::LPR, GT = Cfg::GT, NWARP = THREADS / 32, ST = S / 8;
+    constexpr int LPR = Cfg::LPR, RPL = Cfg::RPL, GT = Cfg::GT, NWARP = THREADS / 32, ST = S / 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int mpad = la.mpad, nks = mpad >> 2;
     double *xi = reinterpret_cast<double *>(smem_raw);                       // [mpad][LDX]
@@ -339,15 +537,24 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
             double *sh = gsh + grp * rows_sh_doubles(W);
             FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
             double *park = la.park + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ROWS_PARK * THREADS + tid;
-            const double qf = frontal_mid_rows<W, LPR, GT>(fv, sh, park, THREADS, tg, 1 + grp);
+            // the solver of the view's window width: one row per lane (or a row over several lanes), or RPL rows per lane
+            auto solve = [&](const FieldView &v, bool half_width) {
+                if constexpr (RPL > 1) {
+                    if (half_width) return frontal_mid_rpl<W / 2, RPL>(v, sh, park, THREADS, tg);
+                    return frontal_mid_rpl<W, RPL>(v, sh, park, THREADS, tg);
+                } else {
+                    if (half_width) return frontal_mid_rows<W / 2, (W / 2 / LPR >= 2 ? LPR : 1), GT>(v, sh, park, THREADS, tg, 1 + grp);
+                    return frontal_mid_rows<W, LPR, GT>(v, sh, park, THREADS, tg, 1 + grp);
+                }
+            };
+            const double qf = solve(fv, false);
             double dq = qf;
             // coarse terms of diff(index), added in the order (lx-1,ly-1), (lx,ly-1), (lx-1,ly); multilevel: one coarse solve
             auto coarse = [&](int stx, int sty) {
                 FieldView cv = fv;
                 cv.stx = stx; cv.sty = sty; cv.Nx = Nx / stx; cv.Ny = Ny / sty;
                 cv.wx = (double)cv.Nx * (double)cv.Nx; cv.wy = (double)cv.Ny * (double)cv.Ny;
-                if (stx == 2) return frontal_mid_rows<W / 2, (W / 2 / LPR >= 2 ? LPR : 1), GT>(cv, sh, park, THREADS, tg, 1 + grp);
-                return frontal_mid_rows<W, LPR, GT>(cv, sh, park, THREADS, tg, 1 + grp);
+                return solve(cv, stx == 2);
             };
             if (la.ndims == 1) {
                 if (la.lx > 0) dq = __dsub_rn(qf, coarse(2, 2));
