@@ -25,6 +25,14 @@
 
 #include "mle_kernels.cuh"
 
+// layout knobs (compile with -DMLE_ROWS_FAT=0 / -DMLE_ROWS_RPL=1 for the A/B measurements quoted in DESIGN.md 3.4)
+#ifndef MLE_ROWS_FAT
+#define MLE_ROWS_FAT 1  // 1: 64 window columns per lane from 64 cells up (255 registers, one resident CTA); 0: 32 (two CTAs)
+#endif
+#ifndef MLE_ROWS_RPL
+#define MLE_ROWS_RPL 2  // window rows per lane for the 16-cell window (1: one row per lane)
+#endif
+
 namespace mle {
 
 struct Lognormal2dRowsArgs {
@@ -446,13 +454,7 @@ __device__ __noinline__ double frontal_mid_rpl(FieldView f, double *sh, double *
 
 // ---- kernel ---------------------------------------------------------------------------------------------------------
 template <int W> struct Rows2dCfg {
-#ifndef MLE_ROWS_FAT
-#define MLE_ROWS_FAT 1  // 1: 64 window columns per lane from 64 cells up (255 registers, one resident CTA); 0: 32 (two CTAs)
-#endif
     static constexpr int LPR = MLE_ROWS_FAT ? (W > 64 ? W / 64 : 1) : (W > 32 ? W / 32 : 1);
-#ifndef MLE_ROWS_RPL
-#define MLE_ROWS_RPL 2  // window rows per lane for the 16-cell window (1: one row per lane)
-#endif
     // measured: two rows per lane is +37 % at 16 cells; at 32 cells its 255 registers cost the second resident CTA and the gain
     static constexpr int RPL = W == 16 ? MLE_ROWS_RPL : 1;
     static constexpr int TGS = W * LPR / RPL;                 // threads per sample
