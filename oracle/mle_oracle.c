@@ -458,7 +458,8 @@ static double tridiag_mid(const double *a /* node values, stride st */, int st, 
 /* full Thomas solve (all unknowns) -- used by tests to cross-check the twisted mid value */
 ORC_API double orc_tridiag_mid_full(const double *a, int N) {
     int n = N - 1;
-    double *c = (double *)malloc(sizeof(double) * (size_t)n), *d = (double *)malloc(sizeof(double) * (size_t)n);
+    if (n < 1) return 0.0;
+    double *c = (double *)calloc((size_t)n, sizeof(double)), *d = (double *)calloc((size_t)n, sizeof(double));
     double h2 = 1.0 / ((double)N * (double)N);
     for (int i = 1; i <= n; ++i) {
         double km = 0.5 * (a[i - 1] + a[i]), kp = 0.5 * (a[i] + a[i + 1]);
