@@ -97,6 +97,19 @@ class AD:
         raise NotImplementedError("get_index_set not implemented for index sets of type AD")  # src/index_set.jl:259
 
 
+class U:
+    """unbiased multilevel / multi-index index set U(d), src/index_set.jl:213-227: no bias, indices drawn at random from a
+    probability mass function over `max_search_space` that is adapted to sqrt(V/C) (src/methods.jl:287-351)"""
+
+    def __init__(self, d):
+        if d <= 0:
+            raise ValueError("to use U, dimension must be greater than 0, got %d" % d)
+        self.ndims = int(d)
+
+    def get_index_set(self, sz):
+        raise NotImplementedError("get_index_set not implemented for index sets of type U")
+
+
 def is_admissable(index_set, index):
     """src/index_set.jl:265-277: index not yet in the set and all its backward neighbours are"""
     s = set(index_set)
@@ -259,8 +272,10 @@ class Estimator:
         if unknown:
             raise ValueError("in Estimator, invalid option %s" % sorted(unknown))  # src/estimator.jl:127-131
         self.adaptive = isinstance(index_set, AD)
-        if not self.adaptive and any(k in options for k in _AD_ONLY):
-            raise ValueError("in Estimator, invalid option %s" % sorted(set(options) & set(_AD_ONLY)))
+        self.unbiased = isinstance(index_set, U)
+        allowed_extra = _AD_ONLY if self.adaptive else (("max_search_space",) if self.unbiased else ())
+        if any(k in options and k not in allowed_extra for k in _AD_ONLY):
+            raise ValueError("in Estimator, invalid option %s" % sorted(set(options) & set(_AD_ONLY) - set(allowed_extra)))
         o = dict(_DEFAULTS)
         o.update(options)
         self.index_set, self.sample_method, self.spec, self.distributions, self.backend = (
@@ -270,7 +285,7 @@ class Estimator:
         if o["max_index_set_param"] is None:
             o["max_index_set_param"] = 10 * d                          # src/parse.jl:193-194
         if o["nb_of_warm_up_samples"] is None:
-            o["nb_of_warm_up_samples"] = 1 if self.qmc else 20          # src/parse.jl:35-36
+            o["nb_of_warm_up_samples"] = (2 if self.unbiased else 1) if self.qmc else 20   # src/parse.jl:35-36
         elif o["nb_of_warm_up_samples"] <= 1:
             raise ValueError("in Estimator, optional key nb_of_warm_up_samples must be larger than 1")  # src/parse.jl:39
         if not callable(o["nb_of_shifts"]):
@@ -285,12 +300,12 @@ class Estimator:
             raise ValueError("in Estimator, optional key aggregation must be 'sum', 'max' or 'norm'")
         if not (0 < o["min_splitting"] <= o["max_splitting"] <= 1):
             raise ValueError("in Estimator, min_splitting / max_splitting must satisfy 0 < min <= max <= 1")
-        if self.adaptive:
+        if self.adaptive or self.unbiased:
             if o["max_search_space"] is None:
-                o["max_search_space"] = TD(d)                           # src/parse.jl:263-264
+                o["max_search_space"] = TD(d)                           # src/parse.jl:263-264 (fails for d = 1 like the reference)
             if getattr(o["max_search_space"], "ndims", None) != d:
                 raise ValueError("in Estimator, dimensions of max_search_space must be equal to %d" % d)  # src/parse.jl:267
-            for key in ("penalization", "acceptance_rate"):
+            for key in ("penalization", "acceptance_rate") if self.adaptive else ():
                 if not (math.isfinite(o[key]) and 0 <= o[key] <= 1):
                     raise ValueError("in Estimator, optional key %s must be in [0, 1]" % key)  # src/parse.jl:277-297
         self.options = o
@@ -303,7 +318,7 @@ class Estimator:
             z = o["point_generator"]  # a generating vector; None -> default LatticeRule32(s), src/parse.jl:251-254
             self.lattice = backend.lattice(z, s)
         # internals (src/internals.jl:35-54): per index cumulative moments [R, q, 2, 3], counters, and one shift per (index, r)
-        space = o["max_search_space"] if self.adaptive else index_set   # src/internals.jl:36,133
+        space = o["max_search_space"] if (self.adaptive or self.unbiased) else index_set   # src/internals.jl:36,133
         box = space.get_index_set(o["max_index_set_param"])
         self.search_space = set(box)
         # ADInternals, src/internals.jl:150-171
@@ -323,13 +338,55 @@ class Estimator:
                     if given is not None else rng.random((R, s))
         self.current_index_set = set()
         self.sz = self.max_sz = 0
+        # UInternals, src/internals.jl:208-225: pmf = normalised product of Geometric(1 - exp(-1.5)) weights; the accumulator is
+        # kept as (n, mean, M2) per (shift, qoi) of the per-sample sums  sum_idx dQ_idx / Prob(idx)
+        self.pmf, self.acc = {}, None
+        if self.unbiased:
+            pg = 1.0 - math.exp(-1.5)
+            self.pmf = {i: math.prod((1.0 - pg) ** k * pg for k in i) for i in sorted(box, key=lambda t: t[::-1])}
+            tot = sum(self.pmf.values())
+            self.pmf = {i: v / tot for i, v in self.pmf.items()}
+            self._u_rng = np.random.default_rng(o["shift_seed"] + 1)
 
     def __getitem__(self, key):  # estimator[:key], src/options.jl:46
         return self.options[key]
 
     # ---- the hot path -----------------------------------------------------------------------------------------------
+    def Prob(self, index):  # src/methods.jl:333: CartesianIndex `>=` is the column-major (last index most significant) order
+        return sum(v for k, v in self.pmf.items() if k[::-1] >= index[::-1])
+
+    def _sample_unbiased(self, index, n):
+        """sample! for U estimators (src/sample.jl:21-34 with the append_samples! of :65-74, :113-124): the sample function of
+        the reference returns (dQ, Qf) for EVERY idx <= index from one input vector.  Here the device model is evaluated once per
+        idx on the same points (same shifts, same point numbers, same leading coordinates) with the raw samples returned, and
+        the per-sample sums  Z = sum_idx dQ_idx / Prob(idx)  are reduced to (n, mean, M2) on the host."""
+        import itertools
+        from .engine import moments_merge
+        istart = self.nb_of_samples[index] + 1
+        m = self.options["nb_of_uncertainties"](index)
+        t0 = _time.perf_counter()
+        Z = None
+        for idx in sorted(itertools.product(*[range(i + 1) for i in index]), key=lambda t: t[::-1]):
+            mom, _t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(idx), self.shifts.get(index),
+                                                     istart - 1, n, m, self.options["mc_seed"], want_samples=True)
+            self.moments[idx] = moments_merge(self.moments[idx], mom) if idx in self.moments else np.array(mom, dtype=np.float64)
+            if self.options["save_samples"]:
+                self.samples.setdefault(idx, []).append(np.array(smp))
+            term = smp[:, :, 0, :] / self.Prob(idx)
+            Z = term if Z is None else Z + term
+        t = _time.perf_counter() - t0
+        zm = Z.mean(axis=-1)
+        part = np.stack([np.full(zm.shape, float(n)), zm, ((Z - zm[..., None]) ** 2).sum(axis=-1)], axis=-1)   # [R, q, 3]
+        self.acc = part if self.acc is None else moments_merge(self.acc, part)
+        self.nb_of_samples[index] += n
+        cm = self.options["cost_model"]
+        self.total_work[index] += 0.0 if cm is None else n * cm(index)
+        self.total_time[index] += t
+
     def sample(self, index, n):
         """sample!(estimator, index, n), src/sample.jl:21-34"""
+        if self.unbiased:
+            return self._sample_unbiased(index, n)
         istart = self.nb_of_samples[index] + 1
         m = self.options["nb_of_uncertainties"](index)
         t0 = _time.perf_counter()
@@ -352,7 +409,12 @@ class Estimator:
         self.total_work[index] += 0.0 if cm is None else n * cm(index)  # src/internals.jl:98
         self.total_time[index] += t                                     # src/internals.jl:106
 
-    def update_samples(self, n_opt):  # src/sample.jl:8-13
+    def update_samples(self, n_opt):  # src/sample.jl:8-13, :15-19 (U: n_opt are numbers of ADDITIONAL samples)
+        if self.unbiased:
+            for index in n_opt:
+                if n_opt[index] > 0:
+                    self.sample(index, n_opt[index])
+            return
         for index in n_opt:
             n_due = n_opt[index] - self.nb_of_samples[index]
             if n_due > 0:
@@ -371,6 +433,8 @@ class Estimator:
         return float(values[self.options["qoi_with_max_var"] - 1])
 
     def _per_qoi(self, index, X, f):
+        if index not in self.moments:           # mean / var of an empty sample vector: NaN like the reference
+            return np.full(self.nqoi, float("nan"))
         mom = self.moments[index][:, :, X, :]  # [R, q, 3]
         with np.errstate(divide="ignore", invalid="ignore"):
             if f == "mean":
@@ -380,6 +444,9 @@ class Estimator:
         return per_shift.mean(axis=0)  # MC: R == 1
 
     def mean(self, index=None):
+        if index is None and self.unbiased:
+            # src/methods.jl:351 reads accumulator(estimator, qoi) = accumulator[qoi, 1]: the FIRST shift only (replicated)
+            return self._aggregate(self.acc[0, :, 1]) if self.acc is not None else float("nan")
         if index is None:
             return sum(self.mean(i) for i in self.keys())
         return self._aggregate(self._per_qoi(index, 0, "mean"))
@@ -394,6 +461,13 @@ class Estimator:
         return self._aggregate(self._per_qoi(index, 1, "var"))
 
     def varest(self, index=None):
+        if index is None and self.unbiased:  # src/methods.jl:341-343
+            if self.acc is None:
+                return float("nan")
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if not self.qmc:
+                    return self._aggregate(self.acc[0, :, 2] / (self.acc[0, :, 0] - 1.0) / self.acc[0, :, 0])
+                return self._aggregate(self.acc[:, :, 1].var(axis=0, ddof=1) / self.acc.shape[0])
         if index is None:
             return sum(self.varest(i) for i in self.keys())
         if not self.qmc:
@@ -404,15 +478,19 @@ class Estimator:
 
     def cost(self, index):  # src/methods.jl:64
         tot = self.total_time if self.options["cost_model"] is None else self.total_work
-        return tot[index] / self.nb_of_samples[index]
+        n = self.nb_of_samples[index]
+        return tot[index] / n if n else float("nan")  # 0/0 = NaN in the reference (U: indices only seen below a larger one)
 
     def time(self, index):
-        return self.total_time[index] / self.nb_of_samples[index]
+        n = self.nb_of_samples[index]
+        return self.total_time[index] / n if n else float("nan")
 
     def keys(self):
         return sorted(self.current_index_set, key=lambda t: t[::-1])
 
     def all_keys(self):
+        if self.unbiased:  # every idx <= a sampled index holds samples
+            return sorted(self.moments, key=lambda t: t[::-1])
         return sorted((i for i, n in self.nb_of_samples.items() if n > 0), key=lambda t: t[::-1])
 
     # ---- rates and regression (src/methods.jl:70-163) -----------------------------------------------------------------------
@@ -568,6 +646,8 @@ class Estimator:
     def bias(self, sz=None):
         if isinstance(self.index_set, SL):
             return 0.0
+        if self.unbiased:
+            return 0.0     # src/methods.jl:347
         sz = self.sz if sz is None else sz
         if self.adaptive:  # src/methods.jl:253-260
             b = lambda indices: abs(sum(self.mean(i) for i in sorted(indices, key=lambda t: t[::-1])))
@@ -601,6 +681,8 @@ class Estimator:
         return math.sqrt(self.mse())
 
     def converged(self, eps, theta):
+        if self.unbiased:
+            return self.mse() <= eps**2  # src/methods.jl:349
         return self.bias() ** 2 <= (1 - theta) * eps**2 or self.mse() <= eps**2
 
     # ---- QMC sample growth (src/methods.jl:265-280) -----------------------------------------------------------------------------
@@ -611,6 +693,33 @@ class Estimator:
         if f <= 1:
             return {index: n + 1}
         return {index: int(math.ceil(n * f))}
+
+    # ---- unbiased estimation (src/methods.jl:287-331) -------------------------------------------------------------------------
+    def next_number_of_samples_unbiased(self):
+        n_total = sum(self.nb_of_samples.values())
+        n0 = max(self.options["nb_of_warm_up_samples"], n_total)
+        f = self.options["sample_mul_factor"]
+        n = 1 if f <= 1 else int(math.ceil(n0 * (f - 1)))
+        u = self._u_rng.random(n)
+        counts, psum = {}, 0.0
+        for index, p in self.pmf.items():  # column-major order (a Dict in the reference: its iteration order is unspecified)
+            counts[index] = int(np.count_nonzero((psum <= u) & (u <= psum + p)))
+            psum += p
+        return counts
+
+    def update_pmf(self):
+        def f(index):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if index not in self.moments or self.nb_of_samples[index] == 0:
+                    return float("nan")
+                return math.sqrt(self.var(index) / self.cost(index)) if self.var(index) >= 0 else float("nan")
+        p = self._interp(lambda i: f(i) if f(i) == f(i) else 0.0)
+        if not np.any(np.isnan(p)) and np.all(p[1:] < 0):
+            for index in self.keys():
+                fi = f(index)
+                self.pmf[index] = 2.0 ** (p[0] + sum(a * b for a, b in zip(p[1:], index))) if (math.isnan(fi) or math.isinf(fi)) else fi
+            tot = sum(self.pmf.values())
+            self.pmf = {i: v / tot for i, v in self.pmf.items()}
 
     def find_index_with_max_var_over_cost(self):
         keys = self.keys()
@@ -642,7 +751,18 @@ def get_tols(est, tol):  # src/methods.jl:15
     return [tol]
 
 
+def _run_unbiased(est, eps):  # src/run.jl:145-200
+    est.current_index_set.update(est.pmf.keys())
+    v = est.varest()
+    while not v <= eps**2:  # NaN (no samples yet) keeps looping, like `is_converged = varest(estimator) <= eps^2` in the reference
+        est.update_samples(est.next_number_of_samples_unbiased())
+        est.update_pmf()
+        v = est.varest()
+
+
 def _run(est, eps):  # src/run.jl:41-142
+    if est.unbiased:
+        return _run_unbiased(est, eps)
     sl = isinstance(est.index_set, SL)
     L = 0
     theta = 0.5 if sl else est["min_splitting"]

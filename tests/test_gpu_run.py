@@ -125,3 +125,19 @@ def test_single_level_mc_c1_run_matches_oracle(engine):
     exact = math.exp(0.5 * sum(a * a for a in w))
     assert abs(hg["mean"] - exact) < 4e-3 and hg["rmse"] <= 1e-3 * 1.01
     assert hg["nb_of_samples"][(0,)] > 100000     # theta = 0.5: N = 2 V / eps^2
+
+
+def test_unbiased_runs_match_oracle(engine):
+    """U(1) x {MC, QMC} and U(2) x QMC on the reference's own test function: the device evaluates every idx <= index on the
+    same points; index draws, pmf updates and estimates agree with the oracle-backed loop"""
+    for method, d in (("MC", 1), ("QMC", 1), ("QMC", 2)):
+        def make(H, backend):
+            kw = dict(max_search_space=H.ML()) if d == 1 else {}
+            return H.Estimator(H.U(d), getattr(H, method)(), H.ModelSpec("problem18", d), [H.Uniform(-0.5, 0.5)] * d, backend,
+                               nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3,
+                               nb_of_shifts=8, **kw)
+        H, g, o = both(engine, make)
+        hg, ho = H.run(g, 5e-3), H.run(o, 5e-3)
+        compare(hg, ho)
+        assert hg["bias"] == 0.0 and abs(hg["rmse"] - ho["rmse"]) <= 1e-9 * ho["rmse"]
+        assert all(abs(g.pmf[k] - o.pmf[k]) <= 1e-9 * o.pmf[k] for k in o.pmf)

@@ -239,3 +239,43 @@ def test_save_samples_history_keys():
         assert sd.shape[0] == 4 and sd.shape[1] == 13 and sd.shape[2] == h["nb_of_samples"][idx]
         assert abs(sd[:, 0, :].mean(axis=1).mean() - h["dE"][idx]) <= 1e-12 * max(1.0, abs(h["dE"][idx]))
         assert abs(h["samples"][idx][:, 0, :].mean(axis=1).mean() - h["E"][idx]) <= 1e-12 * max(1.0, abs(h["E"][idx]))
+
+
+@pytest.mark.parametrize("method", ["MC", "QMC"])
+def test_regression_problem18_unbiased(method):
+    """test/regression.jl:128-160: run(Estimator(U(1), MC()/QMC(), test_function2, Uniform(-0.5, 0.5); nb_of_qoi = 13,
+    max_index_set_param = 3, max_search_space = ML()), tol): every idx <= the drawn index is evaluated on the same inputs, the
+    per-sample sums of dQ_idx / Prob(idx) are the unbiased estimator; bias = 0 in the History"""
+    H = host()
+    with pytest.raises(ValueError):
+        H.U(0)
+    with pytest.raises(NotImplementedError):
+        H.U(1).get_index_set(2)
+    est = H.Estimator(H.U(1), getattr(H, method)(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(),
+                      nb_of_qoi=13, max_index_set_param=3, max_search_space=H.ML(), cost_model=lambda i: 2.0 ** i[0],
+                      nb_of_tols=5, save_samples=True)
+    assert est["nb_of_warm_up_samples"] == (20 if method == "MC" else 2)          # src/parse.jl:36
+    assert abs(sum(est.pmf.values()) - 1.0) < 1e-15 and abs(est.Prob((0,)) - 1.0) < 1e-15
+    p = [est.pmf[(l,)] for l in range(4)]
+    assert all(abs(p[l + 1] / p[l] - math.exp(-1.5)) < 1e-12 for l in range(3))    # Geometric(1 - exp(-1.5)), src/internals.jl:221
+    h = H.run(est, 2e-3)
+    assert len(h) == 5 and h["bias"] == 0.0 and h["type"] == "Estimator{U, %s}" % method
+    assert h["rmse"] <= 2e-3 and abs(h["mean"] - 4.0) < 6 * 2e-3
+    assert abs(sum(est.pmf.values()) - 1.0) < 1e-12
+    # the samples of idx come from every call at an index >= idx (src/sample.jl:65-74)
+    n_at_or_above = {i: sum(n for j, n in h["nb_of_samples"].items() if j[0] >= i[0]) for i in h["index_set"]}
+    assert all(h["samples_diff"][i].shape[-1] == n_at_or_above[i] for i in h["index_set"])
+
+
+def test_unbiased_multi_index_run():
+    """test/regression.jl:163-181: U(2) with the default TD(2) search space"""
+    H = host()
+    est = H.Estimator(H.U(2), H.QMC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(), nb_of_qoi=13,
+                      max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3, nb_of_shifts=8)
+    assert set(est.pmf) == set(H.TD(2).get_index_set(3))
+    # Prob(index) sums the pmf over the indices at or after `index` in column-major order (CartesianIndex `>=`, src/methods.jl:333)
+    assert abs(est.Prob((0, 1)) - sum(v for k, v in est.pmf.items() if (k[1], k[0]) >= (1, 0))) < 1e-15
+    h = H.run(est, 1e-2)
+    assert h["rmse"] <= 1e-2 and h["ndims"] == 2 and h["bias"] == 0.0
+    with pytest.raises(ValueError):
+        H.Estimator(H.U(1), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend())   # TD(1) does not exist
