@@ -1,0 +1,86 @@
+"""Randomised differential test: the CUDA path through the C ABI against the CPU oracle on random (model, index, shifts,
+point range, dimension count, distribution mix, lattice / MC) cases.  Per-sample values must be bit-identical, moments within
+1e-12.  usage: python tools/fuzz_parity.py [cases] [seed]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import mle_b200
+import mle_b200.kl as kl
+from oracle import oracle as O
+
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+O.build()
+eng = mle_b200.Engine(0)
+DISTS = [(1, [0.0, 1.0]), (0, [-1.0, 2.0]), (2, [0.0, 1.0, -2.0, 2.0]), (1, [0.3, 0.6]), (2, [0.5, 2.0, -1.0, 3.0])]
+t0 = time.time()
+bad = 0
+for case in range(cases):
+    model = rng.choice(["expsum", "problem18", "lognormal1d", "lognormal2d", "lognormal2d_mi"])
+    mc = bool(rng.integers(0, 2))
+    general = bool(rng.integers(0, 3) == 0)
+    R = 1 if mc else int(rng.integers(1, 6))
+    k0 = int(rng.choice([0, 1, 7, 1000, 2**20 + 3, 2**31 + 11]))
+    if model == "expsum":
+        m = int(rng.integers(1, 140)); index = [int(rng.integers(0, 4))]; ndims = 1
+        w = list(rng.random(m) * 0.3)
+        gm, om = eng.model("expsum", 1, [2.0] + w), O.Model(O.MODEL_EXPSUM, 1, [2.0] + w)
+        n = int(rng.integers(1, 700))
+    elif model == "problem18":
+        ndims = int(rng.integers(1, 3)); m = ndims; index = [int(x) for x in rng.integers(0, 4, ndims)]
+        gm, om = eng.model("problem18", ndims), O.Model(O.MODEL_PROBLEM18, ndims, [])
+        n = int(rng.integers(1, 500)); general = False
+    elif model == "lognormal1d":
+        n0 = int(rng.choice([4, 8, 16, 24])); lev = int(rng.integers(0, 5)); m = int(rng.integers(1, 150)); index = [lev]; ndims = 1
+        phi = (0.2 + 0.6 * rng.random()) * kl.kl_basis_1d(lev, m=m, n0=n0)
+        gm, om = eng.model("lognormal1d", 1, [n0]), O.Model(O.MODEL_LOGNORMAL1D, 1, [float(n0)])
+        gm.set_basis(lev, phi); om.set_basis(lev, phi)
+        n = int(rng.integers(1, 300))
+    else:
+        ndims = 2 if model == "lognormal2d_mi" else 1
+        n0 = int(rng.choice([2, 4, 4, 4, 6]))
+        if ndims == 1:
+            lev = int(rng.integers(0, 4 if n0 <= 4 else 3)); index = [lev]; key = lev
+        else:
+            index = [int(rng.integers(0, 4)), int(rng.integers(0, 4))]; key = tuple(index)
+        m = int(rng.integers(1, 90))
+        phi = (0.2 + 0.6 * rng.random()) * kl.kl_basis_2d(key, m=m, n0=n0)
+        gm, om = eng.model("lognormal2d", ndims, [n0]), O.Model(O.MODEL_LOGNORMAL2D, ndims, [float(n0)])
+        gm.set_basis(key, phi); om.set_basis(key, phi)
+        cells = (n0 << index[0]) * (n0 << index[-1])
+        n = int(rng.integers(1, max(2, 60000 // (cells * max(8, n0 << index[0])))))
+    if model == "problem18":
+        dl = [(0, [-0.5, 0.5])] * m
+    elif general:
+        dl = [DISTS[int(i)] for i in rng.integers(0, len(DISTS), m)]
+    else:
+        dl = [DISTS[0]] * m
+    s = m + int(rng.integers(0, 3)) if not mc else m
+    d = eng.dists(dl)
+    if mc:
+        seed = int(rng.integers(0, 2**31))
+        got, smp = eng.sample_batch(gm, None, d, index, None, k0, n, m=m, mc_seed=seed, want_samples=True)
+        want, smp_w = O.sample_batch(om, None, dl, index, None, k0, n, m=m, mc_seed=seed, want_samples=True)
+    else:
+        z = O.genvec("K_3600_32", s)
+        sh = rng.random((R, s))
+        got, smp = eng.sample_batch(gm, eng.lattice(z, s), d, index, sh, k0, n, m=m, want_samples=True)
+        want, smp_w = O.sample_batch(om, z, dl, index, sh, k0, n, m=m, want_samples=True)
+    ok = np.array_equal(smp, smp_w, equal_nan=True) and np.array_equal(got[..., 0], want[..., 0])
+    scale = np.sqrt(want[..., 2] / np.maximum(want[..., 0], 1)) + np.abs(want[..., 1])
+    # M2 within 1e-12 relative, plus the conditioning of a Float64 variance: samples that agree to 6+ digits (|mean| >> std) lose
+    # eps * n * mean^2 absolutely in ANY double-precision evaluation, the reference's two-pass `var` included
+    m2_tol = 1e-12 * np.abs(want[..., 2]) + 1e-18 * want[..., 0] * want[..., 1] ** 2 + 1e-300
+    ok = ok and np.all(np.abs(got[..., 1] - want[..., 1]) <= 1e-12 * scale) and np.all(np.abs(got[..., 2] - want[..., 2]) <= m2_tol)
+    if not ok:
+        bad += 1
+        print("MISMATCH case %d: %s index=%s ndims=%d mc=%s general=%s R=%d k0=%d n=%d m=%d s=%d  max|d|=%.3e" % (
+            case, model, index, ndims, mc, general, R, k0, n, m, s, np.nanmax(np.abs(smp - smp_w))), flush=True)
+        print("   samples equal:", np.array_equal(smp, smp_w, equal_nan=True), " got", got.reshape(-1, 3)[:4].tolist(), " want", want.reshape(-1, 3)[:4].tolist())
+    gm.close()
+print("%d cases, %d mismatches, %.1f s" % (cases, bad, time.time() - t0))
+sys.exit(1 if bad else 0)
