@@ -117,6 +117,12 @@ function merge_moments!(estimator, index, part::Array{Float64, 4})
     end
 end
 
+# Index sets: the reference's own code keeps driving everything above parallel_sample! -- SL, ML, FT, TD, HC, ZC and AD need
+# nothing else.  Unbiased estimators (`U`, src/sample.jl:65-74, :113-124) expect the sample function to return (dQ, Qf) for every
+# idx <= index from one input vector: for those, call mle_sample_batch once per idx in `zero(index):index` with the SAME shifts
+# and point range and a `samples` buffer, append the raw samples to `samples_diff[idx]` / `samples[idx]` and add
+# `dQ_idx / Prob(idx)` to the accumulator, exactly as host.py:Estimator._sample_unbiased does (tested there).
+#
 # ---- the hot path: one ccall per parallel_sample! (replaces the pmap of src/sample.jl:79-102) ----------------------------
 function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
     model = estimator.sample_function
