@@ -76,7 +76,7 @@ def algorithmic_flops_per_sample(level):
     gen = M_KL * (3 + 0.75 * 31 + 0.1875 * 35 + 0.0625 * 72)
     kl = 2.0 * (N + 1) * M_KL
     ex = 34.0 * (N + 1)
-    solve = 8.0 * (N - 1) + (8.0 * (N // 2 - 1) if level > 0 else 0.0) + 12
+    solve = 6.0 * N + (6.0 * (N // 2) if level > 0 else 0.0) + 8  # per edge: mean, 1/kappa, A += r, D = fma(w, r, D)
     return gen + kl + ex + solve
 
 

@@ -340,38 +340,25 @@ __host__ __device__ constexpr int ln_ldx(int bt) { return bt + 4; }
 __host__ __device__ constexpr int ln_ldf(int bt) { return bt + 8; }
 
 struct SweepState {
-    double a_prev, k_prev, p, y;
+    double a_prev, A, D;  // last node value, sum of r = 1/kappa, sum of w*r over the edges seen so far
 };
 
-// one elimination step on arrival of node value `a` (node number ip on this side, ascending); rows 1..M-1
-__device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, double h2) {
-    if (ip == 0) { s.a_prev = a; return; }
-    double k_new = __dmul_rn(0.5, __dadd_rn(s.a_prev, a));
-    if (ip >= 2) {
-        double b = __dadd_rn(s.k_prev, k_new);
-        if (ip == 2) { s.p = b; s.y = h2; }
-        else {
-            double w = __ddiv_rn(s.k_prev, s.p);
-            s.p = __fma_rn(-w, s.k_prev, b);
-            s.y = __fma_rn(w, s.y, h2);
-        }
+// one edge on arrival of node value `a` (node number ip on this side, counted from the boundary; M = N/2): the closed form of
+// the mid value (oracle/mle_oracle.c:tridiag_mid) needs only two running sums per side; the division is off the chain
+__device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, int M) {
+    if (ip > 0) {
+        const double kap = __dmul_rn(0.5, __dadd_rn(s.a_prev, a));
+        const double r = __ddiv_rn(1.0, kap);
+        s.A = __dadd_rn(s.A, r);
+        s.D = __fma_rn((double)(M - ip) + 0.5, r, s.D);
     }
-    s.k_prev = k_new;
     s.a_prev = a;
 }
 
-// combine the left state L and the right (mirrored) state Rr at the mid node; M = number of half-cells per side
-__device__ __forceinline__ double sweep_combine(const SweepState &L, const SweepState &Rr, int M, double h2) {
-    double den = __dadd_rn(L.k_prev, Rr.k_prev), num = h2;
-    if (M >= 2) {
-        double w = __ddiv_rn(L.k_prev, L.p);
-        den = __fma_rn(-w, L.k_prev, den);
-        num = __fma_rn(w, L.y, num);
-        w = __ddiv_rn(Rr.k_prev, Rr.p);
-        den = __fma_rn(-w, Rr.k_prev, den);
-        num = __fma_rn(w, Rr.y, num);
-    }
-    return __ddiv_rn(num, den);
+// u(1/2) = h^2 (D_R A_L + D_L A_R) / (A_L + A_R) from the left state L and the right (mirrored) state Rr
+__device__ __forceinline__ double sweep_combine(const SweepState &L, const SweepState &Rr, double h2) {
+    const double num = __fma_rn(Rr.D, L.A, __dmul_rn(L.D, Rr.A));
+    return __dmul_rn(h2, __ddiv_rn(num, __dadd_rn(L.A, Rr.A)));
 }
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
@@ -453,7 +440,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         }
 
         MLE_PH(0);
-        SweepState sf{0, 0, 0, 0}, scs{0, 0, 0, 0};
+        SweepState sf{0, 0, 0}, scs{0, 0, 0};
         const int side = tid / BT, b = tid & (BT - 1);  // sweep role (threads 0 .. 2*BT-1)
 
         for (int c = 0; c < la.nchunks; ++c) {
@@ -537,8 +524,8 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
                     const int ip = ip0 + q;
                     if (ip <= M) {
                         const double a = F[(2 * q + side) * LDF + b];
-                        sweep_step(sf, ip, a, la.h2);
-                        if (la.level > 0 && (ip & 1) == 0) sweep_step(scs, ip >> 1, a, la.h2c);
+                        sweep_step(sf, ip, a, M);
+                        if (la.level > 0 && (ip & 1) == 0) sweep_step(scs, ip >> 1, a, M / 2);
                     }
                 }
             }
@@ -548,9 +535,9 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         if (tid < 2 * BT && side == 1) { xch[b] = sf; xch[BT + b] = scs; }
         __syncthreads();
         if (tid < BT) {
-            const double qf = sweep_combine(sf, xch[b], M, la.h2);
+            const double qf = sweep_combine(sf, xch[b], la.h2);
             double dq = qf;
-            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(scs, xch[BT + b], M / 2, la.h2c));
+            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(scs, xch[BT + b], la.h2c));
             if (b < Pt) {
                 if (samples) {
                     samples[((size_t)r * 2 + 0) * g.n + i0 + b] = dq;
@@ -684,7 +671,7 @@ __global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs 
                 named_bar_arrive(FULL0 + (c & 1), THREADS);
             }
         } else {
-            SweepState fl{0, 0, 0, 0}, fr{0, 0, 0, 0}, cl{0, 0, 0, 0}, cr{0, 0, 0, 0};
+            SweepState fl{0, 0, 0}, fr{0, 0, 0}, cl{0, 0, 0}, cr{0, 0, 0};
             for (int c = 0; c < la.nchunks; ++c) {
                 named_bar_sync(FULL0 + (c & 1), THREADS);
                 const double *Fc = F + (c & 1) * RC * LDF + lane;
@@ -694,19 +681,19 @@ __global__ void __launch_bounds__(LNW_THREADS, 4) lognormal1d_ws_kernel(GenArgs 
                     const int ip = ip0 + q;
                     if (ip <= M) {
                         const double al = Fc[(2 * q) * LDF], ar = Fc[(2 * q + 1) * LDF];
-                        sweep_step(fl, ip, al, la.h2);
-                        sweep_step(fr, ip, ar, la.h2);
+                        sweep_step(fl, ip, al, M);
+                        sweep_step(fr, ip, ar, M);
                         if (la.level > 0 && (ip & 1) == 0) {
-                            sweep_step(cl, ip >> 1, al, la.h2c);
-                            sweep_step(cr, ip >> 1, ar, la.h2c);
+                            sweep_step(cl, ip >> 1, al, M / 2);
+                            sweep_step(cr, ip >> 1, ar, M / 2);
                         }
                     }
                 }
                 if (c + 2 < la.nchunks) named_bar_arrive(EMPTY0 + (c & 1), THREADS);
             }
-            const double qf = sweep_combine(fl, fr, M, la.h2);
+            const double qf = sweep_combine(fl, fr, la.h2);
             double dq = qf;
-            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(cl, cr, M / 2, la.h2c));
+            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(cl, cr, la.h2c));
             if (lane < Pt) {
                 if (samples) {
                     samples[((size_t)r * 2 + 0) * g.n + i0 + lane] = dq;

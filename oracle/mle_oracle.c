@@ -414,45 +414,33 @@ static void problem18_eval(int ndims, const int *idx, const double *xi, double *
  * level l: N = n0 * 2^l cells, nodes 0..N; log a at node i = sum_k Phi_l[i][k] xi_k (k ascending, fused);
  * interface coefficient kappa_{i+1/2} = 0.5*(a_i + a_{i+1});
  * (kappa_{i-1/2} + kappa_{i+1/2}) u_i - kappa_{i-1/2} u_{i-1} - kappa_{i+1/2} u_{i+1} = h^2, i = 1..N-1, h = 1/N;
- * QoI = u at node N/2.  The mid value comes from a two-sided (twisted) Thomas elimination: left sweep up to
- * N/2 - 1, right sweep down to N/2 + 1, then the 1x1 system at N/2.  The coarse problem uses the even nodes of
- * the fine field (docs/src/example.md:120) with N/2 cells. */
+ * QoI = u at node N/2, in closed form: the discrete flux F_{i+1/2} = kappa_{i+1/2} (u_{i+1} - u_i) / h drops by h per cell,
+ * so with r_i = 1/kappa_{i+1/2} and the distance w_i = |i + 1/2 - N/2| of edge i from the mid node (in cells)
+ *     u_{N/2} = h^2 (D_R A_L + D_L A_R) / (A_L + A_R),   A = sum r_i,  D = sum w_i r_i  over the left / right half
+ * -- the exact solution of the tridiagonal system above (all terms positive: no cancellation).  Both halves are summed from
+ * the boundary towards the mid node, one edge at a time (A += r; D = fma(w, r, D)): the only sequential dependence per edge is
+ * one addition, the divisions are independent -- on the GPU the two running sums replace the division-latency-bound
+ * elimination recurrence.  The coarse problem uses the even nodes of the fine field (docs/src/example.md:120) with N/2 cells. */
 static double tridiag_mid(const double *a /* node values, stride st */, int st, int N) {
     int M = N / 2;
     double h2 = 1.0 / ((double)N * (double)N);
-#define KAPPA(i) (0.5 * (a[(size_t)(i) * st] + a[(size_t)((i) + 1) * st])) /* kappa_{i+1/2} */
-    /* left sweep: rows 1 .. M-1 */
-    double p = 0.0, y = 0.0;
-    int have_left = 0;
-    for (int i = 1; i <= M - 1; ++i) {
-        double km = KAPPA(i - 1), kp = KAPPA(i);
-        double b = km + kp;
-        if (!have_left) { p = b; y = h2; have_left = 1; }
-        else {
-            double w = km / p;
-            p = fma(-w, km, b);
-            y = fma(w, y, h2);
-        }
+    double AL = 0.0, DL = 0.0, AR = 0.0, DR = 0.0;
+    /* left half: nodes 0 .. M arrive in ascending order; edge (ip-1, ip) has weight M - ip + 1/2 */
+    for (int ip = 1; ip <= M; ++ip) {
+        double kap = 0.5 * (a[(size_t)(ip - 1) * st] + a[(size_t)ip * st]);
+        double r = 1.0 / kap;
+        AL = AL + r;
+        DL = fma((double)(M - ip) + 0.5, r, DL);
     }
-    /* right sweep: rows N-1 .. M+1 */
-    double q = 0.0, zz = 0.0;
-    int have_right = 0;
-    for (int i = N - 1; i >= M + 1; --i) {
-        double km = KAPPA(i - 1), kp = KAPPA(i);
-        double b = km + kp;
-        if (!have_right) { q = b; zz = h2; have_right = 1; }
-        else {
-            double w = kp / q;
-            q = fma(-w, kp, b);
-            zz = fma(w, zz, h2);
-        }
+    /* right half: nodes N .. M arrive in descending order (mirrored node number ip = N - i); same weights */
+    for (int ip = 1; ip <= M; ++ip) {
+        double kap = 0.5 * (a[(size_t)(N - ip + 1) * st] + a[(size_t)(N - ip) * st]);
+        double r = 1.0 / kap;
+        AR = AR + r;
+        DR = fma((double)(M - ip) + 0.5, r, DR);
     }
-    double km = KAPPA(M - 1), kp = KAPPA(M);
-    double den = km + kp, num = h2;
-    if (have_left) { double w = km / p; den = fma(-w, km, den); num = fma(w, y, num); }
-    if (have_right) { double w = kp / q; den = fma(-w, kp, den); num = fma(w, zz, num); }
-#undef KAPPA
-    return num / den;
+    double num = fma(DR, AL, DL * AR);
+    return h2 * (num / (AL + AR));
 }
 
 /* full Thomas solve (all unknowns) -- used by tests to cross-check the twisted mid value */
