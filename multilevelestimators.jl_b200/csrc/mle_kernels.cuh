@@ -348,7 +348,8 @@ struct SweepState {
 __device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, int M) {
     if (ip > 0) {
         const double kap = __dmul_rn(0.5, __dadd_rn(s.a_prev, a));
-        const double r = __ddiv_rn(1.0, kap);
+        const double r = ddiv_normal(1.0, kap);  // == 1.0 / kap for every kappa in the normal range (a = exp(g), |g| < 700); branch-free,
+                                                 // so the divisions of successive edges pipeline
         s.A = __dadd_rn(s.A, r);
         s.D = __fma_rn((double)(M - ip) + 0.5, r, s.D);
     }
