@@ -90,6 +90,8 @@ int mle_dists_destroy(mle_ctx ctx, mle_dists dists);
  *   "problem18"    the reference's own analytic test function, test/regression.jl:17-46 (ndims = 1) and
  *                  :69-103 (ndims = 2) with the multi-index difference of src/index.jl:49-58; 13 QoI; no params
  *   "lognormal1d"  -(a u')' = 1 on (0,1), u(0)=u(1)=0, log a = KL expansion; level l has n0 2^l cells; params = {n0};
+ *                  3-point stencil with arithmetic-mean interface coefficients, u(1/2) from the closed-form flux sums
+ *                  (field values must stay in the normal double range, |log a| < 700);
  *                  structure of docs/src/example.md:106-128 (coarse field = even nodes of the fine field, QoI = u(1/2));
  *                  needs mle_model_set_basis for every level used; 1 QoI; ndims = 1
  *   "lognormal2d"  -div(a grad u) = 1 on the unit square, u = 0 on the boundary, QoI = u(1/2,1/2); params = {n0} (default 4);

@@ -4,7 +4,7 @@
 //                        tile staged in shared memory and written with one TMA bulk store per tile
 //   sample_simple_kernel K5+K6: fused generate -> analytic sample function -> per-CTA moments (no per-sample HBM traffic)
 //   lognormal1d_kernel   K1+K3+K4+K6 fused: generate xi tile -> KL contraction (FP64 register-tiled GEMM fed by TMA bulk
-//                        loads of the basis) -> exp -> two-sided Thomas sweeps for fine and coarse grids -> moments
+//                        loads of the basis) -> exp -> two-sided flux sums for fine and coarse grids -> moments
 //   finalize_kernel      fixed-order Chan merge of the per-CTA partial moments
 #pragma once
 #include "mle_device.cuh"
@@ -309,11 +309,11 @@ __global__ void finalize_kernel(const Moment *__restrict__ partials, int G, int 
 //      mma.sync.m8n8k4.f64 (DMMA), accumulators chained over k.  On B200 one DMMA is bit-identical to four fused
 //      multiply-adds in ascending k (tools/dmma_order_test.cu: 262144/262144), so the field equals the oracle's
 //      sequential-FMA field bit for bit.  A "row" is (half-node i', side): side 0 = node i', side 1 = the mirrored node
-//      N-i', so BOTH elimination sweeps of the two-sided Thomas solve consume rows in ascending order.  Rows are
+//      N-i', so the sweeps of BOTH halves consume rows in ascending order.  Rows are
 //      processed in chunks of RC = 32 (4 row tiles x 8 sample tiles, each warp a 2x2 block of 8x8 tiles).  The basis is
 //      stored in HBM in fragment order, so an A fragment is one fully coalesced 256-byte load served by L1/L2; the B
 //      fragment comes from the xi tile (padded stride: conflict-free).  Epilogue: a = exp(G) -> F[row][sample] (smem).
-//   C. sweeps: thread (side, sample) advances the fine elimination by one row per half-node and the coarse one on every
+//   C. sweeps: thread (side, sample) adds one edge per half-node to the fine flux sums and one to the coarse ones on every
 //      even half-node (coarse field = even nodes of the fine field, docs/src/example.md:120); only running scalars are
 //      kept -- the field never leaves the SM and nothing per-sample is written to HBM.
 //   D. the two sides meet at the mid node: Qf, Qc, dQ = Qf - Qc; corrected two-pass block moments; Chan merge.
