@@ -306,9 +306,9 @@ def run_ours(args):
     sh_np = sh_pinned.numpy()
 
     def step_e2e():
-        out = []
-        for li, lev in enumerate(LEVELS):
-            out.append(eng.sample_batch(model, lat, dists, [lev], sh_np[li], rank * n_l[li], n_l[li], M_KL))
+        # one `update_samples` call (src/sample.jl:8-13): the seven levels' batches, host buffers in and out, one synchronisation
+        out = eng.update_samples(model, lat, dists, [([lev], sh_np[li], rank * n_l[li], n_l[li], M_KL)
+                                                     for li, lev in enumerate(LEVELS)])
         mom = np.stack(out)
         if world > 1:
             t = torch.from_numpy(mom).cuda()

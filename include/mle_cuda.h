@@ -140,6 +140,13 @@ int mle_sample_batch(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists di
 int mle_sample_batch_dev(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
                          const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
                          double *moments_dev, double *samples_dev);
+/* One `update_samples` call (src/sample.jl:8-13): `count` independent `sample!` requests -- entry e has its own index
+ * (indices + e*d), shifts (shifts[e], [s x R[e]], or NULL entries for MC), point range k0[e] .. k0[e]+n[e]-1, dimension count
+ * m[e] and moment table moments[e] ([3 x 2 x q x R[e]]) -- issued back to back on the context's stream with ONE
+ * synchronisation at the end instead of one per index.  Results are identical to `count` calls of mle_sample_batch. */
+int mle_update_samples(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, int count, const int32_t *indices,
+                       int d, const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n, const int *m,
+                       uint64_t mc_seed, double *const *moments);
 /* Block until everything issued on the context's stream has finished. */
 int mle_sync(mle_ctx ctx);
 

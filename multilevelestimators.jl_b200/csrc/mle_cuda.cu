@@ -95,6 +95,8 @@ struct mle_ctx_s {
     size_t zero_cap = 0;
     double *d_moments = nullptr;
     size_t moments_cap = 0;
+    double *d_batch = nullptr;  // mle_update_samples: shifts and moment tables of all entries
+    size_t batch_cap = 0;
     double *h_pinned = nullptr;
     size_t pinned_cap = 0;  // doubles
 };
@@ -273,6 +275,7 @@ extern "C" int mle_destroy(mle_ctx ctx) {
     if (ctx->d_shifts) cudaFree(ctx->d_shifts);
     if (ctx->d_zero) cudaFree(ctx->d_zero);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_batch) cudaFree(ctx->d_batch);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0);
@@ -962,6 +965,56 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     }
     if (d_samples) cudaFree(d_samples);
     return rc;
+}
+
+// `update_samples`: several sample! requests, one synchronisation (include/mle_cuda.h)
+extern "C" int mle_update_samples(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *indices,
+                                  int d, const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n,
+                                  const int *m, uint64_t mc_seed, double *const *moments) {
+    MLE_API_SCOPE;
+    if (!ctx || !M || count < 0 || (count && (!indices || !R || !k0 || !n || !m || !moments))) return MLE_ERR_ARG;
+    if (count == 0) return MLE_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // one arena for all shifts and all moment tables (device and pinned host), laid out entry by entry
+    size_t sh_total = 0, mom_total = 0;
+    for (int e = 0; e < count; ++e) {
+        if (R[e] < 1 || !moments[e]) return fail(ctx, MLE_ERR_ARG, "update_samples: every entry needs R >= 1 and a moment table");
+        if (shifts && shifts[e] && !lat) return fail(ctx, MLE_ERR_ARG, "MC sampling takes no shifts");
+        if (lat && shifts && shifts[e]) sh_total += (size_t)R[e] * (size_t)lat->s;
+        mom_total += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
+    }
+    int rc = ensure_dev(ctx, &ctx->d_batch, &ctx->batch_cap, sh_total + mom_total);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, sh_total + mom_total + 4096);
+    if (rc) return rc;
+    ctx->shifts_staged = 0;  // the pinned area is reused as this call's staging arena
+    size_t off = 0;
+    for (int e = 0; e < count; ++e)
+        if (lat && shifts && shifts[e]) {
+            const size_t cnt = (size_t)R[e] * (size_t)lat->s;
+            memcpy(ctx->h_pinned + off, shifts[e], cnt * sizeof(double));
+            off += cnt;
+        }
+    if (sh_total) CU_TRY(ctx, cudaMemcpyAsync(ctx->d_batch, ctx->h_pinned, sh_total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    size_t sh_off = 0, mom_off = sh_total;
+    for (int e = 0; e < count && rc == MLE_OK; ++e) {
+        const double *sh_dev = nullptr;
+        if (lat && shifts && shifts[e]) { sh_dev = ctx->d_batch + sh_off; sh_off += (size_t)R[e] * (size_t)lat->s; }
+        rc = mle_sample_batch_dev(ctx, M, lat, dists, indices + (size_t)e * d, d, sh_dev, R[e], k0[e], n[e], m[e], mc_seed,
+                                  ctx->d_batch + mom_off, nullptr);
+        mom_off += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
+    }
+    if (rc != MLE_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    cudaError_t err = cudaMemcpyAsync(ctx->h_pinned + sh_total, ctx->d_batch + sh_total, mom_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_update_samples: ") + cudaGetErrorString(err)); }
+    mom_off = sh_total;
+    for (int e = 0; e < count; ++e) {
+        const size_t nm = (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
+        memcpy(moments[e], ctx->h_pinned + mom_off, nm * sizeof(double));
+        mom_off += nm;
+    }
+    return MLE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

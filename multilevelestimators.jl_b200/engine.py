@@ -216,6 +216,30 @@ class Engine:
             out += (t.value,)
         return out[0] if len(out) == 1 else out
 
+    def update_samples(self, model, lattice, dists, entries, mc_seed=0):
+        """One `update_samples` call: entries = [(index, shifts or None, k0, n, m), ...] -> list of moment tables
+        float64[R, nqoi, 2, 3]; all batches are issued back to back with a single synchronisation (mle_update_samples)"""
+        cnt = len(entries)
+        if cnt == 0:
+            return []
+        d = len(np.atleast_1d(entries[0][0]))
+        idx = np.ascontiguousarray([np.atleast_1d(e[0]) for e in entries], dtype=np.int32).reshape(cnt, d)
+        sh = [None if e[1] is None else np.ascontiguousarray(e[1], dtype=np.float64) for e in entries]
+        for a in sh:
+            if a is not None and (lattice is None or a.ndim != 2 or a.shape[1] != lattice.s):
+                raise MLEArgumentError("shifts must have shape [R, s]")
+        R = (C.c_int * cnt)(*[1 if a is None else a.shape[0] for a in sh])
+        k0 = (C.c_uint64 * cnt)(*[int(e[2]) for e in entries])
+        n = (C.c_uint64 * cnt)(*[int(e[3]) for e in entries])
+        m = (C.c_int * cnt)(*[int(e[4]) for e in entries])
+        moms = [np.empty((R[i], model.nqoi, 2, 3)) for i in range(cnt)]
+        shp = (_dp * cnt)(*[_as_dp(a) if a is not None else None for a in sh])
+        mop = (_dp * cnt)(*[_as_dp(a) for a in moms])
+        self._check(self.lib.mle_update_samples(self.ctx, model.handle, lattice.handle if lattice else None,
+                                                dists.handle if dists else None, cnt, idx.ctypes.data_as(C.POINTER(C.c_int32)), d,
+                                                shp, R, k0, n, m, int(mc_seed), mop))
+        return moms
+
     def sample_batch_dev(self, model, lattice, dists, index, shifts_ptr, R, k0, n, m, moments_ptr, samples_ptr=None,
                          mc_seed=0):
         """device-pointer variant: asynchronous on self.stream, nothing crosses PCIe"""

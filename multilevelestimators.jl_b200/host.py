@@ -185,6 +185,10 @@ class GpuBackend:
             m.set_basis(level, phi)
         return m
 
+    def update_samples(self, model, lattice, dists, entries, mc_seed):
+        """entries = [(index, shifts, k0, n, m)] -> list of moment tables; one device synchronisation for all of them"""
+        return self.engine.update_samples(model, lattice, dists, entries, mc_seed=mc_seed)
+
     def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         """-> (moments, seconds) or, with want_samples (the `save_samples` option), (moments, seconds, samples[R, q, 2, n])"""
         out = self.engine.sample_batch(model, lattice, dists, index, shifts, k0, n, m=m, mc_seed=mc_seed,
@@ -409,16 +413,36 @@ class Estimator:
         self.total_work[index] += 0.0 if cm is None else n * cm(index)  # src/internals.jl:98
         self.total_time[index] += t                                     # src/internals.jl:106
 
+    def _sample_many(self, due):
+        from .engine import moments_merge
+        entries = [(list(index), self.shifts.get(index), self.nb_of_samples[index], n, self.options["nb_of_uncertainties"](index))
+                   for index, n in due]
+        t0 = _time.perf_counter()
+        moms = self.backend.update_samples(self.model, self.lattice, self.dists, entries, self.options["mc_seed"])
+        t = _time.perf_counter() - t0
+        cm = self.options["cost_model"]
+        work = [n * cm(index) for index, n in due]
+        for (index, n), mom, w in zip(due, moms, work):
+            self.moments[index] = moments_merge(self.moments[index], mom) if index in self.moments else np.array(mom, dtype=np.float64)
+            self.nb_of_samples[index] += n
+            self.total_work[index] += w
+            self.total_time[index] += t * w / sum(work)   # the call's wall time, shared out by modelled work
+
     def update_samples(self, n_opt):  # src/sample.jl:8-13, :15-19 (U: n_opt are numbers of ADDITIONAL samples)
         if self.unbiased:
             for index in n_opt:
                 if n_opt[index] > 0:
                     self.sample(index, n_opt[index])
             return
-        for index in n_opt:
-            n_due = n_opt[index] - self.nb_of_samples[index]
-            if n_due > 0:
-                self.sample(index, n_due)
+        due = [(index, n_opt[index] - self.nb_of_samples[index]) for index in n_opt if n_opt[index] > self.nb_of_samples[index]]
+        # with a deterministic cost model the per-index wall time is not needed, so all due indices go to the device in ONE
+        # call (mle_update_samples: batches back to back, a single synchronisation); otherwise index by index like the reference,
+        # whose default cost model is the measured time of each sample! call (src/sample.jl:27)
+        if len(due) > 1 and self.options["cost_model"] is not None and hasattr(self.backend, "update_samples") \
+                and not self.options["save_samples"]:
+            return self._sample_many(due)
+        for index, n_due in due:
+            self.sample(index, n_due)
 
     def has_samples_at_index(self, index):
         return self.nb_of_samples.get(index, 0) > 0

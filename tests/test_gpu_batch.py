@@ -410,3 +410,25 @@ def test_lognormal1d_many_kl_terms(engine, oracle, m, level):
     want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, 11, 150, want_samples=True)
     assert np.array_equal(smp, smp_w)
     check_moments(got, want)
+
+
+def test_update_samples_matches_individual_calls(engine, oracle):
+    """mle_update_samples: several sample! requests (different levels, shift counts, point ranges) in one call with one
+    synchronisation return exactly what the individual mle_sample_batch calls return"""
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 100, [0, 1, 3])
+    entries = []
+    for i, (lev, R, k0, n) in enumerate([(0, 16, 0, 700), (1, 16, 5, 300), (3, 4, 0, 33), (0, 16, 700, 1)]):
+        entries.append(([lev], splitmix_uniforms(50 + i, R * 100).reshape(R, 100), k0, n, 100))
+    got = engine.update_samples(gm, lat, d, entries)
+    for (idx, sh, k0, n, m), g in zip(entries, got):
+        assert np.array_equal(g, engine.sample_batch(gm, lat, d, idx, sh, k0, n))
+        check_moments(g, oracle.sample_batch(om, z, dl, idx, sh, k0, n))
+    # MC entries (no shifts) and the argument checks
+    w = [0.1] * 8
+    ge = engine.model("expsum", 1, [2] + w)
+    d8 = engine.dists([NORMAL01] * 8)
+    mc = engine.update_samples(ge, None, d8, [([0], None, 0, 50, 8), ([2], None, 50, 20, 8)], mc_seed=4)
+    assert np.array_equal(mc[1], engine.sample_batch(ge, None, d8, [2], None, 50, 20, m=8, mc_seed=4))
+    import mle_b200
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.update_samples(gm, lat, d, [([0], entries[0][1], 0, 0, 100)])    # n = 0 is refused like in mle_sample_batch
