@@ -123,6 +123,10 @@ end
 # and point range and a `samples` buffer, append the raw samples to `samples_diff[idx]` / `samples[idx]` and add
 # `dQ_idx / Prob(idx)` to the accumulator, exactly as host.py:Estimator._sample_unbiased does (tested there).
 #
+# Optional: `update_samples(estimator, n_opt)` (src/sample.jl:8-13) can hand all due indices to the device at once with
+# mle_update_samples (arrays of indices / shift pointers / point ranges / moment tables, one synchronisation) when the
+# estimator has a deterministic `cost_model`; host.py:Estimator._sample_many is the tested twin.
+#
 # ---- the hot path: one ccall per parallel_sample! (replaces the pmap of src/sample.jl:79-102) ----------------------------
 function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
     model = estimator.sample_function
