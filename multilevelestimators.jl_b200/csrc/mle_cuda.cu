@@ -808,7 +808,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             const int threads = ln_threads(bt), W = threads / 32;
             const int qdims = m < 256 ? ((m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims
             const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
-            const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)2 * bt * sizeof(SweepState) +
+            const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)3 * bt * sizeof(SweepState) +
                                 (size_t)2 * bt * sizeof(Moment) + ((W + 3) & ~3) * 4 + (lat ? (size_t)m * 16 : 0) +
                                 (qbytes <= fbytes ? 0 : qbytes) + 16;
             const int occ = bt == 64 ? MLE_OCC_BY_MODE(g.mode, lognormal1d_k64, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal1d_k32, threads, smem);

@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
     const int mpad = la.mpad;
     double *xi = reinterpret_cast<double *>(smem_raw);           // [mpad][LDX]
     double *F = xi + (size_t)mpad * LDX;                         // [RC][LDF]
-    SweepState *xch = reinterpret_cast<SweepState *>(F + RC * LDF);  // [2][BT] right-side states (fine, coarse)
-    Moment *mred = reinterpret_cast<Moment *>(xch + 2 * BT);     // [2][BT] final per-thread moments
+    SweepState *xch = reinterpret_cast<SweepState *>(F + RC * LDF);  // [3][BT]: fine right, coarse left, coarse right states
+    Moment *mred = reinterpret_cast<Moment *>(xch + 3 * BT);     // [2][BT] final per-thread moments
     GenScratch sc;
     sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * BT);       // [W]
     // generator queue [BT * min(m, 256)]: lives inside F when it fits (F is idle while the inputs are generated)
@@ -441,8 +441,9 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
         }
 
         MLE_PH(0);
-        SweepState sf{0, 0, 0}, scs{0, 0, 0};
-        const int side = tid / BT, b = tid & (BT - 1);  // sweep role (threads 0 .. 2*BT-1)
+        // sweep roles: thread (grid, side, sample) = (tid / (2 BT), (tid / BT) & 1, tid % BT); grid 0 = fine, 1 = coarse (even nodes)
+        SweepState st{0, 0, 0};
+        const int side = (tid / BT) & 1, coarse = tid / (2 * BT), b = tid & (BT - 1);
 
         for (int c = 0; c < la.nchunks; ++c) {
             // B. contraction for rows [c*RC, c*RC + RC).  A full chunk (4 live row tiles) is split 2x2 per warp: row tiles
@@ -517,28 +518,33 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
             }
             __syncthreads();
             MLE_PH(3);
-            // C. sweeps over the RC/2 half-nodes of this chunk (threads 0 .. 2*BT-1)
-            if (tid < 2 * BT && !(la.skip & 8)) {
+            // C. sweeps over the RC/2 half-nodes of this chunk: warps 0-1 the fine grid (every half-node), warps 2-3 the coarse
+            // grid (every second one; idle at level 0)
+            if (!(la.skip & 8)) {
                 const int ip0 = c * (RC / 2);
+                if (!coarse) {
 #pragma unroll 4
-                for (int q = 0; q < RC / 2; ++q) {
-                    const int ip = ip0 + q;
-                    if (ip <= M) {
-                        const double a = F[(2 * q + side) * LDF + b];
-                        sweep_step(sf, ip, a, M);
-                        if (la.level > 0 && (ip & 1) == 0) sweep_step(scs, ip >> 1, a, M / 2);
+                    for (int q = 0; q < RC / 2; ++q) {
+                        const int ip = ip0 + q;
+                        if (ip <= M) sweep_step(st, ip, F[(2 * q + side) * LDF + b], M);
+                    }
+                } else if (la.level > 0) {
+#pragma unroll 4
+                    for (int q = 0; q < RC / 2; q += 2) {  // ip0 is even: the even half-nodes of the chunk
+                        const int ip = ip0 + q;
+                        if (ip <= M) sweep_step(st, ip >> 1, F[(2 * q + side) * LDF + b], M / 2);
                     }
                 }
             }
         }
         MLE_PH(4);
-        // D. meet in the middle
-        if (tid < 2 * BT && side == 1) { xch[b] = sf; xch[BT + b] = scs; }
+        // D. meet in the middle: thread b collects the fine right state and both coarse states
+        if (tid >= BT) xch[(tid / BT - 1) * BT + b] = st;
         __syncthreads();
         if (tid < BT) {
-            const double qf = sweep_combine(sf, xch[b], la.h2);
+            const double qf = sweep_combine(st, xch[b], la.h2);
             double dq = qf;
-            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(scs, xch[BT + b], la.h2c));
+            if (la.level > 0) dq = __dsub_rn(qf, sweep_combine(xch[BT + b], xch[2 * BT + b], la.h2c));
             if (b < Pt) {
                 if (samples) {
                     samples[((size_t)r * 2 + 0) * g.n + i0 + b] = dq;
