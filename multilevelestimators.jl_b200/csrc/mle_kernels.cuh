@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(4 * BT, (BT == 64) ? 2 : 5) lognormal1d_kernel
             if (!(la.skip & 8)) {
                 const int ip0 = c * (RC / 2);
                 if (!coarse) {
-#pragma unroll 4
+#pragma unroll 8
                     for (int q = 0; q < RC / 2; ++q) {
                         const int ip = ip0 + q;
                         if (ip <= M) sweep_step(st, ip, F[(2 * q + side) * LDF + b], M);
