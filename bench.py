@@ -349,11 +349,11 @@ def run_ours(args):
                     "frac": (achieved_tf / peak_tf) if peak_tf else None,
                     "peak_source": "measured live by tools/fp64_microbench (MEASURED_PEAKS.json has no FP64 figure)",
                     # dram__bytes_read.sum + dram__bytes_write.sum of the 7 launches of one step, from the ncu --set full capture
-                    # of this command (profiles/r01_final_kernels.csv): 0.10+0.12+0.14+0.19+0.30+0.50+0.91 MB read, 0 B written
+                    # of this command (profiles/r01_final_kernels.csv): 0.11+0.12+0.14+0.19+0.30+0.50+0.91 MB read, 0 B written
                     "traffic": 2.27e6, "traffic_unit": "bytes per step (all 7 launches); algorithmic HBM bytes per sample: 0",
                     # FP64 + DMMA pipe-busy fractions of the 7 launches in that capture (sm__inst_executed_pipe_fp64 +
                     # sm__pipe_tensor_cycles_active, profiles/r01_final_kernels.csv): not a live measurement
-                    "pipe_busy_ncu_per_level": [0.57, 0.60, 0.55, 0.45, 0.45, 0.37, 0.41],
+                    "pipe_busy_ncu_per_level": [0.56, 0.62, 0.57, 0.60, 0.56, 0.53, 0.45],
                     "per_level_ms": lvl_ms,
                     "per_level_samples_per_s": [n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) for li in range(len(LEVELS))],
                     "per_level_tflops": [algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) * 1e-12
