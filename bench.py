@@ -271,7 +271,12 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # evict L2 between steps (torch's stream)
+        # the previous step has finished before the flush starts: a fill kernel that overlaps a step (it did in an earlier
+        # version of this loop: the next iteration's flush was enqueued while the step's kernels were still running) makes the
+        # FP64-bound kernels 7-11 % FASTER -- tools/concurrent_fill_experiment.py, profiles/r01_concurrent_fill_experiment.txt --
+        # which is not the steady state of back-to-back sample batches
+        torch.cuda.synchronize()
+        flush.fill_(i & 0xFF)     # evict L2 between steps (torch's stream)
         torch.cuda.synchronize()
         ev[i][0].record(stream)
         step_device()
