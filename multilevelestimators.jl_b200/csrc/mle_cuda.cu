@@ -1033,6 +1033,10 @@ extern "C" int mle_moments_merge(double *acc, const double *part, size_t count) 
 
 #ifdef MLE_PHASE_TIMING
 // debug builds only (-DMLE_PHASE_TIMING): wall cycles thread 0 of every CTA spent per phase of lognormal1d_kernel
+extern "C" int mle_debug_cta_times(unsigned long long *out, int n) {
+    if (cudaMemcpyFromSymbol(out, mle::g_cta_times, sizeof(unsigned long long) * 3 * (size_t)n) != cudaSuccess) return -2;
+    return 0;
+}
 extern "C" int mle_debug_phase_cycles(unsigned long long *out8, int reset) {
     MLE_API_SCOPE;
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -378,11 +378,18 @@ __device__ __forceinline__ void welford_add(Welford &w, double x, double inv_n) 
     w.m2 += d * (x - w.mean);
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 #ifdef MLE_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[8];
-#define MLE_PH_DECL long long ph_t = clock64(); long long ph_acc[6] = {0, 0, 0, 0, 0, 0};
+__device__ unsigned long long g_cta_times[3 * 4096];  // per CTA of the last lognormal1d launch: start ns, end ns, SM id
+#define MLE_PH_DECL long long ph_t = clock64(); long long ph_acc[6] = {0, 0, 0, 0, 0, 0}; if (threadIdx.x == 0) { unsigned smid_; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_)); const unsigned l_ = blockIdx.y * gridDim.x + blockIdx.x; if (l_ < 4096) { g_cta_times[3 * l_] = global_timer_ns(); g_cta_times[3 * l_ + 2] = smid_; } }
 #define MLE_PH(i) do { long long ph_n = clock64(); ph_acc[i] += ph_n - ph_t; ph_t = ph_n; } while (0)
-#define MLE_PH_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_phase_cycles[i_], (unsigned long long)ph_acc[i_]); } while (0)
+#define MLE_PH_FLUSH do { if (threadIdx.x == 0) { for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_phase_cycles[i_], (unsigned long long)ph_acc[i_]); const unsigned l_ = blockIdx.y * gridDim.x + blockIdx.x; if (l_ < 4096) g_cta_times[3 * l_ + 1] = global_timer_ns(); } } while (0)
 #else
 #define MLE_PH_DECL
 #define MLE_PH(i)
