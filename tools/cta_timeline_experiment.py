@@ -33,6 +33,13 @@ for mode in ("alone", "fill", "fill", "alone"):
         dict(zip(*np.unique(per_sm, return_counts=True)))))
     late = np.argsort(end)[-5:]
     print("       slowest CTAs: ", [(int(i), int(sm[i]), round(float(life[i]), 2), int(per_sm[sm[i]])) for i in late], "(cta, sm, lifetime ms, CTAs on that SM)")
+    sm_end = np.array([end[sm == q].max() if (sm == q).any() else np.nan for q in range(148)])
+    sm_mean = np.array([life[sm == q].mean() if (sm == q).any() else np.nan for q in range(148)])
+    print("       per-SM finish time: min %.2f max %.2f ms; mean CTA lifetime on SMs 0-73: %.3f, on SMs 74-147: %.3f ms; spread WITHIN an SM (max-min lifetime), mean over SMs: %.3f ms" % (
+        np.nanmin(sm_end), np.nanmax(sm_end), np.nanmean(sm_mean[:74]), np.nanmean(sm_mean[74:]),
+        np.mean([life[sm == q].max() - life[sm == q].min() for q in range(148) if (sm == q).any()])))
+    order = np.argsort(sm_end)
+    print("       earliest-finishing SMs:", [(int(q), round(float(sm_end[q]), 2)) for q in order[:6]], " latest:", [(int(q), round(float(sm_end[q]), 2)) for q in order[-6:]])
     for k in np.unique(per_sm):
         sel = per_sm[sm] == k
         print("       CTAs on SMs holding %d CTAs: mean lifetime %.3f ms (n=%d)" % (k, life[sel].mean(), sel.sum()))
