@@ -79,7 +79,8 @@ static long long churn_grid_x(long long gx_resident, long long tiles_per_shift) 
     if (getenv("MLE_PERSISTENT_GRID")) return gx_resident;  // A/B switch
     const long long per_cta = tiles_per_shift / std::max<long long>(1, gx_resident);  // tiles of a resident-grid CTA
     const long long K = std::min<long long>(16, std::max<long long>(1, per_cta / 8));
-    const long long gx = (tiles_per_shift + K - 1) / K;
+    long long gx = (tiles_per_shift + K - 1) / K;
+    gx = std::min(gx, 64 * gx_resident);  // at most 64 waves: the per-CTA partials stay small for huge batches
     return std::max(gx, gx_resident);
 }
 
@@ -688,6 +689,7 @@ extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, con
     const size_t smem = 2 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + (POINTS_THREADS / 32) * 4;
     long long grid = (long long)ctx->sm_count * MLE_OCC_BY_MODE(g.mode, points_k, POINTS_THREADS, smem);
     if (grid > ntiles) grid = ntiles;
+    grid = churn_grid_x(grid, ntiles);
     MLE_LAUNCH_BY_MODE(g.mode, points_k, (unsigned)grid, POINTS_THREADS, smem, ctx->stream, g, out_dev, P, tps, ntiles);
     ctx->launches += 1;
     CU_TRY(ctx, cudaGetLastError());
@@ -762,7 +764,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                             (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + ((W + 3) & ~3) * 4 + 2 * SIMPLE_MC * 16;
         const int occ = M->kind == MODEL_EXPSUM ? MLE_OCC_BY_MODE(g.mode, expsum_k, SIMPLE_THREADS, smem)
                                                 : MLE_OCC_BY_MODE(g.mode, problem18_k, SIMPLE_THREADS, smem);
-        gx = grid_x_for(ctx, tps, R, occ);
+        gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
         rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
         if (rc) return rc;
         dim3 grid((unsigned)gx, (unsigned)R);
