@@ -358,7 +358,7 @@ def run_ours(args):
                     "traffic": 2.27e6, "traffic_unit": "bytes per step (all 7 launches); algorithmic HBM bytes per sample: 0",
                     # FP64 + DMMA pipe-busy fractions of the 7 launches in that capture (sm__inst_executed_pipe_fp64 +
                     # sm__pipe_tensor_cycles_active, profiles/r01_final_kernels.csv): not a live measurement
-                    "pipe_busy_ncu_per_level": [0.56, 0.62, 0.57, 0.60, 0.56, 0.53, 0.45],
+                    "pipe_busy_ncu_per_level": [0.63, 0.67, 0.65, 0.62, 0.59, 0.54, 0.47],
                     "per_level_ms": lvl_ms,
                     "per_level_samples_per_s": [n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) for li in range(len(LEVELS))],
                     "per_level_tflops": [algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) * 1e-12
