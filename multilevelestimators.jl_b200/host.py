@@ -17,6 +17,7 @@ Out of scope: AD and U index sets, printing, JLD2 output, `sav
 The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
 """
 import math
+import os
 import random as _random
 import time as _time
 
@@ -121,6 +122,9 @@ def is_admissable(index_set, index):
             if nb not in s:
                 return False
     return True
+
+
+AbstractIndexSet = (SL, ML, _Weighted, AD, U)
 
 
 class MC:
@@ -259,9 +263,153 @@ _DEFAULTS = dict(nb_of_qoi=None, aggregation="max", qoi_with_max_var=1, continua
                  continuation_mul_factor=1.3, min_splitting=0.5, max_splitting=0.99, robustify_bias_estimate=True,
                  do_mse_splitting=True, do_regression=True, min_index_set_param=2, max_index_set_param=None,
                  sample_mul_factor=1.2, nb_of_warm_up_samples=None, nb_of_shifts=10, nb_of_uncertainties=None,
-                 cost_model=None, point_generator=None, shifts=None, shift_seed=0, mc_seed=1, name="UntitledEstimator",
-                 verbose=False, max_search_space=None, penalization=0.5, acceptance_rate=1.0, save_samples=False)
+                 cost_model=None, point_generator=None, shifts=None, shift_seed=0, mc_seed=1, name=None, folder=None,
+                 save=False, verbose=False, nb_of_workers=None, max_search_space=None, penalization=0.5, acceptance_rate=1.0,
+                 save_samples=False)
+# which keys an estimator accepts, src/options.jl:10-41
+_COMMON_KEYS = ("nb_of_warm_up_samples", "nb_of_qoi", "qoi_with_max_var", "aggregation", "nb_of_tols", "continuation_mul_factor",
+                "continuate", "save", "save_samples", "verbose", "folder", "name", "cost_model", "nb_of_workers",
+                "nb_of_uncertainties", "max_index_set_param", "min_index_set_param")
+_INDEX_SET_KEYS = ("min_splitting", "max_splitting", "robustify_bias_estimate", "do_mse_splitting", "do_regression")
 _AD_ONLY = ("max_search_space", "penalization", "acceptance_rate")  # src/options.jl:36
+_U_KEYS = ("max_search_space", "sample_mul_factor")                 # src/options.jl:37
+_QMC_KEYS = ("nb_of_shifts", "point_generator", "sample_mul_factor")  # src/options.jl:41-43
+_ENGINE_KEYS = ("shifts", "shift_seed", "mc_seed")  # not in the reference: its random inputs come from Julia's global RNG
+
+
+def valid_options(index_set, sample_method):
+    """get_valid_options(index_set, sample_method), src/options.jl:27-43, plus the engine's own seeding keys"""
+    keys = list(_COMMON_KEYS)
+    if isinstance(index_set, AD):
+        keys += _INDEX_SET_KEYS + _AD_ONLY
+    elif isinstance(index_set, U):
+        keys += _U_KEYS
+    elif not isinstance(index_set, SL):
+        keys += _INDEX_SET_KEYS
+    if isinstance(sample_method, QMC):
+        keys += _QMC_KEYS
+    return list(dict.fromkeys(keys + list(_ENGINE_KEYS)))
+
+
+def _is_int(v):
+    return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
+
+
+def _is_real(v):
+    return isinstance(v, (int, float, np.integer, np.floating)) and not isinstance(v, (bool, np.bool_))
+
+
+def _check_type(key, val, ok, wanted):  # check_type, src/check_input.jl:25
+    if not ok:
+        raise ValueError("in Estimator, optional key %s must be of type %s, got %s" % (key, wanted, type(val).__name__))
+
+
+def _check(key, ok, what):  # check_larger_than & co., src/check_input.jl:9-13
+    if not ok:
+        raise ValueError("in Estimator, optional key %s must be %s." % (key, what))
+
+
+def _check_real(key, val, lo=None, lo_open=True, hi=None):
+    _check_type(key, val, _is_real(val), "Real")
+    _check(key, math.isfinite(val), "finite")
+    if lo is not None:
+        _check(key, val > lo if lo_open else val >= lo, ("larger than %s" if lo_open else "larger than or equal to %s") % lo)
+    if hi is not None:
+        _check(key, val <= hi, "smaller than or equal to %s" % hi)
+
+
+def parse_options(index_set, sample_method, distributions, options):
+    """The option checks of src/parse.jl:35-307 (same defaults, same rules, ArgumentError -> ValueError).  Returns the complete
+    option dict.  Differences, all on the control-plane side: `save` defaults to False and writes JSON instead of JLD2,
+    `verbose` defaults to False (nothing is printed), `nb_of_workers` is validated and ignored (the device backend decides)."""
+    unknown = [k for k in options if k not in valid_options(index_set, sample_method)]
+    if unknown:
+        raise ValueError("in Estimator, invalid option %s found" % sorted(unknown)[0])  # src/estimator.jl:126-130
+    qmc, unbiased, adaptive = isinstance(sample_method, QMC), isinstance(index_set, U), isinstance(index_set, AD)
+    d = index_set.ndims
+    o = dict(_DEFAULTS)
+    o.update(options)
+    if o["nb_of_warm_up_samples"] is None:
+        o["nb_of_warm_up_samples"] = (2 if unbiased else 1) if qmc else 20          # src/parse.jl:35-36
+    else:
+        _check_type("nb_of_warm_up_samples", o["nb_of_warm_up_samples"], _is_int(o["nb_of_warm_up_samples"]), "Signed")
+        _check("nb_of_warm_up_samples", o["nb_of_warm_up_samples"] > 1, "larger than 1")  # src/parse.jl:39
+    if o["nb_of_qoi"] is not None:                                                  # src/parse.jl:44-51
+        _check_type("nb_of_qoi", o["nb_of_qoi"], _is_int(o["nb_of_qoi"]), "Signed")
+        _check("nb_of_qoi", o["nb_of_qoi"] > 0, "larger than 0")
+    _check_type("aggregation", o["aggregation"], isinstance(o["aggregation"], str), "String")
+    if o["aggregation"] not in ("max", "sum", "norm"):
+        raise ValueError("in Estimator, optional key aggregation must be 'sum', 'max' or 'norm'")  # src/parse.jl:58
+    for key in ("continuate", "save_samples", "save", "verbose", "robustify_bias_estimate", "do_mse_splitting", "do_regression"):
+        _check_type(key, o[key], isinstance(o[key], (bool, np.bool_)), "Bool")
+    _check_type("nb_of_tols", o["nb_of_tols"], _is_int(o["nb_of_tols"]), "Integer")
+    _check("nb_of_tols", o["nb_of_tols"] > 0, "larger than 0")                       # src/parse.jl:70-77
+    _check_real("continuation_mul_factor", o["continuation_mul_factor"], lo=1)      # src/parse.jl:79-87
+    for key in ("min_splitting", "max_splitting"):                                  # src/parse.jl:89-113
+        _check_real(key, o[key], lo=0, hi=1)
+    if not o["min_splitting"] <= o["max_splitting"]:
+        raise ValueError("in Estimator, optional key min_splitting must be smaller than or equal to optional key max_splitting")
+    if o["folder"] is None:
+        o["folder"] = os.getcwd()                                                   # src/parse.jl:116-117
+    _check_type("folder", o["folder"], isinstance(o["folder"], str), "String")
+    if o["save"] and not os.path.isdir(o["folder"]):
+        raise ValueError("%s is not a directory!" % o["folder"])                    # src/parse.jl:122
+    if o["name"] is None:                                                           # get_valid_filename, src/parse.jl:142-153
+        stem, cntr = "UntitledEstimator", 0
+        if o["save"]:
+            while os.path.isfile(os.path.join(o["folder"], "%s%s.json" % (stem, cntr or ""))):
+                cntr += 1
+        o["name"] = "%s%s.jld2" % (stem, cntr or "")
+    else:
+        _check_type("name", o["name"], isinstance(o["name"], str), "String")
+        if not o["name"].endswith(".jld2"):
+            if "." in o["name"]:
+                raise ValueError("in Estimator, optional key name must not contain a .")  # src/parse.jl:134
+            o["name"] += ".jld2"
+    if o["cost_model"] is not None:
+        _check_type("cost_model", o["cost_model"], callable(o["cost_model"]), "Function")  # src/parse.jl:173-176
+    if o["max_index_set_param"] is None:
+        o["max_index_set_param"] = 10 * d                                           # src/parse.jl:193-194
+    for key in ("max_index_set_param", "min_index_set_param"):                      # src/parse.jl:193-213
+        _check_type(key, o[key], _is_int(o[key]), "Signed")
+        _check(key, o[key] > 0, "larger than 0")
+    if not o["min_index_set_param"] <= o["max_index_set_param"]:
+        raise ValueError("in Estimator, optional key min_index_set_param must be smaller than or equal to "
+                         "optional key max_index_set_param")
+    _check_real("sample_mul_factor", o["sample_mul_factor"])                        # src/parse.jl:215-222
+    if o["nb_of_workers"] is None:
+        o["nb_of_workers"] = lambda index: 1
+    elif not callable(o["nb_of_workers"]):                                          # src/parse.jl:224-235
+        _check_type("nb_of_workers", o["nb_of_workers"], _is_int(o["nb_of_workers"]), "Union{Integer, Function}")
+        _check("nb_of_workers", o["nb_of_workers"] > 0, "larger than 0")
+        nw = int(o["nb_of_workers"])
+        o["nb_of_workers"] = lambda index: nw
+    if callable(o["nb_of_shifts"]):
+        if unbiased:
+            raise ValueError("in Estimator, optional key nb_of_shifts cannot be a Function when using unbiased estimation")
+    else:                                                                           # src/parse.jl:237-249
+        _check_type("nb_of_shifts", o["nb_of_shifts"], _is_int(o["nb_of_shifts"]), "Union{Integer, Function}")
+        _check("nb_of_shifts", o["nb_of_shifts"] > 1, "larger than 1")
+        R = int(o["nb_of_shifts"])
+        o["nb_of_shifts"] = lambda index: R
+    if o["nb_of_uncertainties"] is None:
+        m_all = len(distributions)
+        o["nb_of_uncertainties"] = lambda index: m_all                              # src/parse.jl:272-275
+    else:
+        _check_type("nb_of_uncertainties", o["nb_of_uncertainties"], callable(o["nb_of_uncertainties"]), "Function")
+    if adaptive or unbiased:
+        if o["max_search_space"] is None:
+            o["max_search_space"] = TD(d)                                           # src/parse.jl:263-264 (fails for d = 1 like the reference)
+        _check_type("max_search_space", o["max_search_space"], isinstance(o["max_search_space"], AbstractIndexSet),
+                    "AbstractIndexSet")
+        if o["max_search_space"].ndims != d:
+            raise ValueError("in Estimator, dimensions of max_search_space must be equal to %d." % d)  # src/parse.jl:267
+    for key in ("penalization", "acceptance_rate"):                                 # src/parse.jl:278-298
+        _check_real(key, o[key], lo=0, lo_open=False, hi=1)
+    _check("qoi_with_max_var", _is_int(o["qoi_with_max_var"]) and o["qoi_with_max_var"] > 0, "larger than 0")  # src/parse.jl:300-307
+    if o["nb_of_qoi"] is not None:
+        _check("qoi_with_max_var", o["qoi_with_max_var"] <= o["nb_of_qoi"], "smaller than or equal to %d" % o["nb_of_qoi"])
+    return o
 
 
 class Estimator:
@@ -272,49 +420,17 @@ class Estimator:
             raise TypeError("sample_function must be a ModelSpec naming a device model (arbitrary closures cannot run on the GPU)")
         if isinstance(distributions, tuple):
             distributions = [distributions]
-        unknown = set(options) - set(_DEFAULTS)
-        if unknown:
-            raise ValueError("in Estimator, invalid option %s" % sorted(unknown))  # src/estimator.jl:127-131
         self.adaptive = isinstance(index_set, AD)
         self.unbiased = isinstance(index_set, U)
-        allowed_extra = _AD_ONLY if self.adaptive else (("max_search_space",) if self.unbiased else ())
-        if any(k in options and k not in allowed_extra for k in _AD_ONLY):
-            raise ValueError("in Estimator, invalid option %s" % sorted(set(options) & set(_AD_ONLY) - set(allowed_extra)))
-        o = dict(_DEFAULTS)
-        o.update(options)
+        self.qmc = isinstance(sample_method, QMC)
+        o = parse_options(index_set, sample_method, list(distributions), options)   # src/estimator.jl:123-134
         self.index_set, self.sample_method, self.spec, self.distributions, self.backend = (
             index_set, sample_method, sample_function, list(distributions), backend)
-        self.qmc = isinstance(sample_method, QMC)
         d = index_set.ndims
-        if o["max_index_set_param"] is None:
-            o["max_index_set_param"] = 10 * d                          # src/parse.jl:193-194
-        if o["nb_of_warm_up_samples"] is None:
-            o["nb_of_warm_up_samples"] = (2 if self.unbiased else 1) if self.qmc else 20   # src/parse.jl:35-36
-        elif o["nb_of_warm_up_samples"] <= 1:
-            raise ValueError("in Estimator, optional key nb_of_warm_up_samples must be larger than 1")  # src/parse.jl:39
-        if not callable(o["nb_of_shifts"]):
-            if o["nb_of_shifts"] <= 1:
-                raise ValueError("in Estimator, optional key nb_of_shifts must be larger than 1")      # src/parse.jl:243
-            R = int(o["nb_of_shifts"])
-            o["nb_of_shifts"] = lambda index: R
-        if o["nb_of_uncertainties"] is None:
-            m_all = len(self.distributions)
-            o["nb_of_uncertainties"] = lambda index: m_all              # src/parse.jl:272-275
-        if o["aggregation"] not in ("max", "sum", "norm"):
-            raise ValueError("in Estimator, optional key aggregation must be 'sum', 'max' or 'norm'")
-        if not (0 < o["min_splitting"] <= o["max_splitting"] <= 1):
-            raise ValueError("in Estimator, min_splitting / max_splitting must satisfy 0 < min <= max <= 1")
-        if self.adaptive or self.unbiased:
-            if o["max_search_space"] is None:
-                o["max_search_space"] = TD(d)                           # src/parse.jl:263-264 (fails for d = 1 like the reference)
-            if getattr(o["max_search_space"], "ndims", None) != d:
-                raise ValueError("in Estimator, dimensions of max_search_space must be equal to %d" % d)  # src/parse.jl:267
-            for key in ("penalization", "acceptance_rate") if self.adaptive else ():
-                if not (math.isfinite(o[key]) and 0 <= o[key] <= 1):
-                    raise ValueError("in Estimator, optional key %s must be in [0, 1]" % key)  # src/parse.jl:277-297
         self.options = o
         self.model = backend.model(sample_function)
         self.nqoi = o["nb_of_qoi"] or getattr(self.model, "nqoi", 1)
+        _check("qoi_with_max_var", o["qoi_with_max_var"] <= self.nqoi, "smaller than or equal to %d" % self.nqoi)  # src/parse.jl:305
         self.dists = backend.dists(self.distributions)
         s = len(self.distributions)
         self.lattice = None
@@ -755,6 +871,8 @@ class Estimator:
 # run (src/run.jl:20-142) and History (src/history.jl)
 # ---------------------------------------------------------------------------------------------------------------
 class History:
+    """History (src/history.jl:8-117): one dict per tolerance; history[key] reads the last entry, history[i] the i-th."""
+
     def __init__(self):
         self.data = []
 
@@ -766,6 +884,60 @@ class History:
 
     def __contains__(self, key):
         return key in self.data[-1]
+
+    def __repr__(self):
+        return "MultilevelEstimators history file"  # src/history.jl:117
+
+    @property
+    def path(self):
+        """Where save() writes: folder/name with the reference's .jld2 suffix replaced by .json (JLD2 itself is a Julia format
+        this mirror does not produce; the Julia glue keeps the reference's own `@save`, src/history.jl:107)."""
+        name = self["name"]
+        return os.path.join(self["folder"], (name[:-5] if name.endswith(".jld2") else name) + ".json")
+
+    def save(self, path=None):
+        """save(history), src/history.jl:107.  Index keys become their string form, arrays become nested lists."""
+        import json
+
+        def enc(v):
+            if isinstance(v, dict):
+                return {(str(tuple(int(c) for c in k)) if isinstance(k, tuple) else str(k)): enc(x) for k, x in v.items()}
+            if isinstance(v, np.ndarray):
+                return enc(v.tolist())
+            if isinstance(v, (list, tuple, set)):
+                return [enc(x) for x in (sorted(v) if isinstance(v, set) else v)]
+            if isinstance(v, np.generic):
+                return v.item()
+            return v
+
+        path = path or self.path
+        tmp = path + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump([enc(h) for h in self.data], f)
+        os.replace(tmp, path)
+        return path
+
+    @classmethod
+    def load(cls, path):
+        import ast
+        import json
+
+        def is_index(k):
+            return k.startswith("(") and k.endswith(")")
+
+        def dec(v, key=None):
+            if isinstance(v, dict):
+                return {(ast.literal_eval(k) if is_index(k) else k): dec(x, k) for k, x in v.items()}
+            if isinstance(v, list):
+                if key in ("current_index_set", "index_set"):
+                    return [tuple(x) for x in v]
+                return [dec(x) for x in v]
+            return v
+
+        h = cls()
+        with open(path) as f:
+            h.data = [dec(e) for e in json.load(f)]
+        return h
 
 
 def get_tols(est, tol):  # src/methods.jl:15
@@ -822,7 +994,7 @@ def _run(est, eps):  # src/run.jl:41-142
 def update_history(history, est, tol, elapsed):  # src/history.jl:55-103
     allk = est.all_keys()
     h = {"type": "Estimator{%s, %s}" % (type(est.index_set).__name__, type(est.sample_method).__name__),
-         "ndims": est.index_set.ndims, "name": est["name"], "elapsed": elapsed, "tol": tol,
+         "ndims": est.index_set.ndims, "name": est["name"], "folder": est["folder"], "elapsed": elapsed, "tol": tol,
          "current_index_set": est.keys(), "index_set": allk, "mse": est.mse(), "rmse": est.rmse(), "mean": est.mean(),
          "varest": est.varest(), "bias": est.bias(),
          "E": {i: est.mean0(i) for i in allk}, "V": {i: est.var0(i) for i in allk},
@@ -838,6 +1010,8 @@ def update_history(history, est, tol, elapsed):  # src/history.jl:55-103
         h["samples"] = {i: a[:, :, 1, :] for i, a in cat.items()}
         h["samples_diff"] = {i: a[:, :, 0, :] for i, a in cat.items()}
     history.data.append(h)
+    if est["save"]:  # src/history.jl:99-102: the file is rewritten after every tolerance
+        history.save()
 
 
 def run(est, tol):

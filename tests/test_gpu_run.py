@@ -133,9 +133,10 @@ def test_unbiased_runs_match_oracle(engine):
     for method, d in (("MC", 1), ("QMC", 1), ("QMC", 2)):
         def make(H, backend):
             kw = dict(max_search_space=H.ML()) if d == 1 else {}
+            if method == "QMC":
+                kw["nb_of_shifts"] = 8   # a QMC-only key, src/options.jl:41
             return H.Estimator(H.U(d), getattr(H, method)(), H.ModelSpec("problem18", d), [H.Uniform(-0.5, 0.5)] * d, backend,
-                               nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3,
-                               nb_of_shifts=8, **kw)
+                               nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3, **kw)
         H, g, o = both(engine, make)
         hg, ho = H.run(g, 5e-3), H.run(o, 5e-3)
         compare(hg, ho)

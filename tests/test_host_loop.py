@@ -56,6 +56,111 @@ def test_option_validation_mirrors_reference():
     assert e["continuation_mul_factor"] == 1.3 and e["sample_mul_factor"] == 1.2  # src/parse.jl:80, :216
 
 
+def test_option_scoping_and_rules_follow_reference(tmp_path):
+    """src/options.jl:10-43 (which keys an estimator accepts) and the per-key rules of src/parse.jl:35-307"""
+    H = host()
+    spec, spec2 = H.ModelSpec("problem18", 1), H.ModelSpec("problem18", 2)
+    be, U1, U2 = OracleBackend(), [H.Uniform(-0.5, 0.5)], [H.Uniform(-0.5, 0.5)] * 2
+
+    def bad(iset, method, sp, dists, **kw):
+        with pytest.raises(ValueError) as e:
+            H.Estimator(iset, method, sp, dists, be, **kw)
+        return str(e.value)
+
+    # scoping: QMC-only, multilevel-only, AD-only and U-only keys
+    assert "invalid option nb_of_shifts" in bad(H.ML(), H.MC(), spec, U1, nb_of_shifts=4)
+    assert "invalid option sample_mul_factor" in bad(H.ML(), H.MC(), spec, U1, sample_mul_factor=2)
+    assert "invalid option point_generator" in bad(H.ML(), H.MC(), spec, U1, point_generator=[1, 3])
+    assert "invalid option do_regression" in bad(H.SL(), H.MC(), spec, U1, do_regression=False)
+    assert "invalid option min_splitting" in bad(H.U(1), H.MC(), spec, U1, max_search_space=H.ML(), min_splitting=0.6)
+    assert "invalid option penalization" in bad(H.U(2), H.QMC(), spec2, U2, penalization=0.3)
+    assert "invalid option max_search_space" in bad(H.TD(2), H.QMC(), spec2, U2, max_search_space=H.FT(2))
+    H.Estimator(H.U(1), H.MC(), spec, U1, be, max_search_space=H.ML(), sample_mul_factor=2)        # valid for U with MC
+    H.Estimator(H.AD(2), H.QMC(), spec2, U2, be, do_regression=False, penalization=0.0, acceptance_rate=1)
+    assert set(H.valid_options(H.SL(), H.MC())) - {"shifts", "shift_seed", "mc_seed"} == {
+        "nb_of_warm_up_samples", "nb_of_qoi", "qoi_with_max_var", "aggregation", "nb_of_tols", "continuation_mul_factor",
+        "continuate", "save", "save_samples", "verbose", "folder", "name", "cost_model", "nb_of_workers",
+        "nb_of_uncertainties", "max_index_set_param", "min_index_set_param"}
+    # types
+    assert "must be of type Signed" in bad(H.ML(), H.MC(), spec, U1, nb_of_warm_up_samples=2.5)
+    assert "must be of type Signed" in bad(H.ML(), H.MC(), spec, U1, nb_of_qoi=True)
+    assert "must be of type String" in bad(H.ML(), H.MC(), spec, U1, aggregation=3)
+    assert "must be of type Bool" in bad(H.ML(), H.MC(), spec, U1, continuate=1)
+    assert "must be of type Bool" in bad(H.ML(), H.MC(), spec, U1, save_samples="yes")
+    assert "must be of type Function" in bad(H.ML(), H.MC(), spec, U1, cost_model=2.0)
+    assert "must be of type Function" in bad(H.ML(), H.MC(), spec, U1, nb_of_uncertainties=1)
+    assert "must be of type Real" in bad(H.ML(), H.MC(), spec, U1, continuation_mul_factor="2")
+    assert "AbstractIndexSet" in bad(H.AD(2), H.MC(), spec2, U2, max_search_space=3)
+    # ranges
+    assert "nb_of_qoi must be larger than 0" in bad(H.ML(), H.MC(), spec, U1, nb_of_qoi=0)
+    assert "nb_of_tols must be larger than 0" in bad(H.ML(), H.MC(), spec, U1, nb_of_tols=0)
+    assert "continuation_mul_factor must be larger than 1" in bad(H.ML(), H.MC(), spec, U1, continuation_mul_factor=1.0)
+    assert "must be finite" in bad(H.ML(), H.MC(), spec, U1, continuation_mul_factor=math.inf)
+    assert "min_splitting must be larger than 0" in bad(H.ML(), H.MC(), spec, U1, min_splitting=0.0)
+    assert "max_splitting must be smaller than or equal to 1" in bad(H.ML(), H.MC(), spec, U1, max_splitting=1.5)
+    assert "min_splitting must be smaller than or equal to optional key max_splitting" in bad(
+        H.ML(), H.MC(), spec, U1, min_splitting=0.9, max_splitting=0.6)
+    assert "min_index_set_param must be smaller than or equal to" in bad(H.ML(), H.MC(), spec, U1, max_index_set_param=1)
+    assert "max_index_set_param must be larger than 0" in bad(H.ML(), H.MC(), spec, U1, max_index_set_param=0, min_index_set_param=0)
+    assert "must be finite" in bad(H.ML(), H.QMC(), spec, U1, sample_mul_factor=math.nan)
+    assert "nb_of_workers must be larger than 0" in bad(H.ML(), H.MC(), spec, U1, nb_of_workers=0)
+    assert "cannot be a Function" in bad(H.U(1), H.QMC(), spec, U1, max_search_space=H.ML(), nb_of_shifts=lambda i: 4)
+    assert "penalization must be larger than or equal to 0" in bad(H.AD(2), H.MC(), spec2, U2, penalization=-0.1)
+    assert "qoi_with_max_var must be larger than 0" in bad(H.ML(), H.MC(), spec, U1, qoi_with_max_var=0)
+    assert "qoi_with_max_var must be smaller than or equal to 13" in bad(H.ML(), H.MC(), spec, U1, nb_of_qoi=13, qoi_with_max_var=14)
+    assert "must not contain a ." in bad(H.ML(), H.MC(), spec, U1, name="my.estimator")
+    assert "is not a directory" in bad(H.ML(), H.MC(), spec, U1, save=True, folder=str(tmp_path / "missing"))
+    # defaults and normalisation
+    e = H.Estimator(H.ML(), H.QMC(), spec, U1, be, name="run7", nb_of_workers=3, nb_of_shifts=lambda i: 4 + i[0])
+    assert e["name"] == "run7.jld2" and e["folder"] == os.getcwd() and e["nb_of_workers"]((2,)) == 3   # src/parse.jl:116-140
+    assert e["nb_of_shifts"]((2,)) == 6 and e["save"] is False
+    assert H.Estimator(H.ML(), H.MC(), spec, U1, be, name="a.jld2")["name"] == "a.jld2"
+    assert H.Estimator(H.U(1), H.QMC(), spec, U1, be, max_search_space=H.ML())["nb_of_warm_up_samples"] == 2   # src/parse.jl:36
+    assert H.Estimator(H.ML(), H.MC(), spec, U1, be)["nb_of_warm_up_samples"] == 20
+
+
+def test_history_is_saved_after_every_tolerance_and_reloads(tmp_path):
+    """src/history.jl:99-107: with save = true the history file under folder/name is rewritten after each tolerance; untitled
+    estimators get UntitledEstimator, UntitledEstimator1, ... (src/parse.jl:142-153).  The mirror writes JSON."""
+    H = host()
+    kw = dict(nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3, save=True,
+              folder=str(tmp_path))
+    est = H.Estimator(H.TD(2), H.QMC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(),
+                      nb_of_shifts=4, save_samples=True, **kw)
+    assert est["name"] == "UntitledEstimator.jld2"
+    h = H.run(est, 2e-2)
+    assert h["folder"] == str(tmp_path) and h.path == str(tmp_path / "UntitledEstimator.json") and os.path.isfile(h.path)
+    assert repr(h) == "MultilevelEstimators history file"
+    g = H.History.load(h.path)
+    assert len(g) == len(h) == 3
+    for i in range(3):
+        a, b = h[i], g[i]
+        assert set(a) == set(b)
+        assert a["current_index_set"] == b["current_index_set"] and a["index_set"] == b["index_set"]
+        assert a["nb_of_samples"] == b["nb_of_samples"] and a["tol"] == b["tol"]
+        for key in ("mean", "varest", "mse", "rmse", "bias", "alpha", "beta", "gamma"):
+            assert np.array_equal(np.asarray(a[key], dtype=float), np.asarray(b[key], dtype=float), equal_nan=True), key
+        for key in ("E", "V", "dE", "dV", "W"):
+            assert set(a[key]) == set(b[key])
+            for idx in a[key]:
+                assert np.array_equal(np.asarray(a[key][idx], dtype=float), np.asarray(b[key][idx], dtype=float), equal_nan=True)
+        for idx in a["samples_diff"]:
+            assert np.array_equal(a["samples_diff"][idx], np.asarray(b["samples_diff"][idx]))
+    # the next untitled estimators in the same folder do not overwrite the first one
+    e2 = H.Estimator(H.ML(), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), save=True,
+                     folder=str(tmp_path))
+    assert e2["name"] == "UntitledEstimator1.jld2"
+    H.run(e2, [5e-2])
+    e3 = H.Estimator(H.ML(), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), save=True,
+                     folder=str(tmp_path))
+    assert e3["name"] == "UntitledEstimator2.jld2"
+    # nothing is written without save
+    e4 = H.Estimator(H.ML(), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), name="quiet",
+                     folder=str(tmp_path))
+    H.run(e4, [5e-2])
+    assert not os.path.exists(tmp_path / "quiet.json")
+
+
 @pytest.mark.parametrize("method", ["MC", "QMC"])
 @pytest.mark.parametrize("aggregation,tol", [("max", 1e-2), ("sum", 1e-1), ("norm", 1e-1)])
 def test_regression_problem18_multilevel(method, aggregation, tol):
