@@ -23,6 +23,7 @@ import MultilevelEstimators: Estimator, AbstractIndexSet, MC, QMC, Index, parall
                              generator, Uniform, Normal, TruncatedNormal, Weibull
 
 const libmle = "libmle_cuda"   # multilevelestimators.jl_b200/lib/libmle_cuda.so on the library path
+const ABI_VERSION = 1           # MLE_ABI_VERSION of include/mle_cuda.h this file was written against
 
 struct MLEDist
     kind::Int32
@@ -48,6 +49,7 @@ mutable struct Context
         rc = ccall((:mle_init, libmle), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ref)
         rc == 0 || error(unsafe_string(ccall((:mle_last_error, libmle), Cstring, (Ptr{Cvoid},), C_NULL)))
         ctx = new(ref[])
+        ccall((:mle_abi_version, libmle), Cint, ()) == ABI_VERSION || error("libmle_cuda: ABI version mismatch")
         finalizer(c -> ccall((:mle_destroy, libmle), Cint, (Ptr{Cvoid},), c.ptr), ctx)
         ctx
     end
@@ -86,7 +88,11 @@ function DeviceModel(ctx::Context, name::String, ndims::Integer, params::Vector{
     q = Ref{Cint}(0)
     ccall((:mle_model_nqoi, libmle), Cint, (Ptr{Cvoid}, Ref{Cint}), ref[], q)
     m = DeviceModel(ctx, ref[], q[], C_NULL, C_NULL)
-    finalizer(x -> ccall((:mle_model_destroy, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.ptr, x.ptr), m)
+    finalizer(m) do x
+        x.lattice == C_NULL || ccall((:mle_lattice_destroy, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.ptr, x.lattice)
+        x.dists == C_NULL || ccall((:mle_dists_destroy, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.ptr, x.dists)
+        ccall((:mle_model_destroy, libmle), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.ptr, x.ptr)
+    end
     m
 end
 
@@ -101,6 +107,45 @@ function ensure_handles!(m::DeviceModel, estimator)
                                m.ctx.ptr, d, length(d), ref))
         m.dists = ref[]
     end
+end
+
+function ensure_lattice!(m::DeviceModel, rule)
+    if m.lattice == C_NULL
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(m.ctx.ptr, ccall((:mle_lattice_create, libmle), Cint, (Ptr{Cvoid}, Ptr{UInt32}, Cint, UInt64, Ref{Ptr{Cvoid}}),
+                               m.ctx.ptr, rule.z, length(rule.z), UInt64(rule.n), ref))
+        m.lattice = ref[]
+    end
+end
+
+# The generating vectors the library embeds (the reference's src/generating_vectors/*.txt): "K_3600_32", "CKN_250_20".
+function genvec(name::String)
+    z, len = Ref{Ptr{UInt32}}(C_NULL), Ref{Cint}(0)
+    ccall((:mle_genvec, libmle), Cint, (Cstring, Ref{Ptr{UInt32}}, Ref{Cint}), name, z, len) == 0 || throw(ArgumentError("unknown generating vector $name"))
+    copy(unsafe_wrap(Array, z[], len[]))
+end
+
+"""
+    device_points(estimator, index, Istart, Iend) -> Array{Float64, 3}  (m x n x R)
+
+Parity hook for stages 1-2: `transform.(distributions[1:m], get_point(generator(estimator, index, r), k)[1:m])` for
+`k = Istart-1 : Iend-1` and every shift `r` (src/sample.jl:84-88), computed on the device.
+"""
+function device_points(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
+    model = estimator.sample_function
+    ensure_handles!(model, estimator)
+    m = estimator[:nb_of_uncertainties](index)
+    R = estimator[:nb_of_shifts](index)
+    gens = [generator(estimator, index, r) for r in 1:R]
+    ensure_lattice!(model, gens[1].lattice_rule)
+    shifts = reduce(hcat, [Vector{Float64}(g.shift) for g in gens])
+    n = Iend - Istart + 1
+    out = Array{Float64}(undef, m, n, R)
+    GC.@preserve shifts out check(model.ctx.ptr,
+        ccall((:mle_points, libmle), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64, Ptr{Float64}),
+              model.ctx.ptr, model.lattice, model.dists, shifts, R, UInt64(Istart - 1), UInt64(n), m, UInt64(0), out))
+    out
 end
 
 # Moment state replaces the stored sample vectors (src/internals.jl:44-45): one (n, mean, M2) triplet per
@@ -123,10 +168,6 @@ end
 # and point range and a `samples` buffer, append the raw samples to `samples_diff[idx]` / `samples[idx]` and add
 # `dQ_idx / Prob(idx)` to the accumulator, exactly as host.py:Estimator._sample_unbiased does (tested there).
 #
-# Optional: `update_samples(estimator, n_opt)` (src/sample.jl:8-13) can hand all due indices to the device at once with
-# mle_update_samples (arrays of indices / shift pointers / point ranges / moment tables, one synchronisation) when the
-# estimator has a deterministic `cost_model`; host.py:Estimator._sample_many is the tested twin.
-#
 # ---- the hot path: one ccall per parallel_sample! (replaces the pmap of src/sample.jl:79-102) ----------------------------
 function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
     model = estimator.sample_function
@@ -135,12 +176,7 @@ function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, I
     R = estimator[:nb_of_shifts](index)
     gens = [generator(estimator, index, r) for r in 1:R]
     rule = gens[1].lattice_rule
-    if model.lattice == C_NULL
-        ref = Ref{Ptr{Cvoid}}(C_NULL)
-        check(model.ctx.ptr, ccall((:mle_lattice_create, libmle), Cint, (Ptr{Cvoid}, Ptr{UInt32}, Cint, UInt64, Ref{Ptr{Cvoid}}),
-                                   model.ctx.ptr, rule.z, length(rule.z), UInt64(rule.n), ref))
-        model.lattice = ref[]
-    end
+    ensure_lattice!(model, rule)
     shifts = reduce(hcat, [Vector{Float64}(g.shift) for g in gens])          # [s x R], shift r in column r
     mom = Array{Float64}(undef, 3, 2, model.nqoi, R)
     idx = Int32[index.I...]
@@ -167,6 +203,71 @@ function device_parallel_sample!(estimator::Estimator{I, <:MC}, index::Index, Is
               model.ctx.ptr, model.ptr, C_NULL, model.dists, idx, length(idx), C_NULL, 1,
               UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, UInt64(1), mom, C_NULL, C_NULL))
     merge_moments!(estimator, index, mom)
+end
+
+# ---- all due indices in one call: update_samples (src/sample.jl:8-13) with ONE synchronisation -----------------------------
+# Needs a deterministic `cost_model` (with the default cost model the reference times every sample! call separately,
+# src/sample.jl:27).  The maintainer's hook is one line at the top of `update_samples`:
+#
+#     estimator.sample_function isa MLECuda.DeviceModel && !(estimator[:cost_model] isa EmptyFunction) &&
+#         return MLECuda.device_update_samples!(estimator, n_opt)
+function device_update_samples!(estimator::Estimator{I, <:QMC}, n_opt::Dict) where I<:AbstractIndexSet
+    model = estimator.sample_function
+    ensure_handles!(model, estimator)
+    due = [(τ, n_opt[τ] - nb_of_samples(estimator, τ)) for τ in keys(n_opt) if n_opt[τ] > nb_of_samples(estimator, τ)]
+    isempty(due) && return
+    d = length(first(due)[1].I)
+    indices = Int32[c for (τ, _) in due for c in τ.I]                      # [count x d], entry e at indices + e*d
+    Rs = Cint[estimator[:nb_of_shifts](τ) for (τ, _) in due]
+    ms = Cint[estimator[:nb_of_uncertainties](τ) for (τ, _) in due]
+    k0 = UInt64[nb_of_samples(estimator, τ) for (τ, _) in due]              # zero-based first point = samples taken so far
+    ns = UInt64[n for (_, n) in due]
+    shifts = [reduce(hcat, [Vector{Float64}(generator(estimator, τ, r).shift) for r in 1:R]) for ((τ, _), R) in zip(due, Rs)]
+    ensure_lattice!(model, generator(estimator, first(due)[1], 1).lattice_rule)
+    moms = [Array{Float64}(undef, 3, 2, model.nqoi, R) for R in Rs]
+    GC.@preserve shifts moms begin
+        sp = Ptr{Float64}[pointer(x) for x in shifts]
+        mp = Ptr{Float64}[pointer(x) for x in moms]
+        check(model.ctx.ptr,
+            ccall((:mle_update_samples, libmle), Cint,
+                  (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Cint, Ptr{Ptr{Float64}}, Ptr{Cint}, Ptr{UInt64},
+                   Ptr{UInt64}, Ptr{Cint}, UInt64, Ptr{Ptr{Float64}}),
+                  model.ctx.ptr, model.ptr, model.lattice, model.dists, length(due), indices, d, sp, Rs, k0, ns, ms, UInt64(0), mp))
+    end
+    for ((τ, n), mom) in zip(due, moms)
+        merge_moments!(estimator, τ, mom)
+        # the bookkeeping of sample! (src/sample.jl:29-31, src/internals.jl:90,98); total_time is not measured per index here
+        MultilevelEstimators.add_to_nb_of_samples(estimator, τ, n)
+        MultilevelEstimators.add_to_total_work(estimator, τ, n)
+    end
+end
+
+# ---- unbiased estimators: every idx <= index on the same points, raw samples back (src/sample.jl:65-74, :113-124) ----------
+# Returns samples[idx] = Array (n x 2 x q x R): [:, 1, :, :] = dQ_idx, [:, 2, :, :] = Qf_idx; the caller appends them and adds
+# dQ_idx / Prob(idx) to the accumulator exactly as the reference's append_samples! for U does.
+function device_sample_unbiased(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
+    model = estimator.sample_function
+    ensure_handles!(model, estimator)
+    m = estimator[:nb_of_uncertainties](index)
+    R = estimator[:nb_of_shifts](index)
+    gens = [generator(estimator, index, r) for r in 1:R]
+    ensure_lattice!(model, gens[1].lattice_rule)
+    shifts = reduce(hcat, [Vector{Float64}(g.shift) for g in gens])
+    n = Iend - Istart + 1
+    out = Dict{Any, Array{Float64, 4}}()
+    for idx in CartesianIndices(index.I .+ 1)
+        sub = Int32[Tuple(idx)...] .- Int32(1)
+        mom = Array{Float64}(undef, 3, 2, model.nqoi, R)
+        smp = Array{Float64}(undef, n, 2, model.nqoi, R)
+        GC.@preserve shifts mom smp sub check(model.ctx.ptr,
+            ccall((:mle_sample_batch, libmle), Cint,
+                  (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
+                   Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                  model.ctx.ptr, model.ptr, model.lattice, model.dists, sub, length(sub), shifts, R,
+                  UInt64(Istart - 1), UInt64(n), m, UInt64(0), mom, smp, C_NULL))
+        out[Index(sub...)] = smp
+    end
+    out
 end
 
 # ---- statistics from the moment state (replace src/methods.jl:44-57, :282 for DeviceModel estimators) ---------------------

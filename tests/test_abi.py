@@ -27,6 +27,77 @@ def test_header_symbols_are_exported_and_bound():
     assert lib.mle_abi_version() == 1
 
 
+def _split_top(text):
+    """split on commas that are not nested in (), [] or {}"""
+    out, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _balanced(text, start):
+    """text[start] == '(' -> index one past its matching ')'"""
+    depth = 0
+    for i in range(start, len(text)):
+        depth += text[i] == "("
+        depth -= text[i] == ")"
+        if depth == 0:
+            return i + 1
+    raise ValueError("unbalanced")
+
+
+def test_julia_binding_matches_the_header():
+    """julia/MLECuda.jl cannot run here (no Julia), so check it statically: every ccall names a symbol the header declares, its
+    type tuple has one entry per C parameter with the right width, as many values as types follow, and the entry points of
+    the hot path are all bound"""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "mle_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char \*)\s*(mle_[a-z0-9_]+)\(([^;]*?)\);", hdr, flags=re.S):
+        params = [] if m.group(2).strip() == "void" else _split_top(" ".join(m.group(2).split()))
+        protos[m.group(1)] = params
+    src = open(os.path.join(ROOT, "julia", "MLECuda.jl")).read()
+    src = "\n".join(line.split("#")[0] if not line.lstrip().startswith("#") else "" for line in src.splitlines())
+    width = {"Cint": ("int", "int32_t"), "UInt64": ("uint64_t",), "Csize_t": ("size_t",), "Cstring": ("const char *",)}
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(mle_[a-z0-9_]+), libmle\), (\w+),\s*", src):
+        name = m.group(1)
+        assert name in protos, "%s is not declared in include/mle_cuda.h" % name
+        seen.add(name)
+        call_end = _balanced(src, m.start() + len("ccall"))
+        rest = src[m.end():call_end - 1]
+        tup_end = _balanced(rest, rest.index("("))
+        types = _split_top(rest[rest.index("(") + 1:tup_end - 1])
+        values = _split_top(rest[tup_end:].lstrip().lstrip(","))
+        want = protos[name]
+        assert len(types) == len(want), (name, types, want)
+        assert len(values) == len(want), (name, values, want)
+        assert m.group(2) == ("Cstring" if name == "mle_last_error" else "Cint")
+        for t, c in zip(types, want):
+            if t in width:   # scalars must have the declared width; pointers are checked by count only
+                assert "*" not in c.replace("const char *", "") and any(c.startswith(w) for w in width[t]), (name, t, c)
+            else:
+                assert t.startswith(("Ptr{", "Ref{")) and ("*" in c or c.split()[0].startswith("mle_")), (name, t, c)
+    for name in ("mle_init", "mle_destroy", "mle_last_error", "mle_lattice_create", "mle_dists_create", "mle_model_create",
+                 "mle_model_set_basis", "mle_points", "mle_sample_batch", "mle_update_samples", "mle_moments_merge",
+                 "mle_lattice_destroy", "mle_dists_destroy", "mle_model_destroy", "mle_abi_version", "mle_genvec"):
+        assert name in seen, "julia/MLECuda.jl does not bind %s" % name
+    assert "const ABI_VERSION = 1" in src and "#define MLE_ABI_VERSION 1" in open(os.path.join(ROOT, "include", "mle_cuda.h")).read()
+    # struct mle_dist {int32 kind; int32 reserved; double p[4]} <-> MLEDist
+    assert re.search(r"struct MLEDist\s+kind::Int32\s+reserved::Int32\s+p::NTuple\{4, Float64\}\s+end", src)
+
+
 def test_no_torch_types_in_the_boundary():
     hdr = open(os.path.join(ROOT, "include", "mle_cuda.h")).read()
     assert "torch" not in hdr and "at::" not in hdr and "std::" not in hdr
