@@ -16,6 +16,7 @@ path is concerned:
 Out of scope: AD and U index sets, printing, JLD2 output, `save_samples`.
 The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
 """
+import itertools
 import math
 import os
 import random as _random
@@ -27,6 +28,30 @@ import numpy as np
 # ---------------------------------------------------------------------------------------------------------------
 # index sets (src/index_set.jl) and sample methods (src/sample_method.jl)
 # ---------------------------------------------------------------------------------------------------------------
+def Index(*i):
+    """Index(i...) (src/index.jl:19): a zero-based multi-index; plain tuples of ints everywhere in this module."""
+    if not i or not all(isinstance(c, (int, np.integer)) and not isinstance(c, (bool, np.bool_)) for c in i):
+        raise TypeError("Index: integer components required")  # MethodError in the reference, test/index.jl:13,25
+    return tuple(int(c) for c in i)
+
+
+def Level(l):
+    """Level(l) (src/index.jl:36): a one-dimensional Index."""
+    return Index(l)
+
+
+def diff(index):
+    """diff(index) (src/index.jl:49-58): the indices kappa in max(0, index - 1) : index other than index itself, each with the
+    sign (-1)^|index - kappa| -- so that dQ(index) = Q(index) + sum_kappa sign * Q(kappa) is the mixed difference."""
+    index = Index(*index)
+    out = {}
+    ranges = [range(max(0, c - 1), c + 1) for c in index]
+    for kappa in itertools.product(*ranges):
+        if kappa != index:
+            out[kappa] = -1 if (sum(index) - sum(kappa)) % 2 else 1
+    return out
+
+
 class SL:
     ndims = 1
 
@@ -392,6 +417,13 @@ def parse_options(index_set, sample_method, distributions, options):
         _check("nb_of_shifts", o["nb_of_shifts"] > 1, "larger than 1")
         R = int(o["nb_of_shifts"])
         o["nb_of_shifts"] = lambda index: R
+    if o["point_generator"] is not None:                                            # src/parse.jl:251-255
+        # the reference wants an AbstractRNG (a LatticeRule32); here the rule is given by its generating vector
+        pg = o["point_generator"]
+        ok = isinstance(pg, (list, tuple, np.ndarray)) and len(pg) > 0 and all(_is_int(v) and 0 <= v < 2**32 for v in pg)
+        _check_type("point_generator", pg, ok, "a generating vector (sequence of UInt32)")
+        if len(pg) < len(distributions):
+            raise ValueError("in Estimator, optional key point_generator must have at least %d dimensions." % len(distributions))
     if o["nb_of_uncertainties"] is None:
         m_all = len(distributions)
         o["nb_of_uncertainties"] = lambda index: m_all                              # src/parse.jl:272-275

@@ -33,6 +33,55 @@ def test_index_sets_match_reference_cardinalities():
         H.HC(1.0, 1.5)
 
 
+def test_level_and_index_like_the_reference_suite():
+    """test/index.jl:6-29"""
+    H = host()
+    level_0, level_2 = H.Level(0), H.Level(2)
+    assert tuple(a + b for a, b in zip(level_0, level_2)) == level_2
+    with pytest.raises(TypeError):
+        H.Level(0.)
+    index_0_0, index_2_3 = H.Index(0, 0), H.Index(2, 3)
+    assert len(index_0_0) == len(index_2_3) == 2
+    assert tuple(a + b for a, b in zip(index_0_0, index_2_3)) == index_2_3
+    with pytest.raises(TypeError):
+        H.Index(0., 2)
+    d_index = H.diff(H.Index(1))
+    assert len(d_index) == 1 and d_index[H.Index(0)] == -1
+    # src/index.jl:49-58 on multi-indices: the mixed difference
+    assert H.diff((0,)) == {} and H.diff((0, 0)) == {}
+    assert H.diff((2, 3)) == {(1, 2): 1, (2, 2): -1, (1, 3): -1}
+    assert H.diff((2, 0)) == {(1, 0): -1} and H.diff((0, 4)) == {(0, 3): -1}
+    assert H.diff((1, 1, 1)) == {(0, 0, 0): -1, (1, 0, 0): 1, (0, 1, 0): 1, (0, 0, 1): 1, (1, 1, 0): -1, (1, 0, 1): -1, (0, 1, 1): -1}
+
+
+@pytest.mark.parametrize("name,index", [("problem18", (2, 1)), ("problem18", (0, 3)), ("lognormal2d", (1, 2)), ("lognormal2d", (2, 0))])
+def test_device_model_differences_follow_diff_signs(name, index):
+    """docs/src/example.md:233-241 / test/regression.jl:93-101: dQ(index) = Qf(index) + sum over diff(index) of sign * Qf(kappa)
+    on the same random inputs -- checked sample by sample with the raw samples of every index involved"""
+    import mle_b200.kl as kl
+    H = host()
+    be = OracleBackend()
+    if name == "problem18":
+        m, dist = 2, H.Uniform(-0.5, 0.5)
+        spec = H.ModelSpec("problem18", 2)
+    else:
+        m, dist = 30, H.Normal()
+        keys = [index] + list(H.diff(index))
+        spec = H.ModelSpec("lognormal2d", 2, [4], {k: kl.kl_basis_2d(k, m=m) for k in keys})
+    model, dists, lat = be.model(spec), be.dists([dist] * m), be.lattice(None, m)
+    shifts = np.random.default_rng(3).random((3, m))
+
+    def raw(idx):
+        return be.sample_batch(model, lat, dists, list(idx), shifts, 5, 40, m, 0, want_samples=True)[2]   # [R, q, X, n]
+
+    top = raw(index)
+    want = top[:, :, 1, :].copy()
+    for kappa, sign in H.diff(index).items():
+        want += sign * raw(kappa)[:, :, 1, :]
+    scale = np.abs(top[:, :, 1, :]).max()
+    assert np.abs(top[:, :, 0, :] - want).max() <= 4e-15 * scale
+
+
 def test_option_validation_mirrors_reference():
     H = host()
     spec = H.ModelSpec("problem18", 1)
@@ -117,6 +166,96 @@ def test_option_scoping_and_rules_follow_reference(tmp_path):
     assert H.Estimator(H.ML(), H.MC(), spec, U1, be, name="a.jld2")["name"] == "a.jld2"
     assert H.Estimator(H.U(1), H.QMC(), spec, U1, be, max_search_space=H.ML())["nb_of_warm_up_samples"] == 2   # src/parse.jl:36
     assert H.Estimator(H.ML(), H.MC(), spec, U1, be)["nb_of_warm_up_samples"] == 20
+
+
+class _NullBackend:
+    """accepts any model / distributions / lattice: for tests of the constructor alone"""
+
+    def model(self, spec):
+        return None
+
+    def dists(self, d):
+        return list(d)
+
+    def lattice(self, z, s):
+        return None
+
+
+def test_estimator_constructor_like_the_reference_suite():
+    """test/estimator.jl:6-99, line by line (ArgumentError -> ValueError; `qoi` is a ModelSpec instead of a closure)"""
+    H = host()
+    ml, ad, mc, qmc = H.ML(), H.AD(3), H.MC(), H.QMC()
+    qoi, distr, distrs, be = H.ModelSpec("expsum", 1, [4.0]), H.Normal(), [H.Normal() for _ in range(1000)], _NullBackend()
+
+    def ok(iset, method, d=distr, **kw):
+        e = H.Estimator(iset, method, qoi, d, be, **kw)
+        assert isinstance(e.index_set, type(iset)) and isinstance(e.sample_method, type(method))
+        return e
+
+    def throws(iset, method, **kw):
+        with pytest.raises(ValueError):
+            H.Estimator(iset, method, qoi, distr, be, **kw)
+
+    assert len(ok(ml, mc, distrs).distributions) == 1000           # :15
+    assert len(ok(ml, qmc).distributions) == 1                     # :16
+    throws(ml, mc, nb_of_warm_up_samples=False)                    # :18-20
+    throws(ml, mc, nb_of_warm_up_samples=0)
+    ok(ml, mc, nb_of_warm_up_samples=10)
+    throws(ml, mc, nb_of_qoi=False)                                # :22-24
+    throws(ml, mc, nb_of_qoi=0)
+    ok(ml, mc, nb_of_qoi=10)
+    throws(ml, mc, continuate="blabla")                            # :26-27
+    ok(ml, mc, continuate=False)
+    throws(ml, mc, nb_of_tols="blabla")                            # :29-31
+    throws(ml, mc, nb_of_tols=0)
+    ok(ml, mc, nb_of_tols=20)
+    throws(ml, mc, continuation_mul_factor="blabla")               # :33-35
+    throws(ml, mc, continuation_mul_factor=math.nan)
+    ok(ml, qmc, continuation_mul_factor=2)
+    throws(ml, mc, folder=1.0)                                     # :37-38
+    ok(ml, mc, folder=".")
+    throws(ml, mc, name=1.0)                                       # :40-41
+    assert ok(ml, mc, name="MyEstimator")["name"] == "MyEstimator.jld2"
+    throws(ml, mc, save_samples=1)                                 # :43-44
+    ok(ml, mc, save_samples=True)
+    throws(ml, mc, verbose=1)                                      # :46-47
+    ok(ml, mc, verbose=True)
+    throws(ml, mc, cost_model="blabla")                            # :49-50
+    ok(ml, mc, cost_model=lambda i: 2 ** sum(i))
+    throws(ml, mc, robustify_bias_estimate="blabla")               # :52-53
+    ok(ml, mc, robustify_bias_estimate=False)
+    throws(ml, mc, do_mse_splitting=1)                             # :55-56
+    ok(ml, mc, do_mse_splitting=False)
+    throws(ml, mc, min_splitting=2)                                # :58-59
+    ok(ml, mc, min_splitting=0.6)
+    throws(ml, mc, max_splitting=0.4)                              # :61-63
+    throws(ml, mc, max_splitting=0.6, min_splitting=0.7)
+    ok(ml, mc, max_splitting=0.8)
+    throws(ml, mc, max_index_set_param=1.0)                        # :65-67
+    throws(ml, mc, max_index_set_param=-1)
+    ok(ml, mc, max_index_set_param=6)
+    throws(ml, mc, sample_mul_factor="blabla")                     # :69-72
+    throws(ml, mc, sample_mul_factor=math.inf)
+    ok(ml, qmc, sample_mul_factor=1.5)
+    ok(ml, qmc, sample_mul_factor=2)
+    throws(ml, mc, nb_of_workers=math.inf)                         # :74-76
+    ok(ml, mc, nb_of_workers=4)
+    assert ok(ml, mc, nb_of_workers=lambda i: 2)["nb_of_workers"]((0,)) == 2
+    throws(ml, qmc, nb_of_shifts="blabla")                         # :78-80
+    assert ok(ml, qmc, nb_of_shifts=16)["nb_of_shifts"]((1,)) == 16
+    assert ok(ml, qmc, nb_of_shifts=lambda i: 32)["nb_of_shifts"]((1,)) == 32
+    throws(ml, qmc, point_generator=3)                             # :82
+    throws(ml, mc, do_regression="blabla")                         # :84-85
+    throws(ml, mc, aggregation="blabla")
+    throws(H.AD(2), mc, max_search_space=True)                     # :87-89
+    throws(ad, mc, max_search_space=H.TD(2))
+    assert isinstance(ok(ad, qmc, max_search_space=H.FT(3))["max_search_space"], H.FT)
+    throws(ad, mc, penalization=-0.1)                              # :91-93
+    throws(ad, mc, penalization=1.1)
+    ok(ad, mc, penalization=0.5)
+    throws(ad, mc, acceptance_rate=-0.1)                           # :95-97
+    throws(ad, mc, acceptance_rate=1.1)
+    ok(ad, mc, acceptance_rate=0.8)
 
 
 def test_history_is_saved_after_every_tolerance_and_reloads(tmp_path):

@@ -1,5 +1,7 @@
 """CPU tests: the oracle (oracle/mle_oracle.c) against every golden vector the reference holds for the hot path
 (SURVEY.md 8c), plus internal consistency of the oracle's own model definitions.  No GPU needed."""
+import math
+
 import numpy as np
 import pytest
 
@@ -246,3 +248,25 @@ def test_lognormal2d_oracle_model(oracle):
     assert d[0][0][0] == d[0][1][0]
     assert abs(d[2][0][0]) < abs(d[1][0][0]) and abs(d[3][0][0]) < abs(d[2][0][0])   # |dQ| decays with the level
     assert abs(sum(x[0][0] for x in d) - d[3][1][0]) < 1e-15                       # telescoping sum = finest Qf
+
+
+def test_approx_pi_like_the_reference_suite(oracle):
+    """test/lattice.jl:23-37: the fraction of the first n points of the 2-d CKN_250_20 rule inside the quarter circle, n = 2^0
+    .. 2^19, against the reference's own tolerances (the zip there stops at the 20 tolerances)"""
+    z = oracle.genvec("CKN_250_20", 2)
+    x = oracle.points(z, None, None, 0, 2**19, nmax=2**20)[0]
+    inside = (x[:, 0] * x[:, 0] + x[:, 1] * x[:, 1] < 1).cumsum()
+    expo = [0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 3, 3, 4, 4, 5]
+    for k, e in enumerate(expo):
+        n = 2**k
+        assert abs(4 * inside[n - 1] / n - math.pi) <= 10.0 ** e   # the reference's tolerances are 10^+e: a smoke bound
+    # and what the rule actually delivers (much tighter than the reference asks for): 1e-3 by 2^12 points, 1e-4 by 2^19
+    assert all(abs(4 * inside[2**k - 1] / 2**k - math.pi) < t for k, t in ((8, 5e-2), (12, 5e-3), (16, 5e-4), (19, 1e-4)))
+
+
+def test_lattice_constructor_rules_like_the_reference_suite(oracle):
+    """test/lattice.jl:39-47 on the embedded generating vectors: 3600 / 250 entries, s in 1..len"""
+    assert len(oracle.genvec("K_3600_32", 3600)) == 3600 and len(oracle.genvec("CKN_250_20", 250)) == 250
+    assert len(oracle.genvec("CKN_250_20", 1)) == 1
+    x = oracle.points(oracle.genvec("K_3600_32", 101), None, None, 100000, 1)[0, 0]   # :16-20
+    assert x.shape == (101,) and (x >= 0).all() and (x < 1).all()
