@@ -52,21 +52,68 @@ def diff(index):
     return out
 
 
-class SL:
+class IndexSetNotImplemented(ValueError, NotImplementedError):
+    """the reference throws ArgumentError here (src/index_set.jl:259-264): a ValueError in this mirror"""
+
+
+class _IndexSetBase:
+    """what every index set type shares: the short name shown by `show` (src/index_set.jl:319-327), `length(idxset, sz)`
+    (:262) and the 2-d picture of `print(idxset, sz)` (:294-317)"""
+
+    def __repr__(self):
+        name = type(self).__name__
+        return name if name in ("SL", "ML") else "%s{%d}" % (name, self.ndims)
+
+    def length(self, sz):
+        return len(self.get_index_set(sz))
+
+    def print(self, sz, file=None):
+        print(format_index_set(self.get_index_set(sz)), end="", file=file)
+
+
+def format_index_set(idxset, idxset2=()):
+    """the picture `print(idxset, idxset2)` draws for 2-d index sets (src/index_set.jl:296-317): one row per second component,
+    top row = largest, a filled square per index of idxset and a framed one per index of idxset2"""
+    idxset, idxset2 = list(idxset), list(idxset2)
+    if any(len(i) != 2 for i in idxset + idxset2):
+        raise ValueError("print only available for index sets with d = 2")
+    if not idxset and not idxset2:
+        return ""
+    n = tuple(max(i[c] for i in idxset + idxset2) for c in range(2))   # `maximum` of CartesianIndex is component-wise
+    a, b = set(idxset), set(idxset2)
+    rows = []
+    for j in range(n[1], -1, -1):
+        row = "  "
+        for i in range(n[0] + 1):
+            if (i, j) in a:
+                row += "\u25FC "
+            if (i, j) in b:
+                row += "\u25A3 "
+        rows.append(row + "\n")
+    return "".join(rows)
+
+
+class SL(_IndexSetBase):
     ndims = 1
+
+    def __init__(self):
+        pass
 
     def get_index_set(self, sz):
         return [(0,)]
 
 
-class ML:
+class ML(_IndexSetBase):
     ndims = 1
+
+    def __init__(self):
+        pass
 
     def get_index_set(self, sz):  # src/index_set.jl:49-55
         return [(l,) for l in range(sz + 1)]
 
 
-class _Weighted:
+class _Weighted(_IndexSetBase):
     """weighted multi-index sets: candidate box 0..sz+1 per dimension, filtered (src/index_set.jl:257); weights in (0, 1]"""
 
     def __init__(self, *weights):
@@ -110,7 +157,7 @@ class ZC(_Weighted):  # Zaremba cross, src/index_set.jl:180
         return math.prod(max(1.0, i / w) for w, i in zip(self.weights, idx)) <= sz
 
 
-class AD:
+class AD(_IndexSetBase):
     """adaptive index set AD(d), src/index_set.jl:195-210: no a-priori shape; grown one index at a time by profit
     (src/methods.jl:206-251) inside `max_search_space` at size `max_index_set_param`"""
 
@@ -120,10 +167,10 @@ class AD:
         self.ndims = int(d)
 
     def get_index_set(self, sz):
-        raise NotImplementedError("get_index_set not implemented for index sets of type AD")  # src/index_set.jl:259
+        raise IndexSetNotImplemented("get_index_set not implemented for index sets of type AD")  # src/index_set.jl:259
 
 
-class U:
+class U(_IndexSetBase):
     """unbiased multilevel / multi-index index set U(d), src/index_set.jl:213-227: no bias, indices drawn at random from a
     probability mass function over `max_search_space` that is adapted to sqrt(V/C) (src/methods.jl:287-351)"""
 
@@ -133,7 +180,7 @@ class U:
         self.ndims = int(d)
 
     def get_index_set(self, sz):
-        raise NotImplementedError("get_index_set not implemented for index sets of type U")
+        raise IndexSetNotImplemented("get_index_set not implemented for index sets of type U")  # src/index_set.jl:261
 
 
 def is_admissable(index_set, index):

@@ -82,6 +82,82 @@ def test_device_model_differences_follow_diff_signs(name, index):
     assert np.abs(top[:, :, 0, :] - want).max() <= 4e-15 * scale
 
 
+def test_index_set_types_like_the_reference_suite(capsys):
+    """the rest of test/index_set.jl:8-20, :54-86: SL / ML, AD, U, sizes 0 and -1, show and print"""
+    H = host()
+    for T, n, first in ((H.SL, 1, 0), (H.ML, 6, 0)):
+        t = T()
+        idxset = t.get_index_set(5)
+        assert len(idxset) == n and idxset[0] == H.Level(first) and t.length(5) == n
+        if T is H.ML:
+            assert idxset[-1] == H.Level(5)
+        with pytest.raises(TypeError):
+            T(2)
+        assert "%s" % t == T.__name__
+    for T, n3 in ((H.FT, 512), (H.TD, 120), (H.HC, 38), (H.ZC, 98)):
+        assert T(3).length(7) == n3 and "%s" % T(3) == "%s{3}" % T.__name__ and "%s" % T(1 / 1, 3 / 5) == "%s{2}" % T.__name__
+        assert (7, 0) not in T(1 / 1, 3 / 5).get_index_set(6)
+        with pytest.raises(ValueError):
+            T(1, 0)
+    ad = H.AD(2)
+    assert ad.ndims == 2 and "%s" % ad == "AD{2}"
+    with pytest.raises(ValueError):
+        ad.get_index_set(4)
+    with pytest.raises(ValueError):
+        H.AD(1)
+    with pytest.raises(TypeError):
+        H.AD()
+    u = H.U(1)
+    assert u.ndims == 1 and "%s" % u == "U{1}" and "%s" % H.U(2) == "U{2}"
+    with pytest.raises(ValueError):
+        u.get_index_set(1)
+    with pytest.raises(TypeError):
+        H.U()
+    with pytest.raises(TypeError):
+        H.U(1, 2)
+    with pytest.raises(ValueError):
+        H.U(2).get_index_set(4)
+    assert len(H.TD(2).get_index_set(0)) == 1 and H.TD(2).get_index_set(-1) == []
+    with pytest.raises(ValueError):
+        H.TD(3).print(4)                    # only for d = 2
+    H.TD(2).print(3)
+    out = capsys.readouterr().out            # the docstring example, src/index_set.jl:286-291
+    assert [row.rstrip() for row in out.splitlines()] == ["  \u25FC", "  \u25FC \u25FC", "  \u25FC \u25FC \u25FC", "  \u25FC \u25FC \u25FC \u25FC"]
+    pic = H.format_index_set([(0, 0), (1, 0)], [(0, 1)])
+    assert pic == "  \u25A3 \n  \u25FC \u25FC \n"
+
+
+def test_distribution_constructors_like_the_reference_suite(oracle):
+    """test/distribution.jl: the constructor rules of all four distributions (the quantile values are pinned in
+    tests/test_oracle_golden.py and, on the device, in tests/test_gpu_points.py)"""
+    from fractions import Fraction
+    H = host()
+    inf, nan = math.inf, math.nan
+    assert H.Uniform() == H.Uniform(0., 1.) == H.Uniform(0, 1.)                                  # :7-9
+    for bad in ((inf, 1.), (0., nan), (1., 0.)):                                                 # :13-15
+        with pytest.raises(ValueError):
+            H.Uniform(*bad)
+    assert H.Normal() == H.Normal(0., 1.) == H.Normal(0, 1.)                                     # :25-27
+    for bad in ((inf, 1.), (0., nan), (0., -1.)):                                                # :31-33
+        with pytest.raises(ValueError):
+            H.Normal(*bad)
+    assert H.TruncatedNormal() == H.TruncatedNormal(0., 1.) == H.TruncatedNormal(0., 1., -2., 2.)  # :45-46
+    assert H.TruncatedNormal(0., 1., -1., 1.)[1][2:] == [-1.0, 1.0]
+    assert H.TruncatedNormal(0., 1., Fraction(-2, 3), 10)[1][2:] == [-2 / 3, 10.0]               # :48
+    for bad in ((inf, 1.), (0., nan), (0., 1., inf, 2.), (0., 1., -2., inf), (0., -1.), (0., 1., 1., 0.)):   # :53-58
+        with pytest.raises(ValueError):
+            H.TruncatedNormal(*bad)
+    assert H.Weibull() == H.Weibull(2., math.sqrt(2.)) and H.Weibull(2, 1.) == H.Weibull(2., 1.)  # :70-72
+    for bad in ((inf, 1.), (0., nan), (1., -1), (-1., 1)):                                       # :76-79
+        with pytest.raises(ValueError):
+            H.Weibull(*bad)
+    # transform(Uniform(), x) == x, test/distribution.jl:18-20, through the same (kind, parameters) pairs the device receives
+    x = np.arange(1, 10) / 10.0
+    z = np.array([1], dtype=np.uint32)
+    pts = oracle.points(z, [H.Uniform()], x.reshape(9, 1), 0, 1)    # point 0 of nine "shifts" = the shifts themselves
+    assert np.array_equal(pts[:, 0, 0], x)
+
+
 def test_option_validation_mirrors_reference():
     H = host()
     spec = H.ModelSpec("problem18", 1)
