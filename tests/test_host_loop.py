@@ -599,3 +599,50 @@ def test_unbiased_multi_index_run():
     assert h["rmse"] <= 1e-2 and h["ndims"] == 2 and h["bias"] == 0.0
     with pytest.raises(ValueError):
         H.Estimator(H.U(1), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend())   # TD(1) does not exist
+
+
+_AGG = [("max", 1e-2), ("sum", 1e-1), ("norm", 1e-1)]   # test/regression.jl:12-14
+
+
+@pytest.mark.parametrize("method", ["MC", "QMC"])
+@pytest.mark.parametrize("iset", ["TD", "FT", "HC", "ZC", "AD"])
+@pytest.mark.parametrize("aggregation,tol", _AGG)
+def test_reference_regression_matrix_multi_index(iset, method, aggregation, tol, tmp_path):
+    """test/regression.jl:106-125, every cell: run(Estimator(T(2), MC()/QMC(), problem_18, 2 x Uniform(-0.5, 0.5); nb_of_qoi = 13,
+    max_index_set_param = 3, save_samples = true, folder = tempdir(), aggregation, qoi_with_max_var = 3), tol) with the default
+    (timing) cost model; the reference asserts completion only, here the History is checked as well"""
+    H = host()
+    est = H.Estimator(getattr(H, iset)(2), getattr(H, method)(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2,
+                      OracleBackend(), nb_of_qoi=13, max_index_set_param=3, save_samples=True, folder=str(tmp_path),
+                      aggregation=aggregation, qoi_with_max_var=3)
+    h = H.run(est, tol)
+    assert len(h) == 10 and h["ndims"] == 2 and h["type"] == "Estimator{%s, %s}" % (iset, method)
+    assert h["folder"] == str(tmp_path) and not os.listdir(tmp_path)          # save defaults to false in this mirror
+    assert math.isfinite(h["rmse"]) and math.isfinite(h["mean"]) and h["varest"] >= 0
+    full = set(est.search_space if iset == "AD" else getattr(H, iset)(2).get_index_set(3))
+    assert set(h["current_index_set"]) <= full and (0, 0) in h["current_index_set"]
+    assert h["rmse"] <= 2 * tol or est.max_level_exceeded() or (iset == "AD" and len(h["current_index_set"]) > 1)
+    for idx in h["current_index_set"]:
+        n = h["nb_of_samples"][idx]
+        assert n >= 1 and h["samples"][idx].shape == h["samples_diff"][idx].shape
+        assert h["samples"][idx].shape[1:] == (13, n)
+    if iset == "AD":
+        assert h["logbook"]
+
+
+@pytest.mark.parametrize("method", ["MC", "QMC"])
+@pytest.mark.parametrize("d", [1, 2])
+@pytest.mark.parametrize("aggregation,tol", _AGG)
+def test_reference_regression_matrix_unbiased(d, method, aggregation, tol):
+    """test/regression.jl:140-178, every cell: U(1) (max_search_space = ML()) and U(2) x MC/QMC x the three aggregations with
+    test_function2 (all idx <= index on the same inputs)"""
+    H = host()
+    kw = dict(max_search_space=H.ML()) if d == 1 else {}
+    est = H.Estimator(H.U(d), getattr(H, method)(), H.ModelSpec("problem18", d), [H.Uniform(-0.5, 0.5)] * d, OracleBackend(),
+                      nb_of_qoi=13, max_index_set_param=3, save_samples=True, aggregation=aggregation, **kw)
+    h = H.run(est, tol)
+    assert len(h) == 10 and h["bias"] == 0.0 and h["rmse"] <= tol * (1 + 1e-12)
+    # an index whose differences have zero sample variance gets probability 0 (f = sqrt(V/C) = 0, src/methods.jl:311-318)
+    assert abs(sum(est.pmf.values()) - 1) < 1e-12 and all(p >= 0 for p in est.pmf.values()) and est.pmf[(0,) * d] > 0
+    # first batch: ceil(max(nb_of_warm_up_samples, 0) * (sample_mul_factor - 1)) draws, src/methods.jl:287-290
+    assert math.isfinite(h["mean"]) and sum(h["nb_of_samples"].values()) >= (1 if method == "QMC" else 4)
