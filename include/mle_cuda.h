@@ -112,6 +112,7 @@ int mle_model_destroy(mle_ctx ctx, mle_model model);
 /* ---- parity hook for stages 1-2:  transform.(D[1:m], get_point(gen[r], k)[1:m])  (src/sample.jl:84-88) ----------
  * out[m x n x R]: out[(r*n + i)*m + j] = coordinate j of point k0+i of shift r (k zero-based, src/sample.jl:84).
  *   lat == NULL   -> MC: counter-based uniforms keyed by (mc_seed, k, j) instead of lattice points (R must be 1)
+ *                    (the index is NOT part of the key: callers give every index its own mc_seed, as the bindings do)
  *   dists == NULL -> raw points in [0,1) (no transform)
  *   shifts        -> [s x R] (shift r at shifts + r*s, the `shift` field of ShiftedLatticeRule, src/lattice.jl:132-137);
  *                    NULL -> unshifted rule, R must be 1 (src/lattice.jl:142-145)
@@ -143,7 +144,8 @@ int mle_sample_batch_dev(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dist
 /* One `update_samples` call (src/sample.jl:8-13): `count` independent `sample!` requests -- entry e has its own index
  * (indices + e*d), shifts (shifts[e], [s x R[e]], or NULL entries for MC), point range k0[e] .. k0[e]+n[e]-1, dimension count
  * m[e] and moment table moments[e] ([3 x 2 x q x R[e]]) -- issued back to back on the context's stream with ONE
- * synchronisation at the end instead of one per index.  Results are identical to `count` calls of mle_sample_batch. */
+ * synchronisation at the end instead of one per index.  Results are identical to `count` calls of mle_sample_batch.
+ * All entries share `mc_seed`: meant for QMC entries (for MC, entries of different indices would see the same uniforms). */
 int mle_update_samples(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, int count, const int32_t *indices,
                        int d, const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n, const int *m,
                        uint64_t mc_seed, double *const *moments);

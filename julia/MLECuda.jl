@@ -190,6 +190,21 @@ function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, I
     merge_moments!(estimator, index, mom)
 end
 
+# MC inputs: the device's uniforms are keyed by (seed, point number, coordinate) and point numbers restart at 0 on every
+# index, so every index gets its own stream (the reference draws rand(m) from one global stream, src/sample.jl:42).
+# Same mixing as host.py:index_seed.
+const MC_SEED = Ref{UInt64}(1)
+function index_seed(seed::UInt64, index::Index)
+    x = seed
+    for c in index.I
+        x += 0x9e3779b97f4a7c15 * UInt64(c + 1)
+        x = (x ⊻ (x >> 30)) * 0xbf58476d1ce4e5b9
+        x = (x ⊻ (x >> 27)) * 0x94d049bb133111eb
+        x ⊻= x >> 31
+    end
+    x
+end
+
 function device_parallel_sample!(estimator::Estimator{I, <:MC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
     model = estimator.sample_function
     ensure_handles!(model, estimator)
@@ -201,7 +216,7 @@ function device_parallel_sample!(estimator::Estimator{I, <:MC}, index::Index, Is
               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
               model.ctx.ptr, model.ptr, C_NULL, model.dists, idx, length(idx), C_NULL, 1,
-              UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, UInt64(1), mom, C_NULL, C_NULL))
+              UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, index_seed(MC_SEED[], index), mom, C_NULL, C_NULL))
     merge_moments!(estimator, index, mom)
 end
 

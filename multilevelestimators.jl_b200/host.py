@@ -491,6 +491,19 @@ def parse_options(index_set, sample_method, distributions, options):
     return o
 
 
+def index_seed(mc_seed, index):
+    """The MC stream of one index: SplitMix64 finaliser over (mc_seed, index).  The device's uniforms are keyed by (seed, point
+    number, coordinate) only, and point numbers restart at 0 on every index, so each index needs its own seed -- the reference
+    draws rand(m) from one global stream (src/sample.jl:42), i.e. independent inputs on every level."""
+    x = int(mc_seed) & 0xFFFFFFFFFFFFFFFF
+    for c in index:
+        x = (x + 0x9E3779B97F4A7C15 * (int(c) + 1)) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+    return x
+
+
 class Estimator:
     """Estimator(index_set, sample_method, sample_function, distributions; options...)  (src/estimator.jl:121)"""
 
@@ -561,13 +574,14 @@ class Estimator:
         the per-sample sums  Z = sum_idx dQ_idx / Prob(idx)  are reduced to (n, mean, M2) on the host."""
         import itertools
         from .engine import moments_merge
-        istart = self.nb_of_samples[index] + 1
+        istart = sum(self.nb_of_samples.values()) + 1   # src/sample.jl:25: U counts the samples of ALL indices
         m = self.options["nb_of_uncertainties"](index)
+        seed = index_seed(self.options["mc_seed"], index)   # one input vector per sample, shared by every idx <= index
         t0 = _time.perf_counter()
         Z = None
         for idx in sorted(itertools.product(*[range(i + 1) for i in index]), key=lambda t: t[::-1]):
             mom, _t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(idx), self.shifts.get(index),
-                                                     istart - 1, n, m, self.options["mc_seed"], want_samples=True)
+                                                     istart - 1, n, m, seed, want_samples=True)
             self.moments[idx] = moments_merge(self.moments[idx], mom) if idx in self.moments else np.array(mom, dtype=np.float64)
             if self.options["save_samples"]:
                 self.samples.setdefault(idx, []).append(np.array(smp))
@@ -588,15 +602,15 @@ class Estimator:
             return self._sample_unbiased(index, n)
         istart = self.nb_of_samples[index] + 1
         m = self.options["nb_of_uncertainties"](index)
+        seed = index_seed(self.options["mc_seed"], index)
         t0 = _time.perf_counter()
         if self.options["save_samples"]:  # src/history.jl:92-95: keep the raw samples as well (single-rank backends)
             mom, _gpu_t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
-                                                         self.shifts.get(index), istart - 1, n, m, self.options["mc_seed"],
-                                                         want_samples=True)
+                                                         self.shifts.get(index), istart - 1, n, m, seed, want_samples=True)
             self.samples.setdefault(index, []).append(np.array(smp))
         else:
             mom, _gpu_t = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
-                                                    self.shifts.get(index), istart - 1, n, m, self.options["mc_seed"])
+                                                    self.shifts.get(index), istart - 1, n, m, seed)
         t = _time.perf_counter() - t0
         if index in self.moments:
             from .engine import moments_merge
@@ -633,7 +647,8 @@ class Estimator:
         # with a deterministic cost model the per-index wall time is not needed, so all due indices go to the device in ONE
         # call (mle_update_samples: batches back to back, a single synchronisation); otherwise index by index like the reference,
         # whose default cost model is the measured time of each sample! call (src/sample.jl:27)
-        if len(due) > 1 and self.options["cost_model"] is not None and hasattr(self.backend, "update_samples") \
+        # (QMC only: mle_update_samples takes ONE mc_seed, and MC needs a different stream on every index)
+        if len(due) > 1 and self.qmc and self.options["cost_model"] is not None and hasattr(self.backend, "update_samples") \
                 and not self.options["save_samples"]:
             return self._sample_many(due)
         for index, n_due in due:

@@ -646,3 +646,45 @@ def test_reference_regression_matrix_unbiased(d, method, aggregation, tol):
     assert abs(sum(est.pmf.values()) - 1) < 1e-12 and all(p >= 0 for p in est.pmf.values()) and est.pmf[(0,) * d] > 0
     # first batch: ceil(max(nb_of_warm_up_samples, 0) * (sample_mul_factor - 1)) draws, src/methods.jl:287-290
     assert math.isfinite(h["mean"]) and sum(h["nb_of_samples"].values()) >= (1 if method == "QMC" else 4)
+
+
+def test_mc_streams_are_independent_across_indices():
+    """the reference draws every MC input from one global stream (src/sample.jl:42): samples on different levels are
+    independent.  The device keys its uniforms by (seed, point number, coordinate), so the host gives every index its own seed"""
+    H = host()
+    seeds = {H.index_seed(1, i) for i in [(0,), (1,), (2,), (0, 0), (1, 0), (0, 1), (1, 1), (2, 1)]}
+    assert len(seeds) == 8 and all(0 <= x < 2**64 for x in seeds)
+    assert H.index_seed(1, (3,)) != H.index_seed(2, (3,)) and H.index_seed(7, (2, 1)) == H.index_seed(7, (2, 1))
+    w = [0.5 / (j + 1) for j in range(16)]
+    est = H.Estimator(H.ML(), H.MC(), H.ModelSpec("expsum", 1, [16] + w), [H.Normal()] * 16, OracleBackend(),
+                      save_samples=True, max_index_set_param=3)
+    est.sample((0,), 4000)
+    est.sample((1,), 4000)
+    q0 = np.concatenate(est.samples[(0,)], axis=-1)[0, 0, 1, :]
+    q1 = np.concatenate(est.samples[(1,)], axis=-1)[0, 0, 1, :]
+    # m_l = min(16, 16 * 2^l) = 16 on both levels: with a shared stream the fine values would be IDENTICAL sample by sample
+    assert not np.array_equal(q0, q1) and abs(np.corrcoef(q0, q1)[0, 1]) < 0.06
+    # continuing an index continues its own stream (point numbers go on, no repeats)
+    est.sample((0,), 4000)
+    q0b = np.concatenate(est.samples[(0,)], axis=-1)[0, 0, 1, :]
+    assert len(np.unique(q0b)) == 8000
+
+
+def test_unbiased_point_numbers_count_all_indices():
+    """src/sample.jl:25: for U estimators Istart = sum of the samples taken on ALL indices + 1"""
+    H = host()
+
+    class Spy(OracleBackend):
+        calls = []
+
+        def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
+            Spy.calls.append((tuple(index), k0, n))
+            return OracleBackend.sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples)
+
+    est = H.Estimator(H.U(1), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], Spy(), nb_of_qoi=13,
+                      max_search_space=H.ML(), max_index_set_param=3, nb_of_shifts=4)
+    est.sample((0,), 5)
+    est.sample((2,), 3)
+    est.sample((0,), 2)
+    assert Spy.calls == [((0,), 0, 5), ((0,), 5, 3), ((1,), 5, 3), ((2,), 5, 3), ((0,), 8, 2)]
+    assert est.nb_of_samples[(0,)] == 7 and est.nb_of_samples[(2,)] == 3
