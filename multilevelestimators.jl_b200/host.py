@@ -768,11 +768,17 @@ class Estimator:
         return self._rate(self.cost, 1)
 
     def _interp(self, f):
-        have = [i for i, n in self.nb_of_samples.items() if (n > 0 if self.qmc else n > 1)]
-        A = np.array([[1.0] + list(i) for i in have])
-        with np.errstate(divide="ignore", invalid="ignore"):
-            y = np.array([math.log2(f(i)) if f(i) > 0 else float("-inf") for i in have])
-        ok = np.isfinite(y)
+        # the reference filters on the LENGTH OF THE STORED SAMPLE VECTORS (src/methods.jl:121-122), which for U estimators also
+        # grow on every idx below a drawn index; n of the first (shift, qoi) moment triplet is that length
+        stored = {i: (int(self.moments[i][0, 0, 1, 0]) if i in self.moments else 0) for i in self.nb_of_samples}
+        have = [i for i, n in stored.items() if (n > 0 if self.qmc else n > 1)]
+        A = np.array([[1.0] + list(i) for i in have]).reshape(len(have), 1 + self.index_set.ndims)
+        vals = [f(i) for i in have]
+        # log2(0) = -Inf rows are dropped (`valid = .!isinf.(y)`), NaN rows are NOT: they poison the fit, as in the reference
+        y = np.array([float("nan") if v != v else (math.log2(v) if v > 0 else float("-inf")) for v in vals])
+        ok = ~np.isinf(y)
+        if np.isnan(y[ok]).any():
+            return np.full(A.shape[1], float("nan"))
         try:
             return np.linalg.lstsq(A[ok], y[ok], rcond=None)[0]
         except Exception:  # noqa: BLE001
@@ -947,7 +953,7 @@ class Estimator:
                 if index not in self.moments or self.nb_of_samples[index] == 0:
                     return float("nan")
                 return math.sqrt(self.var(index) / self.cost(index)) if self.var(index) >= 0 else float("nan")
-        p = self._interp(lambda i: f(i) if f(i) == f(i) else 0.0)
+        p = self._interp(f)
         if not np.any(np.isnan(p)) and np.all(p[1:] < 0):
             for index in self.keys():
                 fi = f(index)
