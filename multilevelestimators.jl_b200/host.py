@@ -306,17 +306,20 @@ class ShardedBackend:
         return self.inner.model(spec)
 
     def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
+        """moments [R, q, 2, 3] of the whole point range (and, on request, the raw samples [R, q, 2, n] of all ranks in point
+        order: `save_samples` and the unbiased estimators' per-sample sums need them on every rank)"""
         import torch
-        if want_samples:
-            raise NotImplementedError("save_samples is a single-rank option: the raw samples of a sharded run stay on their ranks")
         start, cnt = split_range(k0, n, self.world, self.rank)
         R = 1 if shifts is None else len(shifts)
         q = getattr(model, "nqoi", 1)
+        smp = None
         if cnt > 0:
-            mom, t = self.inner.sample_batch(model, lattice, dists, index, shifts, start, cnt, m, mc_seed)
+            out = self.inner.sample_batch(model, lattice, dists, index, shifts, start, cnt, m, mc_seed, want_samples=want_samples)
+            mom, t = out[0], out[1]
+            smp = out[2] if want_samples else None
         else:
             mom, t = np.zeros((R, q, 2, 3)), 0.0
-        payload = torch.from_numpy(np.concatenate([mom.reshape(-1), [t]]))
+        payload = torch.from_numpy(np.concatenate([np.asarray(mom, dtype=np.float64).reshape(-1), [t]]))
         if self.device is not None:
             payload = payload.to(self.device)
         out = [torch.empty_like(payload) for _ in range(self.world)]
@@ -325,7 +328,22 @@ class ShardedBackend:
         acc = parts[0][:-1].reshape(mom.shape).copy()
         for p in parts[1:]:
             acc = self.merge(acc, p[:-1].reshape(mom.shape))
-        return acc, max(float(p[-1]) for p in parts)
+        tmax = max(float(p[-1]) for p in parts)
+        if not want_samples:
+            return acc, tmax
+        # second all-gather: the raw samples, padded to the largest slice (slices differ by at most one point)
+        counts = [split_range(k0, n, self.world, r)[1] for r in range(self.world)]
+        width = max(counts)
+        mine = np.zeros((R, q, 2, width))
+        if cnt > 0:
+            mine[..., :cnt] = smp
+        send = torch.from_numpy(mine)
+        if self.device is not None:
+            send = send.to(self.device)
+        recv = [torch.empty_like(send) for _ in range(self.world)]
+        self.dist.all_gather(recv, send, group=self.group)
+        full = np.concatenate([r.cpu().numpy()[..., :c] for r, c in zip(recv, counts)], axis=-1)
+        return acc, tmax, full
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -604,7 +622,7 @@ class Estimator:
         m = self.options["nb_of_uncertainties"](index)
         seed = index_seed(self.options["mc_seed"], index)
         t0 = _time.perf_counter()
-        if self.options["save_samples"]:  # src/history.jl:92-95: keep the raw samples as well (single-rank backends)
+        if self.options["save_samples"]:  # src/history.jl:92-95: keep the raw samples as well
             mom, _gpu_t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
                                                          self.shifts.get(index), istart - 1, n, m, seed, want_samples=True)
             self.samples.setdefault(index, []).append(np.array(smp))

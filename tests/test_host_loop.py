@@ -461,6 +461,48 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _make_unbiased(H, backend, method):
+    return H.Estimator(H.U(2), getattr(H, method)(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, backend,
+                       nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=3, save_samples=True)
+
+
+def _worker_unbiased(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import mle_b200.host as H
+    res = []
+    for method in ("MC", "QMC"):
+        est = _make_unbiased(H, H.ShardedBackend(OracleBackend()), method)
+        h = H.run(est, 5e-3)
+        first = h["samples_diff"][(0, 0)]
+        res += [h["mean"], h["varest"], float(sum(h["nb_of_samples"].values())), float(first.shape[-1]), float(first.sum())]
+    if rank == 0:
+        np.save(out, np.array(res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_unbiased_run_matches_single_rank(tmp_path):
+    """U(2) x {MC, QMC} with save_samples on two gloo ranks: each rank evaluates its slice of the points for every idx <= index,
+    a second all-gather brings the raw samples back in point order, and the per-sample sums, pmf updates and index draws are
+    identical on all ranks and equal to the single-rank run"""
+    import torch.multiprocessing as mp
+    H = host()
+    want = []
+    for method in ("MC", "QMC"):
+        h = H.run(_make_unbiased(H, OracleBackend(), method), 5e-3)
+        first = h["samples_diff"][(0, 0)]
+        want += [h["mean"], h["varest"], float(sum(h["nb_of_samples"].values())), float(first.shape[-1]), float(first.sum())]
+    out = str(tmp_path / "u.npy")
+    mp.spawn(_worker_unbiased, args=(2, 29531, out), nprocs=2, join=True)
+    got = np.load(out)
+    for g, w, tol in zip(got, want, [1e-12, 1e-9, 0, 0, 1e-12] * 2):
+        assert abs(g - w) <= tol * abs(w), (got, want)
+
+
 def test_two_rank_sharding_matches_single_rank(tmp_path):
     """world_size-2 gloo run: every sample_batch is split over the ranks, one all-gather merges the moments"""
     import torch.multiprocessing as mp
