@@ -305,6 +305,43 @@ class ShardedBackend:
     def model(self, spec):
         return self.inner.model(spec)
 
+    def update_samples(self, model, lattice, dists, entries, mc_seed):
+        """all due indices of one `update_samples` (src/sample.jl:8-13) at once: every rank runs its slice of every entry
+        (one device synchronisation through the inner backend's batched call when it has one) and ONE all-gather carries the
+        moment tables of all entries"""
+        import torch
+        q = getattr(model, "nqoi", 1)
+        mine, local = [], []
+        for index, shifts, k0, n, m in entries:
+            start, cnt = split_range(k0, n, self.world, self.rank)
+            if cnt > 0:
+                mine.append(len(local))
+                local.append((index, shifts, start, cnt, m))
+            else:
+                mine.append(None)
+        if local and hasattr(self.inner, "update_samples"):
+            moms = self.inner.update_samples(model, lattice, dists, local, mc_seed)
+        else:
+            moms = [self.inner.sample_batch(model, lattice, dists, i, sh, k0, n, m, mc_seed)[0] for i, sh, k0, n, m in local]
+        shapes = [((1 if e[1] is None else len(e[1])), q, 2, 3) for e in entries]
+        parts = [np.asarray(moms[j], dtype=np.float64).reshape(-1) if j is not None else np.zeros(int(np.prod(sh)))
+                 for j, sh in zip(mine, shapes)]
+        payload = torch.from_numpy(np.concatenate(parts))
+        if self.device is not None:
+            payload = payload.to(self.device)
+        out = [torch.empty_like(payload) for _ in range(self.world)]
+        self.dist.all_gather(out, payload, group=self.group)
+        flat = [o.cpu().numpy() for o in out]
+        result, off = [], 0
+        for sh in shapes:
+            size = int(np.prod(sh))
+            acc = flat[0][off:off + size].reshape(sh).copy()
+            for f in flat[1:]:
+                acc = self.merge(acc, f[off:off + size].reshape(sh))
+            result.append(acc)
+            off += size
+        return result
+
     def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         """moments [R, q, 2, 3] of the whole point range (and, on request, the raw samples [R, q, 2, n] of all ranks in point
         order: `save_samples` and the unbiased estimators' per-sample sums need them on every rank)"""

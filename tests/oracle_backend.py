@@ -25,6 +25,11 @@ class OracleBackend:
     def model(self, spec):
         return _OModel(spec)
 
+    def update_samples(self, model, lattice, dists, entries, mc_seed):
+        """the batched call of the device backend, entry by entry (entries = [(index, shifts, k0, n, m)])"""
+        self.batched_calls = getattr(self, "batched_calls", 0) + 1
+        return [self.sample_batch(model, lattice, dists, index, shifts, k0, n, m, mc_seed)[0] for index, shifts, k0, n, m in entries]
+
     def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         z, nmax = lattice if lattice is not None else (None, 2**32 - 1)
         if want_samples:

@@ -730,3 +730,76 @@ def test_unbiased_point_numbers_count_all_indices():
     est.sample((0,), 2)
     assert Spy.calls == [((0,), 0, 5), ((0,), 5, 3), ((1,), 5, 3), ((2,), 5, 3), ((0,), 8, 2)]
     assert est.nb_of_samples[(0,)] == 7 and est.nb_of_samples[(2,)] == 3
+
+
+def test_batched_update_samples_equals_index_by_index():
+    """with a deterministic cost model all due indices of one update_samples (src/sample.jl:8-13) go to the backend in one
+    batched call (QMC only: MC needs one stream per index); the run is the same as index by index"""
+    H = host()
+
+    class OneByOne(OracleBackend):
+        update_samples = property()   # hasattr(...) is False: the host falls back to sample! per index
+
+    def make(backend, method="QMC"):
+        return H.Estimator(H.ML(), getattr(H, method)(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], backend, nb_of_qoi=13,
+                           max_index_set_param=3, cost_model=lambda i: 2.0 ** i[0], nb_of_tols=4,
+                           **(dict(nb_of_shifts=4) if method == "QMC" else {}))
+
+    assert not hasattr(OneByOne(), "update_samples")
+    b1, b2 = OracleBackend(), OneByOne()
+    e1, e2 = make(b1), make(b2)
+    # the QMC loop grows one index at a time, so drive update_samples directly with several due indices
+    for e in (e1, e2):
+        e.current_index_set.update([(0,), (1,), (2,)])
+        e.update_samples({(0,): 8, (1,): 5, (2,): 3})
+        e.update_samples({(0,): 8, (1,): 9, (2,): 4})      # (0,) is not due
+    assert getattr(b1, "batched_calls", 0) == 2
+    assert e1.nb_of_samples == e2.nb_of_samples and e1.total_work == e2.total_work
+    for idx in ((0,), (1,), (2,)):
+        assert np.array_equal(e1.moments[idx], e2.moments[idx])
+    assert e1.total_time[(2,)] >= 0 and e1.mean() == e2.mean() and e1.varest() == e2.varest()
+    # MC never takes the batched path
+    b3 = OracleBackend()
+    H.run(make(b3, "MC"), 2e-2)
+    assert getattr(b3, "batched_calls", 0) == 0
+
+
+def _drive_batched(H, backend):
+    est = H.Estimator(H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], backend, nb_of_qoi=13,
+                      max_index_set_param=3, cost_model=lambda i: 2.0 ** i[0], nb_of_shifts=4)
+    est.current_index_set.update([(0,), (1,), (2,), (3,)])
+    est.update_samples({(0,): 9, (1,): 5, (2,): 1, (3,): 2})     # (2,): one point -> rank 1 has nothing to do for it
+    est.update_samples({(0,): 20, (1,): 5, (2,): 4, (3,): 3})
+    return est
+
+
+def _worker_batched(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import mle_b200.host as H
+    inner = OracleBackend()
+    est = _drive_batched(H, H.ShardedBackend(inner))
+    assert inner.batched_calls == 2
+    if rank == 0:
+        np.save(out, np.stack([est.moments[(l,)] for l in range(4)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_batched_update_samples(tmp_path):
+    """ShardedBackend.update_samples: every rank runs its slice of every due index through the inner backend's batched call and
+    one all-gather merges the moment tables of all entries"""
+    import torch.multiprocessing as mp
+    H = host()
+    want = _drive_batched(H, OracleBackend())
+    out = str(tmp_path / "b.npy")
+    mp.spawn(_worker_batched, args=(2, 29543, out), nprocs=2, join=True)
+    got = np.load(out)
+    for l in range(4):
+        w = want.moments[(l,)]
+        assert np.array_equal(got[l][..., 0], w[..., 0])
+        assert np.allclose(got[l][..., 1], w[..., 1], rtol=1e-13, atol=0)
+        assert np.allclose(got[l][..., 2], w[..., 2], rtol=1e-10, atol=1e-28)
