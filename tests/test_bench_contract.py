@@ -43,3 +43,33 @@ def test_workload_definition_matches_baseline_config():
     assert bench.points_per_shift(0) == 1 << 20 and bench.points_per_shift(6) == 2048
     sh = bench.level_shifts()
     assert sh.shape == (7, 16, 100) and (sh >= 0).all() and (sh < 1).all()
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """the round's measured bench lines under profiles/ (N = 1, 2, 4, 8): every key of the bench contract, consistent values"""
+    import json
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    single = None
+    for n, fn in ((1, "r01_final_bench_1gpu.json"), (2, "r01_bench_2gpu.json"), (4, "r01_bench_4gpu.json"), (8, "r01_bench_8gpu.json")):
+        d = json.loads(open(os.path.join(ROOT, "profiles", fn)).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in d, (fn, key)
+        assert d["n_gpus"] == n and d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64"
+        assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert str(base.get("metric", d["metric"])).split()[0].lower() in d["metric"].lower() or "samples" in d["metric"]
+        e = d["e2e"]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+        r = d["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6 and 0 < r["frac"] < 1
+        c = d["clocks"]
+        assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        per_step = d["config"]["samples_per_step_per_gpu"] * n
+        assert abs(d["value"] - per_step / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+        if n == 1:
+            single = d["value"]
+            cb = d["cpu_baseline"]
+            assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
+        else:
+            assert 0.95 * n * single <= d["value"] <= 1.05 * n * single      # weak scaling
