@@ -151,3 +151,57 @@ def test_product_package_never_uses_the_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not bad.search(src), fn
     assert seen >= 5
+
+
+_NULL_CALLS = r'''
+import json
+ROOT = %r
+import sys, ctypes as C
+sys.path.insert(0, ROOT)
+import mle_b200
+lib = mle_b200._lib.load()
+N = None
+z = (C.c_uint32 * 4)(1, 2, 3, 4)
+h = C.c_void_p()
+dbl = (C.c_double * 16)()
+i32 = (C.c_int32 * 2)(0, 0)
+res = {}
+res["lattice_create"] = lib.mle_lattice_create(N, z, 4, 100, C.byref(h))
+res["lattice_destroy"] = lib.mle_lattice_destroy(N, N)
+res["dists_create"] = lib.mle_dists_create(N, N, 1, C.byref(h))
+res["dists_destroy"] = lib.mle_dists_destroy(N, N)
+res["model_create"] = lib.mle_model_create(N, b"expsum", 1, dbl, 2, C.byref(h))
+res["model_set_basis"] = lib.mle_model_set_basis(N, N, 0, 2, 2, dbl)
+q = C.c_int()
+res["model_nqoi"] = lib.mle_model_nqoi(N, C.byref(q))
+res["model_destroy"] = lib.mle_model_destroy(N, N)
+res["points"] = lib.mle_points(N, N, N, N, 1, 0, 1, 1, 0, dbl)
+res["points_dev"] = lib.mle_points_dev(N, N, N, N, 1, 0, 1, 1, 0, dbl)
+res["sample_batch"] = lib.mle_sample_batch(N, N, N, N, i32, 1, N, 1, 0, 1, 1, 0, dbl, N, N)
+res["sample_batch_dev"] = lib.mle_sample_batch_dev(N, N, N, N, i32, 1, N, 1, 0, 1, 1, 0, dbl, N)
+res["update_samples"] = lib.mle_update_samples(N, N, N, N, 1, i32, 1, N, N, N, N, N, 0, N)
+res["sync"] = lib.mle_sync(N)
+res["stream"] = lib.mle_stream(N, C.byref(h))
+cnt = C.c_uint64()
+res["launch_count"] = lib.mle_launch_count(N, C.byref(cnt))
+sm, cc, hb = C.c_int(), C.c_int(), C.c_size_t()
+res["device_info"] = lib.mle_device_info(N, C.byref(sm), C.byref(hb), C.byref(cc))
+res["destroy"] = lib.mle_destroy(N)
+res["moments_merge_null"] = lib.mle_moments_merge(N, N, 1)
+res["genvec_unknown"] = lib.mle_genvec(b"nope", C.byref(C.POINTER(C.c_uint32)()), C.byref(q))
+print(json.dumps(res))
+'''
+
+
+def test_every_entry_point_refuses_null_handles_without_crashing():
+    """no exception or crash crosses the boundary: with a NULL context (what a caller holds after a failed mle_init) every
+    entry point returns MLE_ERR_ARG; the destroy functions accept NULL like free()"""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, "-c", _NULL_CALLS % ROOT], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert len(res) == 20
+    for name, rc in res.items():
+        assert rc == (0 if name.endswith("destroy") else -1), (name, rc)
