@@ -913,7 +913,10 @@ class Estimator:
                         self.active_set.add(nb)
                         new.append(nb)
                     else:
-                        self.max_index_set.add(nb)  # outside the search space: ignored (src/print.jl:247)
+                        import warnings
+                        warnings.warn("Trying to add index %s outside search space to index set, ignoring..." % (nb,),
+                                      stacklevel=2)  # warn_max_index, src/print.jl:247 (unconditional in the reference)
+                        self.max_index_set.add(nb)
         self.logbook.append((set(self.old_set), set(self.active_set), max_index))
         return new
 
@@ -1139,6 +1142,10 @@ def _run(est, eps):  # src/run.jl:41-142
         else:
             done = L > est["min_index_set_param"] and est.converged(eps, theta)
             if not done and est.max_level_exceeded():
+                if est["verbose"]:  # warn_max_level, src/print.jl:241 (the only console output this mirror keeps)
+                    import warnings
+                    warnings.warn("Maximum %s L = %d reached, no convergence yet." % (
+                        "level" if est.index_set.ndims == 1 else "index set parameter", est["max_index_set_param"]))
                 done = True
             elif not done:
                 L += 1

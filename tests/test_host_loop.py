@@ -803,3 +803,27 @@ def test_two_rank_batched_update_samples(tmp_path):
         assert np.array_equal(got[l][..., 0], w[..., 0])
         assert np.allclose(got[l][..., 1], w[..., 1], rtol=1e-13, atol=0)
         assert np.allclose(got[l][..., 2], w[..., 2], rtol=1e-10, atol=1e-28)
+
+
+def test_warnings_of_the_reference_are_kept():
+    """src/print.jl:241-247: `Maximum level L = .. reached, no convergence yet.` (verbose only, src/run.jl:126) and `Trying to add
+    index .. outside search space` (always, src/methods.jl:242)"""
+    import warnings
+    H = host()
+    est = H.Estimator(H.ML(), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                      max_index_set_param=1, min_index_set_param=1, verbose=True)
+    with pytest.warns(UserWarning, match="Maximum level L = 1 reached, no convergence yet."):
+        H.run(est, [1e-2])   # convergence is only tested for L > min_index_set_param (src/run.jl:124)
+    est = H.Estimator(H.ML(), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                      max_index_set_param=1, min_index_set_param=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        H.run(est, [1e-2])                     # silent without verbose
+    ad = H.Estimator(H.AD(2), H.MC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(), nb_of_qoi=13,
+                     max_index_set_param=1, min_index_set_param=1, max_search_space=H.TD(2))
+    for idx in ((0, 0), (1, 0), (0, 1)):
+        ad.sample(idx, 4)
+    ad.old_set, ad.active_set = {(0, 0)}, {(1, 0), (0, 1)}
+    with pytest.warns(UserWarning, match="outside search space"):
+        new = ad.new_index_set(2)      # the most profitable active index moves to the old set; its forward neighbour (2, 0)
+    assert len(new) == 1 and ad.max_index_set and ad.max_index_set <= {(2, 0), (0, 2), (1, 1)}   # or (0, 2) is outside TD(2) at size 1
