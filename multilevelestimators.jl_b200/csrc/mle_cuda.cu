@@ -796,7 +796,9 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.mpad = M->basis_mpad[level];
         la.nchunks = M->basis_nchunks[level];
         la.nrows = la.N + 2;
-        if (const char *e = getenv("MLE_SKIP")) la.skip = atoi(e);  // debug: timing experiments only
+#ifdef MLE_PHASE_TIMING
+        if (const char *e = getenv("MLE_SKIP")) la.skip = atoi(e);  // debug builds only: phase-skipping timing experiments
+#endif
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));

@@ -1,4 +1,5 @@
-"""Debug: marginal cost of each phase of lognormal1d_kernel (MLE_SKIP bitmask; results are invalid, only the times matter)."""
+"""Debug: marginal cost of each phase of lognormal1d_kernel (MLE_SKIP bitmask, honoured by debug builds only --
+`make EXTRA=-DMLE_PHASE_TIMING`; results are invalid, only the times matter)."""
 import os, sys, subprocess, json
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
