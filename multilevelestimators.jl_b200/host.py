@@ -5,15 +5,21 @@ This is the Python twin of the Julia glue in julia/MLECuda.jl (Julia is not inst
 control loop is restated here to make `run` testable end to end).  It follows the reference line by line where the hot
 path is concerned:
 
-  sample! / update_samples      src/sample.jl:8-34      point numbers continue across calls (Istart = N + 1)
+  Index / Level / diff          src/index.jl:19-58
+  SL, ML, FT, TD, HC, ZC, AD, U src/index_set.jl:49-227 (get_index_set, is_admissable, length, show, print)
+  option parsing                src/options.jl:10-43, src/parse.jl:35-307 (same keys per estimator type, defaults, rules)
+  sample! / update_samples      src/sample.jl:8-34      point numbers continue across calls (Istart = N + 1; U: total + 1)
   parallel_sample!              src/sample.jl:39-56, :79-102   -> ONE `sample_batch` call on the backend (libmle_cuda)
-  append_samples!               src/sample.jl:58-63, :104-111  -> Chan merge of (n, mean, M2) per (qoi, shift)
+  append_samples!               src/sample.jl:58-74, :104-124  -> Chan merge of (n, mean, M2) per (qoi, shift); U: per-sample sums
   mean / var / varest / cost    src/methods.jl:44-68, :282
-  _run (SL / ML / multi-index)  src/run.jl:41-142
+  _run (SL / ML / multi-index)  src/run.jl:41-142;  unbiased estimators src/run.jl:145-200
   rates, regression, bias, MSE splitting, optimal_nb_of_samples   src/methods.jl:70-201
-  History keys                  src/history.jl:55-103
+  adaptive index sets (AD)      src/methods.jl:206-261, src/internals.jl:150-206
+  unbiased estimators (U)       src/methods.jl:287-351, src/internals.jl:208-225
+  History keys, save            src/history.jl:55-107 (JSON instead of JLD2)
+  backends                      GpuBackend (one GPU through the C ABI), ShardedBackend (one rank of a torch.distributed group)
 
-Out of scope: AD and U index sets, printing, JLD2 output, `save_samples`.
+Out of scope: console output (`verbose`; only the two warnings of src/print.jl:241-247 are kept), the JLD2 / Reporter.jl formats.
 The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
 """
 import itertools
