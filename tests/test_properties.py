@@ -16,7 +16,7 @@ def host():
     return H
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(k0=st.integers(0, 2**32), n=st.integers(0, 10**7), world=st.integers(1, 16))
 def test_split_range_is_a_partition(k0, n, world):
     """the ranks' slices are contiguous, ordered, cover k0 .. k0+n-1 exactly once and differ by at most one point"""
@@ -34,7 +34,7 @@ def triplet(x):
     return np.array([len(x), x.mean(), ((x - x.mean()) ** 2).sum()]) if len(x) else np.zeros(3)
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=100, deadline=None, derandomize=True)
 @given(data=st.lists(st.floats(-1e6, 1e6, allow_nan=False, width=64), min_size=1, max_size=200),
        cuts=st.lists(st.integers(0, 200), min_size=0, max_size=5))
 def test_moment_merge_equals_one_pass(data, cuts):
@@ -50,13 +50,13 @@ def test_moment_merge_equals_one_pass(data, cuts):
     scale = max(1.0, np.abs(np.asarray(data)).max())
     assert acc[0, 0] == want[0]
     assert abs(acc[0, 1] - want[1]) <= 1e-12 * scale
-    assert abs(acc[0, 2] - want[2]) <= 1e-10 * max(want[2], scale * scale * 1e-4)
+    assert abs(acc[0, 2] - want[2]) <= 1e-10 * max(want[2], scale * scale)   # both sides carry eps * n * scale^2
 
 
 WEIGHTS = st.lists(st.sampled_from([1.0, 0.9, 0.75, 0.6, 0.5, 1 / 3]), min_size=2, max_size=3)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(kind=st.sampled_from(["FT", "TD", "HC", "ZC"]), weights=WEIGHTS, sz=st.integers(0, 6))
 def test_index_sets_are_nested_and_downward_closed(kind, weights, sz):
     """src/index_set.jl:77-193: every a-priori index set grows with its size parameter, contains the origin, is downward closed
@@ -79,7 +79,7 @@ def test_index_sets_are_nested_and_downward_closed(kind, weights, sz):
     assert not any(H.is_admissable(s, idx) for idx in cur)
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=100, deadline=None, derandomize=True)
 @given(index=st.lists(st.integers(0, 5), min_size=1, max_size=3))
 def test_diff_signs_telescope(index):
     """src/index.jl:49-58: sum over kappa in the box max(0, index-1) .. index of sign(kappa) is 0 unless index = 0 (the mixed
@@ -93,7 +93,7 @@ def test_diff_signs_telescope(index):
         assert all(0 <= a - b <= 1 for a, b in zip(index, kappa)) and sign == (-1) ** sum(a - b for a, b in zip(index, kappa))
 
 
-@settings(max_examples=50, deadline=None)
+@settings(max_examples=50, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2**64 - 1), a=st.lists(st.integers(0, 12), min_size=1, max_size=3),
        b=st.lists(st.integers(0, 12), min_size=1, max_size=3))
 def test_index_seeds_do_not_collide(seed, a, b):
