@@ -19,7 +19,9 @@ path is concerned:
   History keys, save            src/history.jl:55-107 (JSON instead of JLD2)
   backends                      GpuBackend (one GPU through the C ABI), ShardedBackend (one rank of a torch.distributed group)
 
-Out of scope: console output (`verbose`; only the two warnings of src/print.jl:241-247 are kept), the JLD2 / Reporter.jl formats.
+  verbose report                src/print.jl (report.py: the same tables and messages, off by default)
+
+Out of scope: the JLD2 / Reporter.jl file formats.
 The sample function is a device model (name + parameters + KL bases), not an arbitrary closure.
 """
 import itertools
@@ -581,6 +583,10 @@ class Estimator:
             index_set, sample_method, sample_function, list(distributions), backend)
         d = index_set.ndims
         self.options = o
+        self.report = None
+        if o["verbose"]:   # src/print.jl: the progress report of a verbose run
+            from .report import Reporter
+            self.report = Reporter(self)
         self.model = backend.model(sample_function)
         self.nqoi = o["nb_of_qoi"] or getattr(self.model, "nqoi", 1)
         _check("qoi_with_max_var", o["qoi_with_max_var"] <= self.nqoi, "smaller than or equal to %d" % self.nqoi)  # src/parse.jl:305
@@ -659,8 +665,16 @@ class Estimator:
 
     def sample(self, index, n):
         """sample!(estimator, index, n), src/sample.jl:21-34"""
+        if self.report:
+            self.report.sample_header(index, n, not self.has_samples_at_index(index))   # src/sample.jl:22-23
         if self.unbiased:
-            return self._sample_unbiased(index, n)
+            self._sample_unbiased(index, n)
+        else:
+            self._sample_index(index, n)
+        if self.report:
+            self.report.sample_footer()
+
+    def _sample_index(self, index, n):
         istart = self.nb_of_samples[index] + 1
         m = self.options["nb_of_uncertainties"](index)
         seed = index_seed(self.options["mc_seed"], index)
@@ -894,8 +908,12 @@ class Estimator:
         profits = [self.profit(i) for i in indices]
         best = int(np.argmax(profits))
         if self._ad_rng.random() < self.options["acceptance_rate"] or len(profits) == 1:
-            return indices[best]
-        return indices[self._ad_rng.choice([t for t in range(len(profits)) if t != best])]
+            max_index = indices[best]
+        else:
+            max_index = indices[self._ad_rng.choice([t for t in range(len(profits)) if t != best])]
+        if self.report:
+            self.report.largest_profit(max_index, profits[best], indices, profits)
+        return max_index
 
     def new_index_set(self, sz):
         """the indices entering at iteration sz: the boundary of the a-priori set, or, for AD, the index with the largest
@@ -1050,7 +1068,7 @@ class History:
         return key in self.data[-1]
 
     def __repr__(self):
-        return "MultilevelEstimators history file"  # src/history.jl:117
+        return "MultilevelEstimators.jl history file"  # src/history.jl:117
 
     @property
     def path(self):
@@ -1112,43 +1130,85 @@ def get_tols(est, tol):  # src/methods.jl:15
 
 
 def _run_unbiased(est, eps):  # src/run.jl:145-200
-    est.current_index_set.update(est.pmf.keys())
+    rep = est.report
+    if rep:
+        rep.header(eps)
+    index_set = sorted(est.pmf, key=lambda t: t[::-1])
+    if rep:
+        rep.index_set(index_set)
+    est.current_index_set.update(index_set)
     v = est.varest()
     while not v <= eps**2:  # NaN (no samples yet) keeps looping, like `is_converged = varest(estimator) <= eps^2` in the reference
-        est.update_samples(est.next_number_of_samples_unbiased())
+        if rep:
+            rep.status()
+        n_opt = est.next_number_of_samples_unbiased()
+        if rep:
+            rep.optimal_nb_of_samples(n_opt)
+        est.update_samples(n_opt)
         est.update_pmf()
+        if rep:
+            rep.pmf()
+            rep.unbiased_convergence(eps)
         v = est.varest()
+        if rep:
+            rep.index_set(index_set)
+    if rep:
+        rep.convergence(True)
 
 
 def _run(est, eps):  # src/run.jl:41-142
     if est.unbiased:
         return _run_unbiased(est, eps)
+    rep = est.report
+    if rep:
+        rep.header(eps)
     sl = isinstance(est.index_set, SL)
+
+    def splitting():
+        return 0.5 if sl else (est.compute_splitting(eps) if est["do_mse_splitting"] else est["min_splitting"])
+
     L = 0
     theta = 0.5 if sl else est["min_splitting"]
     done = False
     while not done:
+        if rep:
+            rep.level(L)
         index_set = est.new_index_set(L)
+        if rep:
+            rep.index_set(index_set)
         ns = est.regress_nb_of_samples(index_set, eps, theta, L)
         for index in index_set:
             if not est.has_samples_at_index(index):
                 est.sample(index, ns[index])
         est.current_index_set.update(index_set)
         est.set_sz(L)
-        theta = 0.5 if sl else (est.compute_splitting(eps) if est["do_mse_splitting"] else est["min_splitting"])
+        if rep:
+            rep.status()
+        theta = splitting()
         if not est.qmc:
             n_opt = {i: est.optimal_nb_of_samples(i, eps, theta) for i in est.keys()}
+            if rep:
+                rep.optimal_nb_of_samples(n_opt)
             est.update_samples(n_opt)
         else:
             while est.varest() > theta * eps**2:
-                est.update_samples(est.next_number_of_samples(est.find_index_with_max_var_over_cost()))
-                theta = 0.5 if sl else (est.compute_splitting(eps) if est["do_mse_splitting"] else est["min_splitting"])
+                n_opt = est.next_number_of_samples(est.find_index_with_max_var_over_cost())
+                if rep:
+                    rep.optimal_nb_of_samples(n_opt)
+                est.update_samples(n_opt)
+                theta = splitting()
+                if rep:
+                    rep.qmc_convergence(eps, theta)
         if sl:
             done = True
         else:
+            if rep:
+                rep.status()
+                if L >= 2:
+                    rep.mse_analysis(eps, theta)
             done = L > est["min_index_set_param"] and est.converged(eps, theta)
             if not done and est.max_level_exceeded():
-                if est["verbose"]:  # warn_max_level, src/print.jl:241 (the only console output this mirror keeps)
+                if est["verbose"]:  # warn_max_level, src/print.jl:241
                     import warnings
                     warnings.warn("Maximum %s L = %d reached, no convergence yet." % (
                         "level" if est.index_set.ndims == 1 else "index set parameter", est["max_index_set_param"]))
@@ -1157,6 +1217,8 @@ def _run(est, eps):  # src/run.jl:41-142
                 L += 1
     if est.adaptive:
         est.ad_boundary = set(est.active_set)  # update_boundary, src/run.jl:138
+    if rep:
+        rep.convergence(True if sl else est.converged(eps, theta))
 
 
 def update_history(history, est, tol, elapsed):  # src/history.jl:55-103

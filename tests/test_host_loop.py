@@ -345,7 +345,7 @@ def test_history_is_saved_after_every_tolerance_and_reloads(tmp_path):
     assert est["name"] == "UntitledEstimator.jld2"
     h = H.run(est, 2e-2)
     assert h["folder"] == str(tmp_path) and h.path == str(tmp_path / "UntitledEstimator.json") and os.path.isfile(h.path)
-    assert repr(h) == "MultilevelEstimators history file"
+    assert repr(h) == "MultilevelEstimators.jl history file"
     g = H.History.load(h.path)
     assert len(g) == len(h) == 3
     for i in range(3):
@@ -827,3 +827,59 @@ def test_warnings_of_the_reference_are_kept():
     with pytest.warns(UserWarning, match="outside search space"):
         new = ad.new_index_set(2)      # the most profitable active index moves to the old set; its forward neighbour (2, 0)
     assert len(new) == 1 and ad.max_index_set and ad.max_index_set <= {(2, 0), (0, 2), (1, 1)}   # or (0, 2) is outside TD(2) at size 1
+
+
+def test_verbose_report_follows_print_jl(capsys):
+    """verbose = true: the tables and messages of src/print.jl (header :34-45, status table :59-83, sample lines :214-222,
+    optimal numbers :97-121, QMC / MSE checks :186-202, AD profits :132-151, U pmf :156-175, footer :47-54); the run itself is
+    unchanged by it"""
+    H = host()
+
+    def run(iset, method, d, tol, **kw):
+        def make(verbose):
+            return H.Estimator(iset, getattr(H, method)(), H.ModelSpec("problem18", d), [H.Uniform(-0.5, 0.5)] * d, OracleBackend(),
+                               nb_of_qoi=13, max_index_set_param=3, cost_model=lambda i: 2.0 ** sum(i), name="demo",
+                               verbose=verbose, **kw)
+        quiet = H.run(make(False), [tol])
+        assert capsys.readouterr().out == ""
+        loud = H.run(make(True), [tol])
+        out = capsys.readouterr().out
+        assert loud["nb_of_samples"] == quiet["nb_of_samples"] and loud["mean"] == quiet["mean"]
+        return out, loud
+
+    out, h = run(H.ML(), "MC", 1, 1e-2)
+    lines = out.splitlines()
+    assert lines[0] == "+" + "-" * 79 + "+" and all(len(ln) == 81 for ln in lines[:6])
+    assert lines[1].startswith("| *** MultilevelEstimators.jl @") and lines[1].endswith("|")
+    assert lines[2].startswith("| *** This is a Estimator{ML, MC}") and lines[3].startswith("| *** Simulating demo ")
+    assert lines[4].startswith("| *** Tolerance on RMSE ϵ = 1.000e-02")
+    assert "Currently running on level 0." in lines and "Taking 20 warm-up samples at level (0)... done" in lines
+    head = "| level         | E             | dE            | V             | dV            | N             | W             | "
+    assert head in lines and "+" + ("-" * 15 + "+") * 7 in lines
+    row = [ln for ln in lines if ln.startswith("| (0)")][-1]
+    assert row == "| (0)           |%s   |%s   |%s   |%s   | %-13s |%s   |" % (
+        "%12.5e" % h["E"][(0,)], "%12.5e" % h["dE"][(0,)], "%12.5e" % h["V"][(0,)], "%12.5e" % h["dV"][(0,)],
+        h["nb_of_samples"][(0,)], "%12.5e" % 1.0)
+    assert "Samples will be updated to" in lines and "| level         | N             | " in lines
+    assert any(ln.startswith("Taking ") and " additional sample" in ln for ln in lines)
+    assert "Checking convergence..." in lines and any(ln.startswith("  ==> Rates: α ≈ ") for ln in lines)
+    assert any(ln.startswith("  ==> MSE splitting parameter ≈ 0.") for ln in lines)
+    assert lines[-4] == "+" + "-" * 79 + "+" and lines[-2].startswith("| *** Successfull termination.") and len(lines[-2]) == 81
+    assert any(ln.startswith("Convergence reached. RMSE ≈") for ln in lines) or h["rmse"] > 1e-2
+
+    out, h = run(H.TD(2), "QMC", 2, 2e-2, nb_of_shifts=4)
+    assert "Currently running with L = 1." in out and "Shape of the index set:" in out and "\u25FC" in out
+    assert "Taking 4 x 1 warm-up sample at index (1, 0)... done" in out
+    assert "Checking if variance of estimator is larger than θ*ϵ^2..." in out and "  ==> " in out
+    assert "| index         | E " in out and "Estimator{TD{2}, QMC}" in out
+
+    out, h = run(H.AD(2), "MC", 2, 2e-2)
+    assert "Shape of the index set (\u25A3 = active set):" in out and "Profit indicators:" in out
+    assert "| index         | profit        | " in out and "Index with max profit is (" in out
+
+    out, h = run(H.U(1), "MC", 1, 2e-2, max_search_space=H.ML())
+    assert "Using approximate probability mass function:" in out and "| level         | P             | " in out
+    assert "Checking if variance of estimator is larger than ϵ^2..." in out and "Convergence reached. RMSE ≈" in out
+
+    out, h = run(H.SL(), "MC", 1, 5e-2)
+    assert "Currently running on finest level." in out and "Checking convergence..." not in out
