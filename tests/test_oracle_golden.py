@@ -308,3 +308,25 @@ def test_all_transforms_against_mpmath_quantiles(oracle):
     # erfinv is an approximation good to a few ulp of the RESULT SCALE (test_erfinv_against_mpmath); Phi(al) + ... loses the
     # usual conditioning of a cdf round trip near the truncation points
     assert worst["normal"] <= 32 and worst["weibull"] <= 8 and worst["truncnormal"] <= 64, worst
+
+
+def test_model_definitions_are_pinned(oracle):
+    """the models this repository defines (expsum, lognormal1d, lognormal2d; problem18 restates reference test code): raw
+    (dQ, Qf) samples against tests/golden/model_goldens.json, bit for bit.  The kernels are compared with the oracle on the GPU;
+    this pins the oracle, so the shared arithmetic cannot drift by changing both sides together."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_model_goldens", os.path.join(here, "make_model_goldens.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = json.load(open(os.path.join(here, "model_goldens.json")))
+    seen = 0
+    for case in gen.cases():
+        name, smp = gen.evaluate(case)
+        w = np.array([float.fromhex(h) for h in want[name]["hex"]]).reshape(want[name]["shape"])
+        assert smp.shape == w.shape and np.array_equal(smp, w), name
+        assert np.isfinite(smp).all() and np.abs(smp[:, :, 1, :]).min() > 0
+        seen += 1
+    assert seen == len(want) == 8
