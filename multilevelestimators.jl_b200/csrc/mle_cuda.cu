@@ -20,11 +20,7 @@ using namespace mle;
 template <int MODE> static constexpr auto points_k = points_kernel<POINTS_THREADS, MODE>;
 template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_EXPSUM, 2, MODE>;
 template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
-template <int MODE> static constexpr auto lognormal1d_k64 = lognormal1d_kernel<MODE, 64>;
-template <int MODE> static constexpr auto lognormal1d_k32 = lognormal1d_kernel<MODE, 32>;
-#ifdef MLE_WITH_WS
-template <int MODE> static constexpr auto lognormal1d_ws = lognormal1d_ws_kernel<MODE>;
-#endif
+template <int MODE> static constexpr auto lognormal1d_k = lognormal1d_kernel<MODE>;
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 template <int MODE> static constexpr auto lognormal2d_r4 = lognormal2d_rows_kernel<MODE, 4>;
@@ -96,12 +92,19 @@ struct mle_ctx_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     uint64_t launches = 0;
-    int ln_bt_override = 0;  // MLE_LN_BT=32|64 in the environment: tuning knob for the lognormal1d tile width
-    int ln_ws = 0;           // MLE_LN_WS=1: warp-specialised lognormal1d kernel
     int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
     // reusable device / pinned scratch
-    Moment *d_partials = nullptr;
-    size_t partials_cap = 0;  // in Moments
+    Partial *d_partials = nullptr;
+    size_t partials_cap = 0;  // in Partials
+    unsigned *d_tickets = nullptr;  // [R + 1] per-shift CTA tickets + finished-shift count of cta_finalize; zero between launches
+    size_t tickets_cap = 0;
+    // results that the host reads without synchronising the stream: a mapped pinned moment table and a mapped flag the last
+    // CTA of a launch sets to the call's sequence number (mle_sample_batch / mle_update_samples poll it)
+    double *h_res = nullptr, *d_res = nullptr;
+    size_t res_cap = 0;  // doubles
+    unsigned *h_flag = nullptr, *d_flag = nullptr;
+    unsigned seq = 0;
+    int zero_copy = 1;  // MLE_NO_ZEROCOPY=1: classic device moments + cudaMemcpyAsync + stream synchronisation
     double *d_shifts = nullptr;
     size_t shifts_cap = 0;
     size_t shifts_staged = 0;  // doubles of h_pinned[0..] that mirror d_shifts (0: nothing valid)
@@ -113,6 +116,9 @@ struct mle_ctx_s {
     size_t moments_cap = 0;
     double *d_batch = nullptr;  // mle_update_samples: shifts and moment tables of all entries
     size_t batch_cap = 0;
+    size_t batch_staged = 0;    // doubles of h_pinned[0..] that mirror the shifts in d_batch (0: nothing valid)
+    double *d_samples = nullptr;  // raw samples of a mle_sample_batch call that asked for them
+    size_t samples_cap = 0;
     double *h_pinned = nullptr;
     size_t pinned_cap = 0;  // doubles
 };
@@ -206,6 +212,7 @@ static int ensure_pinned(mle_ctx ctx, size_t need) {
     if (ctx->h_pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_pinned); }  // copies from it may be in flight
     ctx->h_pinned = nullptr; ctx->pinned_cap = 0;
     ctx->shifts_staged = 0;
+    ctx->batch_staged = 0;
     size_t want = need + need / 2 + 64;
     cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_pinned), want * sizeof(double));
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMallocHost failed"); }
@@ -260,11 +267,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(points_k, 200 * 1024);
     MLE_SET_SMEM(expsum_k, 200 * 1024);
     MLE_SET_SMEM(problem18_k, 200 * 1024);
-    MLE_SET_SMEM(lognormal1d_k64, 220 * 1024);
-    MLE_SET_SMEM(lognormal1d_k32, 220 * 1024);
-#ifdef MLE_WITH_WS
-    MLE_SET_SMEM(lognormal1d_ws, 220 * 1024);
-#endif
+    MLE_SET_SMEM(lognormal1d_k, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r4, 220 * 1024);
@@ -275,9 +278,19 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(lognormal2d_r128, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
-    if (const char *e = getenv("MLE_LN_BT")) { int v = atoi(e); if (v == 32 || v == 64) ctx->ln_bt_override = v; }
-    if (const char *e = getenv("MLE_LN_WS")) ctx->ln_ws = atoi(e) != 0;
     if (const char *e = getenv("MLE_2D_WINDOW_SMEM")) ctx->ln2d_old = atoi(e) != 0;
+    if (const char *e = getenv("MLE_NO_ZEROCOPY")) ctx->zero_copy = atoi(e) == 0;
+    // the mapped completion flag (zero-copy result path); without it the library falls back to copy + synchronise
+    if (ctx->zero_copy) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_flag), 64, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->d_flag), ctx->h_flag, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+            ctx->h_flag = nullptr; ctx->d_flag = nullptr; ctx->zero_copy = 0;
+        } else {
+            *ctx->h_flag = 0;
+        }
+    }
     *out = ctx;
     return MLE_OK;
 }
@@ -288,10 +301,14 @@ extern "C" int mle_destroy(mle_ctx ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_partials) cudaFree(ctx->d_partials);
+    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->d_shifts) cudaFree(ctx->d_shifts);
     if (ctx->d_zero) cudaFree(ctx->d_zero);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_batch) cudaFree(ctx->d_batch);
+    if (ctx->d_samples) cudaFree(ctx->d_samples);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0);
@@ -558,15 +575,17 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
     if (rows != N + 1) return fail(ctx, MLE_ERR_ARG, "set_basis: rows must be n0*2^level + 1 (nodes of the level's grid)");
     if (cols < 1 || cols > 352) return fail(ctx, MLE_ERR_ARG, "set_basis: 1 <= KL terms <= 352 (the xi tile must fit in shared memory)");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    // Row r' = 2*i' + side: side 0 -> node i', side 1 -> mirrored node N - i' (i' = 0..N/2), so both elimination sweeps
-    // read rows in ascending order.  Stored in DMMA A-fragment order: [row tile rt][k step ks][lane] holds
-    // Phi'[8 rt + lane/4][4 ks + lane%4], zero padded in rows (to whole chunks) and in k (to a multiple of 4).
+    // Row r' = 2*i' + side, i' < N/2: side 0 -> node i', side 1 -> mirrored node N - i', so both sweeps read rows in ascending
+    // order.  Stored in DMMA A-fragment order: [row tile rt][k step ks][lane] holds Phi'[8 rt + lane/4][4 ks + lane%4], zero
+    // padded in rows (to whole 8-row tiles) and in k (to a multiple of 4); the row of the MID node N/2 follows as a plain
+    // vector of mpad doubles (the kernel evaluates it as one fused-multiply-add chain per sample).
     const int Mh = (int)(N / 2);
-    const int nrows = 2 * (Mh + 1);
-    const int nchunks = (nrows + LN_RC - 1) / LN_RC;
+    const int nrows = 2 * Mh;
+    const int ntiles = (nrows + 7) / 8;
+    const int nchunks = (ntiles + 3) / 4;
     const int mpad = (cols + 3) & ~3;
-    const int nks = mpad / 4, ntiles = nchunks * (LN_RC / 8);
-    std::vector<double> packed((size_t)ntiles * nks * 32, 0.0);
+    const int nks = mpad / 4;
+    std::vector<double> packed((size_t)ntiles * nks * 32 + (size_t)mpad, 0.0);
     for (int rp = 0; rp < nrows; ++rp) {
         const int ip = rp >> 1, side = rp & 1;
         const long long node = side ? N - ip : ip;
@@ -574,6 +593,7 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
         for (int k = 0; k < cols; ++k)
             packed[((size_t)rt * nks + k / 4) * 32 + lr * 4 + (k % 4)] = phi[(size_t)node * cols + k];
     }
+    for (int k = 0; k < cols; ++k) packed[(size_t)ntiles * nks * 32 + k] = phi[(size_t)Mh * cols + k];
     double *d = nullptr;
     if (MLE_MALLOC(&d, packed.size() * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(basis)"); }
     cudaError_t e = cudaMemcpyAsync(d, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
@@ -585,6 +605,7 @@ extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows
     M->basis_cols[level] = cols;
     M->basis_mpad[level] = mpad;
     M->basis_nchunks[level] = nchunks;
+    M->frag_tiles[level] = ntiles;
     return MLE_OK;
 }
 
@@ -642,6 +663,7 @@ static int make_gen_args(mle_ctx ctx, mle_lattice lat, mle_dists dists, const do
     g->n = n;
     g->s = lat ? lat->s : 0;
     g->m = m;
+    g->mkey = m;
     g->R = R;
     g->mode = (dists ? dists->mode : GEN_RAW) | (lat ? 0 : GEN_MC);
     return MLE_OK;
@@ -663,6 +685,7 @@ static int upload_shifts(mle_ctx ctx, mle_lattice lat, const double *shifts, int
     if (ctx->shifts_staged != cnt || memcmp(ctx->h_pinned, shifts, cnt * sizeof(double)) != 0) {
         memcpy(ctx->h_pinned, shifts, cnt * sizeof(double));
         ctx->shifts_staged = 0;
+        ctx->batch_staged = 0;
         CU_TRY(ctx, cudaMemcpyAsync(ctx->d_shifts, ctx->h_pinned, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->shifts_staged = cnt;
     }
@@ -732,10 +755,11 @@ static long long grid_x_for(mle_ctx ctx, long long tiles_per_shift, int R, int c
     return gx;
 }
 
-extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
-                                    const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
-                                    double *moments_dev, double *samples_dev) {
-    MLE_API_SCOPE;
+// one launch = one parallel_sample! call; `flag_dev` (optional, mapped host memory) receives `seq` once the moments of every
+// shift have been written (cta_finalize)
+static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                        const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
+                        double *moments_dev, double *samples_dev, unsigned *flag_dev, unsigned seq) {
     if (!ctx || !M || !index || !moments_dev) return MLE_ERR_ARG;
     if (d != M->ndims) return fail(ctx, MLE_ERR_ARG, "index dimension does not match the model");
     for (int t = 0; t < d; ++t)
@@ -751,6 +775,15 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const int V = 2 * M->nqoi;
     long long gx = 0;
+    if (R > 65535) return fail(ctx, MLE_ERR_ARG, "at most 65535 shifts per call");
+    if (ctx->tickets_cap < (size_t)R + 1) {  // ticket counters of cta_finalize: zeroed once, every launch leaves them at zero
+        const size_t before = ctx->tickets_cap;
+        rc = ensure_dev(ctx, &ctx->d_tickets, &ctx->tickets_cap, (size_t)R + 1);
+        if (rc) return rc;
+        (void)before;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_tickets, 0, ctx->tickets_cap * sizeof(unsigned), ctx->stream));
+    }
+    FinArgs fa{nullptr, ctx->d_tickets, moments_dev, flag_dev, seq};
     if (M->kind == MODEL_EXPSUM || M->kind == MODEL_PROBLEM18) {
         const long long tps = (long long)((n + SIMPLE_THREADS - 1) / SIMPLE_THREADS);
         SimpleModelArgs ma{};
@@ -760,13 +793,14 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         ma.idx0 = index[0];
         ma.idx1 = d > 1 ? index[1] : 0;
         const int W = SIMPLE_THREADS / 32;
-        const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_MC * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Moment) +
+        const size_t smem = (size_t)SIMPLE_THREADS * SIMPLE_MC * 8 + (size_t)3 * V * W * 8 + (size_t)V * sizeof(Partial) +
                             (size_t)SIMPLE_THREADS * SIMPLE_MC * 2 + ((W + 3) & ~3) * 4 + 2 * SIMPLE_MC * 16;
         const int occ = M->kind == MODEL_EXPSUM ? MLE_OCC_BY_MODE(g.mode, expsum_k, SIMPLE_THREADS, smem)
                                                 : MLE_OCC_BY_MODE(g.mode, problem18_k, SIMPLE_THREADS, smem);
         gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
         rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
         if (rc) return rc;
+        fa.partials = ctx->d_partials;
         dim3 grid((unsigned)gx, (unsigned)R);
         if (M->kind == MODEL_EXPSUM) {
             if (index[0] > 30) return fail(ctx, MLE_ERR_ARG, "expsum: level too large");
@@ -781,70 +815,44 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
             }
             ma.ml = (int)ml;
             ma.mlc = (int)mlc;
-            MLE_LAUNCH_BY_MODE(g.mode, expsum_k, grid, SIMPLE_THREADS, smem, ctx->stream, g, ma, ctx->d_partials, samples_dev, tps);
+            MLE_LAUNCH_BY_MODE(g.mode, expsum_k, grid, SIMPLE_THREADS, smem, ctx->stream, g, ma, fa, samples_dev, tps);
         } else {
             if (m < M->ndims) return fail(ctx, MLE_ERR_ARG, "problem18: needs one uncertainty per index dimension");
-            MLE_LAUNCH_BY_MODE(g.mode, problem18_k, grid, SIMPLE_THREADS, smem, ctx->stream, g, ma, ctx->d_partials, samples_dev, tps);
+            MLE_LAUNCH_BY_MODE(g.mode, problem18_k, grid, SIMPLE_THREADS, smem, ctx->stream, g, ma, fa, samples_dev, tps);
         }
     } else if (M->kind == MODEL_LOGNORMAL1D) {
         const int level = index[0];
         if (level >= MLE_MAX_LEVELS || !M->d_basis[level]) return fail(ctx, MLE_ERR_STATE, "lognormal1d: no KL basis set for this level (mle_model_set_basis)");
-        if (m != M->basis_cols[level]) return fail(ctx, MLE_ERR_ARG, "lognormal1d: nb_of_uncertainties must equal the number of KL terms of the level's basis");
+        // the sample function reads the leading KL terms and ignores surplus coordinates, like a reference closure would
+        if (m < M->basis_cols[level]) return fail(ctx, MLE_ERR_ARG, "lognormal1d: nb_of_uncertainties is smaller than the number of KL terms of the level's basis");
+        g.m = M->basis_cols[level];
         Lognormal1dArgs la{};
         la.basis = M->d_basis[level];
         la.N = M->n0 << level;
         la.mpad = M->basis_mpad[level];
         la.nchunks = M->basis_nchunks[level];
-        la.nrows = la.N + 2;
-#ifdef MLE_PHASE_TIMING
-        if (const char *e = getenv("MLE_SKIP")) la.skip = atoi(e);  // debug builds only: phase-skipping timing experiments
-#endif
+        la.ntiles = M->frag_tiles[level];
+        la.mid = la.basis + (size_t)la.ntiles * (la.mpad / 4) * 32;
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
-        // Schedule: the phase-synchronous kernel with 32-sample tiles (measured fastest on the C2 step); MLE_LN_BT=64
-        // selects 64-sample tiles and MLE_LN_WS=1 the warp-specialised kernel (kept for A/B measurements).
-#ifdef MLE_WITH_WS
-        const int bt = ctx->ln_ws ? LNW_BT : (ctx->ln_bt_override ? ctx->ln_bt_override : 32);
-#else
-        const int bt = ctx->ln_bt_override ? ctx->ln_bt_override : 32;
-#endif
-        const long long tps = (long long)((n + bt - 1) / bt);
-#ifdef MLE_WITH_WS
-        if (ctx->ln_ws) {
-            const int Gd = LNW_THREADS / LNW_BT;
-            const int qdims = m <= 32 * Gd ? ((m + Gd - 1) / Gd) * Gd : 64 * Gd;
-            const size_t smem = (size_t)la.mpad * LNW_LDX * 8 + (size_t)2 * LN_RC * LNW_LDF * 8 + (size_t)2 * LNW_BT * sizeof(Moment) +
-                                8 * 4 + (size_t)LNW_BT * qdims * 2 + 16;
-            gx = grid_x_for(ctx, tps, R, MLE_OCC_BY_MODE(g.mode, lognormal1d_ws, LNW_THREADS, smem));
-            rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
-            if (rc) return rc;
-            dim3 grid((unsigned)gx, (unsigned)R);
-            MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_ws, grid, LNW_THREADS, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
-        } else
-#endif
-        {
-            const int threads = ln_threads(bt), W = threads / 32;
-            const int qdims = m < 256 ? ((m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims
-            const size_t fbytes = (size_t)LN_RC * ln_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
-            const size_t smem = (size_t)la.mpad * ln_ldx(bt) * 8 + fbytes + (size_t)3 * bt * sizeof(SweepState) +
-                                (size_t)2 * bt * sizeof(Moment) + ((W + 3) & ~3) * 4 + (lat ? (size_t)m * 16 : 0) +
-                                (qbytes <= fbytes ? 0 : qbytes) + 16;
-            const int occ = bt == 64 ? MLE_OCC_BY_MODE(g.mode, lognormal1d_k64, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal1d_k32, threads, smem);
-            gx = grid_x_for(ctx, tps, R, occ);
-            gx = churn_grid_x(gx, tps);
-            rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
-            if (rc) return rc;
-            dim3 grid((unsigned)gx, (unsigned)R);
-            if (bt == 64) MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k64, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
-            else MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k32, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev, tps);
-        }
+        // warp-autonomous kernel: CTA tiles of LN_BT samples, two warps of 16 samples each (mle_kernel_ln1d.cuh)
+        const long long tps = (long long)((n + LN_BT - 1) / LN_BT);
+        const size_t smem = ln1d_smem_bytes(la.mpad, lat ? g.m : 0);
+        const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_k, LN_THREADS, smem);
+        gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
+        rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+        if (rc) return rc;
+        fa.partials = ctx->d_partials;
+        dim3 grid((unsigned)gx, (unsigned)R);
+        MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k, grid, LN_THREADS, smem, ctx->stream, g, la, fa, samples_dev, tps);
     } else if (M->kind == MODEL_LOGNORMAL2D) {
         const int lx = index[0], ly = d == 2 ? index[1] : index[0];
         if (lx > 12 || ly > 12) return fail(ctx, MLE_ERR_ARG, "lognormal2d: index out of range");
         const int key = d == 2 ? lx + 16 * ly : lx;
         if (key >= MLE_MAX_LEVELS || !M->d_basis[key]) return fail(ctx, MLE_ERR_STATE, "lognormal2d: no KL basis set for this index (mle_model_set_basis)");
-        if (m != M->basis_cols[key]) return fail(ctx, MLE_ERR_ARG, "lognormal2d: nb_of_uncertainties must equal the number of KL terms of the index's basis");
+        if (m < M->basis_cols[key]) return fail(ctx, MLE_ERR_ARG, "lognormal2d: nb_of_uncertainties is smaller than the number of KL terms of the index's basis");
+        g.m = M->basis_cols[key];
         // register-window kernel (power-of-two Nx <= 64) when its shared memory fits; else the shared-memory-window kernel
         bool rows_done = false;
         if (M->d_frag[key] && !ctx->ln2d_old) {
@@ -858,7 +866,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                 ra.mpad = M->frag_mpad[key]; ra.ntiles = M->frag_tiles[key];                                           \
                 const size_t fbytes = (size_t)ra.ntiles * 8 * Cfg::LDF * 8, qbytes = (size_t)32 * Cfg::THREADS * 2;    \
                 const size_t fixed = (size_t)ra.mpad * Cfg::LDX * 8 + (size_t)Cfg::CS * rows_sh_doubles(WW) * 8 +     \
-                                     (size_t)2 * Cfg::S * 8 + (size_t)2 * Cfg::S * sizeof(Moment) +                    \
+                                     (size_t)2 * Cfg::S * 8 + (size_t)2 * Cfg::S * sizeof(Partial) +                    \
                                      (((Cfg::THREADS / 32) + 3) & ~3) * 4 + 128;                                       \
                 ra.use_scratch = (fixed + fbytes + (qbytes > fbytes ? qbytes : 0) > 200 * 1024) ? 1 : 0;               \
                 const size_t smem = fixed + (ra.use_scratch ? qbytes : fbytes + (qbytes > fbytes ? qbytes : 0));       \
@@ -868,6 +876,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                 gx = grid_x_for(ctx, tps, R, occ);                                                                     \
                 rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);                \
                 if (rc) return rc;                                                                                     \
+                fa.partials = ctx->d_partials;                                                                         \
                 {                                                                                                      \
                     const size_t park = (size_t)gx * R * ROWS_PARK * Cfg::THREADS;                                            \
                     rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, park + (ra.use_scratch ? (size_t)gx * R * (fbytes / 8) : 0)); \
@@ -876,7 +885,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                     ra.scratch = ctx->d_scratch + park;                                                                \
                 }                                                                                                      \
                 dim3 grid((unsigned)gx, (unsigned)R);                                                                  \
-                MLE_LAUNCH_BY_MODE(g.mode, KK, grid, Cfg::THREADS, smem, ctx->stream, g, ra, ctx->d_partials, samples_dev, tps); \
+                MLE_LAUNCH_BY_MODE(g.mode, KK, grid, Cfg::THREADS, smem, ctx->stream, g, ra, fa, samples_dev, tps); \
                 rows_rc = 0;                                                                                           \
             } break;
             switch (Nx) {
@@ -900,7 +909,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         la.ndims = d;
         la.lx = lx;
         la.ly = ly;
-        const int nn = la.Nx - 1, W = la.Nx, nodes = (la.Nx + 1) * (la.Ny + 1), mpad = (m + 3) & ~3;
+        const int nn = la.Nx - 1, W = la.Nx, nodes = (la.Nx + 1) * (la.Ny + 1), mpad = (g.m + 3) & ~3;
         la.scratch_per_group = 2ll * nn * nn + nodes;
         // a warp per sample while window, centre blocks and field of 4 samples fit in shared memory; else a CTA per sample
         // with the centre blocks and the field in (L2-resident) global scratch
@@ -909,32 +918,70 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
         const int threads = big ? 256 : 128, groups = big ? 1 : 4;
         la.use_scratch = big ? 1 : 0;
         const size_t per_group = (size_t)mpad + (size_t)W * W + 5 * (size_t)W + (big ? 0 : (size_t)la.scratch_per_group);
-        const size_t smem = per_group * groups * sizeof(double) + 2 * groups * sizeof(Moment) + 16;
+        const size_t smem = per_group * groups * sizeof(double) + 2 * groups * sizeof(Partial) + 16;
         if (smem > 220 * 1024) return fail(ctx, MLE_ERR_ARG, "lognormal2d: KL terms x grid do not fit in shared memory");
         const long long tps = (long long)((n + groups - 1) / groups);
         const int occ = big ? MLE_OCC_BY_MODE(g.mode, lognormal2d_c, threads, smem) : MLE_OCC_BY_MODE(g.mode, lognormal2d_w, threads, smem);
         gx = grid_x_for(ctx, tps, R, occ);
         rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
         if (rc) return rc;
+        fa.partials = ctx->d_partials;
         if (big) {
             rc = ensure_dev(ctx, &ctx->d_scratch, &ctx->scratch_cap, (size_t)gx * R * groups * (size_t)la.scratch_per_group);
             if (rc) return rc;
             la.scratch = ctx->d_scratch;
         }
         dim3 grid((unsigned)gx, (unsigned)R);
-        if (big) MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_c, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev);
-        else MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_w, grid, threads, smem, ctx->stream, g, la, ctx->d_partials, samples_dev);
+        if (big) MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_c, grid, threads, smem, ctx->stream, g, la, fa, samples_dev);
+        else MLE_LAUNCH_BY_MODE(g.mode, lognormal2d_w, grid, threads, smem, ctx->stream, g, la, fa, samples_dev);
         }
     } else {
         return fail(ctx, MLE_ERR_ARG, "unknown model kind");
     }
     ctx->launches += 1;
     CU_TRY(ctx, cudaGetLastError());
-    const int RV = R * V;
-    const int warps_per_block = 4;
-    finalize_kernel<<<(RV + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->stream>>>(ctx->d_partials, (int)gx, RV, moments_dev);
-    ctx->launches += 1;
-    CU_TRY(ctx, cudaGetLastError());
+    return MLE_OK;
+}
+
+extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                                    const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
+                                    double *moments_dev, double *samples_dev) {
+    MLE_API_SCOPE;
+    return launch_batch(ctx, M, lat, dists, index, d, shifts_dev, R, k0, n, m, mc_seed, moments_dev, samples_dev, nullptr, 0);
+}
+
+// Wait for the launch that carries sequence number `seq` to raise the mapped completion flag.  The host spins on its own
+// memory (the GPU writes the moment table and then the flag over PCIe, __threadfence_system in between), which saves the
+// stream synchronisation and the device-to-host copy of the classic path: 10-15 us per call, i.e. most of a small call.  The
+// stream is queried now and then so that a failed launch is reported instead of spinning forever.
+static int wait_flag(mle_ctx ctx, unsigned seq, const char *who) {
+    volatile unsigned *flag = ctx->h_flag;
+    for (unsigned long long spins = 0;; ++spins) {
+        if (*flag == seq) { __sync_synchronize(); return MLE_OK; }
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) {  // everything has run: the flag must be there now
+                if (*flag == seq) { __sync_synchronize(); return MLE_OK; }
+                return fail(ctx, MLE_ERR_CUDA, std::string(who) + ": the kernel finished without raising the completion flag");
+            }
+            if (q != cudaErrorNotReady) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(q)); }
+        }
+    }
+}
+
+static int ensure_res(mle_ctx ctx, size_t need) {
+    if (ctx->res_cap >= need) return MLE_OK;
+    if (ctx->h_res) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_res); }
+    ctx->h_res = nullptr; ctx->d_res = nullptr; ctx->res_cap = 0;
+    const size_t want = need + need / 2 + 512;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_res), want * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->d_res), ctx->h_res, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (ctx->h_res) cudaFreeHost(ctx->h_res);
+        ctx->h_res = nullptr; ctx->d_res = nullptr;
+        return fail(ctx, MLE_ERR_NOMEM, "cudaHostAlloc(mapped result table) failed");
+    }
+    ctx->res_cap = want;
     return MLE_OK;
 }
 
@@ -949,42 +996,53 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     int rc = upload_shifts(ctx, lat, shifts, R, &sh_dev);
     if (rc) return rc;
     const size_t nm = (size_t)R * 2 * (size_t)M->nqoi * 3;
-    rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, nm);
-    if (rc) return rc;
-    const size_t mom_off = (shifts && lat) ? (size_t)R * (size_t)lat->s : 0;  // staging for the moments: behind the shifts image
-    if (mom_off + nm > ctx->pinned_cap) {
-        ctx->shifts_staged = 0;  // growing the staging area discards the shifts image (re-uploaded by the next call)
-        rc = ensure_pinned(ctx, mom_off + nm + 4096);
-        if (rc) return rc;
-        if (mom_off) { sh_dev = nullptr; rc = upload_shifts(ctx, lat, shifts, R, &sh_dev); if (rc) return rc; }
-    }
-    double *d_samples = nullptr;
     const size_t ns = samples ? (size_t)R * 2 * (size_t)M->nqoi * n : 0;
-    if (samples && ns) {
-        if (MLE_MALLOC(&d_samples, ns * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_NOMEM, "cudaMalloc(samples)"); }
+    // zero-copy: the last CTA writes the moment table straight into mapped host memory and raises a flag the host polls
+    const bool zc = ctx->zero_copy && !ns;
+    if (zc) rc = ensure_res(ctx, nm);
+    else rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, nm);
+    if (rc) return rc;
+    if (!zc && nm + 64 > ctx->pinned_cap) {  // staging for the moments (classic path)
+        ctx->shifts_staged = 0;
+        rc = ensure_pinned(ctx, nm + (shifts && lat ? (size_t)R * (size_t)lat->s : 0) + 4096);
+        if (rc) return rc;
+        if (shifts && lat) { sh_dev = nullptr; rc = upload_shifts(ctx, lat, shifts, R, &sh_dev); if (rc) return rc; }
+    }
+    if (ns) {  // raw samples: device buffer kept across calls
+        rc = ensure_dev(ctx, &ctx->d_samples, &ctx->samples_cap, ns);
+        if (rc) return rc;
     }
     if (gpu_seconds) cudaEventRecord(ctx->ev0, ctx->stream);  // timing is optional: two event records cost ~4 us per call
-    rc = mle_sample_batch_dev(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, ctx->d_moments, d_samples);
+    const unsigned seq = ++ctx->seq ? ctx->seq : ++ctx->seq;  // never 0 (the flag's initial value)
+    rc = launch_batch(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, zc ? ctx->d_res : ctx->d_moments,
+                      ns ? ctx->d_samples : nullptr, zc ? ctx->d_flag : nullptr, seq);
     if (gpu_seconds) cudaEventRecord(ctx->ev1, ctx->stream);
-    if (rc == MLE_OK) {
-        // the moment table comes back through the pinned staging area (behind the shifts image): a pageable destination
-        // would make the copy synchronous inside the driver
-        double *stage = (ctx->h_pinned && mom_off + nm <= ctx->pinned_cap) ? ctx->h_pinned + mom_off : nullptr;
-        cudaError_t e = cudaMemcpyAsync(stage ? stage : moments, ctx->d_moments, nm * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && d_samples) e = cudaMemcpyAsync(samples, d_samples, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_batch: ") + cudaGetErrorString(e)); }
-        else if (stage) memcpy(moments, stage, nm * sizeof(double));
-        if (rc == MLE_OK && gpu_seconds) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-            *gpu_seconds = (double)ms * 1e-3;
+    if (rc != MLE_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    if (zc) {
+        rc = wait_flag(ctx, seq, "mle_sample_batch");
+        if (rc) return rc;
+        memcpy(moments, ctx->h_res, nm * sizeof(double));
+        if (gpu_seconds) {
+            cudaError_t e = cudaEventSynchronize(ctx->ev1);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_batch: ") + cudaGetErrorString(e)); }
         }
     } else {
-        cudaStreamSynchronize(ctx->stream);
+        // the moment table comes back through the pinned staging area (behind the shifts image): a pageable destination
+        // would make the copy synchronous inside the driver
+        const size_t mom_off = (shifts && lat) ? (size_t)R * (size_t)lat->s : 0;
+        double *stage = (ctx->h_pinned && mom_off + nm <= ctx->pinned_cap) ? ctx->h_pinned + mom_off : nullptr;
+        cudaError_t e = cudaMemcpyAsync(stage ? stage : moments, ctx->d_moments, nm * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && ns) e = cudaMemcpyAsync(samples, ctx->d_samples, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_batch: ") + cudaGetErrorString(e)); }
+        if (stage) memcpy(moments, stage, nm * sizeof(double));
     }
-    if (d_samples) cudaFree(d_samples);
-    return rc;
+    if (gpu_seconds) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        *gpu_seconds = (double)ms * 1e-3;
+    }
+    return MLE_OK;
 }
 
 // `update_samples`: several sample! requests, one synchronisation (include/mle_cuda.h)
@@ -995,7 +1053,7 @@ extern "C" int mle_update_samples(mle_ctx ctx, mle_model M, mle_lattice lat, mle
     if (!ctx || !M || count < 0 || (count && (!indices || !R || !k0 || !n || !m || !moments))) return MLE_ERR_ARG;
     if (count == 0) return MLE_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    // one arena for all shifts and all moment tables (device and pinned host), laid out entry by entry
+    // one arena for all shifts (device + pinned host) and one for all moment tables (mapped host when zero-copy)
     size_t sh_total = 0, mom_total = 0;
     for (int e = 0; e < count; ++e) {
         if (R[e] < 1 || !moments[e]) return fail(ctx, MLE_ERR_ARG, "update_samples: every entry needs R >= 1 and a moment table");
@@ -1003,35 +1061,63 @@ extern "C" int mle_update_samples(mle_ctx ctx, mle_model M, mle_lattice lat, mle
         if (lat && shifts && shifts[e]) sh_total += (size_t)R[e] * (size_t)lat->s;
         mom_total += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
     }
-    int rc = ensure_dev(ctx, &ctx->d_batch, &ctx->batch_cap, sh_total + mom_total);
+    const bool zc = ctx->zero_copy != 0;
+    const double *batch_before = ctx->d_batch;
+    int rc = ensure_dev(ctx, &ctx->d_batch, &ctx->batch_cap, sh_total + (zc ? 0 : mom_total));
     if (rc) return rc;
-    rc = ensure_pinned(ctx, sh_total + mom_total + 4096);
+    if (ctx->d_batch != batch_before) ctx->batch_staged = 0;
+    rc = ensure_pinned(ctx, sh_total + (zc ? 0 : mom_total) + 4096);
     if (rc) return rc;
-    ctx->shifts_staged = 0;  // the pinned area is reused as this call's staging arena
+    if (zc) { rc = ensure_res(ctx, mom_total); if (rc) return rc; }
+    // unchanged shifts are not uploaded again (the adaptive loop calls with the same shifts of every index for a whole run)
+    bool same = ctx->batch_staged == sh_total && sh_total > 0;
     size_t off = 0;
-    for (int e = 0; e < count; ++e)
+    for (int e = 0; e < count && same; ++e)
         if (lat && shifts && shifts[e]) {
             const size_t cnt = (size_t)R[e] * (size_t)lat->s;
-            memcpy(ctx->h_pinned + off, shifts[e], cnt * sizeof(double));
+            same = memcmp(ctx->h_pinned + off, shifts[e], cnt * sizeof(double)) == 0;
             off += cnt;
         }
-    if (sh_total) CU_TRY(ctx, cudaMemcpyAsync(ctx->d_batch, ctx->h_pinned, sh_total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    size_t sh_off = 0, mom_off = sh_total;
+    ctx->shifts_staged = 0;  // the pinned area is this entry point's staging arena now
+    if (!same) {
+        ctx->batch_staged = 0;
+        off = 0;
+        for (int e = 0; e < count; ++e)
+            if (lat && shifts && shifts[e]) {
+                const size_t cnt = (size_t)R[e] * (size_t)lat->s;
+                memcpy(ctx->h_pinned + off, shifts[e], cnt * sizeof(double));
+                off += cnt;
+            }
+        if (sh_total) CU_TRY(ctx, cudaMemcpyAsync(ctx->d_batch, ctx->h_pinned, sh_total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->batch_staged = sh_total;
+    }
+    double *mom_base = zc ? ctx->d_res : ctx->d_batch + sh_total;
+    const unsigned seq = ++ctx->seq ? ctx->seq : ++ctx->seq;
+    size_t sh_off = 0, mom_off = 0;
     for (int e = 0; e < count && rc == MLE_OK; ++e) {
         const double *sh_dev = nullptr;
         if (lat && shifts && shifts[e]) { sh_dev = ctx->d_batch + sh_off; sh_off += (size_t)R[e] * (size_t)lat->s; }
-        rc = mle_sample_batch_dev(ctx, M, lat, dists, indices + (size_t)e * d, d, sh_dev, R[e], k0[e], n[e], m[e], mc_seed,
-                                  ctx->d_batch + mom_off, nullptr);
+        const bool last = e == count - 1;
+        rc = launch_batch(ctx, M, lat, dists, indices + (size_t)e * d, d, sh_dev, R[e], k0[e], n[e], m[e], mc_seed, mom_base + mom_off,
+                          nullptr, (zc && last) ? ctx->d_flag : nullptr, seq);
         mom_off += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
     }
     if (rc != MLE_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
-    cudaError_t err = cudaMemcpyAsync(ctx->h_pinned + sh_total, ctx->d_batch + sh_total, mom_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
-    if (err != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_update_samples: ") + cudaGetErrorString(err)); }
-    mom_off = sh_total;
+    const double *host_mom;
+    if (zc) {
+        rc = wait_flag(ctx, seq, "mle_update_samples");
+        if (rc) return rc;
+        host_mom = ctx->h_res;
+    } else {
+        cudaError_t err = cudaMemcpyAsync(ctx->h_pinned + sh_total, ctx->d_batch + sh_total, mom_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+        if (err != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_update_samples: ") + cudaGetErrorString(err)); }
+        host_mom = ctx->h_pinned + sh_total;
+    }
+    mom_off = 0;
     for (int e = 0; e < count; ++e) {
         const size_t nm = (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
-        memcpy(moments[e], ctx->h_pinned + mom_off, nm * sizeof(double));
+        memcpy(moments[e], host_mom + mom_off, nm * sizeof(double));
         mom_off += nm;
     }
     return MLE_OK;

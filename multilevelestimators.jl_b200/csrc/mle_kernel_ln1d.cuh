@@ -1,0 +1,247 @@
+// mle_kernel_ln1d.cuh -- the headline kernel: 1-D lognormal diffusion, fully fused (sm_100a).
+//
+// Model (defined in oracle/mle_oracle.c and DESIGN.md; structure of docs/src/example.md:106-128): -(a u')' = 1 on (0,1),
+// u(0) = u(1) = 0, N = n0 2^l cells, log a(x_i) = sum_k Phi_l[i][k] xi_k, interface coefficient = mean of the two node values,
+// QoI u(1/2) from the closed-form flux sums, coarse problem = even nodes of the fine field, dQ = Qf - Qc.
+//
+// Schedule: WARP-AUTONOMOUS.  A CTA is two warps that share nothing but the read-only {z_j, shift_j} table; each warp takes
+// 16 consecutive samples through the whole pipeline on its own and only ever executes __syncwarp():
+//   A. inputs: gen_warp16 (mle_device.cuh): lattice point -> shift -> Phi^-1 with all three erfinv branches compacted,
+//      xi[k][16] in shared memory (XOR-swizzled, no padding).
+//   B. KL contraction on the FP64 tensor instruction, rows in chunks of 32 (16 half-nodes x 2 sides): the warp owns a
+//      4 x 2 block of 8x8 tiles (four row tiles x two sample tiles: 6 fragment loads per 8 DMMA), A fragments from the
+//      fragment-ordered basis in L1/L2, B fragments from xi.  On B200 one mma.sync.m8n8k4.f64 is bit-identical to four
+//      fused multiply-adds in ascending k (tools/dmma_order_test.cu), so the field equals the oracle's sequential-FMA field.
+//      Row r' = 2 i' + side (i' < N/2): side 0 = node i', side 1 = the mirrored node N - i', so the sweeps of both halves
+//      consume rows in ascending order.  The MID node is not a DMMA row (N is a multiple of 8, N + 1 is not): its value is
+//      one chain of m fused multiply-adds per sample on the FP64 pipe -- the same ascending-k chain.
+//   C. epilogue a = exp(G) -> F[32][16] (warp-private, swizzled), then the sweeps: lane (side, sample) adds one edge per
+//      half-node to the fine flux sums and one per even half-node to the coarse ones.
+//   D. the sides meet through a shuffle; per-lane pivoted statistics (mle_device.cuh), merged per CTA at the very end; the
+//      CTA that finishes last for its shift reduces the per-CTA partials (cta_finalize): one launch per sample! call.
+// Nothing per-sample is written to HBM unless the caller asks for the raw samples.
+#pragma once
+#include "mle_device.cuh"
+
+namespace mle {
+
+struct Lognormal1dArgs {
+    const double *basis;  // [row tile][k step][lane]: rows r' = 2 i' + side, i' < N/2, zero padded to whole 8-row tiles
+    const double *mid;    // [mpad] basis row of the mid node N/2 (zero padded in k)
+    int N;                // fine cells
+    int mpad;             // KL terms padded to a multiple of 4
+    int ntiles;           // 8-row tiles = ceil(N / 8)
+    int nchunks;          // chunks of 4 row tiles
+    int level;
+    double h2, h2c;       // 1/N^2, 1/(N/2)^2
+};
+
+constexpr int LN_WS = 16;                    // samples per warp
+constexpr int LN_WARPS = 2;                  // warps per CTA
+constexpr int LN_BT = LN_WS * LN_WARPS;      // samples per CTA tile
+constexpr int LN_THREADS = 32 * LN_WARPS;
+constexpr int LN_GEN_PIECE = 128;            // dims per generator call (64-bit class masks, queue inside F)
+constexpr int LN_F_DOUBLES = 32 * 16;        // per-warp field chunk
+
+__host__ __device__ constexpr size_t ln1d_smem_bytes(int mpad, int m_lattice) {
+    return (size_t)m_lattice * 16 + (size_t)mpad * 8 + (size_t)LN_WARPS * ((size_t)mpad * 16 + LN_F_DOUBLES) * 8 + 16;
+}
+
+struct SweepState {
+    double a_prev, A, D;  // last node value, sum of r = 1/kappa, sum of w*r over the edges seen so far
+};
+
+// one edge on arrival of node value `a` (node number ip on this side, counted from the boundary; M = N/2): the closed form of
+// the mid value (oracle/mle_oracle.c:tridiag_mid) needs only two running sums per side; the division is off the chain
+__device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, int M) {
+    if (ip > 0) {
+        const double kap = __dmul_rn(0.5, __dadd_rn(s.a_prev, a));
+        const double r = ddiv_normal(1.0, kap);  // == 1.0 / kap for every kappa in the normal range (a = exp(g), |g| < 700)
+        s.A = __dadd_rn(s.A, r);
+        s.D = __fma_rn((double)(M - ip) + 0.5, r, s.D);
+    }
+    s.a_prev = a;
+}
+
+// u(1/2) = h^2 (D_R A_L + D_L A_R) / (A_L + A_R)
+__device__ __forceinline__ double sweep_combine(double LA, double LD, double RA, double RD, double h2) {
+    const double num = __fma_rn(RD, LA, __dmul_rn(LD, RA));
+    return __dmul_rn(h2, __ddiv_rn(num, __dadd_rn(LA, RA)));
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// contraction + epilogue of one chunk: RT live row tiles (1..4), sample tile 1 only when `two`.  With MID the chain of fused
+// multiply-adds of the mid-node row (smid[k] * xi[k][b], ascending k: the lane's own sample b) rides along in the k loop, in
+// the shadow of the DMMAs.
+template <int RT, bool MID>
+__device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const double *__restrict__ B0,
+                                           const double *__restrict__ B1, int nks, bool two, double *__restrict__ F, int lane,
+                                           const double *__restrict__ smid, const double *__restrict__ xi, double &gm) {
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[RT][2][2];
+#pragma unroll
+    for (int t = 0; t < RT; ++t) { acc[t][0][0] = acc[t][0][1] = acc[t][1][0] = acc[t][1][1] = 0.0; }
+    const size_t ts = (size_t)nks * 32;
+    double a[RT], b0, b1;
+#pragma unroll
+    for (int t = 0; t < RT; ++t) a[t] = __ldg(A + t * ts);
+    b0 = B0[0]; b1 = B1[0];
+    const int b = lane & 15;
+    const double *x0 = xi + b, *x1 = xi + 16 + (b ^ 4), *x2 = xi + 32 + (b ^ 8), *x3 = xi + 48 + (b ^ 12);
+    double g0 = 0.0;
+#pragma unroll 2
+    for (int ks = 0; ks < nks; ++ks) {
+        const int kn = (ks + 1 < nks) ? ks + 1 : ks;  // next k step's fragments
+        double na[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) na[t] = __ldg(A + t * ts + kn * 32);
+        const double nb0 = B0[kn * 64], nb1 = B1[kn * 64];
+        double2 p01, p23;
+        double y0, y1, y2, y3;
+        if (MID) {
+            p01 = *reinterpret_cast<const double2 *>(smid + 4 * ks);
+            p23 = *reinterpret_cast<const double2 *>(smid + 4 * ks + 2);
+            y0 = x0[ks * 64]; y1 = x1[ks * 64]; y2 = x2[ks * 64]; y3 = x3[ks * 64];
+        }
+#pragma unroll
+        for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][0][0], acc[t][0][1], a[t], b0);
+        if (two) {
+#pragma unroll
+            for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][1][0], acc[t][1][1], a[t], b1);
+        }
+        if (MID) {
+            g0 = __fma_rn(p01.x, y0, g0);
+            g0 = __fma_rn(p01.y, y1, g0);
+            g0 = __fma_rn(p23.x, y2, g0);
+            g0 = __fma_rn(p23.y, y3, g0);
+        }
+#pragma unroll
+        for (int t = 0; t < RT; ++t) a[t] = na[t];
+        b0 = nb0; b1 = nb1;
+    }
+    if (MID) gm = g0;
+    // epilogue: a = exp(G) -> F[row][sample ^ 8*(row & 1)]; the lane holds row lr, samples 2 lk, 2 lk + 1 of each 8x8 tile
+    const int sw = (lr & 1) << 3;
+    double *f0 = F + lr * 16 + ((2 * lk) ^ sw), *f1 = F + lr * 16 + ((2 * lk) ^ sw ^ 8);
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
+        double2 v;
+        v.x = exp_det(acc[t][0][0]); v.y = exp_det(acc[t][0][1]);
+        *reinterpret_cast<double2 *>(f0 + t * 128) = v;
+        if (two) {
+            v.x = exp_det(acc[t][1][0]); v.y = exp_det(acc[t][1][1]);
+            *reinterpret_cast<double2 *>(f1 + t * 128) = v;
+        }
+    }
+}
+
+template <bool MID>
+__device__ __forceinline__ void ln1d_chunk_any(int live, const double *__restrict__ A, const double *__restrict__ B0,
+                                               const double *__restrict__ B1, int nks, bool two, double *__restrict__ F, int lane,
+                                               const double *__restrict__ smid, const double *__restrict__ xi, double &gm) {
+    if (live == 4) ln1d_chunk<4, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    else if (live == 2) ln1d_chunk<2, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    else if (live == 3) ln1d_chunk<3, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    else ln1d_chunk<1, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(LN_THREADS, 6) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la, FinArgs fa,
+                                                                    double *__restrict__ samples, long long tiles_per_shift) {
+    constexpr bool lattice = (MODE & GEN_MC) == 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int mpad = la.mpad, nks = mpad >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
+    double2 *zs = reinterpret_cast<double2 *>(smem_raw);                                  // [m] (lattice modes)
+    double *smid = reinterpret_cast<double *>(zs + (lattice ? g.m : 0));                  // [mpad] basis row of the mid node
+    double *wbase = smid + mpad + (size_t)warp * ((size_t)mpad * 16 + LN_F_DOUBLES);
+    double *xi = wbase;                                                                   // [mpad][16] swizzled
+    double *F = xi + (size_t)mpad * 16;                                                   // [32][16] swizzled
+    unsigned short *queue = reinterpret_cast<unsigned short *>(F);                        // generator queue (F is idle then)
+    if (lattice) stage_lattice_row<LN_THREADS>(zs, g, r);
+    for (int e = tid; e < mpad; e += LN_THREADS) smid[e] = __ldg(la.mid + e);
+    for (int e = lane; e < (mpad - g.m) * 16; e += 32) xi[(size_t)g.m * 16 + e] = 0.0;    // k padding rows
+    __syncthreads();
+
+    const int M = la.N >> 1, lvl = la.level;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int side = lane >> 4, b = lane & 15;
+    // B fragments: row 4 ks + lk, sample 8 st + lr at column (8 st + lr) ^ 4 (row & 3), and row & 3 = lk
+    const double *B0 = xi + lk * 16 + (lr ^ (lk << 2)), *B1 = xi + lk * 16 + (lr ^ (lk << 2) ^ 8);
+    const double *Fr = F + side * 16 + (b ^ (side << 3)); // sweeps: row 2 q + side, sample b
+    Partial pdq{0.0, 0.0, 0.0, 0.0}, pqf{0.0, 0.0, 0.0, 0.0};
+
+    for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
+        const unsigned long long i0 = (unsigned long long)ti * LN_BT + (unsigned long long)(warp * LN_WS);
+        if (i0 >= g.n) continue;  // this warp's half of the last tile is empty (warp-uniform)
+        const unsigned long long left = g.n - i0;
+        const int Pt = left < (unsigned long long)LN_WS ? (int)left : LN_WS;
+        const bool two = Pt > 8;
+        // A. inputs (always all 16 points: surplus ones are masked out of the statistics)
+        for (int j0 = 0; j0 < g.m; j0 += LN_GEN_PIECE)
+            gen_warp16<MODE, lattice>(xi + (size_t)j0 * 16, queue, j0, min(LN_GEN_PIECE, g.m - j0), g.k0 + i0, g, r, zs);
+
+        SweepState sf{0.0, 0.0, 0.0}, sc{0.0, 0.0, 0.0};
+        double gm = 0.0;
+        for (int c = 0; c < la.nchunks; ++c) {
+            // B. contraction + exp for row tiles 4c .. 4c + live - 1
+            const int live = min(4, la.ntiles - 4 * c);
+            const double *A = la.basis + (size_t)(4 * c) * nks * 32 + lane;
+            if (c == la.nchunks - 1) ln1d_chunk_any<true>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
+            else ln1d_chunk_any<false>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
+            __syncwarp();
+            // C. sweeps over the half-nodes of this chunk (ip0 is a multiple of 16: even half-nodes are the coarse nodes)
+            const int ip0 = 16 * c;
+            const int nh = min(16, M - ip0);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q < nh) {
+                    const double a = Fr[q * 32];
+                    sweep_step(sf, ip0 + q, a, M);
+                    if (!(q & 1) && lvl > 0) sweep_step(sc, (ip0 + q) >> 1, a, M >> 1);
+                }
+            }
+            __syncwarp();  // F is rewritten by the next chunk's epilogue
+        }
+        // mid node (its chain of fused multiply-adds rode along in the last chunk)
+        const double amid = exp_det(gm);
+        sweep_step(sf, M, amid, M);
+        if (lvl > 0) sweep_step(sc, M >> 1, amid, M >> 1);
+        // D. the two sides meet: lanes 0..15 hold the left states, their partners lane + 16 the right ones
+        const double fA = __shfl_xor_sync(0xffffffffu, sf.A, 16), fD = __shfl_xor_sync(0xffffffffu, sf.D, 16);
+        const double cA = __shfl_xor_sync(0xffffffffu, sc.A, 16), cD = __shfl_xor_sync(0xffffffffu, sc.D, 16);
+        if (lane < Pt) {
+            const double qf = sweep_combine(sf.A, sf.D, fA, fD, la.h2);
+            double dq = qf;
+            if (lvl > 0) dq = __dsub_rn(qf, sweep_combine(sc.A, sc.D, cA, cD, la.h2c));
+            if (samples) {
+                samples[((size_t)r * 2 + 0) * g.n + i0 + lane] = dq;
+                samples[((size_t)r * 2 + 1) * g.n + i0 + lane] = qf;
+            }
+            partial_add(pdq, dq);
+            partial_add(pqf, qf);
+        }
+        __syncwarp();
+    }
+    // merge the per-lane statistics of the CTA in slot order (slot = warp * 16 + lane)
+    __syncthreads();
+    Partial *slots = reinterpret_cast<Partial *>(smid + mpad);  // [2][LN_BT] over warp 0's xi / F
+    if (lane < LN_WS) {
+        slots[warp * LN_WS + lane] = pdq;
+        slots[LN_BT + warp * LN_WS + lane] = pqf;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        Partial a{0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < LN_BT; ++i) a = partial_merge(a, slots[tid * LN_BT + i]);
+        fa.partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
+    }
+    cta_finalize(fa, 2);
+}
+
+}  // namespace mle

@@ -19,7 +19,7 @@
 // Kernel: one CTA iteration = S samples.  A: inputs (gen_tile_owned) -> xi[m][S] in shared memory.  B: field = exp(Phi xi)
 // with mma.sync.m8n8k4.f64 over node tiles (basis in HBM/L2 in A-fragment order) -> F[node][S] (shared memory, or an
 // L2-resident global scratch for the large grids).  C: CS = THREADS / (NW*LPR) samples are solved concurrently, S / CS
-// rounds; fine solve + the coarse solves of diff(index) on strided views of F.  D: per-slot Welford, fixed-order merge.
+// rounds; fine solve + the coarse solves of diff(index) on strided views of F.  D: per-slot pivoted sums, fixed-order merge.
 #pragma once
 #include <cuda/std/type_traits>
 
@@ -468,8 +468,7 @@ template <int W> struct Rows2dCfg {
 };
 
 template <int MODE, int W>
-__global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la,
-                                                                                Moment *__restrict__ partials,
+__global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la, FinArgs fa,
                                                                                 double *__restrict__ samples,
                                                                                 long long tiles_per_shift) {
     static_assert(W >= 4, "the coarse solve needs W / 2 >= 2");
@@ -481,7 +480,7 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
     double *xi = reinterpret_cast<double *>(smem_raw);                       // [mpad][LDX]
     double *gsh = xi + (size_t)mpad * LDX;                                   // [CS][rows_sh_doubles(W)]
     double *res = gsh + CS * rows_sh_doubles(W);                             // [S][2]
-    Moment *mred = reinterpret_cast<Moment *>(res + 2 * S);                  // [2][S]
+    Partial *mred = reinterpret_cast<Partial *>(res + 2 * S);                // [2][S]
     GenScratch sc;
     sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * S);                    // [NWARP]
     double *tail = reinterpret_cast<double *>(sc.wtot + ((NWARP + 3) & ~3));
@@ -496,8 +495,7 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
     const int lr = lane >> 2, lk = lane & 3;
     for (int e = tid; e < (mpad - g.m) * LDX; e += THREADS) xi[(size_t)g.m * LDX + e] = 0.0;  // k padding rows
     __syncthreads();
-    Welford wdq{0.0, 0.0}, wqf{0.0, 0.0};
-    double ncount = 0.0;
+    Partial pdq{0.0, 0.0, 0.0, 0.0}, pqf{0.0, 0.0, 0.0, 0.0};
     const int Nx = la.Nx, Ny = la.Ny;
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
@@ -575,23 +573,22 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
                 samples[((size_t)r * 2 + 0) * g.n + i0 + tid] = dq;
                 samples[((size_t)r * 2 + 1) * g.n + i0 + tid] = qf;
             }
-            ncount += 1.0;
-            const double inv_n = 1.0 / ncount;
-            welford_add(wdq, dq, inv_n);
-            welford_add(wqf, qf, inv_n);
+            partial_add(pdq, dq);
+            partial_add(pqf, qf);
         }
         // (the barriers of the next tile's generator order the res reads above before res is rewritten)
     }
     if (tid < S) {
-        mred[tid] = Moment{ncount, wdq.mean, wdq.m2};
-        mred[S + tid] = Moment{ncount, wqf.mean, wqf.m2};
+        mred[tid] = pdq;
+        mred[S + tid] = pqf;
     }
     __syncthreads();
     if (tid < 2) {
-        Moment a{0.0, 0.0, 0.0};
-        for (int i = 0; i < S; ++i) a = moment_merge(a, mred[tid * S + i]);
-        partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
+        Partial a{0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < S; ++i) a = partial_merge(a, mred[tid * S + i]);
+        fa.partials[((size_t)r * 2 + tid) * gridDim.x + blockIdx.x] = a;
     }
+    cta_finalize(fa, 2);
 }
 
 }  // namespace mle

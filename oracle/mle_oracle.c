@@ -735,8 +735,12 @@ ORC_API int orc_sample_batch(const orc_model *M, const uint32_t *z, int s, uint6
         long double sum = 0.0L;
         for (uint64_t i = 0; i < n; ++i) sum += x[i];
         long double mean = n ? sum / (long double)n : 0.0L;
-        long double m2 = 0.0L;
-        for (uint64_t i = 0; i < n; ++i) { long double d = x[i] - mean; m2 += d * d; }
+        /* corrected two-pass: the rounding of `mean` (2^-64 relative) would otherwise add n e^2, which matters when the
+         * samples agree to 15+ digits */
+        long double m2 = 0.0L, sd = 0.0L;
+        for (uint64_t i = 0; i < n; ++i) { long double d = x[i] - mean; m2 += d * d; sd += d; }
+        if (n) m2 -= sd * sd / (long double)n;
+        if (m2 < 0.0L) m2 = 0.0L;
         moments[v * 3 + 0] = (double)n;
         moments[v * 3 + 1] = (double)mean;
         moments[v * 3 + 2] = (double)m2;

@@ -50,7 +50,7 @@ def test_moment_merge_equals_one_pass(data, cuts):
     scale = max(1.0, np.abs(np.asarray(data)).max())
     assert acc[0, 0] == want[0]
     assert abs(acc[0, 1] - want[1]) <= 1e-12 * scale
-    assert abs(acc[0, 2] - want[2]) <= 1e-10 * max(want[2], scale * scale)   # both sides carry eps * n * scale^2
+    assert abs(acc[0, 2] - want[2]) <= 1e-10 * max(want[2], scale * scale * 1e-4)
 
 
 WEIGHTS = st.lists(st.sampled_from([1.0, 0.9, 0.75, 0.6, 0.5, 1 / 3]), min_size=2, max_size=3)
