@@ -9,6 +9,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmle_cuda.so")
+# tuning builds (tools/build_variant.sh) are selected with MLE_CUDA_LIB=<path to an alternative libmle_cuda.so>
+LIB_PATH = os.environ.get("MLE_CUDA_LIB", LIB_PATH)
 
 MLE_OK, MLE_ERR_ARG, MLE_ERR_CUDA, MLE_ERR_RANGE, MLE_ERR_STATE, MLE_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 UNIFORM, NORMAL, TRUNCNORMAL, WEIBULL = 0, 1, 2, 3

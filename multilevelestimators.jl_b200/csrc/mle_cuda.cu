@@ -20,7 +20,8 @@ using namespace mle;
 template <int MODE> static constexpr auto points_k = points_kernel<POINTS_THREADS, MODE>;
 template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_EXPSUM, 2, MODE>;
 template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
-template <int MODE> static constexpr auto lognormal1d_k = lognormal1d_kernel<MODE>;
+template <int MODE> static constexpr auto lognormal1d_k16 = lognormal1d_kernel<MODE, 16>;
+template <int MODE> static constexpr auto lognormal1d_kb = lognormal1d_block_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 template <int MODE> static constexpr auto lognormal2d_r4 = lognormal2d_rows_kernel<MODE, 4>;
@@ -92,6 +93,7 @@ struct mle_ctx_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     uint64_t launches = 0;
+    int ln_block = -1;       // MLE_LN_BLOCK=0|1: force the warp-autonomous / phase-synchronous lognormal1d kernel (default: by grid size)
     int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
     // reusable device / pinned scratch
     Partial *d_partials = nullptr;
@@ -267,7 +269,8 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(points_k, 200 * 1024);
     MLE_SET_SMEM(expsum_k, 200 * 1024);
     MLE_SET_SMEM(problem18_k, 200 * 1024);
-    MLE_SET_SMEM(lognormal1d_k, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_k16, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_kb, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r4, 220 * 1024);
@@ -279,6 +282,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     if (const char *e = getenv("MLE_2D_WINDOW_SMEM")) ctx->ln2d_old = atoi(e) != 0;
+    if (const char *e = getenv("MLE_LN_BLOCK")) ctx->ln_block = atoi(e) != 0;
     if (const char *e = getenv("MLE_NO_ZEROCOPY")) ctx->zero_copy = atoi(e) == 0;
     // the mapped completion flag (zero-copy result path); without it the library falls back to copy + synchronise
     if (ctx->zero_copy) {
@@ -836,16 +840,44 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         la.level = level;
         la.h2 = 1.0 / ((double)la.N * (double)la.N);
         la.h2c = 1.0 / ((double)(la.N / 2) * (double)(la.N / 2));
-        // warp-autonomous kernel: CTA tiles of LN_BT samples, two warps of 16 samples each (mle_kernel_ln1d.cuh)
+        // warp-autonomous kernel (mle_kernel_ln1d.cuh): CTA tiles of LN_BT samples, a warp owns WS of them.  WS = 8 (four
+        // warps per CTA, 20 resident warps per SM) wins while the generator dominates (small grids); WS = 16 (4 x 2 DMMA
+        // warp tiles, half the basis traffic per sample) wins once the KL contraction dominates.  MLE_LN_WS overrides.
+        // Two schedules of the same arithmetic (bit-identical results, same basis layout): the phase-synchronous CTA kernel
+        // (mle_kernel_ln1d_block.cuh) and the warp-autonomous one (mle_kernel_ln1d.cuh).  Measured on the C2 step
+        // (profiles/r02_ln1d_variants.txt): grids of a single half chunk (N <= 16: the generator is 70 % of the work and the
+        // mid-node chain would make one warp of a barrier-synchronised CTA the straggler) run 6 % faster warp-autonomous,
+        // every larger grid 7-15 % faster phase-synchronous (its four warps walk the basis together: L1 hits).
+        // MLE_LN_BLOCK=0|1 forces one of them.
+        const bool block = ctx->ln_block >= 0 ? ctx->ln_block != 0 : la.ntiles > 2;
+        if (block) {
+            const int bt = 32, threads = lnb_threads(bt), W = threads / 32;
+            const long long tps = (long long)((n + bt - 1) / bt);
+            const int qdims = g.m < 256 ? ((g.m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims
+            const size_t fbytes = (size_t)LN_RC * lnb_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
+            const size_t smem = (size_t)la.mpad * lnb_ldx(bt) * 8 + fbytes + (size_t)3 * bt * sizeof(SweepState) +
+                                (size_t)2 * bt * sizeof(Partial) + (size_t)bt * 8 + (size_t)la.mpad * 8 + ((W + 3) & ~3) * 4 +
+                                (lat ? (size_t)g.m * 16 : 0) + (qbytes <= fbytes ? 0 : qbytes) + 16;
+            const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_kb, threads, smem);
+            gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
+            rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+            if (rc) return rc;
+            fa.partials = ctx->d_partials;
+            dim3 grid((unsigned)gx, (unsigned)R);
+            MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kb, grid, threads, smem, ctx->stream, g, la, fa, samples_dev, tps);
+        } else {
+        const int ws = 16;  // samples per warp (the 8-sample instantiation never won a level and was dropped)
         const long long tps = (long long)((n + LN_BT - 1) / LN_BT);
-        const size_t smem = ln1d_smem_bytes(la.mpad, lat ? g.m : 0);
-        const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_k, LN_THREADS, smem);
+        const size_t smem = ln1d_smem_bytes(la.mpad, lat ? g.m : 0, ws);
+        const int threads = ln_threads(ws);
+        const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_k16, threads, smem);
         gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
         rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
         if (rc) return rc;
         fa.partials = ctx->d_partials;
         dim3 grid((unsigned)gx, (unsigned)R);
-        MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k, grid, LN_THREADS, smem, ctx->stream, g, la, fa, samples_dev, tps);
+        MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_k16, grid, threads, smem, ctx->stream, g, la, fa, samples_dev, tps);
+        }
     } else if (M->kind == MODEL_LOGNORMAL2D) {
         const int lx = index[0], ly = d == 2 ? index[1] : index[0];
         if (lx > 12 || ly > 12) return fail(ctx, MLE_ERR_ARG, "lognormal2d: index out of range");

@@ -36,15 +36,11 @@ struct Lognormal1dArgs {
     double h2, h2c;       // 1/N^2, 1/(N/2)^2
 };
 
-constexpr int LN_WS = 16;                    // samples per warp
-constexpr int LN_WARPS = 2;                  // warps per CTA
-constexpr int LN_BT = LN_WS * LN_WARPS;      // samples per CTA tile
-constexpr int LN_THREADS = 32 * LN_WARPS;
-constexpr int LN_GEN_PIECE = 128;            // dims per generator call (64-bit class masks, queue inside F)
-constexpr int LN_F_DOUBLES = 32 * 16;        // per-warp field chunk
-
-__host__ __device__ constexpr size_t ln1d_smem_bytes(int mpad, int m_lattice) {
-    return (size_t)m_lattice * 16 + (size_t)mpad * 8 + (size_t)LN_WARPS * ((size_t)mpad * 16 + LN_F_DOUBLES) * 8 + 16;
+constexpr int LN_BT = 32;                    // samples per CTA tile; a warp owns WS = 8 or 16 of them (template parameter)
+constexpr int LN_GEN_PIECE = 128;            // dims per generator call (class masks, queue inside F)
+__host__ __device__ constexpr int ln_threads(int ws) { return 32 * (LN_BT / ws); }
+__host__ __device__ constexpr size_t ln1d_smem_bytes(int mpad, int m_lattice, int ws) {
+    return (size_t)m_lattice * 16 + (size_t)mpad * 8 + (size_t)(LN_BT / ws) * ((size_t)mpad * ws + 32 * ws) * 8 + 16;
 }
 
 struct SweepState {
@@ -75,24 +71,28 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// contraction + epilogue of one chunk: RT live row tiles (1..4), sample tile 1 only when `two`.  With MID the chain of fused
-// multiply-adds of the mid-node row (smid[k] * xi[k][b], ascending k: the lane's own sample b) rides along in the k loop, in
-// the shadow of the DMMAs.
-template <int RT, bool MID>
+// contraction + epilogue of one chunk: RT live row tiles (1..4) x ST = WS/8 sample tiles (the second one only when `two`).
+// With MID the chain of fused multiply-adds of the mid-node row (smid[k] * xi[k][b], ascending k: the lane's own sample b)
+// rides along in the k loop, in the shadow of the DMMAs.
+template <int RT, bool MID, int WS>
 __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const double *__restrict__ B0,
                                            const double *__restrict__ B1, int nks, bool two, double *__restrict__ F, int lane,
                                            const double *__restrict__ smid, const double *__restrict__ xi, double &gm) {
+    constexpr int ST = WS / 8, KS = 4 * WS;  // doubles of xi per k step
     const int lr = lane >> 2, lk = lane & 3;
-    double acc[RT][2][2];
+    double acc[RT][ST][2];
 #pragma unroll
-    for (int t = 0; t < RT; ++t) { acc[t][0][0] = acc[t][0][1] = acc[t][1][0] = acc[t][1][1] = 0.0; }
+    for (int t = 0; t < RT; ++t)
+#pragma unroll
+        for (int st = 0; st < ST; ++st) acc[t][st][0] = acc[t][st][1] = 0.0;
     const size_t ts = (size_t)nks * 32;
-    double a[RT], b0, b1;
+    double a[RT], b0, b1 = 0.0;
 #pragma unroll
     for (int t = 0; t < RT; ++t) a[t] = __ldg(A + t * ts);
-    b0 = B0[0]; b1 = B1[0];
-    const int b = lane & 15;
-    const double *x0 = xi + b, *x1 = xi + 16 + (b ^ 4), *x2 = xi + 32 + (b ^ 8), *x3 = xi + 48 + (b ^ 12);
+    b0 = B0[0];
+    if (ST == 2) b1 = B1[0];
+    const int b = lane & (WS - 1);
+    const double *x0 = xi + swz<WS>(0, b), *x1 = xi + swz<WS>(1, b), *x2 = xi + swz<WS>(2, b), *x3 = xi + swz<WS>(3, b);
     double g0 = 0.0;
 #pragma unroll 2
     for (int ks = 0; ks < nks; ++ks) {
@@ -100,19 +100,21 @@ __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const d
         double na[RT];
 #pragma unroll
         for (int t = 0; t < RT; ++t) na[t] = __ldg(A + t * ts + kn * 32);
-        const double nb0 = B0[kn * 64], nb1 = B1[kn * 64];
+        const double nb0 = B0[kn * KS];
+        double nb1 = 0.0;
+        if (ST == 2) nb1 = B1[kn * KS];
         double2 p01, p23;
         double y0, y1, y2, y3;
         if (MID) {
             p01 = *reinterpret_cast<const double2 *>(smid + 4 * ks);
             p23 = *reinterpret_cast<const double2 *>(smid + 4 * ks + 2);
-            y0 = x0[ks * 64]; y1 = x1[ks * 64]; y2 = x2[ks * 64]; y3 = x3[ks * 64];
+            y0 = x0[ks * KS]; y1 = x1[ks * KS]; y2 = x2[ks * KS]; y3 = x3[ks * KS];
         }
 #pragma unroll
         for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][0][0], acc[t][0][1], a[t], b0);
-        if (two) {
+        if (ST == 2 && two) {
 #pragma unroll
-            for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][1][0], acc[t][1][1], a[t], b1);
+            for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][ST - 1][0], acc[t][ST - 1][1], a[t], b1);
         }
         if (MID) {
             g0 = __fma_rn(p01.x, y0, g0);
@@ -125,66 +127,70 @@ __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const d
         b0 = nb0; b1 = nb1;
     }
     if (MID) gm = g0;
-    // epilogue: a = exp(G) -> F[row][sample ^ 8*(row & 1)]; the lane holds row lr, samples 2 lk, 2 lk + 1 of each 8x8 tile
-    const int sw = (lr & 1) << 3;
-    double *f0 = F + lr * 16 + ((2 * lk) ^ sw), *f1 = F + lr * 16 + ((2 * lk) ^ sw ^ 8);
+    // epilogue: a = exp(G) -> F[row][sample]; the lane holds row lr, samples 2 lk, 2 lk + 1 of each 8x8 tile
+    // (WS = 16: columns XOR-swizzled by 8 (row & 1) so that the 16-byte stores of a quarter warp hit 8 distinct bank groups)
+    const int sw = WS == 16 ? (lr & 1) << 3 : 0;
+    double *f0 = F + lr * WS + ((2 * lk) ^ sw), *f1 = F + lr * WS + ((2 * lk) ^ sw ^ 8);
 #pragma unroll
     for (int t = 0; t < RT; ++t) {
         double2 v;
         v.x = exp_det(acc[t][0][0]); v.y = exp_det(acc[t][0][1]);
-        *reinterpret_cast<double2 *>(f0 + t * 128) = v;
-        if (two) {
-            v.x = exp_det(acc[t][1][0]); v.y = exp_det(acc[t][1][1]);
-            *reinterpret_cast<double2 *>(f1 + t * 128) = v;
+        *reinterpret_cast<double2 *>(f0 + t * 8 * WS) = v;
+        if (ST == 2 && two) {
+            v.x = exp_det(acc[t][ST - 1][0]); v.y = exp_det(acc[t][ST - 1][1]);
+            *reinterpret_cast<double2 *>(f1 + t * 8 * WS) = v;
         }
     }
 }
 
-template <bool MID>
+template <bool MID, int WS>
 __device__ __forceinline__ void ln1d_chunk_any(int live, const double *__restrict__ A, const double *__restrict__ B0,
                                                const double *__restrict__ B1, int nks, bool two, double *__restrict__ F, int lane,
                                                const double *__restrict__ smid, const double *__restrict__ xi, double &gm) {
-    if (live == 4) ln1d_chunk<4, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
-    else if (live == 2) ln1d_chunk<2, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
-    else if (live == 3) ln1d_chunk<3, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
-    else ln1d_chunk<1, MID>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    if (live == 4) ln1d_chunk<4, MID, WS>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    else if (live == 2) ln1d_chunk<2, MID, WS>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    else if (live == 3) ln1d_chunk<3, MID, WS>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
+    else ln1d_chunk<1, MID, WS>(A, B0, B1, nks, two, F, lane, smid, xi, gm);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(LN_THREADS, 6) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la, FinArgs fa,
-                                                                    double *__restrict__ samples, long long tiles_per_shift) {
+template <int MODE, int WS>
+__global__ void __launch_bounds__(32 * (LN_BT / WS), WS == 16 ? 6 : 5) lognormal1d_kernel(GenArgs g, Lognormal1dArgs la, FinArgs fa,
+                                                                                          double *__restrict__ samples,
+                                                                                          long long tiles_per_shift) {
     constexpr bool lattice = (MODE & GEN_MC) == 0;
+    constexpr int WARPS = LN_BT / WS, THREADS = 32 * WARPS, FD = 32 * WS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int mpad = la.mpad, nks = mpad >> 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = blockIdx.y;
     double2 *zs = reinterpret_cast<double2 *>(smem_raw);                                  // [m] (lattice modes)
     double *smid = reinterpret_cast<double *>(zs + (lattice ? g.m : 0));                  // [mpad] basis row of the mid node
-    double *wbase = smid + mpad + (size_t)warp * ((size_t)mpad * 16 + LN_F_DOUBLES);
-    double *xi = wbase;                                                                   // [mpad][16] swizzled
-    double *F = xi + (size_t)mpad * 16;                                                   // [32][16] swizzled
+    double *xi = smid + mpad + (size_t)warp * ((size_t)mpad * WS + FD);                   // [mpad][WS] swizzled
+    double *F = xi + (size_t)mpad * WS;                                                   // [32][WS]
     unsigned short *queue = reinterpret_cast<unsigned short *>(F);                        // generator queue (F is idle then)
-    if (lattice) stage_lattice_row<LN_THREADS>(zs, g, r);
-    for (int e = tid; e < mpad; e += LN_THREADS) smid[e] = __ldg(la.mid + e);
-    for (int e = lane; e < (mpad - g.m) * 16; e += 32) xi[(size_t)g.m * 16 + e] = 0.0;    // k padding rows
+    if (lattice) stage_lattice_row<THREADS>(zs, g, r);
+    for (int e = tid; e < mpad; e += THREADS) smid[e] = __ldg(la.mid + e);
+    for (int e = lane; e < (mpad - g.m) * WS; e += 32) xi[(size_t)g.m * WS + e] = 0.0;    // k padding rows
     __syncthreads();
 
     const int M = la.N >> 1, lvl = la.level;
     const int lr = lane >> 2, lk = lane & 3;
-    const int side = lane >> 4, b = lane & 15;
-    // B fragments: row 4 ks + lk, sample 8 st + lr at column (8 st + lr) ^ 4 (row & 3), and row & 3 = lk
-    const double *B0 = xi + lk * 16 + (lr ^ (lk << 2)), *B1 = xi + lk * 16 + (lr ^ (lk << 2) ^ 8);
-    const double *Fr = F + side * 16 + (b ^ (side << 3)); // sweeps: row 2 q + side, sample b
+    // B fragments: row 4 ks + lk (row & 3 = lk), sample 8 st + lr at the swizzled column
+    const double *B0 = xi + swz<WS>(lk, lr), *B1 = xi + swz<WS>(lk, (lr + 8) & (WS - 1));
+    // sweep roles.  WS = 16: lane (side, sample) carries the fine and the coarse state of its side;
+    //               WS = 8:  lane (grid, side, sample): lanes 0..15 the fine grid, lanes 16..31 the coarse one (even half-nodes)
+    const int side = WS == 16 ? lane >> 4 : (lane >> 3) & 1, b = lane & (WS - 1), grid = WS == 16 ? 0 : lane >> 4;
+    const double *Fr = F + side * WS + (WS == 16 ? (b ^ (side << 3)) : b);  // row 2 q + side, sample b
     Partial pdq{0.0, 0.0, 0.0, 0.0}, pqf{0.0, 0.0, 0.0, 0.0};
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
-        const unsigned long long i0 = (unsigned long long)ti * LN_BT + (unsigned long long)(warp * LN_WS);
-        if (i0 >= g.n) continue;  // this warp's half of the last tile is empty (warp-uniform)
+        const unsigned long long i0 = (unsigned long long)ti * LN_BT + (unsigned long long)(warp * WS);
+        if (i0 >= g.n) continue;  // this warp's part of the last tile is empty (warp-uniform)
         const unsigned long long left = g.n - i0;
-        const int Pt = left < (unsigned long long)LN_WS ? (int)left : LN_WS;
+        const int Pt = left < (unsigned long long)WS ? (int)left : WS;
         const bool two = Pt > 8;
-        // A. inputs (always all 16 points: surplus ones are masked out of the statistics)
+        // A. inputs (always all WS points: surplus ones are masked out of the statistics)
         for (int j0 = 0; j0 < g.m; j0 += LN_GEN_PIECE)
-            gen_warp16<MODE, lattice>(xi + (size_t)j0 * 16, queue, j0, min(LN_GEN_PIECE, g.m - j0), g.k0 + i0, g, r, zs);
+            gen_warp<MODE, lattice, WS>(xi + (size_t)j0 * WS, queue, j0, min(LN_GEN_PIECE, g.m - j0), g.k0 + i0, g, r, zs);
 
         SweepState sf{0.0, 0.0, 0.0}, sc{0.0, 0.0, 0.0};
         double gm = 0.0;
@@ -192,33 +198,56 @@ __global__ void __launch_bounds__(LN_THREADS, 6) lognormal1d_kernel(GenArgs g, L
             // B. contraction + exp for row tiles 4c .. 4c + live - 1
             const int live = min(4, la.ntiles - 4 * c);
             const double *A = la.basis + (size_t)(4 * c) * nks * 32 + lane;
-            if (c == la.nchunks - 1) ln1d_chunk_any<true>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
-            else ln1d_chunk_any<false>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
+            if (c == la.nchunks - 1) ln1d_chunk_any<true, WS>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
+            else ln1d_chunk_any<false, WS>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
             __syncwarp();
             // C. sweeps over the half-nodes of this chunk (ip0 is a multiple of 16: even half-nodes are the coarse nodes)
             const int ip0 = 16 * c;
             const int nh = min(16, M - ip0);
+            if (WS == 16) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                if (q < nh) {
-                    const double a = Fr[q * 32];
-                    sweep_step(sf, ip0 + q, a, M);
-                    if (!(q & 1) && lvl > 0) sweep_step(sc, (ip0 + q) >> 1, a, M >> 1);
+                for (int q = 0; q < 16; ++q) {
+                    if (q < nh) {
+                        const double a = Fr[q * 2 * WS];
+                        sweep_step(sf, ip0 + q, a, M);
+                        if (!(q & 1) && lvl > 0) sweep_step(sc, (ip0 + q) >> 1, a, M >> 1);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (q < nh) {
+                        const double a = Fr[q * 2 * WS];
+                        if (!grid) sweep_step(sf, ip0 + q, a, M);
+                        else if (!(q & 1) && lvl > 0) sweep_step(sf, (ip0 + q) >> 1, a, M >> 1);
+                    }
                 }
             }
             __syncwarp();  // F is rewritten by the next chunk's epilogue
         }
         // mid node (its chain of fused multiply-adds rode along in the last chunk)
         const double amid = exp_det(gm);
-        sweep_step(sf, M, amid, M);
-        if (lvl > 0) sweep_step(sc, M >> 1, amid, M >> 1);
-        // D. the two sides meet: lanes 0..15 hold the left states, their partners lane + 16 the right ones
-        const double fA = __shfl_xor_sync(0xffffffffu, sf.A, 16), fD = __shfl_xor_sync(0xffffffffu, sf.D, 16);
-        const double cA = __shfl_xor_sync(0xffffffffu, sc.A, 16), cD = __shfl_xor_sync(0xffffffffu, sc.D, 16);
-        if (lane < Pt) {
-            const double qf = sweep_combine(sf.A, sf.D, fA, fD, la.h2);
-            double dq = qf;
+        double qf, dq;
+        if (WS == 16) {
+            sweep_step(sf, M, amid, M);
+            if (lvl > 0) sweep_step(sc, M >> 1, amid, M >> 1);
+            // D. the two sides meet: lanes 0..15 hold the left states, their partners lane + 16 the right ones
+            const double fA = __shfl_xor_sync(0xffffffffu, sf.A, 16), fD = __shfl_xor_sync(0xffffffffu, sf.D, 16);
+            const double cA = __shfl_xor_sync(0xffffffffu, sc.A, 16), cD = __shfl_xor_sync(0xffffffffu, sc.D, 16);
+            qf = sweep_combine(sf.A, sf.D, fA, fD, la.h2);
+            dq = qf;
             if (lvl > 0) dq = __dsub_rn(qf, sweep_combine(sc.A, sc.D, cA, cD, la.h2c));
+        } else {
+            if (!grid) sweep_step(sf, M, amid, M);
+            else if (lvl > 0) sweep_step(sf, M >> 1, amid, M >> 1);
+            // D. left states in lanes with side 0, right states in lane + 8; the coarse value of sample b sits in lane b + 16
+            const double xA = __shfl_xor_sync(0xffffffffu, sf.A, 8), xD = __shfl_xor_sync(0xffffffffu, sf.D, 8);
+            const double q = sweep_combine(sf.A, sf.D, xA, xD, grid ? la.h2c : la.h2);
+            const double qc = __shfl_down_sync(0xffffffffu, q, 16);
+            qf = q;
+            dq = lvl > 0 ? __dsub_rn(q, qc) : q;
+        }
+        if (lane < Pt) {
             if (samples) {
                 samples[((size_t)r * 2 + 0) * g.n + i0 + lane] = dq;
                 samples[((size_t)r * 2 + 1) * g.n + i0 + lane] = qf;
@@ -228,12 +257,12 @@ __global__ void __launch_bounds__(LN_THREADS, 6) lognormal1d_kernel(GenArgs g, L
         }
         __syncwarp();
     }
-    // merge the per-lane statistics of the CTA in slot order (slot = warp * 16 + lane)
+    // merge the per-lane statistics of the CTA in slot order (slot = warp * WS + lane)
     __syncthreads();
     Partial *slots = reinterpret_cast<Partial *>(smid + mpad);  // [2][LN_BT] over warp 0's xi / F
-    if (lane < LN_WS) {
-        slots[warp * LN_WS + lane] = pdq;
-        slots[LN_BT + warp * LN_WS + lane] = pqf;
+    if (lane < WS) {
+        slots[warp * WS + lane] = pdq;
+        slots[LN_BT + warp * WS + lane] = pqf;
     }
     __syncthreads();
     if (tid < 2) {

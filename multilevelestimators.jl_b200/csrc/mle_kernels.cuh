@@ -9,6 +9,7 @@
 #pragma once
 #include "mle_device.cuh"
 #include "mle_kernel_ln1d.cuh"
+#include "mle_kernel_ln1d_block.cuh"
 
 namespace mle {
 
