@@ -13,7 +13,8 @@
  *   - all pointers are caller-owned HOST memory unless the name says `_dev`; the library never returns memory
  *     it allocated.  Handles are opaque and freed by the matching `*_destroy`.
  *   - arrays are dense, first index fastest (Julia / column-major order) and documented as [fastest x ... x slowest].
- *   - one context per process and GPU; calls on one context are blocking and not re-entrant
+ *   - one context per process and GPU (or per process and set of GPUs, mle_init_multi); calls on one context are blocking and
+ *     not re-entrant
  *     (the reference has a single caller too: `sample!` <- `update_samples` <- `_run`, src/sample.jl:8-34).
  *   - there is NO CPU fallback: every entry point that computes fails with MLE_ERR_CUDA when no sm_100 device is usable.
  */
@@ -61,6 +62,17 @@ int mle_abi_version(void);
 /* Create a context on CUDA device `device` (ordinal as seen by this process).  Replaces nothing in the reference:
  * it is where the `pmap` worker pool of src/sample.jl:43-45 / :89-91 turns into one GPU. */
 int mle_init(int device, mle_ctx *ctx);
+/* Multi-GPU context on `ndev` distinct devices of this process (devices[0] is member 0).  This is the reference's
+ * `nb_of_workers` option (src/parse.jl:224-234, consumed by the pmap calls of src/sample.jl:43-45, :89-91): the worker pool
+ * becomes a set of GPUs behind ONE context and one calling thread.  Handles created through the context are replicated on
+ * every member.  mle_sample_batch (without `samples`) and mle_update_samples split each request over the members -- whole
+ * shifts per member when R >= members in use (each member's moment triplets are final: no merge), else slices of the point
+ * range merged on the host in member order (Chan et al.) -- and use only as many members as the request has multiples of
+ * MLE_SHARD_MIN (default 24576) samples: small requests stay on member 0.  All members are issued before the first wait.
+ * The device-resident entry points (`*_dev`), mle_points and raw-sample output run on member 0. */
+int mle_init_multi(const int *devices, int ndev, mle_ctx *ctx);
+/* Number of member devices of the context (1 for mle_init). */
+int mle_device_count(mle_ctx ctx, int *ndev);
 int mle_destroy(mle_ctx ctx);
 /* Message of the last failing call on `ctx` (ctx == NULL: last failing mle_init of this thread). */
 const char *mle_last_error(mle_ctx ctx);

@@ -29,6 +29,8 @@ SIGNATURES = {
     "mle_last_error": (C.c_char_p, [_vp]),
     "mle_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "mle_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mle_init_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "mle_device_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "mle_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "mle_genvec": (C.c_int, [C.c_char_p, C.POINTER(_u32p), C.POINTER(C.c_int)]),
     "mle_lattice_create": (C.c_int, [_vp, _u32p, C.c_int, C.c_uint64, C.POINTER(_vp)]),

@@ -85,6 +85,10 @@ static long long churn_grid_x(long long gx_resident, long long tiles_per_shift) 
 // handles
 // ---------------------------------------------------------------------------------------------------------------
 struct mle_ctx_s {
+    // multi-GPU context (mle_init_multi): this object is member 0, `peers` are the contexts of the other devices.  Handles
+    // created through it carry one replica per peer; mle_sample_batch / mle_update_samples split each request over the members.
+    std::vector<mle_ctx> peers;
+    uint64_t shard_min = 24576;  // a member is only used if it gets at least this many (shift, point) samples (MLE_SHARD_MIN)
     int device = -1;
     int sm_count = 0;
     int cc = 0;
@@ -126,12 +130,14 @@ struct mle_ctx_s {
 };
 
 struct mle_lattice_s {
+    std::vector<mle_lattice> rep;  // replicas on the peers of a multi-GPU context
     int s = 0;
     uint64_t nmax = 0;
     double *d_z = nullptr;  // z as Float64 (exact)
 };
 
 struct mle_dists_s {
+    std::vector<mle_dists> rep;
     int m = 0;
     int mode = GEN_GENERAL;
     int *d_kind = nullptr;
@@ -140,6 +146,7 @@ struct mle_dists_s {
 
 static const int MLE_MAX_LEVELS = 256;  // levels, or packed multi-indices lx + 16*ly (lognormal2d with ndims = 2)
 struct mle_model_s {
+    std::vector<mle_model> rep;
     int kind = 0, ndims = 1, nqoi = 1, n0 = 0;
     int nweights = 0;
     double *d_weights = nullptr;
@@ -299,9 +306,40 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     return MLE_OK;
 }
 
+extern "C" int mle_init_multi(const int *devices, int ndev, mle_ctx *out) {
+    MLE_API_SCOPE;
+    if (!out) return fail(nullptr, MLE_ERR_ARG, "mle_init_multi: ctx is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1) return fail(nullptr, MLE_ERR_ARG, "mle_init_multi: need at least one device");
+    // (MLE_ALLOW_DUP_DEVICES=1 lets a test box with one GPU exercise the multi-member logic: two members on the same device)
+    for (int i = 0; i < ndev && !getenv("MLE_ALLOW_DUP_DEVICES"); ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, MLE_ERR_ARG, "mle_init_multi: device listed twice");
+    mle_ctx ctx = nullptr;
+    int rc = mle_init(devices[0], &ctx);
+    for (int i = 1; rc == MLE_OK && i < ndev; ++i) {
+        mle_ctx p = nullptr;
+        rc = mle_init(devices[i], &p);
+        if (rc == MLE_OK) ctx->peers.push_back(p);
+    }
+    if (rc != MLE_OK) { if (ctx) mle_destroy(ctx); return rc; }
+    if (const char *e = getenv("MLE_SHARD_MIN")) { long long v = atoll(e); if (v >= 1) ctx->shard_min = (uint64_t)v; }
+    *out = ctx;
+    return MLE_OK;
+}
+
+extern "C" int mle_device_count(mle_ctx ctx, int *ndev) {
+    MLE_API_SCOPE;
+    if (!ctx || !ndev) return MLE_ERR_ARG;
+    *ndev = 1 + (int)ctx->peers.size();
+    return MLE_OK;
+}
+
 extern "C" int mle_destroy(mle_ctx ctx) {
     MLE_API_SCOPE;
     if (!ctx) return MLE_OK;
+    for (mle_ctx p : ctx->peers) mle_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_partials) cudaFree(ctx->d_partials);
@@ -345,13 +383,19 @@ extern "C" int mle_launch_count(mle_ctx ctx, uint64_t *count) {
     MLE_API_SCOPE;
     if (!ctx || !count) return MLE_ERR_ARG;
     *count = ctx->launches;
+    for (mle_ctx p : ctx->peers) *count += p->launches;
     return MLE_OK;
 }
 
 extern "C" int mle_sync(mle_ctx ctx) {
     MLE_API_SCOPE;
     if (!ctx) return MLE_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (mle_ctx p : ctx->peers) {
+        CU_TRY(ctx, cudaSetDevice(p->device));
+        CU_TRY(ctx, cudaStreamSynchronize(p->stream));
+    }
     return MLE_OK;
 }
 
@@ -366,8 +410,7 @@ extern "C" int mle_genvec(const char *name, const uint32_t **z, int *len) {
     return MLE_ERR_ARG;
 }
 
-extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_t nmax, mle_lattice *out) {
-    MLE_API_SCOPE;
+static int lattice_create_one(mle_ctx ctx, const uint32_t *z, int s, uint64_t nmax, mle_lattice *out) {
     if (!ctx || !out) return MLE_ERR_ARG;
     *out = nullptr;
     // check_args, src/lattice.jl:181-185: s > 0, s <= length(z) (caller's contract), n <= 2^32
@@ -393,8 +436,7 @@ extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_
     return MLE_OK;
 }
 
-extern "C" int mle_lattice_destroy(mle_ctx ctx, mle_lattice lat) {
-    MLE_API_SCOPE;
+static int lattice_destroy_one(mle_ctx ctx, mle_lattice lat) {
     if (!lat) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(lat->d_z);
@@ -411,8 +453,7 @@ static double host_normcdf(double x) {  // Phi(x) = 1/2*(1 + erf(x/sqrt(2)))    
     return 0.5 * e;
 }
 
-extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists *out) {
-    MLE_API_SCOPE;
+static int dists_create_one(mle_ctx ctx, const mle_dist *d, int m, mle_dists *out) {
     if (!ctx || !out) return MLE_ERR_ARG;
     *out = nullptr;
     if (!d || m <= 0) return fail(ctx, MLE_ERR_ARG, "distributions: need at least one distribution");
@@ -474,8 +515,7 @@ extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists
     return MLE_OK;
 }
 
-extern "C" int mle_dists_destroy(mle_ctx ctx, mle_dists dists) {
-    MLE_API_SCOPE;
+static int dists_destroy_one(mle_ctx ctx, mle_dists dists) {
     if (!dists) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(dists->d_kind);
@@ -487,8 +527,7 @@ extern "C" int mle_dists_destroy(mle_ctx ctx, mle_dists dists) {
 // ---------------------------------------------------------------------------------------------------------------
 // model registry
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *out) {
-    MLE_API_SCOPE;
+static int model_create_one(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *out) {
     if (!ctx || !out || !name) return MLE_ERR_ARG;
     *out = nullptr;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -526,8 +565,7 @@ extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const 
     return MLE_OK;
 }
 
-extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows, int cols, const double *phi) {
-    MLE_API_SCOPE;
+static int model_set_basis_one(mle_ctx ctx, mle_model M, int level, int rows, int cols, const double *phi) {
     if (!ctx || !M || !phi) return MLE_ERR_ARG;
     if (M->kind != MODEL_LOGNORMAL1D && M->kind != MODEL_LOGNORMAL2D) return fail(ctx, MLE_ERR_ARG, "set_basis: model takes no KL basis");
     if (level < 0 || level >= MLE_MAX_LEVELS) return fail(ctx, MLE_ERR_ARG, "set_basis: level out of range");
@@ -620,14 +658,82 @@ extern "C" int mle_model_nqoi(mle_model M, int *nqoi) {
     return MLE_OK;
 }
 
-extern "C" int mle_model_destroy(mle_ctx ctx, mle_model M) {
-    MLE_API_SCOPE;
+static int model_destroy_one(mle_ctx ctx, mle_model M) {
     if (!M) return MLE_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(M->d_weights);
     for (int l = 0; l < MLE_MAX_LEVELS; ++l) { cudaFree(M->d_basis[l]); cudaFree(M->d_frag[l]); }
     delete M;
     return MLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// public handle constructors: one object on the context's device plus one replica per peer of a multi-GPU context
+// ---------------------------------------------------------------------------------------------------------------
+static inline int group_size(mle_ctx ctx) { return 1 + (int)ctx->peers.size(); }
+static inline mle_ctx member_ctx(mle_ctx ctx, int i) { return i == 0 ? ctx : ctx->peers[(size_t)i - 1]; }
+template <typename H> static inline H member_handle(H h, int i) { return (!h || i == 0) ? h : h->rep[(size_t)i - 1]; }
+static int peer_fail(mle_ctx ctx, mle_ctx peer, int rc) { ctx->err = "device " + std::to_string(peer->device) + ": " + peer->err; return rc; }
+
+extern "C" int mle_lattice_create(mle_ctx ctx, const uint32_t *z, int s, uint64_t nmax, mle_lattice *out) {
+    MLE_API_SCOPE;
+    int rc = lattice_create_one(ctx, z, s, nmax, out);
+    for (size_t i = 0; rc == MLE_OK && i < ctx->peers.size(); ++i) {
+        mle_lattice r = nullptr;
+        rc = lattice_create_one(ctx->peers[i], z, s, nmax, &r);
+        if (rc == MLE_OK) (*out)->rep.push_back(r); else peer_fail(ctx, ctx->peers[i], rc);
+    }
+    if (rc != MLE_OK && out && *out) { mle_lattice_destroy(ctx, *out); *out = nullptr; }
+    return rc;
+}
+extern "C" int mle_lattice_destroy(mle_ctx ctx, mle_lattice lat) {
+    MLE_API_SCOPE;
+    if (!lat) return MLE_OK;
+    for (size_t i = 0; i < lat->rep.size(); ++i) lattice_destroy_one(ctx && i < ctx->peers.size() ? ctx->peers[i] : nullptr, lat->rep[i]);
+    return lattice_destroy_one(ctx, lat);
+}
+extern "C" int mle_dists_create(mle_ctx ctx, const mle_dist *d, int m, mle_dists *out) {
+    MLE_API_SCOPE;
+    int rc = dists_create_one(ctx, d, m, out);
+    for (size_t i = 0; rc == MLE_OK && i < ctx->peers.size(); ++i) {
+        mle_dists r = nullptr;
+        rc = dists_create_one(ctx->peers[i], d, m, &r);
+        if (rc == MLE_OK) (*out)->rep.push_back(r); else peer_fail(ctx, ctx->peers[i], rc);
+    }
+    if (rc != MLE_OK && out && *out) { mle_dists_destroy(ctx, *out); *out = nullptr; }
+    return rc;
+}
+extern "C" int mle_dists_destroy(mle_ctx ctx, mle_dists dists) {
+    MLE_API_SCOPE;
+    if (!dists) return MLE_OK;
+    for (size_t i = 0; i < dists->rep.size(); ++i) dists_destroy_one(ctx && i < ctx->peers.size() ? ctx->peers[i] : nullptr, dists->rep[i]);
+    return dists_destroy_one(ctx, dists);
+}
+extern "C" int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *out) {
+    MLE_API_SCOPE;
+    int rc = model_create_one(ctx, name, ndims, params, nparams, out);
+    for (size_t i = 0; rc == MLE_OK && i < ctx->peers.size(); ++i) {
+        mle_model r = nullptr;
+        rc = model_create_one(ctx->peers[i], name, ndims, params, nparams, &r);
+        if (rc == MLE_OK) (*out)->rep.push_back(r); else peer_fail(ctx, ctx->peers[i], rc);
+    }
+    if (rc != MLE_OK && out && *out) { mle_model_destroy(ctx, *out); *out = nullptr; }
+    return rc;
+}
+extern "C" int mle_model_set_basis(mle_ctx ctx, mle_model M, int level, int rows, int cols, const double *phi) {
+    MLE_API_SCOPE;
+    int rc = model_set_basis_one(ctx, M, level, rows, cols, phi);
+    for (size_t i = 0; rc == MLE_OK && M && i < M->rep.size() && i < ctx->peers.size(); ++i) {
+        rc = model_set_basis_one(ctx->peers[i], M->rep[i], level, rows, cols, phi);
+        if (rc != MLE_OK) peer_fail(ctx, ctx->peers[i], rc);
+    }
+    return rc;
+}
+extern "C" int mle_model_destroy(mle_ctx ctx, mle_model M) {
+    MLE_API_SCOPE;
+    if (!M) return MLE_OK;
+    for (size_t i = 0; i < M->rep.size(); ++i) model_destroy_one(ctx && i < ctx->peers.size() ? ctx->peers[i] : nullptr, M->rep[i]);
+    return model_destroy_one(ctx, M);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -982,6 +1088,11 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
     return launch_batch(ctx, M, lat, dists, index, d, shifts_dev, R, k0, n, m, mc_seed, moments_dev, samples_dev, nullptr, 0);
 }
 
+extern "C" int mle_moments_merge(double *acc, const double *part, size_t count);
+static int update_samples_group(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *indices, int d,
+                                const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n, const int *m,
+                                uint64_t mc_seed, double *const *moments, double *gpu_seconds);
+
 // Wait for the launch that carries sequence number `seq` to raise the mapped completion flag.  The host spins on its own
 // memory (the GPU writes the moment table and then the flag over PCIe, __threadfence_system in between), which saves the
 // stream synchronisation and the device-to-host copy of the classic path: 10-15 us per call, i.e. most of a small call.  The
@@ -1024,6 +1135,12 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     if (!ctx || !M || !moments) return MLE_ERR_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (R < 1) return fail(ctx, MLE_ERR_ARG, "number of shifts must be at least 1");
+    if (!ctx->peers.empty() && !samples) {  // multi-GPU context: split over the members (raw samples stay on member 0)
+        if (!index) return MLE_ERR_ARG;
+        const double *shp = shifts;
+        double *mp = moments;
+        return update_samples_group(ctx, M, lat, dists, 1, index, d, shifts ? &shp : nullptr, &R, &k0, &n, &m, mc_seed, &mp, gpu_seconds);
+    }
     const double *sh_dev = nullptr;
     int rc = upload_shifts(ctx, lat, shifts, R, &sh_dev);
     if (rc) return rc;
@@ -1077,18 +1194,22 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     return MLE_OK;
 }
 
-// `update_samples`: several sample! requests, one synchronisation (include/mle_cuda.h)
-extern "C" int mle_update_samples(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *indices,
-                                  int d, const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n,
-                                  const int *m, uint64_t mc_seed, double *const *moments) {
-    MLE_API_SCOPE;
-    if (!ctx || !M || count < 0 || (count && (!indices || !R || !k0 || !n || !m || !moments))) return MLE_ERR_ARG;
-    if (count == 0) return MLE_OK;
+// `update_samples`: several sample! requests, one synchronisation (include/mle_cuda.h).  Split in two halves so that a
+// multi-GPU context can issue the work of every member before it waits for any of them.
+struct IssueState {
+    bool used = false, zc = false, timed = false;
+    size_t sh_total = 0, mom_total = 0;
+    unsigned seq = 0;
+};
+
+static int update_issue(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *const *indices,
+                        int d, const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n, const int *m,
+                        uint64_t mc_seed, bool timed, IssueState *st) {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     // one arena for all shifts (device + pinned host) and one for all moment tables (mapped host when zero-copy)
     size_t sh_total = 0, mom_total = 0;
     for (int e = 0; e < count; ++e) {
-        if (R[e] < 1 || !moments[e]) return fail(ctx, MLE_ERR_ARG, "update_samples: every entry needs R >= 1 and a moment table");
+        if (R[e] < 1) return fail(ctx, MLE_ERR_ARG, "update_samples: every entry needs R >= 1 and a moment table");
         if (shifts && shifts[e] && !lat) return fail(ctx, MLE_ERR_ARG, "MC sampling takes no shifts");
         if (lat && shifts && shifts[e]) sh_total += (size_t)R[e] * (size_t)lat->s;
         mom_total += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
@@ -1124,35 +1245,144 @@ extern "C" int mle_update_samples(mle_ctx ctx, mle_model M, mle_lattice lat, mle
         ctx->batch_staged = sh_total;
     }
     double *mom_base = zc ? ctx->d_res : ctx->d_batch + sh_total;
-    const unsigned seq = ++ctx->seq ? ctx->seq : ++ctx->seq;
+    const unsigned seq = ++ctx->seq ? ctx->seq : ++ctx->seq;  // never 0 (the flag's initial value)
+    if (timed) cudaEventRecord(ctx->ev0, ctx->stream);
     size_t sh_off = 0, mom_off = 0;
     for (int e = 0; e < count && rc == MLE_OK; ++e) {
         const double *sh_dev = nullptr;
         if (lat && shifts && shifts[e]) { sh_dev = ctx->d_batch + sh_off; sh_off += (size_t)R[e] * (size_t)lat->s; }
         const bool last = e == count - 1;
-        rc = launch_batch(ctx, M, lat, dists, indices + (size_t)e * d, d, sh_dev, R[e], k0[e], n[e], m[e], mc_seed, mom_base + mom_off,
+        rc = launch_batch(ctx, M, lat, dists, indices[e], d, sh_dev, R[e], k0[e], n[e], m[e], mc_seed, mom_base + mom_off,
                           nullptr, (zc && last) ? ctx->d_flag : nullptr, seq);
         mom_off += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
     }
+    if (timed) cudaEventRecord(ctx->ev1, ctx->stream);
     if (rc != MLE_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    st->used = true; st->zc = zc; st->timed = timed; st->sh_total = sh_total; st->mom_total = mom_total; st->seq = seq;
+    return MLE_OK;
+}
+
+static int update_collect(mle_ctx ctx, mle_model M, int count, const int *R, double *const *moments, const IssueState &st,
+                          double *gpu_seconds) {
+    if (!st.used) return MLE_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     const double *host_mom;
-    if (zc) {
-        rc = wait_flag(ctx, seq, "mle_update_samples");
+    if (st.zc) {
+        int rc = wait_flag(ctx, st.seq, "mle_update_samples");
         if (rc) return rc;
         host_mom = ctx->h_res;
     } else {
-        cudaError_t err = cudaMemcpyAsync(ctx->h_pinned + sh_total, ctx->d_batch + sh_total, mom_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t err = cudaMemcpyAsync(ctx->h_pinned + st.sh_total, ctx->d_batch + st.sh_total, st.mom_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
         if (err != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_update_samples: ") + cudaGetErrorString(err)); }
-        host_mom = ctx->h_pinned + sh_total;
+        host_mom = ctx->h_pinned + st.sh_total;
     }
-    mom_off = 0;
+    size_t mom_off = 0;
     for (int e = 0; e < count; ++e) {
         const size_t nm = (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
         memcpy(moments[e], host_mom + mom_off, nm * sizeof(double));
         mom_off += nm;
     }
+    if (st.timed && gpu_seconds) {
+        cudaError_t e = cudaEventSynchronize(ctx->ev1);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_update_samples: ") + cudaGetErrorString(e)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        *gpu_seconds = (double)ms * 1e-3;
+    }
     return MLE_OK;
+}
+
+// contiguous balanced slice i of g over `total` items: [lo, lo + len)
+static inline void split_range(uint64_t total, int g, int i, uint64_t *lo, uint64_t *len) {
+    const uint64_t base = total / (uint64_t)g, rem = total % (uint64_t)g;
+    *len = base + ((uint64_t)i < rem ? 1 : 0);
+    *lo = (uint64_t)i * base + std::min<uint64_t>((uint64_t)i, rem);
+}
+
+// The requests of one update_samples call over the members of a (possibly multi-GPU) context.  Every (shift, point) is
+// independent (pmap over the product, src/sample.jl:95), so a request splits without any data-path exchange:
+//   - it uses g = clamp(samples / shard_min, 1, G) members: a request smaller than about one wave of CTAs per extra GPU
+//     stays on one device (more devices would add launch latency, not throughput);
+//   - R >= g: WHOLE SHIFTS per member (contiguous, balanced).  A member's moment triplets are final and land at their place
+//     in the caller's table: no merge at all;
+//   - R < g (MC: R = 1): every member takes a slice of the point numbers of every shift; the members' triplets are merged on
+//     the host in member order (Chan), deterministically.
+// All members' kernels are issued before the first wait; each member signals through its own mapped flag.
+static int update_samples_group(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *indices, int d,
+                                const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n, const int *m,
+                                uint64_t mc_seed, double *const *moments, double *gpu_seconds) {
+    const int G = group_size(ctx);
+    const size_t V3 = (size_t)2 * (size_t)M->nqoi * 3;
+    struct Sub { std::vector<const int32_t *> idx; std::vector<const double *> sh; std::vector<int> R, m, entry; std::vector<uint64_t> k0, n; std::vector<double *> mom; };
+    std::vector<Sub> sub((size_t)G);
+    std::vector<std::vector<double>> tmp;  // member tables of point-split entries
+    tmp.reserve((size_t)count * (size_t)G);
+    struct Merge { int entry; std::vector<double *> parts; };
+    std::vector<Merge> merges;
+    for (int e = 0; e < count; ++e) {
+        if (R[e] < 1 || !moments[e]) return fail(ctx, MLE_ERR_ARG, "update_samples: every entry needs R >= 1 and a moment table");
+        const uint64_t total = n[e] * (uint64_t)R[e];
+        int g = (int)std::min<uint64_t>((uint64_t)G, std::max<uint64_t>(1, total / std::max<uint64_t>(1, ctx->shard_min)));
+        const bool by_shift = R[e] >= g;
+        if (!by_shift && n[e] < (uint64_t)g) g = (int)std::max<uint64_t>(1, n[e]);
+        Merge mg; mg.entry = e;
+        for (int i = 0; i < g; ++i) {
+            Sub &S = sub[(size_t)i];
+            uint64_t lo, len;
+            S.idx.push_back(indices + (size_t)e * d);
+            S.m.push_back(m[e]);
+            S.entry.push_back(e);
+            if (by_shift) {
+                split_range((uint64_t)R[e], g, i, &lo, &len);
+                S.sh.push_back(shifts && shifts[e] && lat ? shifts[e] + lo * (size_t)lat->s : nullptr);
+                S.R.push_back((int)len); S.k0.push_back(k0[e]); S.n.push_back(n[e]);
+                S.mom.push_back(moments[e] + lo * V3);
+            } else {
+                split_range(n[e], g, i, &lo, &len);
+                S.sh.push_back(shifts ? shifts[e] : nullptr);
+                S.R.push_back(R[e]); S.k0.push_back(k0[e] + lo); S.n.push_back(len);
+                if (i == 0) S.mom.push_back(moments[e]);
+                else { tmp.emplace_back((size_t)R[e] * V3); S.mom.push_back(tmp.back().data()); mg.parts.push_back(tmp.back().data()); }
+            }
+        }
+        if (!mg.parts.empty()) merges.push_back(std::move(mg));
+    }
+    std::vector<IssueState> st((size_t)G);
+    int rc = MLE_OK;
+    for (int i = 0; i < G && rc == MLE_OK; ++i) {
+        Sub &S = sub[(size_t)i];
+        if (S.idx.empty()) continue;
+        mle_ctx c = member_ctx(ctx, i);
+        rc = update_issue(c, member_handle(M, i), member_handle(lat, i), member_handle(dists, i), (int)S.idx.size(), S.idx.data(), d,
+                          S.sh.data(), S.R.data(), S.k0.data(), S.n.data(), S.m.data(), mc_seed, gpu_seconds != nullptr, &st[(size_t)i]);
+        if (rc != MLE_OK && i > 0) peer_fail(ctx, c, rc);
+    }
+    double tmax = 0.0;
+    for (int i = 0; i < G; ++i) {  // collect from every member that was issued, even after a failure elsewhere
+        Sub &S = sub[(size_t)i];
+        if (!st[(size_t)i].used) continue;
+        mle_ctx c = member_ctx(ctx, i);
+        double t = 0.0;
+        const int rc2 = update_collect(c, member_handle(M, i), (int)S.idx.size(), S.R.data(), S.mom.data(), st[(size_t)i], gpu_seconds ? &t : nullptr);
+        if (rc2 != MLE_OK && rc == MLE_OK) { rc = rc2; if (i > 0) peer_fail(ctx, c, rc2); }
+        tmax = std::max(tmax, t);
+    }
+    if (G > 1) cudaSetDevice(ctx->device);
+    if (rc != MLE_OK) return rc;
+    for (const Merge &mg : merges)
+        for (double *part : mg.parts) mle_moments_merge(moments[mg.entry], part, (size_t)R[mg.entry] * 2 * (size_t)M->nqoi);
+    if (gpu_seconds) *gpu_seconds = tmax;
+    return MLE_OK;
+}
+
+extern "C" int mle_update_samples(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *indices,
+                                  int d, const double *const *shifts, const int *R, const uint64_t *k0, const uint64_t *n,
+                                  const int *m, uint64_t mc_seed, double *const *moments) {
+    MLE_API_SCOPE;
+    if (!ctx || !M || count < 0 || (count && (!indices || !R || !k0 || !n || !m || !moments))) return MLE_ERR_ARG;
+    if (count == 0) return MLE_OK;
+    return update_samples_group(ctx, M, lat, dists, count, indices, d, shifts, R, k0, n, m, mc_seed, moments, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1169,17 +1399,3 @@ extern "C" int mle_moments_merge(double *acc, const double *part, size_t count) 
     return MLE_OK;
 }
 
-#ifdef MLE_PHASE_TIMING
-// debug builds only (-DMLE_PHASE_TIMING): wall cycles thread 0 of every CTA spent per phase of lognormal1d_kernel
-extern "C" int mle_debug_cta_times(unsigned long long *out, int n) {
-    if (cudaMemcpyFromSymbol(out, mle::g_cta_times, sizeof(unsigned long long) * 3 * (size_t)n) != cudaSuccess) return -2;
-    return 0;
-}
-extern "C" int mle_debug_phase_cycles(unsigned long long *out8, int reset) {
-    MLE_API_SCOPE;
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemcpyFromSymbol(out8, mle::g_phase_cycles, sizeof(z)) != cudaSuccess) return -2;
-    if (reset && cudaMemcpyToSymbol(mle::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -2;
-    return 0;
-}
-#endif

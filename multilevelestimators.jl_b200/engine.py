@@ -69,17 +69,24 @@ class DeviceModel(_Handle):
 
 class Engine:
     def __init__(self, device=0):
+        """device: a CUDA ordinal, or a list of ordinals for ONE multi-GPU context (mle_init_multi: the reference's
+        `nb_of_workers`, src/parse.jl:224-234 -- requests are split over the devices inside the library)"""
         self.lib = _lib.load()
         ctx = C.c_void_p()
-        rc = self.lib.mle_init(int(device), C.byref(ctx))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(x) for x in device])
+            rc = self.lib.mle_init_multi(devs, len(device), C.byref(ctx))
+        else:
+            rc = self.lib.mle_init(int(device), C.byref(ctx))
         if rc != _lib.MLE_OK:
             msg = self.lib.mle_last_error(None).decode()
             raise MLEError("mle_init failed (%d): %s" % (rc, msg))
         self.ctx = ctx
         self.device = device
-        sm, hbm, cc = C.c_int(), C.c_size_t(), C.c_int()
+        sm, hbm, cc, nd = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
         self.lib.mle_device_info(self.ctx, C.byref(sm), C.byref(hbm), C.byref(cc))
-        self.sm_count, self.hbm_bytes, self.cc = sm.value, hbm.value, cc.value
+        self.lib.mle_device_count(self.ctx, C.byref(nd))
+        self.sm_count, self.hbm_bytes, self.cc, self.device_count = sm.value, hbm.value, cc.value, nd.value
 
     # ---- plumbing ----------------------------------------------------------------------------------------------
     def _check(self, rc):

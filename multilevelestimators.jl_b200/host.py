@@ -257,6 +257,15 @@ class GpuBackend:
         model is the wall time of the call, like the reference's (src/sample.jl:27), and does not need it"""
         self.engine, self.time_kernels = engine, time_kernels
 
+    @classmethod
+    def for_workers(cls, nb_of_workers=1, first_device=0, **kw):
+        """the reference's `nb_of_workers` option (src/parse.jl:224-234: the size of the pmap worker pool of src/sample.jl:43-45,
+        :89-91) as a number of GPUs: ONE multi-GPU context (mle_init_multi) on devices first_device .. first_device+nb_of_workers-1;
+        the library splits every request over them (whole shifts per GPU, small requests stay on one GPU)"""
+        from .engine import Engine
+        devs = list(range(first_device, first_device + int(nb_of_workers)))
+        return cls(Engine(devs if len(devs) > 1 else devs[0]), **kw)
+
     def lattice(self, z, s, nmax=2**32 - 1):
         return self.engine.lattice(z, s, nmax)
 
@@ -300,6 +309,11 @@ class ShardedBackend:
         import torch.distributed as dist
         self.inner, self.dist, self.group, self.device = inner, dist, group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        # every rank must take the same adaptive decisions, so the time charged to an index (the reference's default cost model is
+        # the wall time of the call, src/sample.jl:27) has to be the SAME number on all ranks: the calls below return the maximum
+        # over the ranks of the local wall time (it travels with the moments in the one all-gather) and the estimator uses it
+        self.consensus_time = True
+        self.last_time = 0.0
         if merge is None:
             from .engine import moments_merge as merge
         self.merge = merge
@@ -327,19 +341,22 @@ class ShardedBackend:
                 local.append((index, shifts, start, cnt, m))
             else:
                 mine.append(None)
+        t0 = _time.perf_counter()
         if local and hasattr(self.inner, "update_samples"):
             moms = self.inner.update_samples(model, lattice, dists, local, mc_seed)
         else:
             moms = [self.inner.sample_batch(model, lattice, dists, i, sh, k0, n, m, mc_seed)[0] for i, sh, k0, n, m in local]
+        t_local = _time.perf_counter() - t0
         shapes = [((1 if e[1] is None else len(e[1])), q, 2, 3) for e in entries]
         parts = [np.asarray(moms[j], dtype=np.float64).reshape(-1) if j is not None else np.zeros(int(np.prod(sh)))
                  for j, sh in zip(mine, shapes)]
-        payload = torch.from_numpy(np.concatenate(parts))
+        payload = torch.from_numpy(np.concatenate(parts + [np.array([t_local])]))
         if self.device is not None:
             payload = payload.to(self.device)
         out = [torch.empty_like(payload) for _ in range(self.world)]
         self.dist.all_gather(out, payload, group=self.group)
         flat = [o.cpu().numpy() for o in out]
+        self.last_time = max(float(f[-1]) for f in flat)
         result, off = [], 0
         for sh in shapes:
             size = int(np.prod(sh))
@@ -358,12 +375,14 @@ class ShardedBackend:
         R = 1 if shifts is None else len(shifts)
         q = getattr(model, "nqoi", 1)
         smp = None
+        t0 = _time.perf_counter()
         if cnt > 0:
             out = self.inner.sample_batch(model, lattice, dists, index, shifts, start, cnt, m, mc_seed, want_samples=want_samples)
-            mom, t = out[0], out[1]
+            mom = out[0]
             smp = out[2] if want_samples else None
         else:
-            mom, t = np.zeros((R, q, 2, 3)), 0.0
+            mom = np.zeros((R, q, 2, 3))
+        t = _time.perf_counter() - t0   # local wall time; the maximum over the ranks is what every rank charges
         payload = torch.from_numpy(np.concatenate([np.asarray(mom, dtype=np.float64).reshape(-1), [t]]))
         if self.device is not None:
             payload = payload.to(self.device)
@@ -374,6 +393,7 @@ class ShardedBackend:
         for p in parts[1:]:
             acc = self.merge(acc, p[:-1].reshape(mom.shape))
         tmax = max(float(p[-1]) for p in parts)
+        self.last_time = tmax
         if not want_samples:
             return acc, tmax
         # second all-gather: the raw samples, padded to the largest slice (slices differ by at most one point)
@@ -645,7 +665,7 @@ class Estimator:
         m = self.options["nb_of_uncertainties"](index)
         seed = index_seed(self.options["mc_seed"], index)   # one input vector per sample, shared by every idx <= index
         t0 = _time.perf_counter()
-        Z = None
+        Z, t_cons = None, 0.0
         for idx in sorted(itertools.product(*[range(i + 1) for i in index]), key=lambda t: t[::-1]):
             mom, _t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(idx), self.shifts.get(index),
                                                      istart - 1, n, m, seed, want_samples=True)
@@ -654,7 +674,8 @@ class Estimator:
                 self.samples.setdefault(idx, []).append(np.array(smp))
             term = smp[:, :, 0, :] / self.Prob(idx)
             Z = term if Z is None else Z + term
-        t = _time.perf_counter() - t0
+            t_cons += _t
+        t = t_cons if getattr(self.backend, "consensus_time", False) else _time.perf_counter() - t0
         zm = Z.mean(axis=-1)
         part = np.stack([np.full(zm.shape, float(n)), zm, ((Z - zm[..., None]) ** 2).sum(axis=-1)], axis=-1)   # [R, q, 3]
         self.acc = part if self.acc is None else moments_merge(self.acc, part)
@@ -686,7 +707,8 @@ class Estimator:
         else:
             mom, _gpu_t = self.backend.sample_batch(self.model, self.lattice, self.dists, list(index),
                                                     self.shifts.get(index), istart - 1, n, m, seed)
-        t = _time.perf_counter() - t0
+        # wall time of the call (src/sample.jl:27); a sharded backend returns the rank-agreed maximum instead (see ShardedBackend)
+        t = _gpu_t if getattr(self.backend, "consensus_time", False) else _time.perf_counter() - t0
         if index in self.moments:
             from .engine import moments_merge
             self.moments[index] = moments_merge(self.moments[index], mom)
@@ -703,9 +725,11 @@ class Estimator:
                    for index, n in due]
         t0 = _time.perf_counter()
         moms = self.backend.update_samples(self.model, self.lattice, self.dists, entries, self.options["mc_seed"])
-        t = _time.perf_counter() - t0
+        t = self.backend.last_time if getattr(self.backend, "consensus_time", False) else _time.perf_counter() - t0
         cm = self.options["cost_model"]
         work = [n * cm(index) for index, n in due]
+        if not sum(work) > 0:   # a cost model that returns 0: share the time out by sample counts
+            work = [float(n) for _, n in due]
         for (index, n), mom, w in zip(due, moms, work):
             self.moments[index] = moments_merge(self.moments[index], mom) if index in self.moments else np.array(mom, dtype=np.float64)
             self.nb_of_samples[index] += n

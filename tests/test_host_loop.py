@@ -518,6 +518,38 @@ def test_two_rank_sharding_matches_single_rank(tmp_path):
     assert abs(got[1] - h["varest"]) <= 1e-9 * abs(h["varest"])
 
 
+def _worker_default_cost(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import mle_b200.host as H
+    res = []
+    for index_set, method, spec, dl in ((H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)]),
+                                        (H.AD(2), H.MC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2)):
+        est = H.Estimator(index_set, method, spec, dl, H.ShardedBackend(OracleBackend()), nb_of_qoi=13, max_index_set_param=3,
+                          nb_of_tols=3, **({"nb_of_shifts": 4} if isinstance(method, H.QMC) else {}))   # cost_model: default (time)
+        h = H.run(est, 2e-2)
+        res += [h["mean"], float(sum(h["nb_of_samples"].values())), float(sum(est.total_time.values()))]
+    np.save(out % rank, np.array(res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_run_with_the_default_time_cost_model(tmp_path):
+    """the reference's default cost model is the measured time of each sample! call (src/sample.jl:27, src/internals.jl:106).
+    Sharded, every rank must charge the SAME time or the ranks request different sample counts and deadlock in the all-gather:
+    the backend returns the maximum of the ranks' wall times and the estimator uses it.  Both ranks finish with identical
+    sample counts, estimates and accumulated times."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "dc%d.npy")
+    mp.spawn(_worker_default_cost, args=(2, 29557, out), nprocs=2, join=True)
+    a, b = np.load(out % 0), np.load(out % 1)
+    assert np.array_equal(a, b), (a, b)
+    assert a[2] > 0 and a[5] > 0
+
+
 def test_adaptive_index_set_mechanics():
     """src/methods.jl:223-251 and test/index_set.jl:54-60: AD starts from the root index, moves the index with the largest
     profit into the old set, activates its admissable forward neighbours inside max_search_space, and logs every step"""
