@@ -869,7 +869,8 @@ static long long grid_x_for(mle_ctx ctx, long long tiles_per_shift, int R, int c
 // shift have been written (cta_finalize)
 static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
                         const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
-                        double *moments_dev, double *samples_dev, unsigned *flag_dev, unsigned seq) {
+                        double *moments_dev, double *samples_dev, double *host_moments_dev = nullptr, unsigned *flag_dev = nullptr,
+                        unsigned seq = 0) {
     if (!ctx || !M || !index || !moments_dev) return MLE_ERR_ARG;
     if (d != M->ndims) return fail(ctx, MLE_ERR_ARG, "index dimension does not match the model");
     for (int t = 0; t < d; ++t)
@@ -893,7 +894,7 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         (void)before;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_tickets, 0, ctx->tickets_cap * sizeof(unsigned), ctx->stream));
     }
-    FinArgs fa{nullptr, ctx->d_tickets, moments_dev, flag_dev, seq};
+    FinArgs fa{nullptr, ctx->d_tickets, moments_dev, host_moments_dev, flag_dev, seq};
     if (M->kind == MODEL_EXPSUM || M->kind == MODEL_PROBLEM18) {
         const long long tps = (long long)((n + SIMPLE_THREADS - 1) / SIMPLE_THREADS);
         SimpleModelArgs ma{};
@@ -1085,7 +1086,7 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
                                     const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
                                     double *moments_dev, double *samples_dev) {
     MLE_API_SCOPE;
-    return launch_batch(ctx, M, lat, dists, index, d, shifts_dev, R, k0, n, m, mc_seed, moments_dev, samples_dev, nullptr, 0);
+    return launch_batch(ctx, M, lat, dists, index, d, shifts_dev, R, k0, n, m, mc_seed, moments_dev, samples_dev);
 }
 
 extern "C" int mle_moments_merge(double *acc, const double *part, size_t count);
@@ -1148,8 +1149,8 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     const size_t ns = samples ? (size_t)R * 2 * (size_t)M->nqoi * n : 0;
     // zero-copy: the last CTA writes the moment table straight into mapped host memory and raises a flag the host polls
     const bool zc = ctx->zero_copy && !ns;
-    if (zc) rc = ensure_res(ctx, nm);
-    else rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, nm);
+    rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, nm);
+    if (rc == MLE_OK && zc) rc = ensure_res(ctx, nm);
     if (rc) return rc;
     if (!zc && nm + 64 > ctx->pinned_cap) {  // staging for the moments (classic path)
         ctx->shifts_staged = 0;
@@ -1163,8 +1164,8 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
     }
     if (gpu_seconds) cudaEventRecord(ctx->ev0, ctx->stream);  // timing is optional: two event records cost ~4 us per call
     const unsigned seq = ++ctx->seq ? ctx->seq : ++ctx->seq;  // never 0 (the flag's initial value)
-    rc = launch_batch(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, zc ? ctx->d_res : ctx->d_moments,
-                      ns ? ctx->d_samples : nullptr, zc ? ctx->d_flag : nullptr, seq);
+    rc = launch_batch(ctx, M, lat, dists, index, d, sh_dev, R, k0, n, m, mc_seed, ctx->d_moments, ns ? ctx->d_samples : nullptr,
+                      zc ? ctx->d_res : nullptr, zc ? ctx->d_flag : nullptr, seq);
     if (gpu_seconds) cudaEventRecord(ctx->ev1, ctx->stream);
     if (rc != MLE_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
     if (zc) {
@@ -1216,7 +1217,7 @@ static int update_issue(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
     }
     const bool zc = ctx->zero_copy != 0;
     const double *batch_before = ctx->d_batch;
-    int rc = ensure_dev(ctx, &ctx->d_batch, &ctx->batch_cap, sh_total + (zc ? 0 : mom_total));
+    int rc = ensure_dev(ctx, &ctx->d_batch, &ctx->batch_cap, sh_total + mom_total);
     if (rc) return rc;
     if (ctx->d_batch != batch_before) ctx->batch_staged = 0;
     rc = ensure_pinned(ctx, sh_total + (zc ? 0 : mom_total) + 4096);
@@ -1244,7 +1245,7 @@ static int update_issue(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         if (sh_total) CU_TRY(ctx, cudaMemcpyAsync(ctx->d_batch, ctx->h_pinned, sh_total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->batch_staged = sh_total;
     }
-    double *mom_base = zc ? ctx->d_res : ctx->d_batch + sh_total;
+    double *mom_base = ctx->d_batch + sh_total;  // device tables; zero-copy: each launch's last CTA mirrors its table to h_res
     const unsigned seq = ++ctx->seq ? ctx->seq : ++ctx->seq;  // never 0 (the flag's initial value)
     if (timed) cudaEventRecord(ctx->ev0, ctx->stream);
     size_t sh_off = 0, mom_off = 0;
@@ -1253,7 +1254,7 @@ static int update_issue(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         if (lat && shifts && shifts[e]) { sh_dev = ctx->d_batch + sh_off; sh_off += (size_t)R[e] * (size_t)lat->s; }
         const bool last = e == count - 1;
         rc = launch_batch(ctx, M, lat, dists, indices[e], d, sh_dev, R[e], k0[e], n[e], m[e], mc_seed, mom_base + mom_off,
-                          nullptr, (zc && last) ? ctx->d_flag : nullptr, seq);
+                          nullptr, zc ? ctx->d_res + mom_off : nullptr, (zc && last) ? ctx->d_flag : nullptr, seq);
         mom_off += (size_t)R[e] * 2 * (size_t)M->nqoi * 3;
     }
     if (timed) cudaEventRecord(ctx->ev1, ctx->stream);

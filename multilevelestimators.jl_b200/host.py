@@ -625,6 +625,11 @@ class Estimator:
         self.ad_boundary = {(0,) * d}
         self._ad_rng = _random.Random(o["shift_seed"])
         self.moments, self.nb_of_samples, self.total_work, self.total_time = {}, {}, {}, {}
+        # the loop queries mean / var / varest / rates of every index many times between two sample! calls (bias, splitting, mse,
+        # history); the values only change when samples arrive, so they are memoised until then (the reference recomputes them
+        # from the stored sample vectors on every query)
+        self._memo = {}
+        self._boundary_cache = {}
         self.samples = {}  # save_samples: index -> list of [R, q, 2, n] blocks (X = 0: differences, 1: fine values)
         self.shifts = {}
         rng = np.random.default_rng(o["shift_seed"])
@@ -679,6 +684,7 @@ class Estimator:
         zm = Z.mean(axis=-1)
         part = np.stack([np.full(zm.shape, float(n)), zm, ((Z - zm[..., None]) ** 2).sum(axis=-1)], axis=-1)   # [R, q, 3]
         self.acc = part if self.acc is None else moments_merge(self.acc, part)
+        self._memo.clear()
         self.nb_of_samples[index] += n
         cm = self.options["cost_model"]
         self.total_work[index] += 0.0 if cm is None else n * cm(index)
@@ -714,6 +720,7 @@ class Estimator:
             self.moments[index] = moments_merge(self.moments[index], mom)
         else:
             self.moments[index] = np.array(mom, dtype=np.float64)
+        self._invalidate(index)
         self.nb_of_samples[index] += n                                  # src/internals.jl:90
         cm = self.options["cost_model"]
         self.total_work[index] += 0.0 if cm is None else n * cm(index)  # src/internals.jl:98
@@ -730,6 +737,7 @@ class Estimator:
         work = [n * cm(index) for index, n in due]
         if not sum(work) > 0:   # a cost model that returns 0: share the time out by sample counts
             work = [float(n) for _, n in due]
+        self._memo.clear()
         for (index, n), mom, w in zip(due, moms, work):
             self.moments[index] = moments_merge(self.moments[index], mom) if index in self.moments else np.array(mom, dtype=np.float64)
             self.nb_of_samples[index] += n
@@ -765,7 +773,25 @@ class Estimator:
             return float(np.linalg.norm(values))
         return float(values[self.options["qoi_with_max_var"] - 1])
 
+    def _cached(self, key, fn):
+        v = self._memo.get(key)
+        if v is None:
+            v = self._memo[key] = fn()
+        return v
+
+    def _invalidate(self, index=None):
+        """new samples at `index` (None: the index sets changed): per-index statistics of the other indices stay valid"""
+        if index is None:
+            drop = [k for k in self._memo if k[0] in ("rates", "bias")]
+        else:
+            drop = [k for k in self._memo if k[0] in ("rates", "bias") or k[1] == index]
+        for k in drop:
+            del self._memo[k]
+
     def _per_qoi(self, index, X, f):
+        return self._cached(("pq", index, X, f), lambda: self._per_qoi_now(index, X, f))
+
+    def _per_qoi_now(self, index, X, f):
         if index not in self.moments:           # mean / var of an empty sample vector: NaN like the reference
             return np.full(self.nqoi, float("nan"))
         mom = self.moments[index][:, :, X, :]  # [R, q, 3]
@@ -805,9 +831,11 @@ class Estimator:
             return sum(self.varest(i) for i in self.keys())
         if not self.qmc:
             return self.var(index) / self.nb_of_samples[index]          # src/methods.jl:66
-        means = self.moments[index][:, :, 0, 1]                         # per-shift means [R, q]
-        R = means.shape[0]
-        return self._aggregate(means.var(axis=0, ddof=1) / R)           # src/methods.jl:282
+
+        def now():
+            means = self.moments[index][:, :, 0, 1]                     # per-shift means [R, q]
+            return self._aggregate(means.var(axis=0, ddof=1) / means.shape[0])   # src/methods.jl:282
+        return self._cached(("varest", index), now)
 
     def cost(self, index):  # src/methods.jl:64
         tot = self.total_time if self.options["cost_model"] is None else self.total_work
@@ -829,10 +857,21 @@ class Estimator:
     # ---- rates and regression (src/methods.jl:70-163) -----------------------------------------------------------------------
     @staticmethod
     def _interp1(x, y):
+        n = len(x)
+        if n >= 2 and len(set(x)) >= 2 and all(math.isfinite(v) for v in y):
+            # straight-line least squares in closed form (the generic solver below costs 60 us per call, and the loop fits
+            # a line two or three times per sample! call)
+            xm, ym = math.fsum(x) / n, math.fsum(y) / n
+            sxx = math.fsum((a - xm) ** 2 for a in x)
+            b = math.fsum((a - xm) * (c - ym) for a, c in zip(x, y)) / sxx
+            return np.array([ym - b * xm, b])
         A = np.column_stack([np.ones(len(x)), np.asarray(x, dtype=float)])
         return np.linalg.lstsq(A, np.asarray(y, dtype=float), rcond=None)[0]
 
     def _rates(self, g, idx, dir):
+        return self._cached(("rates", getattr(g, "__name__", None) or id(g), idx, dir), lambda: self._rates_now(g, idx, dir))
+
+    def _rates_now(self, g, idx, dir):
         m = idx[dir] - 1
         if m < 2:
             return (float("nan"), float("nan"))
@@ -966,6 +1005,7 @@ class Estimator:
                                       stacklevel=2)  # warn_max_index, src/print.jl:247 (unconditional in the reference)
                         self.max_index_set.add(nb)
         self.logbook.append((set(self.old_set), set(self.active_set), max_index))
+        self._invalidate()
         return new
 
     def set_sz(self, n):  # src/internals.jl:256-262
@@ -986,6 +1026,12 @@ class Estimator:
         self.logbook.clear()
 
     def boundary(self, cntr):
+        b = self._boundary_cache.get(cntr)
+        if b is None:
+            b = self._boundary_cache[cntr] = self._boundary_now(cntr)
+        return b
+
+    def _boundary_now(self, cntr):
         prev = set(self.index_set.get_index_set(cntr - 1)) if cntr > 0 else set()
         return [i for i in self.index_set.get_index_set(cntr) if i not in prev]
 
@@ -995,6 +1041,9 @@ class Estimator:
         if self.unbiased:
             return 0.0     # src/methods.jl:347
         sz = self.sz if sz is None else sz
+        return self._cached(("bias", sz, self.max_sz), lambda: self._bias_now(sz))
+
+    def _bias_now(self, sz):
         if self.adaptive:  # src/methods.jl:253-260
             b = lambda indices: abs(sum(self.mean(i) for i in sorted(indices, key=lambda t: t[::-1])))
             return b(self.active_set) if sz != self.max_sz else min(b(self.active_set), b(self.ad_boundary))
@@ -1161,6 +1210,7 @@ def _run_unbiased(est, eps):  # src/run.jl:145-200
     if rep:
         rep.index_set(index_set)
     est.current_index_set.update(index_set)
+    est._invalidate()
     v = est.varest()
     while not v <= eps**2:  # NaN (no samples yet) keeps looping, like `is_converged = varest(estimator) <= eps^2` in the reference
         if rep:
@@ -1205,6 +1255,7 @@ def _run(est, eps):  # src/run.jl:41-142
             if not est.has_samples_at_index(index):
                 est.sample(index, ns[index])
         est.current_index_set.update(index_set)
+        est._invalidate()
         est.set_sz(L)
         if rep:
             rep.status()
