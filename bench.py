@@ -10,6 +10,12 @@ solves -> (dQ, Qf) -> per-(level, shift) moments.  Multi-GPU: each rank owns its
 for every shift (weak scaling: n_l per rank fixed) and one NCCL all-gather per step combines the moment triplets,
 merged in rank order with Chan's formula.
 
+Extra keys of the JSON line: `strong` (the same step with every level's points SPLIT over the ranks: fixed total
+work), `extra.c3` (config C3: MLMC on the 2-D lognormal model, 400 KL terms, levels 0-5, point slices per rank + merge),
+`extra.c5` (config C5: 2^24 lattice points x 1000 dims, fused generate -> integrand -> moments), `run_e2e` (N = 1: wall time of
+run(estimator, tol) on the GPU backend vs the CPU oracle backend, tools/run_e2e.py).
+Launched WITHOUT torchrun and --gpus N > 1 the bench runs single-process on ONE multi-GPU context (mle_init_multi).
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
 import argparse
@@ -203,6 +209,149 @@ def workload_config():
                   "buffer is rewritten between steps, outside the per-step event pairs"}
 
 
+
+def _ncu_rows():
+    """rows of the committed ncu summary of this command (tools/summarize_profiles.py -> profiles/r02_final_kernels.csv)"""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02_final_kernels.csv")
+    try:
+        rows = list(csv.DictReader(open(path)))
+    except Exception:  # noqa: BLE001
+        return None
+    return [r for r in rows if "lognormal1d" in r.get("Kernel Name", "")][:len(LEVELS)] or None
+
+
+def ncu_pipe_busy():
+    rows = _ncu_rows()
+    if not rows:
+        return None
+    try:
+        return [round((float(r["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active [%]"]) +
+                       float(r["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed [%]"])) / 100.0, 3) for r in rows]
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def ncu_traffic():
+    rows = _ncu_rows()
+    if not rows:
+        return None
+    try:
+        return sum(float(r["dram__bytes_read.sum [Kbyte]"]) * 1e3 + float(r["dram__bytes_write.sum [byte]"]) for r in rows)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configs C3 and C5 (BASELINE.json configs[2], configs[4]) at the --gpus the driver passes
+# ---------------------------------------------------------------------------------------------------------------
+C3_M, C3_LEVELS = 400, list(range(6))
+C3_POINTS = [1 << 20, 1 << 18, 1 << 16, 1 << 13, 1 << 11, 1184]   # MC samples per level and rank (1184 = 148 SMs x 8 samples per CTA)
+C5_DIMS, C5_LOG2_POINTS = 1000, 24
+
+
+def c3_flops_per_sample(level):
+    """2-D model: field 2 (N+1)^2 m + exp 34 (N+1)^2 + frontal elimination 2 N^4 (full-window rank-1 updates), coarse solve 1/16"""
+    N = 4 << level
+    nodes = (N + 1) ** 2
+    return 2.0 * nodes * C3_M + 34.0 * nodes + 2.0 * float(N) ** 4 * (1.0 + (1.0 / 16 if level else 0.0))
+
+
+def bench_extras(eng, torch, dist, stream, world, rank):
+    import mle_b200
+    import mle_b200.kl as kl
+    out = {}
+    def tmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    # ---- C3: ML()/MC() on the 2-D lognormal diffusion, 400 KL terms, levels 0-5; rank r takes points [r n, (r+1) n) ---------
+    try:
+        d3 = eng.dists([(mle_b200.NORMAL, [0.0, 1.0])] * C3_M)
+        g3 = eng.model("lognormal2d", 1, [4])
+        for lev in C3_LEVELS:
+            g3.set_basis(lev, kl.kl_basis_2d(lev, m=C3_M))
+        mom = torch.zeros(len(C3_LEVELS), 6, dtype=torch.float64, device="cuda")
+        gat = torch.zeros(world, mom.numel(), dtype=torch.float64, device="cuda") if world > 1 else None
+
+        def step_c3():
+            for li, lev in enumerate(C3_LEVELS):
+                eng.sample_batch_dev(g3, None, d3, [lev], None, 1, rank * C3_POINTS[li], C3_POINTS[li], C3_M, mom[li].data_ptr(),
+                                     mc_seed=1000 + lev)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(gat.view(-1), mom.view(-1))
+        step_c3(); torch.cuda.synchronize()
+        lvl = []
+        for li, lev in enumerate(C3_LEVELS):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            eng.sample_batch_dev(g3, None, d3, [lev], None, 1, rank * C3_POINTS[li], C3_POINTS[li], C3_M, mom[li].data_ptr(), mc_seed=1000 + lev)
+            b.record(stream); torch.cuda.synchronize()
+            lvl.append(a.elapsed_time(b))
+        if world > 1:
+            dist.barrier()
+        reps = 3
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record(stream)
+        for _ in range(reps):
+            step_c3()
+        b.record(stream); torch.cuda.synchronize()
+        ms = tmax(a.elapsed_time(b) / reps)
+        per_rank = sum(C3_POINTS)
+        flops = sum(c3_flops_per_sample(lev) * C3_POINTS[li] for li, lev in enumerate(C3_LEVELS))
+        out["c3"] = {"workload": "C3: ML()/MC() 2-D lognormal diffusion, 400-term KL, levels 0-5 (grid 4*2^l squared), MC points per level "
+                                 "and rank %s, ranks take disjoint point slices, one all-gather of the moments" % C3_POINTS,
+                     "value": per_rank * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "scaling": "weak",
+                     "per_level_ms_rank0": lvl,
+                     "per_level_samples_per_s_rank0": [C3_POINTS[i] / (lvl[i] * 1e-3) for i in range(len(lvl))],
+                     "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops / (sum(lvl) * 1e-3) * 1e-12,
+                                  "note": "algorithmic FP64 operations (field 2(N+1)^2 m, exp, frontal elimination 2N^4) / kernel "
+                                          "time on rank 0; peak = the FP64 roof of `roofline.peak`"}}
+        g3.close()
+    except Exception as e:  # noqa: BLE001
+        out["c3"] = {"error": repr(e)}
+    # ---- C5: 2^24 lattice points x 1000 dims, 16 shifts, fused generate -> exp(sum a_j xi_j) -> moments ------------------------
+    try:
+        s5 = C5_DIMS
+        z5 = eng.genvec("K_3600_32")[:s5]
+        l5 = eng.lattice(z5, s5)
+        d5 = eng.dists([(mle_b200.NORMAL, [0.0, 1.0])] * s5)
+        g5 = eng.model("expsum", 1, [float(s5)] + [0.5 / (j + 1) for j in range(s5)])
+        sh5 = torch.from_numpy(splitmix_uniforms(2024, R_SHIFTS * s5).reshape(R_SHIFTS, s5)).cuda()
+        n5 = (1 << C5_LOG2_POINTS) // R_SHIFTS   # points per shift and rank
+        mom5 = torch.zeros(R_SHIFTS * 6, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            eng.sample_batch_dev(g5, l5, d5, [0], sh5.data_ptr(), R_SHIFTS, rank * n5, n5, s5, mom5.data_ptr())
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(3):
+            eng.sample_batch_dev(g5, l5, d5, [0], sh5.data_ptr(), R_SHIFTS, rank * n5, n5, s5, mom5.data_ptr())
+        b.record(stream); torch.cuda.synchronize()
+        ms = tmax(a.elapsed_time(b) / 3)
+        coords = float(n5) * R_SHIFTS * s5
+        est = mom5.cpu().numpy().reshape(R_SHIFTS, 2, 3)[:, 1, 1]
+        exact = float(np.exp(0.5 * sum((0.5 / (j + 1)) ** 2 for j in range(s5))))
+        fp64_per_coord = 40.0   # FP64-pipe instructions per coordinate of the generator (SASS count, DESIGN.md 3.1)
+        ceiling = 148 * 64 * 1.965e9 / fp64_per_coord
+        out["c5"] = {"workload": "C5: 2^%d lattice points x %d dims per rank, 16 shifts, Normal inverse CDF, integrand exp(sum a_j xi_j), "
+                                 "shift-averaged moments; fused kernel, 0 HBM bytes per coordinate" % (C5_LOG2_POINTS, s5),
+                     "value": coords * world / (ms * 1e-3), "unit": "coordinates/s", "ms": ms, "scaling": "weak",
+                     "estimate": float(est.mean()), "closed_form": exact,
+                     "std_errors_off": float(abs(est.mean() - exact) / (est.std(ddof=1) / np.sqrt(R_SHIFTS))),
+                     "roofline": {"bound": "min(hbm, fp64)", "achieved": coords / (ms * 1e-3), "peak": ceiling, "unit": "coordinates/s",
+                                  "frac": coords / (ms * 1e-3) / ceiling,
+                                  "note": "the fused sweep writes nothing per coordinate, so HBM does not bound it; the FP64 pipe does: "
+                                          "148 SMs x 64 lanes x 1.965 GHz / 40 FP64 instructions per coordinate"}}
+        g5.close()
+    except Exception as e:  # noqa: BLE001
+        out["c5"] = {"error": repr(e)}
+    return out
+
 # ---------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -307,11 +456,16 @@ def run_ours(args):
         lvl_ms.append(a.elapsed_time(b) / reps)
 
     # ---- end-to-end arm through the host-buffer C-ABI call (H2D of the shifts + D2H of the moments every call) -----------
-    sh_pinned = torch.from_numpy(sh_host.copy()).pin_memory()
-    sh_np = sh_pinned.numpy()
+    # two shift sets used in turn: the library skips the upload of shifts it already holds (an adaptive run keeps one shift
+    # vector per (index, shift) for its whole life, src/internals.jl:138), and this arm must pay the H2D copy every step
+    sh_sets = [torch.from_numpy(sh_host.copy()).pin_memory().numpy(),
+               torch.from_numpy(np.ascontiguousarray(1.0 - sh_host)).pin_memory().numpy()]
+    e2e_calls = [0]
 
     def step_e2e():
         # one `update_samples` call (src/sample.jl:8-13): the seven levels' batches, host buffers in and out, one synchronisation
+        sh_np = sh_sets[e2e_calls[0] & 1]
+        e2e_calls[0] += 1
         out = eng.update_samples(model, lat, dists, [([lev], sh_np[li], rank * n_l[li], n_l[li], M_KL)
                                                      for li, lev in enumerate(LEVELS)])
         mom = np.stack(out)
@@ -327,9 +481,10 @@ def run_ours(args):
         return mom
 
     step_e2e()
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = 2 * max(2, args.steps // 4)  # even: ends on the shift set the device-resident arm used
     for _ in range(e2e_steps):
         mom_e2e = step_e2e()
     barrier()
@@ -338,7 +493,42 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = samples_per_step * world / float(e2e_t.item())
-    assert np.allclose(mom_e2e[..., 1], final[..., 1], rtol=1e-12), "device-resident and host-buffer arms disagree"
+    del mom_e2e
+    mom_chk = eng.update_samples(model, lat, dists, [([lev], sh_sets[0][li], rank * n_l[li], n_l[li], M_KL) for li, lev in enumerate(LEVELS)])
+    mom_chk = np.stack(mom_chk)
+    if world == 1:
+        assert np.allclose(mom_chk[..., 1], final[..., 1], rtol=1e-12), "device-resident and host-buffer arms disagree"
+
+    # ---- strong scaling: the same step with every level's n_l points SPLIT over the ranks (fixed total work) ------------------
+    strong = None
+    if world > 1:
+        def step_strong():
+            for li, lev in enumerate(LEVELS):
+                base, rem = divmod(n_l[li], world)
+                cnt = base + (1 if rank < rem else 0)
+                k0 = rank * base + min(rank, rem)
+                eng.sample_batch_dev(model, lat, dists, [lev], sh_dev[li].data_ptr(), R_SHIFTS, k0, max(cnt, 1), M_KL, mom_dev[li].data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered.view(-1), mom_dev.view(-1))
+        for _ in range(3):
+            step_strong()
+        barrier()
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            torch.cuda.synchronize()
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            sev[i][0].record(stream)
+            step_strong()
+            sev[i][1].record(stream)
+        barrier()
+        st = torch.tensor([sum(a.elapsed_time(b) for a, b in sev) / len(sev)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "value": samples_per_step / (float(st.item()) * 1e-3), "unit": "samples/s",
+                  "ms_per_step": float(st.item()), "samples_per_step_total": samples_per_step,
+                  "note": "every level's n_l points per shift split over the ranks (contiguous slices), one all-gather of the moments"}
+
+    extra = bench_extras(eng, torch, dist, stream, world, rank)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -354,11 +544,11 @@ def run_ours(args):
                     "frac": (achieved_tf / peak_tf) if peak_tf else None,
                     "peak_source": "measured live by tools/fp64_microbench (MEASURED_PEAKS.json has no FP64 figure)",
                     # dram__bytes_read.sum + dram__bytes_write.sum of the 7 launches of one step, from the ncu --set full capture
-                    # of this command (profiles/r01_final_kernels.csv): 0.11+0.12+0.14+0.19+0.30+0.50+0.91 MB read, 0 B written
-                    "traffic": 2.27e6, "traffic_unit": "bytes per step (all 7 launches); algorithmic HBM bytes per sample: 0",
-                    # FP64 + DMMA pipe-busy fractions of the 7 launches in that capture (sm__inst_executed_pipe_fp64 +
-                    # sm__pipe_tensor_cycles_active, profiles/r01_final_kernels.csv): not a live measurement
-                    "pipe_busy_ncu_per_level": [0.63, 0.67, 0.65, 0.62, 0.59, 0.54, 0.47],
+                    # of this command (profiles/r02_final_kernels.csv)
+                    "traffic": ncu_traffic(), "traffic_unit": "bytes per step (all 7 launches); algorithmic HBM bytes per sample: 0",
+                    # FP64 + DMMA pipe-busy fractions of the 7 launches, read from the committed ncu summary of this command
+                    # (profiles/r02_final_kernels.csv: sm__inst_executed_pipe_fp64 + sm__pipe_tensor_cycles_active); None when absent
+                    "pipe_busy_ncu_per_level": ncu_pipe_busy(),
                     "per_level_ms": lvl_ms,
                     "per_level_samples_per_s": [n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) for li in range(len(LEVELS))],
                     "per_level_tflops": [algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) * 1e-12
@@ -402,6 +592,14 @@ def run_ours(args):
             hbm["raw"] = {"achieved": gbs_raw, "frac": gbs_raw / hbm_peak, "unit": "GB/s",
                           "coordinates_per_s": out.numel() / (ms_raw * 1e-3)}
             del out
+        run_e2e = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import run_e2e as RE
+                run_e2e = RE.measure(1, tols=(1e-4, 2e-5, 5e-6, 1e-6), reps=3)
+            except Exception as e:  # noqa: BLE001
+                run_e2e = {"error": repr(e)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             total, dt, cores = cpu_reference_run(0.5)
@@ -413,7 +611,7 @@ def run_ours(args):
                 "config": workload_config(), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(sh_host.nbytes),
                         "d2h_bytes_per_step": int(len(LEVELS) * nmom * 8), "ms_per_step": float(e2e_t.item()) * 1e3},
-                "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "strong": strong, "extra": extra, "run_e2e": run_e2e, "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
                 "fp64_microbench": fp64 or None,
                 "estimate": {"mean_dQ_per_level": [float(final[li, :, 0, 0, 1].mean()) for li in range(len(LEVELS))],
                              "sum": float(sum(final[li, :, 0, 0, 1].mean() for li in range(len(LEVELS))))}}

@@ -599,6 +599,18 @@ ORC_API double orc_frontal_mid_rect(const double *a, int lda, int stx, int sty, 
     return frontal_mid(a, lda, stx, sty, Nx, Ny);
 }
 
+/* per-thread scratch that grows on demand: no allocation per sample in the timed CPU arm */
+static double *orc_scratch(size_t n) {
+    static __thread double *buf = NULL;
+    static __thread size_t cap = 0;
+    if (cap < n) {
+        free(buf);
+        buf = (double *)malloc(sizeof(double) * n);
+        cap = buf ? n : 0;
+    }
+    return buf;
+}
+
 /* index = (l) for the multilevel model (Nx = Ny = n0 2^l) or (lx, ly) for the multi-index model (Nx = n0 2^lx,
  * Ny = n0 2^ly, anisotropic coarsening as in docs/src/example.md:221-243); the KL basis of an index is stored under the key
  * lx + 16*ly.  dQ = Qf + sum over diff(index) of +-Q_kappa, coarse fields = strided views of the fine field
@@ -612,7 +624,8 @@ static int lognormal2d_eval(const orc_model *M, const int *index, const double *
     const int Nx = M->n0 << lx, Ny = M->n0 << ly, nodes = (Nx + 1) * (Ny + 1);
     if (M->basis_rows[key] != nodes || M->basis_cols[key] < m) return -3;
     const int ld = M->basis_cols[key];
-    double *a = (double *)malloc(sizeof(double) * (size_t)nodes);
+    double *a = orc_scratch((size_t)nodes);
+    if (!a) return -5;
     for (int i = 0; i < nodes; ++i) {
         double gsum = 0.0;
         const double *row = Phi + (size_t)i * ld;
@@ -630,7 +643,6 @@ static int lognormal2d_eval(const orc_model *M, const int *index, const double *
         if (lx > 0) dq = dq - frontal_mid(a, Nx + 1, 2, 1, Nx / 2, Ny);
     }
     *dQ = dq;
-    free(a);
     return 0;
 }
 
@@ -669,10 +681,7 @@ ORC_API int orc_model_eval(const orc_model *M, const int *index, const double *x
     }
     case ORC_MODEL_LOGNORMAL1D: {
         int N = M->n0 << index[0];
-        double *work = (double *)malloc(sizeof(double) * (size_t)(N + 1));
-        int rc = lognormal1d_eval(M, index[0], xi, m, dQ, Qf, work);
-        free(work);
-        return rc;
+        return lognormal1d_eval(M, index[0], xi, m, dQ, Qf, orc_scratch((size_t)(N + 1)));
     }
     case ORC_MODEL_LOGNORMAL2D:
         return lognormal2d_eval(M, index, xi, m, dQ, Qf);
@@ -706,7 +715,7 @@ ORC_API int orc_sample_batch(const orc_model *M, const uint32_t *z, int s, uint6
         double *dq = (double *)malloc(sizeof(double) * (size_t)q * 2);
         double *qf = dq + q;
         /* the reference farms out one (shift, k) item at a time (pmap, batch_size = 1, src/sample.jl:93-95) */
-#pragma omp for schedule(dynamic, 8) collapse(2)
+#pragma omp for schedule(dynamic, 1) collapse(2)
         for (int r = 0; r < R; ++r)
             for (int64_t i = 0; i < (int64_t)n; ++i) {
                 uint64_t k = k0 + (uint64_t)i;
