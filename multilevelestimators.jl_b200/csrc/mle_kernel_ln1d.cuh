@@ -37,7 +37,7 @@ struct Lognormal1dArgs {
 };
 
 constexpr int LN_BT = 32;                    // samples per CTA tile; a warp owns WS = 8 or 16 of them (template parameter)
-constexpr int LN_GEN_PIECE = 128;            // dims per generator call (class masks, queue inside F)
+constexpr int LN_GEN_PIECE = 128;            // dims per generator call (private lists + queue inside F)
 __host__ __device__ constexpr int ln_threads(int ws) { return 32 * (LN_BT / ws); }
 __host__ __device__ constexpr size_t ln1d_smem_bytes(int mpad, int m_lattice, int ws) {
     return (size_t)m_lattice * 16 + (size_t)mpad * 8 + (size_t)(LN_BT / ws) * ((size_t)mpad * ws + 32 * ws) * 8 + 16;
@@ -59,6 +59,86 @@ __device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, int 
     s.a_prev = a;
 }
 
+// reciprocal of kappa = (a0 + a1)/2: the Newton / Markstein sequence of ddiv_normal(1.0, kappa) without the product 1.0 * r
+// (exact, so the result is the same correctly rounded 1/kappa)
+__device__ __forceinline__ double rcp_kappa(double a0, double a1) {
+    const double den = __dmul_rn(0.5, __dadd_rn(a0, a1));
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = __fma_rn(-den, r, 1.0);
+    e = __fma_rn(e, e, e);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-den, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double rem = __fma_rn(-den, r, 1.0);
+    return __fma_rn(r, rem, r);
+}
+
+// NN consecutive nodes of one side at once (node numbers ip0 .. ip0+NN-1 counted from the boundary, values a[]): the same
+// arithmetic as NN calls of sweep_step, arranged as straight-line code -- all reciprocals are independent of each other and of the
+// running sums, so their Newton chains interleave; only the two accumulations per edge are sequential.
+// `first`: node ip0 is the boundary node (no edge in front of it).
+template <int NN>
+__device__ __forceinline__ void sweep_nodes(SweepState &s, const double (&a)[NN], int ip0, int M, bool first) {
+    double r[NN];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) r[q] = rcp_kappa(q ? a[q - 1] : s.a_prev, a[q]);
+    const double w0 = (double)(M - ip0) + 0.5;
+#pragma unroll
+    for (int q = 0; q < NN; ++q) {
+        if (q == 0 && first) continue;  // warp-uniform
+        s.A = __dadd_rn(s.A, r[q]);
+        s.D = __fma_rn(w0 - (double)q, r[q], s.D);  // exact: small half-integers
+    }
+    s.a_prev = a[NN - 1];
+}
+
+// NN half-nodes of one side (rows 2 q + side of F, q = g0 .. g0+NN-1 of a chunk that starts at half-node ip0, an even number),
+// optionally followed by the mid node: the fine state takes every node, the coarse state the even ones.
+template <int NN, bool LAST>
+__device__ __forceinline__ void sweep_group(SweepState &sf, SweepState &sc, const double *__restrict__ Fq, int stride, int ip,
+                                            int M, bool coarse, double amid) {
+    double a[NN + (LAST ? 1 : 0)];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) a[q] = Fq[q * stride];
+    if (LAST) a[NN] = amid;
+    sweep_nodes<NN + (LAST ? 1 : 0)>(sf, a, ip, M, ip == 0);
+    if (coarse) {
+        double ac[NN / 2 + (LAST ? 1 : 0)];
+#pragma unroll
+        for (int q = 0; q < NN / 2; ++q) ac[q] = a[2 * q];
+        if (LAST) ac[NN / 2] = amid;
+        sweep_nodes<NN / 2 + (LAST ? 1 : 0)>(sc, ac, ip >> 1, M >> 1, ip == 0);
+    }
+}
+
+// nn consecutive nodes of one grid and side from shared memory (node ip+q at Fq[q * stride]), in straight-line groups of 8 / 4
+// nodes and single steps for the rest; with `last` the mid node (value amid, node number M) closes the run.
+template <int NN, bool LAST>
+__device__ __forceinline__ void sweep_run_group(SweepState &s, const double *__restrict__ Fq, int stride, int ip, int M, double amid) {
+    double a[NN + (LAST ? 1 : 0)];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) a[q] = Fq[q * stride];
+    if (LAST) a[NN] = amid;
+    sweep_nodes<NN + (LAST ? 1 : 0)>(s, a, ip, M, ip == 0);
+}
+__device__ __forceinline__ void sweep_run(SweepState &s, const double *__restrict__ Fq, int stride, int nn, int ip, int M, bool last,
+                                          double amid) {
+    int g0 = 0;
+    for (; g0 + 8 <= nn; g0 += 8) {
+        if (last && g0 + 8 == nn) sweep_run_group<8, true>(s, Fq + g0 * stride, stride, ip + g0, M, amid);
+        else sweep_run_group<8, false>(s, Fq + g0 * stride, stride, ip + g0, M, amid);
+    }
+    for (; g0 + 4 <= nn; g0 += 4) {
+        if (last && g0 + 4 == nn) sweep_run_group<4, true>(s, Fq + g0 * stride, stride, ip + g0, M, amid);
+        else sweep_run_group<4, false>(s, Fq + g0 * stride, stride, ip + g0, M, amid);
+    }
+    if (g0 < nn || (last && nn == 0)) {
+        for (; g0 < nn; ++g0) sweep_step(s, ip + g0, Fq[g0 * stride], M);
+        if (last) sweep_step(s, M, amid, M);
+    }
+}
+
 // u(1/2) = h^2 (D_R A_L + D_L A_R) / (A_L + A_R)
 __device__ __forceinline__ double sweep_combine(double LA, double LD, double RA, double RD, double h2) {
     const double num = __fma_rn(RD, LA, __dmul_rn(LD, RA));
@@ -71,9 +151,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// contraction + epilogue of one chunk: RT live row tiles (1..4) x ST = WS/8 sample tiles (the second one only when `two`).
+// contraction + epilogue of one chunk: RT live row tiles (1..4) x ST = WS/8 sample tiles (always both: the inputs of surplus
+// points of a last, partial tile exist and are masked out of the statistics only).
 // With MID the chain of fused multiply-adds of the mid-node row (smid[k] * xi[k][b], ascending k: the lane's own sample b)
-// rides along in the k loop, in the shadow of the DMMAs.
+// rides along in the k loop, in the shadow of the DMMAs, and gm returns the FIELD VALUE exp(.) at the mid node.
 template <int RT, bool MID, int WS>
 __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const double *__restrict__ B0,
                                            const double *__restrict__ B1, int nks, bool two, double *__restrict__ F, int lane,
@@ -112,7 +193,7 @@ __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const d
         }
 #pragma unroll
         for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][0][0], acc[t][0][1], a[t], b0);
-        if (ST == 2 && two) {
+        if (ST == 2) {
 #pragma unroll
             for (int t = 0; t < RT; ++t) dmma_m8n8k4(acc[t][ST - 1][0], acc[t][ST - 1][1], a[t], b1);
         }
@@ -126,7 +207,7 @@ __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const d
         for (int t = 0; t < RT; ++t) a[t] = na[t];
         b0 = nb0; b1 = nb1;
     }
-    if (MID) gm = g0;
+    if (MID) gm = exp_det(g0);  // field value at the mid node (straight-line with the exps below: the chains interleave)
     // epilogue: a = exp(G) -> F[row][sample]; the lane holds row lr, samples 2 lk, 2 lk + 1 of each 8x8 tile
     // (WS = 16: columns XOR-swizzled by 8 (row & 1) so that the 16-byte stores of a quarter warp hit 8 distinct bank groups)
     const int sw = WS == 16 ? (lr & 1) << 3 : 0;
@@ -136,7 +217,7 @@ __device__ __forceinline__ void ln1d_chunk(const double *__restrict__ A, const d
         double2 v;
         v.x = exp_det(acc[t][0][0]); v.y = exp_det(acc[t][0][1]);
         *reinterpret_cast<double2 *>(f0 + t * 8 * WS) = v;
-        if (ST == 2 && two) {
+        if (ST == 2) {
             v.x = exp_det(acc[t][ST - 1][0]); v.y = exp_det(acc[t][ST - 1][1]);
             *reinterpret_cast<double2 *>(f1 + t * 8 * WS) = v;
         }
@@ -166,7 +247,7 @@ __global__ void __launch_bounds__(32 * (LN_BT / WS), WS == 16 ? 6 : 5) lognormal
     double *smid = reinterpret_cast<double *>(zs + (lattice ? g.m : 0));                  // [mpad] basis row of the mid node
     double *xi = smid + mpad + (size_t)warp * ((size_t)mpad * WS + FD);                   // [mpad][WS] swizzled
     double *F = xi + (size_t)mpad * WS;                                                   // [32][WS]
-    unsigned short *queue = reinterpret_cast<unsigned short *>(F);                        // generator queue (F is idle then)
+    unsigned char *gscratch = reinterpret_cast<unsigned char *>(F);                       // generator lists + queue (F is idle then)
     if (lattice) stage_lattice_row<THREADS>(zs, g, r);
     for (int e = tid; e < mpad; e += THREADS) smid[e] = __ldg(la.mid + e);
     for (int e = lane; e < (mpad - g.m) * WS; e += 32) xi[(size_t)g.m * WS + e] = 0.0;    // k padding rows
@@ -190,7 +271,7 @@ __global__ void __launch_bounds__(32 * (LN_BT / WS), WS == 16 ? 6 : 5) lognormal
         const bool two = Pt > 8;
         // A. inputs (always all WS points: surplus ones are masked out of the statistics)
         for (int j0 = 0; j0 < g.m; j0 += LN_GEN_PIECE)
-            gen_warp<MODE, lattice, WS>(xi + (size_t)j0 * WS, queue, j0, min(LN_GEN_PIECE, g.m - j0), g.k0 + i0, g, r, zs);
+            gen_warp<MODE, lattice, WS>(xi + (size_t)j0 * WS, gscratch, FD * 8, j0, min(LN_GEN_PIECE, g.m - j0), g.k0 + i0, g, r, zs);
 
         SweepState sf{0.0, 0.0, 0.0}, sc{0.0, 0.0, 0.0};
         double gm = 0.0;
@@ -201,16 +282,38 @@ __global__ void __launch_bounds__(32 * (LN_BT / WS), WS == 16 ? 6 : 5) lognormal
             if (c == la.nchunks - 1) ln1d_chunk_any<true, WS>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
             else ln1d_chunk_any<false, WS>(live, A, B0, B1, nks, two, F, lane, smid, xi, gm);
             __syncwarp();
-            // C. sweeps over the half-nodes of this chunk (ip0 is a multiple of 16: even half-nodes are the coarse nodes)
+            // C. sweeps over the half-nodes of this chunk (ip0 is a multiple of 16: even half-nodes are the coarse nodes), in
+            // straight-line groups of 8 or 4 nodes; the mid node closes the last group
             const int ip0 = 16 * c;
             const int nh = min(16, M - ip0);
+            const bool last = c == la.nchunks - 1;
             if (WS == 16) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    if (q < nh) {
-                        const double a = Fr[q * 2 * WS];
-                        sweep_step(sf, ip0 + q, a, M);
-                        if (!(q & 1) && lvl > 0) sweep_step(sc, (ip0 + q) >> 1, a, M >> 1);
+                const bool co = lvl > 0;
+                const int st = 2 * WS;
+#ifndef LN_SWEEP_NN
+#define LN_SWEEP_NN 8
+#endif
+                constexpr int NN = LN_SWEEP_NN;  // nodes per straight-line group
+                int g0 = 0;
+                if (NN == 8) {
+                    for (; g0 + 8 <= nh; g0 += 8) {
+                        if (last && g0 + 8 == nh) sweep_group<8, true>(sf, sc, Fr + g0 * st, st, ip0 + g0, M, co, gm);
+                        else sweep_group<8, false>(sf, sc, Fr + g0 * st, st, ip0 + g0, M, co, 0.0);
+                    }
+                }
+                for (; g0 + 4 <= nh; g0 += 4) {
+                    if (last && g0 + 4 == nh) sweep_group<4, true>(sf, sc, Fr + g0 * st, st, ip0 + g0, M, co, gm);
+                    else sweep_group<4, false>(sf, sc, Fr + g0 * st, st, ip0 + g0, M, co, 0.0);
+                }
+                if (g0 < nh) {  // grids whose half is not a multiple of four nodes: the rest one node at a time
+                    for (; g0 < nh; ++g0) {
+                        const double a = Fr[g0 * st];
+                        sweep_step(sf, ip0 + g0, a, M);
+                        if (co && !(g0 & 1)) sweep_step(sc, (ip0 + g0) >> 1, a, M >> 1);
+                    }
+                    if (last) {
+                        sweep_step(sf, M, gm, M);
+                        if (co) sweep_step(sc, M >> 1, gm, M >> 1);
                     }
                 }
             } else {
@@ -225,12 +328,10 @@ __global__ void __launch_bounds__(32 * (LN_BT / WS), WS == 16 ? 6 : 5) lognormal
             }
             __syncwarp();  // F is rewritten by the next chunk's epilogue
         }
-        // mid node (its chain of fused multiply-adds rode along in the last chunk)
-        const double amid = exp_det(gm);
+        // the mid node (its chain of fused multiply-adds rode along in the last chunk; WS = 16: already consumed above)
+        const double amid = gm;
         double qf, dq;
         if (WS == 16) {
-            sweep_step(sf, M, amid, M);
-            if (lvl > 0) sweep_step(sc, M >> 1, amid, M >> 1);
             // D. the two sides meet: lanes 0..15 hold the left states, their partners lane + 16 the right ones
             const double fA = __shfl_xor_sync(0xffffffffu, sf.A, 16), fD = __shfl_xor_sync(0xffffffffu, sf.D, 16);
             const double cA = __shfl_xor_sync(0xffffffffu, sc.A, 16), cD = __shfl_xor_sync(0xffffffffu, sc.D, 16);
