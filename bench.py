@@ -622,6 +622,62 @@ def run_ours(args):
     eng.close()
 
 
+def run_single_process_multi(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: one process, ONE multi-GPU context (mle_init_multi, the library's
+    nb_of_workers analogue).  Every level's request carries N x n_l points per shift (weak scaling: the same per-GPU work as the
+    N = 1 line); the library splits each request over its devices (whole shifts per device when R >= N), issues all members and
+    merges on the host.  There is no device-resident arm across several devices, so `value` and `e2e` are the same host-buffer
+    measurement (wall clock around the blocking `mle_update_samples` call)."""
+    import torch
+    import mle_b200
+    import mle_b200.kl as kl
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit("bench.py --gpus %d: only %d CUDA devices visible" % (N, torch.cuda.device_count()))
+    eng = mle_b200.Engine(list(range(N)))
+    z = eng.genvec("K_3600_32")[:M_KL]
+    lat = eng.lattice(z, M_KL)
+    dists = eng.dists([(mle_b200.NORMAL, [0.0, 1.0])] * M_KL)
+    model = eng.model("lognormal1d", 1, [16])
+    for lev in LEVELS:
+        model.set_basis(lev, kl.kl_basis_1d(lev, m=M_KL))
+    sh_host = level_shifts()
+    sh_sets = [sh_host.copy(), np.ascontiguousarray(1.0 - sh_host)]
+    n_l = [points_per_shift(lev) * N for lev in LEVELS]
+    samples_per_step = sum(n_l) * R_SHIFTS
+    calls = [0]
+
+    def step():
+        sh_np = sh_sets[calls[0] & 1]
+        calls[0] += 1
+        return eng.update_samples(model, lat, dists, [([lev], sh_np[li], 0, n_l[li], M_KL) for li, lev in enumerate(LEVELS)])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = eng.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mom = step()
+    dt = (time.perf_counter() - t0) / args.steps
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop()
+    mom = np.stack(mom)
+    value = samples_per_step / dt
+    cfg = workload_config()
+    cfg["parallelism"] = "single process, one multi-GPU context (mle_init_multi): every request split over %d devices inside the library" % N
+    emit({"metric": "fine+coarse samples/sec", "value": value, "unit": "samples/s", "n_gpus": N, "steps": args.steps,
+          "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
+          "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": int(sh_host.nbytes),
+                  "d2h_bytes_per_step": int(len(LEVELS) * R_SHIFTS * 6 * 8), "ms_per_step": dt * 1e3},
+          "gpu_launches": int(launches), "launcher": "single process (no torchrun)",
+          "estimate": {"mean_dQ_per_level": [float(mom[li, :, 0, 0, 1].mean()) for li in range(len(LEVELS))],
+                       "sum": float(sum(mom[li, :, 0, 0, 1].mean() for li in range(len(LEVELS))))}})
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -638,6 +694,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_single_process_multi(args)
     else:
         run_ours(args)
 

@@ -963,7 +963,7 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
             const int qdims = g.m < 256 ? ((g.m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims
             const size_t fbytes = (size_t)LN_RC * lnb_ldf(bt) * 8, qbytes = (size_t)bt * qdims * 2;
             const size_t smem = (size_t)la.mpad * lnb_ldx(bt) * 8 + fbytes + (size_t)3 * bt * sizeof(SweepState) +
-                                (size_t)2 * bt * sizeof(Partial) + (size_t)bt * 8 + (size_t)la.mpad * 8 + ((W + 3) & ~3) * 4 +
+                                (size_t)bt * 8 + (size_t)la.mpad * 8 + ((W + 3) & ~3) * 4 +
                                 (lat ? (size_t)g.m * 16 : 0) + (qbytes <= fbytes ? 0 : qbytes) + 16;
             const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_kb, threads, smem);
             gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);

@@ -142,7 +142,7 @@ __device__ __forceinline__ void sweep_run(SweepState &s, const double *__restric
 // u(1/2) = h^2 (D_R A_L + D_L A_R) / (A_L + A_R)
 __device__ __forceinline__ double sweep_combine(double LA, double LD, double RA, double RD, double h2) {
     const double num = __fma_rn(RD, LA, __dmul_rn(LD, RA));
-    return __dmul_rn(h2, __ddiv_rn(num, __dadd_rn(LA, RA)));
+    return __dmul_rn(h2, ddiv_normal(num, __dadd_rn(LA, RA)));  // sums of reciprocals of kappa = mean of exp(.): normal range
 }
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {

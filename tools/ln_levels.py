@@ -1,9 +1,10 @@
-"""Per-level timing of the lognormal1d kernel at the C2 bench sizes: python tools/ln_levels.py  (env knobs: MLE_LN_WS, MLE_CUDA_LIB)"""
+"""Per-level timing of the lognormal1d kernel at the C2 bench sizes: python tools/ln_levels.py  (env knobs: MLE_CUDA_LIB, MLE_LEVELS=0,1)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import mle_b200, mle_b200.kl as kl
 import bench as B
+if os.environ.get("MLE_LEVELS"): B.LEVELS = [int(x) for x in os.environ["MLE_LEVELS"].split(",")]
 
 eng = mle_b200.Engine(0)
 m, R = B.M_KL, B.R_SHIFTS
