@@ -88,6 +88,67 @@ ORC_API double orc_log_tail(double w) {
     return s + lo;
 }
 
+/* log(w) for ANY positive normal double, as an unevaluated sum hi + lo (|lo| <= ulp(hi)/2) -- Weibull's log(1 - x) and the
+ * logarithm inside pow (src/distribution.jl:182; Julia's Base.log / Base.^ are not in the reference tree).  Away from 1 this
+ * is the table algorithm of orc_log_tail (absolute error ~2^-68, so relative error < 2^-59 because |log w| >= 2^-7.02
+ * there); for w in [1 - 1/128, 1 + 1/128) the centre is c = 1: r = w - 1 exactly and log w = r + r^2 P(r) with ten series
+ * terms (relative error < 2^-60).  Rounded to one double the result is correctly rounded except with probability ~1e-3. */
+static const double LOG1P_C[10] = {-0.5, 0x1.5555555555555p-2, -0.25, 0x1.999999999999ap-3, -0x1.5555555555555p-3,
+                                   0x1.2492492492492p-3, -0.125, 0x1.c71c71c71c71cp-4, -0x1.999999999999ap-4,
+                                   0x1.745d1745d1746p-4};
+ORC_API double orc_log_pos(double w, double *lo_out) {
+    uint64_t bits = double_as_u64(w);
+    int e = (int)(bits >> 52) - 1023;
+    int i = (int)((bits >> 45) & 127);
+    double hi, lo;
+    if ((e == 0 && i == 0) || (e == -1 && i >= 126)) {
+        double r = w - 1.0; /* exact */
+        double q = LOG1P_C[9];
+        for (int k = 8; k >= 0; --k) q = fma(q, r, LOG1P_C[k]);
+        q = (r * r) * q;
+        hi = r + q;
+        lo = (r - hi) + q; /* Fast2Sum, |r| >= |q| */
+    } else {
+        double m = u64_as_double((bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+        double invc = LOGT[3 * i], logc_hi = LOGT[3 * i + 1], logc_lo = LOGT[3 * i + 2];
+        double p_hi = m * invc;
+        double p_lo = fma(m, invc, -p_hi);
+        double r_hi = p_hi - 1.0;
+        double r = r_hi + p_lo;
+        double q = -0.125;
+        q = fma(q, r, 0x1.2492492492492p-3);
+        q = fma(q, r, -0x1.5555555555555p-3);
+        q = fma(q, r, 0.2);
+        q = fma(q, r, -0.25);
+        q = fma(q, r, 0x1.5555555555555p-2);
+        q = fma(q, r, -0.5);
+        q = (r * r) * q;
+        double ed = (double)e;
+        double A = ed * MLE_LOGT_LN2_HI + logc_hi; /* exact; |A| >= 2^-7.02 > |r_hi| outside the branch above */
+        double s = A + r_hi;
+        double err = r_hi - (s - A);
+        double l = fma(ed, MLE_LOGT_LN2_LO, logc_lo) + p_lo;
+        l = l + q;
+        l = l + err;
+        hi = s + l;
+        lo = (s - hi) + l;
+    }
+    if (lo_out) *lo_out = lo;
+    return hi;
+}
+
+/* L^p for a positive normal double L: exp(p log L) with the product carried as th + tl (two-product of p and the hi part, p
+ * times the lo part), the exponential of th by orc_exp and the factor 1 + tl applied with one fused multiply-add.
+ * Error < 1 ulp (tests/test_oracle_golden.py checks it against mpmath). */
+ORC_API double orc_exp(double x);
+ORC_API double orc_pow_pos(double L, double p) {
+    double ll, lh = orc_log_pos(L, &ll);
+    double th = p * lh;
+    double tl = fma(p, lh, -th) + p * ll;
+    double E = orc_exp(th);
+    return fma(E, tl, E);
+}
+
 /* exp(x): k = rint(x log2 e), r = x - k ln2 (two-step), degree-13 Taylor polynomial, scaling by 2^k in two exact-then-
  * rounded steps.  Error < 1 ulp; the lognormal / expsum models are DEFINED with this exp on both sides. */
 ORC_API double orc_exp(double x) {
@@ -249,9 +310,9 @@ ORC_API double orc_transform(int kind, const double *p, double x) {
     }
     case ORC_WEIBULL: { /* :182  lambda * (-log(1 - x))^(1/k) */
         double om = 1.0 - x;
-        double l = -log(om);
+        double l = -orc_log_pos(om, 0);
         double ik = 1.0 / p[0];
-        double pw = pow(l, ik);
+        double pw = (l > 0.0) ? orc_pow_pos(l, ik) : 0.0; /* x = 0: log 1 = 0, 0^(1/k) = 0 */
         return p[1] * pw;
     }
     default:

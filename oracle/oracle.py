@@ -43,6 +43,10 @@ def lib():
         for name in ("orc_erfinv", "orc_norminv", "orc_normcdf"):
             getattr(L, name).restype = C.c_double
             getattr(L, name).argtypes = [C.c_double]
+        L.orc_log_pos.restype = C.c_double
+        L.orc_log_pos.argtypes = [C.c_double, dp]
+        L.orc_pow_pos.restype = C.c_double
+        L.orc_pow_pos.argtypes = [C.c_double, C.c_double]
         L.orc_transform.restype = C.c_double
         L.orc_transform.argtypes = [C.c_int, dp, C.c_double]
         L.orc_splitmix64.restype = C.c_uint64

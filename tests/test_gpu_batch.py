@@ -126,6 +126,17 @@ def test_lognormal1d_levels(engine, oracle, level, R, k0, n):
         check_moments(got, want)
 
 
+def test_lognormal1d_level6_bench_slice(engine, oracle):
+    """the finest level of the C2 bench step at its bench size: level 6 (1024 cells), 16 shifts x 2048 points, point numbers
+    starting where a second rank's slice would start; per-sample values bit-identical, moments to 1e-12"""
+    z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 100, [6])
+    sh = splitmix_uniforms(2024, 16 * 100).reshape(16, 100)
+    got, smp = engine.sample_batch(gm, lat, d, [6], sh, 2048, 2048, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [6], sh, 2048, 2048, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
+
+
 def test_lognormal1d_small_kl_and_errors(engine, oracle):
     import mle_b200
     z, lat, dl, d, gm, om = lognormal_setup(engine, oracle, 10, [0, 1])
@@ -214,6 +225,17 @@ def test_lognormal2d_levels(engine, oracle, level, R, k0, n, m):
     assert np.array_equal(smp, smp_w)
     if n > 1:
         check_moments(got, want)
+
+
+@pytest.mark.parametrize("level,n", [(0, 64), (2, 24), (4, 6), (5, 3)])
+def test_lognormal2d_c3_shape_400_terms_mc(engine, oracle, level, n):
+    """config C3 at its stated size: ML()/MC(), 400-term KL field, levels up to 5 (128 x 128 cells), MC inputs; per-sample
+    (dQ, Qf) bit-identical to the oracle"""
+    z, lat, dl, d, gm, om = lognormal2d_setup(engine, oracle, 400, [level])
+    got, smp = engine.sample_batch(gm, None, d, [level], None, 0, n, mc_seed=11, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, None, dl, [level], None, 0, n, mc_seed=11, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    check_moments(got, want)
 
 
 def test_lognormal2d_mc(engine, oracle):

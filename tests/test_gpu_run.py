@@ -50,6 +50,23 @@ def test_mlqmc_lognormal1d_run_matches_oracle(engine):
     assert 0.05 < hg["mean"] < 0.3
 
 
+def test_mlqmc_lognormal1d_run_to_level_6(engine):
+    """config C2 at its stated depth: ML()/QMC(), 16 shifts, 100-term KL, max_index_set_param = 6; the tolerance is small
+    enough that the loop adds every level up to 6 (grid 1024), and both backends take the same decisions all the way"""
+    import mle_b200.kl as kl
+
+    def make(H, backend):
+        spec = H.ModelSpec("lognormal1d", 1, [16], {lev: kl.kl_basis_1d(lev, m=100) for lev in range(7)})
+        return H.Estimator(H.ML(), H.QMC(), spec, [H.Normal()] * 100, backend, nb_of_shifts=16, max_index_set_param=6,
+                           cost_model=lambda i: 2.0 ** i[0], shift_seed=7, nb_of_tols=6)
+
+    H, g, o = both(engine, make)
+    hg, ho = H.run(g, 1e-6), H.run(o, 1e-6)
+    compare(hg, ho)
+    assert hg["current_index_set"][-1] == (6,)
+    assert 0.119 < hg["mean"] < 0.120
+
+
 def test_mlmc_expsum_run_matches_oracle(engine):
     def make(H, backend):
         w = [0.5 / (j + 1) for j in range(64)]
