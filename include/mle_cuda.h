@@ -153,6 +153,19 @@ int mle_sample_batch(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists di
 int mle_sample_batch_dev(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
                          const double *shifts_dev, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
                          double *moments_dev, double *samples_dev);
+/* One `sample!` call of an UNBIASED estimator (Estimator{<:U}; src/sample.jl:15-19, :65-74, :113-124; accumulator and pmf in
+ * src/methods.jl:287-351).  The reference's sample function returns (dQ, Qf) for EVERY idx in zero(index):index from one input
+ * vector, `append_samples!` stores them per idx and adds  1/Prob(idx) * dQ_idx  to a per-sample accumulator.  Here:
+ *   inv_prob   [prod(index + 1)]: 1 / Prob(idx) for idx in zero(index):index, column-major (first entry of idx fastest)
+ *   moments    [prod(index + 1)][3 x 2 x q x R]: one moment table per idx, laid out like mle_sample_batch's
+ *   acc        [3 x q x R]: (n, mean, M2) of the accumulator values Z_i = sum_idx inv_prob[idx] * dQ_idx,i per (QoI, shift)
+ * Every idx is evaluated on the same points (same shifts, point numbers k0 .. k0+n-1, same leading m coordinates); the terms
+ * are multiplied and added in idx order with separately rounded operations, like the reference.  The per-sample values stay
+ * on the device (a buffer the library keeps across calls): only the tables come back.  On a multi-GPU context the call runs
+ * on member 0. */
+int mle_sample_unbiased(mle_ctx ctx, mle_model model, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                        const double *shifts, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed, const double *inv_prob,
+                        double *moments, double *acc, double *gpu_seconds);
 /* One `update_samples` call (src/sample.jl:8-13): `count` independent `sample!` requests -- entry e has its own index
  * (indices + e*d), shifts (shifts[e], [s x R[e]], or NULL entries for MC), point range k0[e] .. k0[e]+n[e]-1, dimension count
  * m[e] and moment table moments[e] ([3 x 2 x q x R[e]]) -- issued back to back on the context's stream with ONE

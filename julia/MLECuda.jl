@@ -1,29 +1,78 @@
 # MLECuda.jl -- the reference-side binding of libmle_cuda: what a MultilevelEstimators.jl maintainer adds so that
 # `Estimator(index_set, sample_method, sample_function, distributions; options...)` / `run(estimator, tol)` keep working
-# unchanged while `parallel_sample!` runs on a B200.
+# unchanged while `parallel_sample!` runs on B200s.
 #
 # NOTE: Julia is not installed in the build container or on the GPU image, so this file has never been executed; it is
-# deliberately thin and mechanical (one `ccall` per entry point of include/mle_cuda.h).  The same calls, in the same order,
-# are exercised by the Python twin (multilevelestimators.jl_b200/host.py + engine.py) in tests/.
+# deliberately thin and mechanical (one `ccall` per entry point of include/mle_cuda.h, checked statically against the header by
+# tests/test_abi.py).  The same calls, in the same order, are exercised by the Python twin
+# (multilevelestimators.jl_b200/host.py + engine.py) in tests/.
 #
-# Hook: `sample_function` must be a `Function` (the field is declared `sample_function::Function`, src/estimator.jl:115),
-# so the device model handle is a callable struct (`struct DeviceModel <: Function`, precedent:
-# `struct EmptyFunction <: Function end`, src/parse.jl:178).  The field is NOT a type parameter of `Estimator`
-# (src/estimator.jl:113-119), so `parallel_sample!` cannot dispatch on it; the maintainer adds ONE line at the top of each
-# of the two methods in src/sample.jl (:39 MC, :79 QMC):
+# ---- how it plugs in ---------------------------------------------------------------------------------------------------------
+# The device returns sufficient statistics (n, mean, M2) instead of raw samples.  Everything the reference computes from its
+# stored sample vectors goes through `length`, `isempty`, `Statistics.mean`, `Statistics.var` and `append!`
+# (src/internals.jl:66-86, src/methods.jl:44-68, :121-122, :282, :336-351, src/history.jl:63-76), so the binding does not
+# replace those functions one by one: it supplies a vector type, `MomentVector <: AbstractVector{Float64}`, that answers exactly
+# those five queries from a moment triplet, and the estimator stores MomentVectors where it stored `Vector{Float64}`.
+# `has_samples_at_index`, `all_keys`, the `interp` filter, `mean/var/mean0/var0/varest`, the U accumulator statistics and the
+# History keys E/V/dE/dV then work UNMODIFIED.  The maintainer's patch is four places:
 #
-#     estimator.sample_function isa MLECuda.DeviceModel && return MLECuda.device_parallel_sample!(estimator, index, Istart, Iend)
+#  P1  src/estimator.jl:132 -- pass the store type to the internals:
+#          store = sample_function isa MLECuda.DeviceModel ? MLECuda.MomentVector : Vector{Float64}
+#          internals = EstimatorInternals(index_set, sample_method, options, store)
+#  P2  src/internals.jl:17-22, :36-46, :205-214 -- thread `store` through EstimatorInternals / DefaultInternals /
+#      IndexSetInternals(::U) and build the sample stores and the U accumulator with `store()` instead of `Vector{T}(undef, 0)`.
+#  P3  src/sample.jl:39 and :79 (first line of both `parallel_sample!` methods):
+#          estimator.sample_function isa MLECuda.DeviceModel && return MLECuda.device_parallel_sample!(estimator, index, Istart, Iend)
+#      `sample!` (src/sample.jl:21-34) keeps timing the call and doing the nb_of_samples / total_work / total_time bookkeeping.
+#  P4  (optional, QMC with a cost model) src/sample.jl:8, first line of `update_samples`:
+#          estimator.sample_function isa MLECuda.DeviceModel && !(estimator[:cost_model] isa EmptyFunction) &&
+#              return MLECuda.device_update_samples!(estimator, n_opt)
+#      all due indices in ONE library call with one synchronisation.
 #
-# and the statistics accessors of src/methods.jl:44-57, :282 read the moment table below instead of the sample vectors
-# when the sample function is a DeviceModel (see `_mean`, `_var`, `_varest_qmc` at the end of this file).
+# `sample_function` must be a `Function` (the field is declared `sample_function::Function`, src/estimator.jl:115), so the device
+# model handle is a callable struct (`struct DeviceModel <: Function`, precedent: `struct EmptyFunction <: Function end`,
+# src/parse.jl:178).  `nb_of_workers` (src/parse.jl:224-234) becomes the number of GPUs of the context: `Context(0:7)` is ONE
+# multi-GPU context (mle_init_multi) and the library splits every request over its devices.
+# `save_samples = true` (src/history.jl:92-95) makes the device return the raw samples as well; a MomentVector then also keeps
+# them (`raw`), so `h[:samples]` / `h[:samples_diff]` hold real values.
 module MLECuda
 
 using MultilevelEstimators
-import MultilevelEstimators: Estimator, AbstractIndexSet, MC, QMC, Index, parallel_sample!, nb_of_samples, distributions,
+using Statistics
+import MultilevelEstimators: Estimator, AbstractIndexSet, MC, QMC, U, Index, parallel_sample!, nb_of_samples, distributions,
                              generator, Uniform, Normal, TruncatedNormal, Weibull
 
 const libmle = "libmle_cuda"   # multilevelestimators.jl_b200/lib/libmle_cuda.so on the library path
 const ABI_VERSION = 1           # MLE_ABI_VERSION of include/mle_cuda.h this file was written against
+
+# ---- the sample store: (n, mean, M2) standing where a Vector{Float64} of samples stood -----------------------------------------
+mutable struct MomentVector <: AbstractVector{Float64}
+    n::Int
+    mean::Float64
+    M2::Float64                 # sum (x - mean)^2
+    raw::Vector{Float64}        # the samples themselves, only with save_samples = true
+end
+MomentVector() = MomentVector(0, NaN, 0.0, Float64[])
+MomentVector(t::AbstractVector{Float64}) = MomentVector(Int(t[1]), t[2], t[3], Float64[])   # one (n, mean, M2) triplet of the ABI
+Base.size(v::MomentVector) = (v.n,)
+Base.length(v::MomentVector) = v.n
+Base.isempty(v::MomentVector) = v.n == 0
+Base.getindex(v::MomentVector, i::Int) = isempty(v.raw) ? error("MomentVector keeps (n, mean, M2), not the samples (set save_samples = true)") : v.raw[i]
+Base.copy(v::MomentVector) = MomentVector(v.n, v.mean, v.M2, copy(v.raw))
+Statistics.mean(v::MomentVector) = v.n == 0 ? NaN : v.mean
+Statistics.var(v::MomentVector; corrected::Bool = true) = v.n == 0 ? NaN : v.M2 / (corrected ? v.n - 1 : v.n)   # n = 1: 0/0 = NaN like var([x])
+# append!: Chan / Golub / LeVeque merge of two triplets by the library's own mle_moments_merge (calls are merged in call order,
+# with the same rounding as the Python twin)
+function Base.append!(v::MomentVector, p::MomentVector)
+    if p.n > 0
+        a = Float64[v.n, v.n == 0 ? 0.0 : v.mean, v.M2]
+        b = Float64[p.n, p.mean, p.M2]
+        ccall((:mle_moments_merge, libmle), Cint, (Ptr{Float64}, Ptr{Float64}, Csize_t), a, b, 1)
+        v.n, v.mean, v.M2 = Int(a[1]), a[2], a[3]
+        append!(v.raw, p.raw)
+    end
+    v
+end
 
 struct MLEDist
     kind::Int32
@@ -42,11 +91,17 @@ function check(ctx, rc)
     (rc == -1 || rc == -3) ? throw(ArgumentError(msg)) : error("libmle_cuda error $rc: $msg")
 end
 
+# One context = the reference's worker pool.  `Context(0)`: one GPU; `Context(0:7)` / `Context(nb_of_workers = 8)`: ONE multi-GPU
+# context (mle_init_multi) -- handles are replicated on every device and each request is split inside the library (whole shifts
+# per GPU; small requests stay on one GPU), so the estimator code never sees more than one handle.
 mutable struct Context
     ptr::Ptr{Cvoid}
-    function Context(device::Integer = 0)
+    function Context(devices = 0; nb_of_workers::Integer = 0)
+        devs = nb_of_workers > 0 ? collect(Cint, 0:nb_of_workers - 1) : collect(Cint, devices)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:mle_init, libmle), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ref)
+        rc = length(devs) == 1 ?
+            ccall((:mle_init, libmle), Cint, (Cint, Ref{Ptr{Cvoid}}), devs[1], ref) :
+            ccall((:mle_init_multi, libmle), Cint, (Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}), devs, length(devs), ref)
         rc == 0 || error(unsafe_string(ccall((:mle_last_error, libmle), Cstring, (Ptr{Cvoid},), C_NULL)))
         ctx = new(ref[])
         ccall((:mle_abi_version, libmle), Cint, ()) == ABI_VERSION || error("libmle_cuda: ABI version mismatch")
@@ -58,8 +113,8 @@ end
 """
     DeviceModel(ctx, name, ndims, params; bases = Dict{Int, Matrix{Float64}}())
 
-A built-in CUDA sample function ("expsum", "problem18", "lognormal1d").  `bases[level]` is the KL basis of the level,
-`size = (nodes, terms)`; it is handed over row-major (`permutedims`).
+A built-in CUDA sample function ("expsum", "problem18", "lognormal1d", "lognormal2d").  `bases[level]` is the KL basis of the
+level, `size = (nodes, terms)`; it is handed over row-major (`permutedims`).
 """
 mutable struct DeviceModel <: Function
     ctx::Context
@@ -148,47 +203,27 @@ function device_points(estimator::Estimator{I, <:QMC}, index::Index, Istart::Int
     out
 end
 
-# Moment state replaces the stored sample vectors (src/internals.jl:44-45): one (n, mean, M2) triplet per
-# (X ∈ {dQ, Qf}, qoi, shift), merged across calls by mle_moments_merge.  Kept in a side table keyed by the estimator.
-const MOMENTS = IdDict{Any, Dict{Any, Array{Float64, 4}}}()
-moments(estimator, index) = get!(() -> Dict{Any, Array{Float64, 4}}(), MOMENTS, estimator)[index]
-
-function merge_moments!(estimator, index, part::Array{Float64, 4})
-    tab = get!(() -> Dict{Any, Array{Float64, 4}}(), MOMENTS, estimator)
-    if haskey(tab, index)
-        ccall((:mle_moments_merge, libmle), Cint, (Ptr{Float64}, Ptr{Float64}, Csize_t), tab[index], part, length(part) ÷ 3)
-    else
-        tab[index] = part
+# ---- results into the estimator: the reference's own append functions, fed with MomentVectors -----------------------------------
+# mom: (3, 2, q, R) = (n, mean, M2) x (dQ, Qf) x QoI x shift;  smp (optional): (n, 2, q, R)
+function part(mom, X, q, r, smp)
+    v = MomentVector(view(mom, :, X, q, r))
+    smp === nothing || (v.raw = smp[:, X, q, r])
+    v
+end
+function store_moments!(estimator::Estimator{<:AbstractIndexSet, <:QMC}, index::Index, mom, smp = nothing)
+    for r in axes(mom, 4), q in axes(mom, 3)
+        MultilevelEstimators.append_samples_diff!(estimator, q, r, index, part(mom, 1, q, r, smp))   # src/internals.jl:80
+        MultilevelEstimators.append_samples!(estimator, q, r, index, part(mom, 2, q, r, smp))        # src/internals.jl:66
+    end
+end
+function store_moments!(estimator::Estimator{<:AbstractIndexSet, <:MC}, index::Index, mom, smp = nothing)
+    for q in axes(mom, 3)
+        MultilevelEstimators.append_samples_diff!(estimator, q, index, part(mom, 1, q, 1, smp))
+        MultilevelEstimators.append_samples!(estimator, q, index, part(mom, 2, q, 1, smp))
     end
 end
 
-# Index sets: the reference's own code keeps driving everything above parallel_sample! -- SL, ML, FT, TD, HC, ZC and AD need
-# nothing else.  Unbiased estimators (`U`, src/sample.jl:65-74, :113-124) expect the sample function to return (dQ, Qf) for every
-# idx <= index from one input vector: for those, call mle_sample_batch once per idx in `zero(index):index` with the SAME shifts
-# and point range and a `samples` buffer, append the raw samples to `samples_diff[idx]` / `samples[idx]` and add
-# `dQ_idx / Prob(idx)` to the accumulator, exactly as host.py:Estimator._sample_unbiased does (tested there).
-#
-# ---- the hot path: one ccall per parallel_sample! (replaces the pmap of src/sample.jl:79-102) ----------------------------
-function device_parallel_sample!(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
-    model = estimator.sample_function
-    ensure_handles!(model, estimator)
-    m = estimator[:nb_of_uncertainties](index)
-    R = estimator[:nb_of_shifts](index)
-    gens = [generator(estimator, index, r) for r in 1:R]
-    rule = gens[1].lattice_rule
-    ensure_lattice!(model, rule)
-    shifts = reduce(hcat, [Vector{Float64}(g.shift) for g in gens])          # [s x R], shift r in column r
-    mom = Array{Float64}(undef, 3, 2, model.nqoi, R)
-    idx = Int32[index.I...]
-    t = Ref{Float64}(0.0)
-    GC.@preserve shifts mom idx check(model.ctx.ptr,
-        ccall((:mle_sample_batch, libmle), Cint,
-              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
-               Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
-              model.ctx.ptr, model.ptr, model.lattice, model.dists, idx, length(idx), shifts, R,
-              UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, UInt64(0), mom, C_NULL, t))
-    merge_moments!(estimator, index, mom)
-end
+shift_matrix(estimator, index, R) = reduce(hcat, [Vector{Float64}(generator(estimator, index, r).shift) for r in 1:R])   # [s x R]
 
 # MC inputs: the device's uniforms are keyed by (seed, point number, coordinate) and point numbers restart at 0 on every
 # index, so every index gets its own stream (the reference draws rand(m) from one global stream, src/sample.jl:42).
@@ -205,27 +240,34 @@ function index_seed(seed::UInt64, index::Index)
     x
 end
 
-function device_parallel_sample!(estimator::Estimator{I, <:MC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
+# ---- the hot path: one ccall per parallel_sample! (replaces the pmap of src/sample.jl:39-56, :79-102) -----------------------------
+function device_parallel_sample!(estimator::Estimator{I, S}, index::Index, Istart::Integer, Iend::Integer) where {I<:AbstractIndexSet, S<:Union{MC, QMC}}
+    I <: U && return device_sample_unbiased!(estimator, index, Istart, Iend)
     model = estimator.sample_function
     ensure_handles!(model, estimator)
     m = estimator[:nb_of_uncertainties](index)
-    mom = Array{Float64}(undef, 3, 2, model.nqoi, 1)
+    qmc = S <: QMC
+    R = qmc ? estimator[:nb_of_shifts](index) : 1
+    qmc && ensure_lattice!(model, generator(estimator, index, 1).lattice_rule)
+    shifts = qmc ? shift_matrix(estimator, index, R) : Float64[]
+    n = Iend - Istart + 1
+    mom = Array{Float64}(undef, 3, 2, model.nqoi, R)
+    smp = estimator[:save_samples] ? Array{Float64}(undef, n, 2, model.nqoi, R) : nothing
     idx = Int32[index.I...]
-    GC.@preserve mom idx check(model.ctx.ptr,
+    GC.@preserve shifts mom smp idx check(model.ctx.ptr,
         ccall((:mle_sample_batch, libmle), Cint,
               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-              model.ctx.ptr, model.ptr, C_NULL, model.dists, idx, length(idx), C_NULL, 1,
-              UInt64(Istart - 1), UInt64(Iend - Istart + 1), m, index_seed(MC_SEED[], index), mom, C_NULL, C_NULL))
-    merge_moments!(estimator, index, mom)
+              model.ctx.ptr, model.ptr, qmc ? model.lattice : C_NULL, model.dists, idx, length(idx),
+              qmc ? pointer(shifts) : Ptr{Float64}(C_NULL), R, UInt64(Istart - 1), UInt64(n), m,
+              qmc ? UInt64(0) : index_seed(MC_SEED[], index), mom, smp === nothing ? Ptr{Float64}(C_NULL) : pointer(smp),
+              Ptr{Float64}(C_NULL)))
+    store_moments!(estimator, index, mom, smp)
 end
 
-# ---- all due indices in one call: update_samples (src/sample.jl:8-13) with ONE synchronisation -----------------------------
-# Needs a deterministic `cost_model` (with the default cost model the reference times every sample! call separately,
-# src/sample.jl:27).  The maintainer's hook is one line at the top of `update_samples`:
-#
-#     estimator.sample_function isa MLECuda.DeviceModel && !(estimator[:cost_model] isa EmptyFunction) &&
-#         return MLECuda.device_update_samples!(estimator, n_opt)
+# ---- all due indices in one call: update_samples (src/sample.jl:8-13) with ONE synchronisation (patch P4) ------------------------
+# Needs a deterministic `cost_model`: with the default cost model the reference charges every sample! call its own wall time
+# (src/sample.jl:27); here the call's wall time is shared out over the indices in proportion to their modelled work.
 function device_update_samples!(estimator::Estimator{I, <:QMC}, n_opt::Dict) where I<:AbstractIndexSet
     model = estimator.sample_function
     ensure_handles!(model, estimator)
@@ -237,10 +279,10 @@ function device_update_samples!(estimator::Estimator{I, <:QMC}, n_opt::Dict) whe
     ms = Cint[estimator[:nb_of_uncertainties](τ) for (τ, _) in due]
     k0 = UInt64[nb_of_samples(estimator, τ) for (τ, _) in due]              # zero-based first point = samples taken so far
     ns = UInt64[n for (_, n) in due]
-    shifts = [reduce(hcat, [Vector{Float64}(generator(estimator, τ, r).shift) for r in 1:R]) for ((τ, _), R) in zip(due, Rs)]
+    shifts = [shift_matrix(estimator, τ, R) for ((τ, _), R) in zip(due, Rs)]
     ensure_lattice!(model, generator(estimator, first(due)[1], 1).lattice_rule)
     moms = [Array{Float64}(undef, 3, 2, model.nqoi, R) for R in Rs]
-    GC.@preserve shifts moms begin
+    t = @elapsed GC.@preserve shifts moms begin
         sp = Ptr{Float64}[pointer(x) for x in shifts]
         mp = Ptr{Float64}[pointer(x) for x in moms]
         check(model.ctx.ptr,
@@ -249,46 +291,47 @@ function device_update_samples!(estimator::Estimator{I, <:QMC}, n_opt::Dict) whe
                    Ptr{UInt64}, Ptr{Cint}, UInt64, Ptr{Ptr{Float64}}),
                   model.ctx.ptr, model.ptr, model.lattice, model.dists, length(due), indices, d, sp, Rs, k0, ns, ms, UInt64(0), mp))
     end
-    for ((τ, n), mom) in zip(due, moms)
-        merge_moments!(estimator, τ, mom)
-        # the bookkeeping of sample! (src/sample.jl:29-31, src/internals.jl:90,98); total_time is not measured per index here
+    work = [n * estimator[:cost_model](τ) for (τ, n) in due]
+    for (((τ, n), mom), w) in zip(zip(due, moms), work)
+        store_moments!(estimator, τ, mom)
+        # the bookkeeping of sample! (src/sample.jl:29-31, src/internals.jl:90,98,106)
         MultilevelEstimators.add_to_nb_of_samples(estimator, τ, n)
         MultilevelEstimators.add_to_total_work(estimator, τ, n)
+        MultilevelEstimators.add_to_total_time(estimator, τ, t * w / sum(work))
     end
 end
 
-# ---- unbiased estimators: every idx <= index on the same points, raw samples back (src/sample.jl:65-74, :113-124) ----------
-# Returns samples[idx] = Array (n x 2 x q x R): [:, 1, :, :] = dQ_idx, [:, 2, :, :] = Qf_idx; the caller appends them and adds
-# dQ_idx / Prob(idx) to the accumulator exactly as the reference's append_samples! for U does.
-function device_sample_unbiased(estimator::Estimator{I, <:QMC}, index::Index, Istart::Integer, Iend::Integer) where I<:AbstractIndexSet
+# ---- unbiased estimators (src/sample.jl:65-74, :113-124): ONE call evaluates every idx in zero(index):index on the same points --
+# and reduces the accumulator  Z = sum_idx 1/Prob(idx) * dQ_idx  per sample on the device (mle_sample_unbiased).  The per-idx
+# moments are appended exactly where the reference's append_samples! for U appends the samples; the accumulator (a MomentVector
+# too, patch P2) takes the (n, mean, M2) of Z: `append_to_accumulator!` + `add_to_accumulator!` collapse into one append.
+function device_sample_unbiased!(estimator::Estimator{I, S}, index::Index, Istart::Integer, Iend::Integer) where {I<:U, S<:Union{MC, QMC}}
     model = estimator.sample_function
     ensure_handles!(model, estimator)
     m = estimator[:nb_of_uncertainties](index)
-    R = estimator[:nb_of_shifts](index)
-    gens = [generator(estimator, index, r) for r in 1:R]
-    ensure_lattice!(model, gens[1].lattice_rule)
-    shifts = reduce(hcat, [Vector{Float64}(g.shift) for g in gens])
+    qmc = S <: QMC
+    R = qmc ? estimator[:nb_of_shifts](index) : 1
+    qmc && ensure_lattice!(model, generator(estimator, index, 1).lattice_rule)
+    shifts = qmc ? shift_matrix(estimator, index, R) : Float64[]
     n = Iend - Istart + 1
-    out = Dict{Any, Array{Float64, 4}}()
-    for idx in CartesianIndices(index.I .+ 1)
-        sub = Int32[Tuple(idx)...] .- Int32(1)
-        mom = Array{Float64}(undef, 3, 2, model.nqoi, R)
-        smp = Array{Float64}(undef, n, 2, model.nqoi, R)
-        GC.@preserve shifts mom smp sub check(model.ctx.ptr,
-            ccall((:mle_sample_batch, libmle), Cint,
-                  (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
-                   Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                  model.ctx.ptr, model.ptr, model.lattice, model.dists, sub, length(sub), shifts, R,
-                  UInt64(Istart - 1), UInt64(n), m, UInt64(0), mom, smp, C_NULL))
-        out[Index(sub...)] = smp
+    box = CartesianIndices(index.I .+ 1)                                   # column-major: the first entry runs fastest
+    inv_prob = Float64[1 / MultilevelEstimators.Prob(estimator, Index((Tuple(c) .- 1)...)) for c in box]
+    moms = Array{Float64}(undef, 3, 2, model.nqoi, R, length(box))
+    acc = Array{Float64}(undef, 3, model.nqoi, R)
+    idx = Int32[index.I...]
+    GC.@preserve shifts moms acc idx inv_prob check(model.ctx.ptr,
+        ccall((:mle_sample_unbiased, libmle), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, UInt64, UInt64, Cint, UInt64,
+               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              model.ctx.ptr, model.ptr, qmc ? model.lattice : C_NULL, model.dists, idx, length(idx),
+              qmc ? pointer(shifts) : Ptr{Float64}(C_NULL), R, UInt64(Istart - 1), UInt64(n), m,
+              qmc ? UInt64(0) : index_seed(MC_SEED[], index), inv_prob, moms, acc, Ptr{Float64}(C_NULL)))
+    for (i, c) in enumerate(box)
+        store_moments!(estimator, Index((Tuple(c) .- 1)...), view(moms, :, :, :, :, i))
     end
-    out
+    for r in 1:R, q in 1:model.nqoi
+        append!(MultilevelEstimators.accumulator(estimator, q, r), MomentVector(view(acc, :, q, r)))
+    end
 end
-
-# ---- statistics from the moment state (replace src/methods.jl:44-57, :282 for DeviceModel estimators) ---------------------
-# mom[:, X, q, r] = (n, mean, M2);  X = 1: dQ (samples_diff), X = 2: Qf (samples)
-_mean(mom, X, q) = sum(mom[2, X, q, r] for r in axes(mom, 4)) / size(mom, 4)
-_var(mom, X, q) = sum(mom[3, X, q, r] / (mom[1, X, q, r] - 1) for r in axes(mom, 4)) / size(mom, 4)
-_varest_qmc(mom, q) = (R = size(mom, 4); μ = [mom[2, 1, q, r] for r in 1:R]; sum(abs2, μ .- sum(μ) / R) / (R - 1) / R)
 
 end # module

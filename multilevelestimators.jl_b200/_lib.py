@@ -49,6 +49,8 @@ SIGNATURES = {
                                        C.c_uint64, _vp, _vp]),
     "mle_update_samples": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i32p, C.c_int, C.POINTER(_dp), C.POINTER(C.c_int),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_uint64, C.POINTER(_dp)]),
+    "mle_sample_unbiased": (C.c_int, [_vp, _vp, _vp, _vp, _i32p, C.c_int, _dp, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                      C.c_uint64, _dp, _dp, _dp, _dp]),
     "mle_sync": (C.c_int, [_vp]),
     "mle_moments_merge": (C.c_int, [_dp, _dp, C.c_size_t]),
 }

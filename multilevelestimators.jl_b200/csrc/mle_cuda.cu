@@ -125,6 +125,8 @@ struct mle_ctx_s {
     size_t batch_staged = 0;    // doubles of h_pinned[0..] that mirror the shifts in d_batch (0: nothing valid)
     double *d_samples = nullptr;  // raw samples of a mle_sample_batch call that asked for them
     size_t samples_cap = 0;
+    double *d_zacc = nullptr;     // mle_sample_unbiased: per-sample accumulator Z [R][q][n]
+    size_t zacc_cap = 0;
     double *h_pinned = nullptr;
     size_t pinned_cap = 0;  // doubles
 };
@@ -351,6 +353,7 @@ extern "C" int mle_destroy(mle_ctx ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_batch) cudaFree(ctx->d_batch);
     if (ctx->d_samples) cudaFree(ctx->d_samples);
+    if (ctx->d_zacc) cudaFree(ctx->d_zacc);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0);
@@ -1187,6 +1190,71 @@ extern "C" int mle_sample_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_d
         if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_batch: ") + cudaGetErrorString(e)); }
         if (stage) memcpy(moments, stage, nm * sizeof(double));
     }
+    if (gpu_seconds) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        *gpu_seconds = (double)ms * 1e-3;
+    }
+    return MLE_OK;
+}
+
+// Unbiased estimators: one call evaluates every idx in zero(index):index on the same points and reduces the per-sample sums
+// Z = sum_idx inv_prob[idx] * dQ_idx on the device (include/mle_cuda.h).  Every idx is a launch of the model's normal kernel that
+// leaves its raw samples in a device buffer the library keeps across calls; nothing per-sample crosses PCIe.
+extern "C" int mle_sample_unbiased(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, const int32_t *index, int d,
+                                   const double *shifts, int R, uint64_t k0, uint64_t n, int m, uint64_t mc_seed,
+                                   const double *inv_prob, double *moments, double *acc, double *gpu_seconds) {
+    MLE_API_SCOPE;
+    if (!ctx || !M || !index || !inv_prob || !moments || !acc) return MLE_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (R < 1) return fail(ctx, MLE_ERR_ARG, "number of shifts must be at least 1");
+    if (d != M->ndims || d < 1 || d > 8) return fail(ctx, MLE_ERR_ARG, "index dimension does not match the model");
+    if (n == 0) return fail(ctx, MLE_ERR_ARG, "sample!: number of samples must be positive");
+    size_t nidx = 1;
+    for (int t = 0; t < d; ++t) {
+        if (index[t] < 0) return fail(ctx, MLE_ERR_ARG, "index must be non-negative");
+        nidx *= (size_t)index[t] + 1;
+    }
+    const double *sh_dev = nullptr;
+    int rc = upload_shifts(ctx, lat, shifts, R, &sh_dev);
+    if (rc) return rc;
+    const size_t q = (size_t)M->nqoi, nm = (size_t)R * 2 * q * 3, na = (size_t)R * q * 3;
+    const size_t ntab = nidx * nm + na;
+    rc = ensure_dev(ctx, &ctx->d_moments, &ctx->moments_cap, ntab);
+    if (rc == MLE_OK) rc = ensure_dev(ctx, &ctx->d_samples, &ctx->samples_cap, (size_t)R * 2 * q * n);
+    if (rc == MLE_OK) rc = ensure_dev(ctx, &ctx->d_zacc, &ctx->zacc_cap, (size_t)R * q * n);
+    if (rc) return rc;
+    const size_t sh_off = (shifts && lat) ? (size_t)R * (size_t)lat->s : 0;
+    if (sh_off + ntab + 64 > ctx->pinned_cap) {  // staging for the tables behind the shifts image
+        ctx->shifts_staged = 0;
+        rc = ensure_pinned(ctx, sh_off + ntab + 4096);
+        if (rc) return rc;
+        if (shifts && lat) { sh_dev = nullptr; rc = upload_shifts(ctx, lat, shifts, R, &sh_dev); if (rc) return rc; }
+    }
+    if (gpu_seconds) cudaEventRecord(ctx->ev0, ctx->stream);
+    const unsigned long long total = (unsigned long long)R * q * n;
+    const unsigned zgrid = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 8);
+    int32_t idx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < nidx; ++i) {  // column-major walk of zero(index):index: the first entry runs fastest
+        rc = launch_batch(ctx, M, lat, dists, idx, d, sh_dev, R, k0, n, m, mc_seed, ctx->d_moments + i * nm, ctx->d_samples);
+        if (rc != MLE_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+        zacc_kernel<<<zgrid, 256, 0, ctx->stream>>>(ctx->d_zacc, ctx->d_samples, inv_prob[i], i == 0 ? 1 : 0, (unsigned long long)n, total);
+        ++ctx->launches;
+        for (int t = 0; t < d; ++t) {
+            if (++idx[t] <= index[t]) break;
+            idx[t] = 0;
+        }
+    }
+    zacc_moments_kernel<<<(unsigned)(R * q), 256, 0, ctx->stream>>>(ctx->d_zacc, (unsigned long long)n, ctx->d_moments + nidx * nm);
+    ++ctx->launches;
+    if (gpu_seconds) cudaEventRecord(ctx->ev1, ctx->stream);
+    double *stage = ctx->h_pinned + sh_off;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stage, ctx->d_moments, ntab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MLE_ERR_CUDA, std::string("mle_sample_unbiased: ") + cudaGetErrorString(e)); }
+    memcpy(moments, stage, nidx * nm * sizeof(double));
+    memcpy(acc, stage + nidx * nm, na * sizeof(double));
     if (gpu_seconds) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);

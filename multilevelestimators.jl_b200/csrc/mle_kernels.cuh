@@ -496,4 +496,33 @@ __global__ void __launch_bounds__(TG == 32 ? 128 : 256) lognormal2d_kernel(GenAr
     cta_finalize(fa, 2);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Unbiased estimators (src/sample.jl:65-74, :113-124): per-sample accumulator  Z_i = sum_{idx <= index} dQ_idx,i / Prob(idx).
+// zacc_kernel adds one idx's term to Z from the raw samples that idx's launch left on the device ([R][q][2][n], X = 0 is dQ);
+// the product and the sum are rounded separately, term by term in idx order, exactly as `add_to_accumulator!` does with
+// `1 / Prob(idx) * s_diff`.  zacc_moments_kernel reduces Z to (n, mean, M2) per (shift, QoI): two passes over the values (they
+// are in memory here), fixed tree order.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zacc_kernel(double *__restrict__ Z, const double *__restrict__ samples, double w, int first,
+                                                   unsigned long long n, unsigned long long total) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * 256) {
+        const unsigned long long rq = i / n, k = i - rq * n;
+        const double term = __dmul_rn(w, samples[(rq * 2) * n + k]);
+        Z[i] = first ? term : __dadd_rn(Z[i], term);
+    }
+}
+
+__global__ void __launch_bounds__(256) zacc_moments_kernel(const double *__restrict__ Z, unsigned long long n, double *__restrict__ out3) {
+    __shared__ double red[8];
+    const double *z = Z + (size_t)blockIdx.x * n;
+    double s = 0.0;
+    for (unsigned long long i = threadIdx.x; i < n; i += 256) s += z[i];
+    const double mean = block_sum<256>(s, red) / (double)n;
+    double q = 0.0;
+    for (unsigned long long i = threadIdx.x; i < n; i += 256) { const double d = z[i] - mean; q = __fma_rn(d, d, q); }
+    const double m2 = block_sum<256>(q, red);
+    if (threadIdx.x == 0) { out3[blockIdx.x * 3 + 0] = (double)n; out3[blockIdx.x * 3 + 1] = mean; out3[blockIdx.x * 3 + 2] = m2; }
+}
+
 }  // namespace mle

@@ -247,6 +247,34 @@ class Engine:
                                                 shp, R, k0, n, m, int(mc_seed), mop))
         return moms
 
+    def sample_unbiased(self, model, lattice, dists, index, shifts, k0, n, inv_prob, m=None, mc_seed=0, want_time=False):
+        """One `sample!` call of an unbiased estimator (mle_sample_unbiased; src/sample.jl:65-74, :113-124): every idx in
+        zero(index):index on the same points.  inv_prob[idx] = 1 / Prob(idx), column-major over the box (first entry fastest).
+        -> (moments float64[nidx, R, nqoi, 2, 3], acc float64[R, nqoi, 3][, seconds])"""
+        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.int32)
+        nidx = int(np.prod(idx.astype(np.int64) + 1))
+        inv_prob = np.ascontiguousarray(inv_prob, dtype=np.float64).ravel()
+        if inv_prob.size != nidx:
+            raise MLEArgumentError("inv_prob must hold one entry per idx in zero(index):index")
+        if shifts is not None:
+            shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+            if lattice is None or shifts.ndim != 2 or shifts.shape[1] != lattice.s:
+                raise MLEArgumentError("shifts must have shape [R, s]")
+            R = shifts.shape[0]
+        else:
+            R = 1
+        if m is None:
+            m = dists.m if dists is not None else lattice.s
+        mom = np.empty((nidx, R, model.nqoi, 2, 3))
+        acc = np.empty((R, model.nqoi, 3))
+        secs = C.c_double(0.0)
+        self._check(self.lib.mle_sample_unbiased(self.ctx, model.handle, lattice.handle if lattice else None,
+                                                 dists.handle if dists else None, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 len(idx), _as_dp(shifts), int(R), int(k0), int(n), int(m), int(mc_seed),
+                                                 _as_dp(inv_prob), _as_dp(mom), _as_dp(acc),
+                                                 C.byref(secs) if want_time else None))
+        return (mom, acc, secs.value) if want_time else (mom, acc)
+
     def sample_batch_dev(self, model, lattice, dists, index, shifts_ptr, R, k0, n, m, moments_ptr, samples_ptr=None,
                          mc_seed=0):
         """device-pointer variant: asynchronous on self.stream, nothing crosses PCIe"""

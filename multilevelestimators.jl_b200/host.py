@@ -282,6 +282,13 @@ class GpuBackend:
         """entries = [(index, shifts, k0, n, m)] -> list of moment tables; one device synchronisation for all of them"""
         return self.engine.update_samples(model, lattice, dists, entries, mc_seed=mc_seed)
 
+    def sample_unbiased(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, inv_prob):
+        """unbiased estimators: every idx <= index on the same points, accumulator reduced on the device (mle_sample_unbiased)
+        -> (moments[nidx, R, q, 2, 3], acc[R, q, 3], seconds)"""
+        out = self.engine.sample_unbiased(model, lattice, dists, index, shifts, k0, n, inv_prob, m=m, mc_seed=mc_seed,
+                                          want_time=self.time_kernels)
+        return out if self.time_kernels else (out[0], out[1], 0.0)
+
     def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         """-> (moments, seconds) or, with want_samples (the `save_samples` option), (moments, seconds, samples[R, q, 2, n])"""
         out = self.engine.sample_batch(model, lattice, dists, index, shifts, k0, n, m=m, mc_seed=mc_seed,
@@ -662,27 +669,40 @@ class Estimator:
     def _sample_unbiased(self, index, n):
         """sample! for U estimators (src/sample.jl:21-34 with the append_samples! of :65-74, :113-124): the sample function of
         the reference returns (dQ, Qf) for EVERY idx <= index from one input vector.  Here the device model is evaluated once per
-        idx on the same points (same shifts, same point numbers, same leading coordinates) with the raw samples returned, and
-        the per-sample sums  Z = sum_idx dQ_idx / Prob(idx)  are reduced to (n, mean, M2) on the host."""
+        idx on the same points (same shifts, same point numbers, same leading coordinates) and the per-sample sums
+        Z = sum_idx (1 / Prob(idx)) dQ_idx  are reduced to (n, mean, M2) on the device (mle_sample_unbiased); backends without
+        that call (the CPU oracle of the tests, the torch.distributed sharding) and `save_samples` runs take the raw samples and
+        reduce on the host."""
         import itertools
         from .engine import moments_merge
         istart = sum(self.nb_of_samples.values()) + 1   # src/sample.jl:25: U counts the samples of ALL indices
         m = self.options["nb_of_uncertainties"](index)
         seed = index_seed(self.options["mc_seed"], index)   # one input vector per sample, shared by every idx <= index
         t0 = _time.perf_counter()
-        Z, t_cons = None, 0.0
-        for idx in sorted(itertools.product(*[range(i + 1) for i in index]), key=lambda t: t[::-1]):
-            mom, _t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(idx), self.shifts.get(index),
-                                                     istart - 1, n, m, seed, want_samples=True)
-            self.moments[idx] = moments_merge(self.moments[idx], mom) if idx in self.moments else np.array(mom, dtype=np.float64)
-            if self.options["save_samples"]:
-                self.samples.setdefault(idx, []).append(np.array(smp))
-            term = smp[:, :, 0, :] / self.Prob(idx)
-            Z = term if Z is None else Z + term
-            t_cons += _t
+        box = sorted(itertools.product(*[range(i + 1) for i in index]), key=lambda t: t[::-1])   # first entry fastest
+        if hasattr(self.backend, "sample_unbiased") and not self.options["save_samples"]:
+            # device reduction: ONE call, every idx on the same points, Z = sum_idx (1/Prob(idx)) dQ_idx summed per sample on the
+            # GPU; only the moment tables come back (include/mle_cuda.h: mle_sample_unbiased)
+            inv_prob = [1.0 / self.Prob(idx) for idx in box]
+            moms, part, t_cons = self.backend.sample_unbiased(self.model, self.lattice, self.dists, list(index),
+                                                              self.shifts.get(index), istart - 1, n, m, seed, inv_prob)
+            for idx, mom in zip(box, moms):
+                self.moments[idx] = moments_merge(self.moments[idx], mom) if idx in self.moments else np.array(mom, dtype=np.float64)
+            part = np.array(part, dtype=np.float64)
+        else:
+            Z, t_cons = None, 0.0
+            for idx in box:
+                mom, _t, smp = self.backend.sample_batch(self.model, self.lattice, self.dists, list(idx), self.shifts.get(index),
+                                                         istart - 1, n, m, seed, want_samples=True)
+                self.moments[idx] = moments_merge(self.moments[idx], mom) if idx in self.moments else np.array(mom, dtype=np.float64)
+                if self.options["save_samples"]:
+                    self.samples.setdefault(idx, []).append(np.array(smp))
+                term = (1.0 / self.Prob(idx)) * smp[:, :, 0, :]   # src/sample.jl:71: 1 / Prob(estimator, idx) * s_diff
+                Z = term if Z is None else Z + term
+                t_cons += _t
+            zm = Z.mean(axis=-1)
+            part = np.stack([np.full(zm.shape, float(n)), zm, ((Z - zm[..., None]) ** 2).sum(axis=-1)], axis=-1)   # [R, q, 3]
         t = t_cons if getattr(self.backend, "consensus_time", False) else _time.perf_counter() - t0
-        zm = Z.mean(axis=-1)
-        part = np.stack([np.full(zm.shape, float(n)), zm, ((Z - zm[..., None]) ** 2).sum(axis=-1)], axis=-1)   # [R, q, 3]
         self.acc = part if self.acc is None else moments_merge(self.acc, part)
         self._memo.clear()
         self.nb_of_samples[index] += n

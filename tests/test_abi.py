@@ -89,8 +89,8 @@ def test_julia_binding_matches_the_header():
                 assert "*" not in c.replace("const char *", "") and any(c.startswith(w) for w in width[t]), (name, t, c)
             else:
                 assert t.startswith(("Ptr{", "Ref{")) and ("*" in c or c.split()[0].startswith("mle_")), (name, t, c)
-    for name in ("mle_init", "mle_destroy", "mle_last_error", "mle_lattice_create", "mle_dists_create", "mle_model_create",
-                 "mle_model_set_basis", "mle_points", "mle_sample_batch", "mle_update_samples", "mle_moments_merge",
+    for name in ("mle_init", "mle_init_multi", "mle_destroy", "mle_last_error", "mle_lattice_create", "mle_dists_create", "mle_model_create",
+                 "mle_model_set_basis", "mle_points", "mle_sample_batch", "mle_update_samples", "mle_sample_unbiased", "mle_moments_merge",
                  "mle_lattice_destroy", "mle_dists_destroy", "mle_model_destroy", "mle_abi_version", "mle_genvec"):
         assert name in seen, "julia/MLECuda.jl does not bind %s" % name
     assert "const ABI_VERSION = 1" in src and "#define MLE_ABI_VERSION 1" in open(os.path.join(ROOT, "include", "mle_cuda.h")).read()
@@ -180,6 +180,7 @@ res["points_dev"] = lib.mle_points_dev(N, N, N, N, 1, 0, 1, 1, 0, dbl)
 res["sample_batch"] = lib.mle_sample_batch(N, N, N, N, i32, 1, N, 1, 0, 1, 1, 0, dbl, N, N)
 res["sample_batch_dev"] = lib.mle_sample_batch_dev(N, N, N, N, i32, 1, N, 1, 0, 1, 1, 0, dbl, N)
 res["update_samples"] = lib.mle_update_samples(N, N, N, N, 1, i32, 1, N, N, N, N, N, 0, N)
+res["sample_unbiased"] = lib.mle_sample_unbiased(N, N, N, N, i32, 1, N, 1, 0, 1, 1, 0, dbl, dbl, dbl, N)
 res["sync"] = lib.mle_sync(N)
 res["stream"] = lib.mle_stream(N, C.byref(h))
 cnt = C.c_uint64()
@@ -202,6 +203,6 @@ def test_every_entry_point_refuses_null_handles_without_crashing():
     p = subprocess.run([sys.executable, "-c", _NULL_CALLS % ROOT], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     res = json.loads(p.stdout.strip().splitlines()[-1])
-    assert len(res) == 20
+    assert len(res) == 21
     for name, rc in res.items():
         assert rc == (0 if name.endswith("destroy") else -1), (name, rc)

@@ -100,6 +100,43 @@ def test_problem18_mc(engine, oracle):
     check_moments(got, want)
 
 
+def test_sample_unbiased_reduces_the_accumulator_on_the_device(engine, oracle):
+    """mle_sample_unbiased (src/sample.jl:65-74, :113-124): every idx in zero(index):index on the same points in ONE call; the
+    per-idx moment tables equal those of separate mle_sample_batch calls bit for bit, and (n, mean, M2) of the per-sample sums
+    Z = sum_idx (1/Prob(idx)) dQ_idx equal the host reduction of the raw samples"""
+    import itertools
+    rng = np.random.default_rng(4)
+    cases = []
+    d1 = engine.dists([(0, [-0.5, 0.5])])
+    cases.append((engine.model("problem18", 1), None, d1, [3], None, 1, 7, 500, 1, 5))
+    z = oracle.genvec("K_3600_32", 2)
+    lat2 = engine.lattice(z, 2)
+    d2 = engine.dists([(0, [-0.5, 0.5])] * 2)
+    sh2 = splitmix_uniforms(9, 4 * 2).reshape(4, 2)
+    cases.append((engine.model("problem18", 2), lat2, d2, [2, 1], sh2, 4, 3, 64, 2, 0))
+    zl, latl, dl, dd, gm, om = lognormal_setup(engine, oracle, 20, [0, 1, 2])
+    shl = splitmix_uniforms(10, 3 * 20).reshape(3, 20)
+    cases.append((gm, latl, dd, [2], shl, 3, 0, 77, 20, 0))
+    for model, lat, dists, index, sh, R, k0, n, m, seed in cases:
+        box = sorted(itertools.product(*[range(i + 1) for i in index]), key=lambda t: t[::-1])
+        w = 1.0 / rng.uniform(0.05, 1.0, len(box))
+        moms, acc = engine.sample_unbiased(model, lat, dists, index, sh, k0, n, w, m=m, mc_seed=seed)
+        Z = None
+        for i, idx in enumerate(box):
+            mom, smp = engine.sample_batch(model, lat, dists, list(idx), sh, k0, n, m=m, mc_seed=seed, want_samples=True)
+            assert np.array_equal(moms[i], mom)
+            term = w[i] * smp[:, :, 0, :]
+            Z = term if Z is None else Z + term
+        zm = Z.mean(axis=-1)
+        assert np.array_equal(acc[..., 0], np.full(zm.shape, float(n)))
+        assert np.allclose(acc[..., 1], zm, rtol=1e-14, atol=0)
+        m2 = ((Z - zm[..., None]) ** 2).sum(axis=-1)
+        assert np.allclose(acc[..., 2], m2, rtol=1e-12, atol=1e-300)
+    import mle_b200
+    with pytest.raises(mle_b200.MLEArgumentError):
+        engine.sample_unbiased(cases[0][0], None, d1, [3], None, 0, 10, [1.0, 1.0], m=1)   # one weight per idx
+
+
 def lognormal_setup(engine, oracle, m, levels, n0=16):
     import mle_b200.kl as kl
     z = oracle.genvec("K_3600_32", m)
