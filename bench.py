@@ -222,12 +222,12 @@ def _ncu_rows():
 
 
 def ncu_pipe_busy():
+    """FP64-pipe + DMMA-pipe busy share per level launch (one physical pipe on B200), from the committed ncu summary"""
     rows = _ncu_rows()
     if not rows:
         return None
     try:
-        return [round((float(r["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active [%]"]) +
-                       float(r["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed [%]"])) / 100.0, 3) for r in rows]
+        return [round(float(r["pipe_fp64_plus_dmma_pct"]) / 100.0, 3) for r in rows]
     except Exception:  # noqa: BLE001
         return None
 
@@ -237,7 +237,7 @@ def ncu_traffic():
     if not rows:
         return None
     try:
-        return sum(float(r["dram__bytes_read.sum [Kbyte]"]) * 1e3 + float(r["dram__bytes_write.sum [byte]"]) for r in rows)
+        return sum(float(r["dram_bytes"]) for r in rows)
     except Exception:  # noqa: BLE001
         return None
 

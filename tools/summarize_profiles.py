@@ -51,11 +51,36 @@ for wname in want:
             cols.append((wname + (" [" + units[i] + "]" if units[i] else ""), i))
             break
 stall = [i for i, h in enumerate(hdr) if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def col(name):
+    for i, h in enumerate(hdr):
+        if h.endswith(name):
+            return i
+    return None
+
+
+def num(r, i, scale_units=False):
+    if i is None or r[i] in ("", "n/a"):
+        return float("nan")
+    v = float(r[i].replace(",", ""))
+    return v * SCALE.get(units[i], 1.0) if scale_units else v
+
+
+i_rd, i_wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+i_fp64 = col("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+i_tens = col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
 with open(os.path.join(root, tag + "_kernels.csv"), "w", newline="") as f:
     w = csv.writer(f)
-    w.writerow([c for c, _ in cols] + ["top warp stall reasons (% of samples)"])
+    # the last four columns are unit-free figures bench.py reads: DRAM bytes of the launch, FP64-pipe and DMMA-pipe busy shares
+    w.writerow([c for c, _ in cols] + ["top warp stall reasons (% of samples)", "dram_bytes", "pipe_fp64_pct", "pipe_dmma_pct",
+                                         "pipe_fp64_plus_dmma_pct"])
     for r in data:
         tot_s = sum(float(r[i] or 0) for i in stall) or 1.0
         top = sorted(((float(r[i] or 0) / tot_s * 100, hdr[i].split("issue_stalled_")[-1]) for i in stall), reverse=True)[:5]
-        w.writerow([r[i][:90] for _, i in cols] + [" ".join("%s=%.1f" % (n, v) for v, n in top)])
+        fp, te = num(r, i_fp64), num(r, i_tens)
+        w.writerow([r[i][:90] for _, i in cols] + [" ".join("%s=%.1f" % (n, v) for v, n in top),
+                                                   "%.0f" % (num(r, i_rd, True) + num(r, i_wr, True)), "%.2f" % fp, "%.2f" % te,
+                                                   "%.2f" % (fp + te)])
 print("wrote profiles/%s_launches.csv and profiles/%s_kernels.csv" % (tag, tag))
