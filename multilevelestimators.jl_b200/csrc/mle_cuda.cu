@@ -30,6 +30,8 @@ template <int MODE> static constexpr auto lognormal2d_r16 = lognormal2d_rows_ker
 template <int MODE> static constexpr auto lognormal2d_r32 = lognormal2d_rows_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_r64 = lognormal2d_rows_kernel<MODE, 64>;
 template <int MODE> static constexpr auto lognormal2d_r128 = lognormal2d_rows_kernel<MODE, 128>;
+template <int MODE> static constexpr auto lognormal2d_d64 = lognormal2d_rows_kernel<MODE, 64, Dmma2dCfg<64>>;
+template <int MODE> static constexpr auto lognormal2d_d128 = lognormal2d_rows_kernel<MODE, 128, Dmma2dCfg<128>>;
 // mode = GEN_RAW | GEN_STDNORMAL | GEN_GENERAL, optionally | GEN_MC: six instantiations per kernel
 #define MLE_LAUNCH_BY_MODE(mode, K, grid, block, smem, stream, ...)                          \
     do {                                                                                       \
@@ -99,6 +101,7 @@ struct mle_ctx_s {
     uint64_t launches = 0;
     int ln_block = -1;       // MLE_LN_BLOCK=0|1: force the warp-autonomous / phase-synchronous lognormal1d kernel (default: by grid size)
     int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
+    int ln2d_dmma = 1;       // MLE_2D_DMMA=0: register-window solver everywhere; 1: blocked DMMA solver at 128 cells; 2: also at 64
     // reusable device / pinned scratch
     Partial *d_partials = nullptr;
     size_t partials_cap = 0;  // in Partials
@@ -288,9 +291,12 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(lognormal2d_r32, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r64, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r128, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_d64, 220 * 1024);
+    MLE_SET_SMEM(lognormal2d_d128, 220 * 1024);
 #undef MLE_SET_SMEM
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return fail(nullptr, MLE_ERR_CUDA, "mle_init: cudaFuncSetAttribute failed"); }
     if (const char *e = getenv("MLE_2D_WINDOW_SMEM")) ctx->ln2d_old = atoi(e) != 0;
+    if (const char *e = getenv("MLE_2D_DMMA")) ctx->ln2d_dmma = atoi(e);
     if (const char *e = getenv("MLE_LN_BLOCK")) ctx->ln_block = atoi(e) != 0;
     if (const char *e = getenv("MLE_NO_ZEROCOPY")) ctx->zero_copy = atoi(e) == 0;
     // the mapped completion flag (zero-copy result path); without it the library falls back to copy + synchronise
@@ -978,7 +984,8 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         } else {
         const int ws = 16;  // samples per warp (the 8-sample instantiation never won a level and was dropped)
         const long long tps = (long long)((n + LN_BT - 1) / LN_BT);
-        const size_t smem = ln1d_smem_bytes(la.mpad, lat ? g.m : 0, ws);
+        size_t smem = ln1d_smem_bytes(la.mpad, lat ? g.m : 0, ws);
+        if (const char *e = getenv("MLE_LN_PAD")) smem += (size_t)atoi(e);  // occupancy experiment: extra bytes per CTA
         const int threads = ln_threads(ws);
         const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_k16, threads, smem);
         gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
@@ -1000,19 +1007,19 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         if (M->d_frag[key] && !ctx->ln2d_old) {
             const int Nx = M->n0 << lx, Ny = M->n0 << ly;
             int rows_rc = -1;
-#define MLE_ROWS_CASE(WW, KK)                                                                                          \
-            case WW: {                                                                                                 \
-                using Cfg = Rows2dCfg<WW>;                                                                             \
+#define MLE_ROWS_BODY(WW, KK, CFG)                                                                                     \
+            {                                                                                                          \
+                using Cfg = CFG;                                                                                       \
                 Lognormal2dRowsArgs ra{};                                                                              \
                 ra.basis = M->d_frag[key]; ra.Nx = Nx; ra.Ny = Ny; ra.ndims = d; ra.lx = lx; ra.ly = ly;               \
                 ra.mpad = M->frag_mpad[key]; ra.ntiles = M->frag_tiles[key];                                           \
                 const size_t fbytes = (size_t)ra.ntiles * 8 * Cfg::LDF * 8, qbytes = (size_t)32 * Cfg::THREADS * 2;    \
-                const size_t fixed = (size_t)ra.mpad * Cfg::LDX * 8 + (size_t)Cfg::CS * rows_sh_doubles(WW) * 8 +     \
+                const size_t fixed = (size_t)ra.mpad * Cfg::LDX * 8 + (size_t)Cfg::CS * Cfg::SH * 8 +                 \
                                      (size_t)2 * Cfg::S * 8 + (size_t)2 * Cfg::S * sizeof(Partial) +                    \
                                      (((Cfg::THREADS / 32) + 3) & ~3) * 4 + 128;                                       \
                 ra.use_scratch = (fixed + fbytes + (qbytes > fbytes ? qbytes : 0) > 200 * 1024) ? 1 : 0;               \
                 const size_t smem = fixed + (ra.use_scratch ? qbytes : fbytes + (qbytes > fbytes ? qbytes : 0));       \
-                if (smem > 220 * 1024) break;                                                                          \
+                if (smem <= 220 * 1024) {                                                                              \
                 const long long tps = (long long)((n + Cfg::S - 1) / Cfg::S);                                          \
                 const int occ = MLE_OCC_BY_MODE(g.mode, KK, Cfg::THREADS, smem);                                       \
                 gx = grid_x_for(ctx, tps, R, occ);                                                                     \
@@ -1029,7 +1036,15 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
                 dim3 grid((unsigned)gx, (unsigned)R);                                                                  \
                 MLE_LAUNCH_BY_MODE(g.mode, KK, grid, Cfg::THREADS, smem, ctx->stream, g, ra, fa, samples_dev, tps); \
                 rows_rc = 0;                                                                                           \
-            } break;
+                }                                                                                                      \
+            }
+#define MLE_ROWS_CASE(WW, KK) case WW: MLE_ROWS_BODY(WW, KK, Rows2dCfg<WW>) break;
+            // blocked DMMA solver: multilevel differences on square grids of 64 / 128 cells
+            // (at 64 cells the register-window solver is still faster -- four samples side by side hide its latencies --, so the
+            // blocked solver is only taken there when forced with MLE_2D_DMMA=2)
+            if (ctx->ln2d_dmma >= 2 && d == 1 && Nx == Ny && Nx == 64) MLE_ROWS_BODY(64, lognormal2d_d64, Dmma2dCfg<64>)
+            else if (ctx->ln2d_dmma && d == 1 && Nx == Ny && Nx == 128) MLE_ROWS_BODY(128, lognormal2d_d128, Dmma2dCfg<128>)
+            if (rows_rc != 0)
             switch (Nx) {
                 MLE_ROWS_CASE(4, lognormal2d_r4)
                 MLE_ROWS_CASE(8, lognormal2d_r8)
@@ -1040,6 +1055,7 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
                 default: break;
             }
 #undef MLE_ROWS_CASE
+#undef MLE_ROWS_BODY
             rows_done = rows_rc == 0;
         }
         if (!rows_done) {

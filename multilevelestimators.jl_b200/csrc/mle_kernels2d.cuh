@@ -452,6 +452,406 @@ __device__ __noinline__ double frontal_mid_rpl(FieldView f, double *sh, double *
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked frontal solver on the FP64 tensor instruction (windows of 64 and 128 cells).
+//
+// Same arithmetic as the oracle's frontal_mid (oracle/mle_oracle.c): every window entry receives fma(-l_q, v_r, M[q][r]) once per
+// pivot, in pivot order.  On B200 one mma.sync.m8n8k4.f64 IS four such fused multiply-adds in ascending k (tools/dmma_order_test.cu),
+// so FOUR CONSECUTIVE PIVOTS can be applied to an 8x8 tile of the window by one DMMA -- provided the multipliers l^(j)_q and the
+// column values v^(j)_r of the four pivots are known, and those depend on each other.  Hence two phases per block of four pivots
+// p .. p+3 (window kept in the oracle's circular slot coordinates, slot = unknown % W, as DMMA accumulator tiles in registers):
+//   1. PANEL.  The four pivot columns are copied from the register tiles to shared memory; thread q (one per window row) takes its
+//      four entries X[q][0..3] and the four pivots are factorised one after the other exactly as the oracle does it for these
+//      entries: step j publishes the entries of the pivot rows, every active row forms l = v * (1/d) and updates its entries of
+//      the later pivot columns and its right-hand side g.  Cost: four small barriers among W threads, O(W) work.
+//   2. TRAILING UPDATE.  A[q][j] = -l^(j)_q and B[j][r] = v^(j)_r go to shared memory and every 8x8 tile takes ONE DMMA: 4 W^2
+//      fused multiply-adds in W^2/64 tensor instructions (the register-window solver above spends ~6 issue slots per DFMA here).
+// Unknown e = p+j+n enters the window at step j in the slot pivot p+j-1 has just left (the oracle's LOAD_UNKNOWN); a row or column
+// that changes owner inside a block simply carries zeros in the operands of the steps before the newcomer arrived (fma(-0, v, x) =
+// x exactly), and its register row / column is re-initialised to the newcomer's stencil entries before the DMMA.  The newcomer's
+// coupling to its pivot (-ky) only ever lives in the panel.  The dense two-sided elimination along the centre line uses the same
+// step with one pivot per block (126 of ~16000 pivots at 128 cells).  Bit-identical to the oracle (tests/test_gpu_batch.py).
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int dmma_sh_doubles(int w) { return 12 * w + 6 * w + 32 + 8 + 4 * 64; }
+
+// warp-uniform dispatch of a runtime tile index to a compile-time one (the accumulators must keep static register indices)
+#define MLE_DISPATCH4(idx, N, CALL)                                  \
+    switch (idx) {                                                   \
+        case 0: { constexpr int I_ = 0; CALL; } break;               \
+        case 1: if constexpr ((N) > 1) { constexpr int I_ = 1; CALL; } break; \
+        case 2: if constexpr ((N) > 2) { constexpr int I_ = 2; CALL; } break; \
+        case 3: if constexpr ((N) > 3) { constexpr int I_ = 3; CALL; } break; \
+        default: break;                                              \
+    }
+
+// correctly rounded 1/d for d well inside the normal range: ddiv_normal(1.0, d) without its exact product 1.0 * r
+__device__ __forceinline__ double drcp_normal(double den) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = __fma_rn(-den, r, 1.0);
+    e = __fma_rn(e, e, e);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-den, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double rem = __fma_rn(-den, r, 1.0);
+    return __fma_rn(r, rem, r);
+}
+
+template <int NW, int TW>
+__device__ __noinline__ double frontal_mid_dmma(FieldView f, double *sh, double *park, int pstride, int tg, int barid) {
+    constexpr int W = NW, n = NW - 1, NT = NW / 8, tc = NW / 2 - 1;
+    constexpr int WR = TW >= 16 ? 4 : 2, WC = TW / WR, TR = NT / WR, TC = NT / WC;
+    static_assert(WR * WC == TW && TR * WR == NT && TC * WC == NT && TR >= 1 && TR <= 4 && TC >= 1 && TC <= 4, "warp grid");
+    static_assert(W % 32 == 0, "the panel barrier counts whole warps");
+    const int lane = tg & 31, warp = tg >> 5, wr = warp / WC, wc = warp % WC, lr = lane >> 2, lk = lane & 3;
+    double *X = sh;               // [W][4] panel as extracted from the register tiles
+    double *LA = sh + 4 * W;      // [W][4] -l^(j)_q   (A operand)
+    double *VB = sh + 8 * W;      // [W][4] v^(j)_r    (B operand, [slot][k])
+    double *coef = sh + 12 * W;   // [2][3][W] diagonal, -kx, -ky of the unknowns of two grid lines (line L in buffer L & 1)
+    double *bc = coef + 6 * W;    // [4][8] step j: entries of the pivot rows in pivot column j, [4] = g of the pivot
+    double *misc = bc + 32;
+    double *patch = misc + 8;     // [2][2][8][8] the tiles that hold the stencil entries of a block's newcomers, on their way through shared memory
+    const int c = f.Ny / 2, P = (c - 1) * n, last = P + n - 1;
+    double acc[TR][TC][2];
+    const bool pt = tg < W;  // panel thread of slot q = tg
+    const bool pt_warp = warp < W / 32;
+    int uk = -1;             // unknown held by this slot (-1: none)
+    double g = 0.0, g2 = 0.0;
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(barid), "n"(TW * 32) : "memory"); };
+
+    // stencil coefficients of grid line L (unknown (i, L), i = tg + 1) -> coef buffer L & 1
+    auto compute_line = [&](int L) {
+        if (tg < n) {
+            const bool own = !(L == c && f.mirror);  // the centre line's own entries are loaded once (lower half)
+            const int i = tg + 1;
+            double *cb = coef + (L & 1) * 3 * W;
+            cb[tg] = own ? f.diag(i, L) : 0.0;
+            cb[W + tg] = (own && i > 1) ? -f.kx(i - 1, L) : 0.0;
+            cb[2 * W + tg] = L > 1 ? -f.ky(i, L - 1) : 0.0;
+        }
+    };
+    // nb (<= 4) pivots at consecutive slots sp .. sp+nb-1 (inside one 8-slot tile), unknowns pv0, pv0 +- 1, ...
+#ifdef MLE_DMMA_TIMING
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define MLE_TICK(i) { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; }
+#else
+#define MLE_TICK(i)
+#endif
+    // (je0, i00): grid line and 0-based position in the line of the first newcomer pv0 + n (half sweeps only)
+    auto block_step = [&](int sp, int pv0, int nb, bool enter, bool desc, int lo, int je0, int i00) {
+        MLE_TICK(5)
+        // newcomers of this block (warp-uniform, computed once: unknown, right-hand side, coupling -ky to its pivot);
+        // a thread whose slot one of them takes adopts it with selects -- a per-thread branch here would serialise the warp
+        int ne[4];
+        double ngv[4], nky[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = pv0 + j + n;
+            const bool ok = enter && j < nb && e <= last;
+            const bool wrap = i00 + j >= n;  // the newcomer starts the next grid line
+            const int je = je0 + (wrap ? 1 : 0), i0 = i00 + j - (wrap ? n : 0);
+            ne[j] = ok ? e : -1;
+            ngv[j] = (je == c && f.mirror) ? 0.0 : 1.0;
+            nky[j] = ok ? coef[(je & 1) * 3 * W + 2 * W + i0] : 0.0;
+        }
+        // (1) the pivot columns -> X
+        {
+            const int cs = sp & 7, b0 = (sp >> 3) - wc * TC;
+            if (b0 >= 0 && b0 < TC) {
+                MLE_DISPATCH4(b0, TC, {
+_Pragma("unroll") for (int a = 0; a < TR; ++a) {
+_Pragma("unroll") for (int e = 0; e < 2; ++e) {
+                            const int col = 2 * lk + e - cs;
+                            if (col >= 0 && col < nb) X[((wr * TR + a) * 8 + lr) * 4 + col] = acc[a][I_][e];
+                        }
+                    }
+                })
+            }
+        }
+        const int rel = (tg - sp + W) & (W - 1);  // 0 .. nb-1: the slot of pivot `rel`;  W-1: the slot the first newcomer takes
+        if (pt && rel < nb) bc[rel] = g;          // right-hand sides of the pivot rows
+        MLE_TICK(0)
+        gsync();
+        MLE_TICK(1)
+        // (2) panel factorisation, without a barrier: EVERY panel thread factorises the 4x4 block of the pivot rows for itself
+        // (the same few operations in the same order, so all threads hold identical values) and then takes its own row
+        // through the four steps
+        // (3) register rows / columns of the newcomers (slots s0, s0+1, ... mod W): zero, except the stencil entries -- the
+        // diagonal, and -kx towards the left neighbour (the slot before).  Branch-free selects (per-lane branches cost a
+        // reconvergence point per element); warps whose tile band holds no newcomer skip it, and the warp that holds the
+        // diagonal entries does this work in the shadow of the other warps' DMMAs.
+        auto fresh_init = [&]() {
+        if (enter) {
+            const int nv = max(0, min(nb, last - (pv0 + n) + 1));  // newcomers of this block (the unknowns enter in order)
+            if (nv > 0) {
+                const int s0 = (sp - 1 + W) & (W - 1);
+                auto in_band = [&](int base, int len) {
+                    const int dd = (s0 - base + W) & (W - 1);
+                    return dd < len || dd + nv > W;
+                };
+                const bool rband = in_band(wr * TR * 8, TR * 8), cband = in_band(wc * TC * 8, TC * 8);  // warp-uniform
+                if (rband || cband) {
+                    int jr[TR], jc[TC][2];
+#pragma unroll
+                    for (int a = 0; a < TR; ++a) {
+                        const int dd = ((wr * TR + a) * 8 + lr - s0 + W) & (W - 1);
+                        jr[a] = dd < nv ? dd : -1;
+                    }
+#pragma unroll
+                    for (int b2 = 0; b2 < TC; ++b2)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int dd = ((wc * TC + b2) * 8 + 2 * lk + e - s0 + W) & (W - 1);
+                            jc[b2][e] = dd < nv ? dd : -1;
+                        }
+                    if (rband) {
+#pragma unroll
+                        for (int a = 0; a < TR; ++a)
+#pragma unroll
+                            for (int b2 = 0; b2 < TC; ++b2) {
+                                acc[a][b2][0] = jr[a] >= 0 ? 0.0 : acc[a][b2][0];
+                                acc[a][b2][1] = jr[a] >= 0 ? 0.0 : acc[a][b2][1];
+                            }
+                    }
+                    if (cband) {
+#pragma unroll
+                        for (int a = 0; a < TR; ++a)
+#pragma unroll
+                            for (int b2 = 0; b2 < TC; ++b2) {
+                                acc[a][b2][0] = jc[b2][0] >= 0 ? 0.0 : acc[a][b2][0];
+                                acc[a][b2][1] = jc[b2][1] >= 0 ? 0.0 : acc[a][b2][1];
+                            }
+                    }
+                    // stencil entries (at most three per newcomer, in at most 2 x 2 tiles around the diagonal): the warp that
+                    // owns such a tile passes it through shared memory, where a few lanes write the entries at computed addresses
+                    // (the register tiles cannot be indexed dynamically)
+                    if (rband && cband) {
+                        const int tlo = ((s0 - 1 + W) & (W - 1)) >> 3, thi = ((s0 + nv - 1) & (W - 1)) >> 3;
+                        // patch[2][2][8][8]: the tile (ti, tj) at [ti != tlo][tj != tlo]; every tile has exactly one owner warp
+#pragma unroll
+                        for (int a = 0; a < TR; ++a)
+#pragma unroll
+                            for (int b2 = 0; b2 < TC; ++b2) {
+                                const int ti = wr * TR + a, tj = wc * TC + b2;
+                                if ((ti == tlo || ti == thi) && (tj == tlo || tj == thi))  // warp-uniform
+                                    *reinterpret_cast<double2 *>(patch + ((ti != tlo) * 2 + (tj != tlo)) * 64 + lr * 8 + 2 * lk) =
+                                        make_double2(acc[a][b2][0], acc[a][b2][1]);
+                            }
+                        __syncwarp();
+                        if (lane < 3 * nv) {
+                            const int j = lane / 3, kind = lane - 3 * j;  // 0: (s, s)  1: (s, s-1)  2: (s-1, s)
+                            const int sj = (s0 + j) & (W - 1), sm = (sj - 1 + W) & (W - 1);
+                            const int R = kind == 2 ? sm : sj, Cc = kind == 1 ? sm : sj;
+                            const int ti = R >> 3, tj = Cc >> 3;
+                            // only the warp that owns the tile writes the entry
+                            if (ti / TR == wr && tj / TC == wc)
+                                {
+                                const bool wrap = i00 + j >= n;
+                                const int je = je0 + (wrap ? 1 : 0), i0 = i00 + j - (wrap ? n : 0);
+                                const double *cb = coef + (je & 1) * 3 * W;
+                                patch[((ti != tlo) * 2 + (tj != tlo)) * 64 + (R & 7) * 8 + (Cc & 7)] = kind == 0 ? cb[i0] : (i0 > 0 ? cb[W + i0] : 0.0);
+                            }
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int a = 0; a < TR; ++a)
+#pragma unroll
+                            for (int b2 = 0; b2 < TC; ++b2) {
+                                const int ti = wr * TR + a, tj = wc * TC + b2;
+                                if ((ti == tlo || ti == thi) && (tj == tlo || tj == thi)) {
+                                    const double2 v = *reinterpret_cast<const double2 *>(patch + ((ti != tlo) * 2 + (tj != tlo)) * 64 + lr * 8 + 2 * lk);
+                                    acc[a][b2][0] = v.x; acc[a][b2][1] = v.y;
+                                }
+                            }
+                    }
+                }
+            }
+        }
+        };
+        // (the number of pivots is a compile-time constant inside: the common case of four is one straight-line block)
+        auto panel = [&](auto nbc) {
+            constexpr int NB = decltype(nbc)::value;
+            double xr[4];
+            {
+                const double2 x01 = *reinterpret_cast<const double2 *>(X + tg * 4), x23 = *reinterpret_cast<const double2 *>(X + tg * 4 + 2);
+                xr[0] = x01.x; xr[1] = x01.y; xr[2] = x23.x; xr[3] = x23.y;
+            }
+            MLE_TICK(6)
+            double D[4][4], gp[4], rcp[4];  // D[k][j], k >= j: entry of pivot row k in pivot column j
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int row = k < NB ? sp + k : sp;  // rows beyond nb are not used
+                const double2 d01 = *reinterpret_cast<const double2 *>(X + row * 4), d23 = *reinterpret_cast<const double2 *>(X + row * 4 + 2);
+                D[k][0] = d01.x; D[k][1] = d01.y; D[k][2] = d23.x; D[k][3] = d23.y;
+                gp[k] = bc[k < NB ? k : 0];
+                rcp[k] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < NB) {
+                    rcp[j] = drcp_normal(D[j][j]);  // pivots of an SPD system: positive, normal range
+#pragma unroll
+                    for (int k = j + 1; k < 4; ++k) {
+                        if (k < NB) {
+                            const double lk2 = __dmul_rn(D[k][j], rcp[j]);
+                            gp[k] = __fma_rn(-lk2, gp[j], gp[k]);
+#pragma unroll
+                            for (int j2 = j + 1; j2 <= k; ++j2) D[k][j2] = __fma_rn(-lk2, D[j2][j], D[k][j2]);
+                        }
+                    }
+                }
+            }
+            MLE_TICK(7)
+            auto arrive = [&](bool me, int j) {  // newcomer j takes this thread's slot; its coupling sits in panel column j
+                if (ne[j] >= 0) {                // warp-uniform
+                    uk = me ? ne[j] : uk;
+                    g = me ? ngv[j] : g;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t >= j) xr[t] = me ? (t == j ? nky[j] : 0.0) : xr[t];
+                }
+            };
+            arrive(rel == W - 1, 0);
+            MLE_TICK(8)
+            double lneg[4] = {0.0, 0.0, 0.0, 0.0}, vv[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < NB) {  // warp-uniform
+                    const int pv = desc ? pv0 - j : pv0 + j;
+                    const bool active = desc ? (uk >= lo && uk < pv) : (uk > pv);
+                    const double v = active ? xr[j] : 0.0;
+                    const double l = active ? __dmul_rn(v, rcp[j]) : 0.0;
+                    if (active) {
+                        g = __fma_rn(-l, gp[j], g);
+#pragma unroll
+                        for (int k = j + 1; k < 4; ++k)
+                            if (k < NB) xr[k] = __fma_rn(-l, D[k][j], xr[k]);
+                    }
+                    // the register row / column of a pivot slot is dead until its newcomer arrives: no terms before that
+                    const bool dead = rel < NB && j <= rel;
+                    lneg[j] = dead ? 0.0 : -l;
+                    vv[j] = dead ? 0.0 : v;
+                    // this slot's pivot is eliminated; the next unknown arrives here at step j + 1
+                    uk = rel == j ? -1 : uk;
+                    if (j + 1 < 4) arrive(rel == j, j + 1);
+                }
+            }
+            MLE_TICK(9)
+            *reinterpret_cast<double2 *>(LA + tg * 4) = make_double2(lneg[0], lneg[1]);
+            *reinterpret_cast<double2 *>(LA + tg * 4 + 2) = make_double2(lneg[2], lneg[3]);
+            *reinterpret_cast<double2 *>(VB + tg * 4) = make_double2(vv[0], vv[1]);
+            *reinterpret_cast<double2 *>(VB + tg * 4 + 2) = make_double2(vv[2], vv[3]);
+        };
+        if (!pt_warp) fresh_init();  // warps without panel rows: in the shadow of the panel factorisation
+        if (pt) {
+            if (nb == 4) panel(cuda::std::integral_constant<int, 4>{});
+            else if (nb == 1) panel(cuda::std::integral_constant<int, 1>{});
+            else if (nb == 2) panel(cuda::std::integral_constant<int, 2>{});
+            else panel(cuda::std::integral_constant<int, 3>{});
+        }
+        MLE_TICK(2)
+        gsync();
+        MLE_TICK(3)
+        if (pt_warp) fresh_init();
+        MLE_TICK(4)
+        // (4) one DMMA per tile: the four pivots' rank-1 updates in pivot order
+        {
+            double a[TR], b[TC];
+#pragma unroll
+            for (int t = 0; t < TR; ++t) a[t] = LA[((wr * TR + t) * 8 + lr) * 4 + lk];
+#pragma unroll
+            for (int t = 0; t < TC; ++t) b[t] = VB[((wc * TC + t) * 8 + lr) * 4 + lk];
+#pragma unroll
+            for (int ta = 0; ta < TR; ++ta)
+#pragma unroll
+                for (int tb = 0; tb < TC; ++tb) dmma_m8n8k4(acc[ta][tb][0], acc[ta][tb][1], a[ta], b[tb]);
+        }
+    };
+
+    for (int half = 0; half < 2; ++half) {
+        f.mirror = half == 0;  // upper half first (y-mirrored field)
+        gsync();               // coef / X of the previous phase are no longer read
+        compute_line(1);
+        gsync();
+        {   // line 1: unknowns 0 .. n-1 in slots 0 .. n-1, tridiagonal
+            const double *cb = coef + 3 * W;
+#pragma unroll
+            for (int a = 0; a < TR; ++a)
+#pragma unroll
+                for (int b = 0; b < TC; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int R = (wr * TR + a) * 8 + lr, Cc = (wc * TC + b) * 8 + 2 * lk + e;
+                        double v = 0.0;
+                        if (R < n && Cc < n) {
+                            if (R == Cc) v = cb[R];
+                            else if (Cc == R - 1) v = cb[W + R];
+                            else if (Cc == R + 1) v = cb[W + Cc];
+                        }
+                        acc[a][b][e] = v;
+                    }
+            uk = (pt && tg < n) ? tg : -1;
+            g = (uk >= 0 && !(c == 1 && f.mirror)) ? 1.0 : 0.0;
+        }
+        int lines_done = 1;
+        int je0 = 2, i00 = 0;  // newcomer p + n of pivot p: grid line p / n + 2, position p % n
+        for (int p = 0; p < P; p += 4) {
+            const int nb = min(4, P - p);
+            const int lneed = min(je0 + (i00 + nb - 1 >= n ? 1 : 0), c);  // grid line of the last unknown that enters in this block
+            if (lneed > lines_done) {
+                for (int L = lines_done + 1; L <= lneed; ++L) compute_line(L);
+                lines_done = lneed;
+                gsync();
+            }
+            block_step(p & (W - 1), p, nb, true, false, 0, je0, i00);
+            i00 += 4;
+            if (i00 >= n) { i00 -= n; ++je0; }
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int a = 0; a < TR; ++a)
+#pragma unroll
+                for (int b = 0; b < TC; ++b) {
+                    park[(size_t)((a * TC + b) * 2) * pstride] = acc[a][b][0];
+                    park[(size_t)((a * TC + b) * 2 + 1) * pstride] = acc[a][b][1];
+                }
+            g2 = g;
+        }
+    }
+    // centre line: S = S(lower) + S(upper), then the dense two-sided elimination, one pivot per step
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+        for (int b = 0; b < TC; ++b) {
+            acc[a][b][0] = __dadd_rn(acc[a][b][0], park[(size_t)((a * TC + b) * 2) * pstride]);
+            acc[a][b][1] = __dadd_rn(acc[a][b][1], park[(size_t)((a * TC + b) * 2 + 1) * pstride]);
+        }
+    g = __dadd_rn(g, g2);
+    for (int t = 0; t < tc; ++t) block_step((P + t) & (W - 1), P + t, 1, false, false, 0, 0, 0);
+    for (int t = n - 1; t > tc; --t) block_step((P + t) & (W - 1), P + t, 1, false, true, P + tc, 0, 0);
+    {   // u = gs[tc] / S[tc][tc]
+        const int sp = (P + tc) % W, cs = sp & 7, b0 = (sp >> 3) - wc * TC;
+        if (b0 >= 0 && b0 < TC) {
+            MLE_DISPATCH4(b0, TC, {
+_Pragma("unroll") for (int a = 0; a < TR; ++a)
+_Pragma("unroll") for (int e = 0; e < 2; ++e)
+                        if (2 * lk + e == cs) X[((wr * TR + a) * 8 + lr) * 4] = acc[a][I_][e];
+            })
+        }
+        gsync();
+        if (pt && tg == sp) misc[0] = __ddiv_rn(g, X[tg * 4]);
+        gsync();
+        const double u = misc[0];
+        gsync();  // the buffers are reused by the next solve
+#ifdef MLE_DMMA_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && NW == 128)
+            printf("warp %2d  extract %lld  wait1 %lld  panel %lld  wait2 %lld  fresh %lld  dmma+loop %lld | xload %lld factor %lld newcomers %lld ownrow %lld\n", warp, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9]);
+#endif
+        return u;
+    }
+}
+#undef MLE_TICK
+
 // ---- kernel ---------------------------------------------------------------------------------------------------------
 template <int W> struct Rows2dCfg {
     static constexpr int LPR = MLE_ROWS_FAT ? (W > 64 ? W / 64 : 1) : (W > 32 ? W / 32 : 1);
@@ -465,21 +865,37 @@ template <int W> struct Rows2dCfg {
     static constexpr int LDX = S + 4, LDF = S == 8 ? 8 : S + 8;
     static constexpr int GT = TGS <= 32 ? 32 : TGS;
     static constexpr int GEN_DIMS = 32 * (THREADS / S);       // dims per generator call (32-bit class masks)
+    static constexpr bool DMMA = false;
+    static constexpr int SH = rows_sh_doubles(W);             // shared-memory doubles of one solver group
 };
 
-template <int MODE, int W>
-__global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la, FinArgs fa,
+// the blocked DMMA solver: 512-thread CTAs, one sample per 16 warps at 128 cells, four samples side by side at 64 cells
+template <int W> struct Dmma2dCfg {
+    static_assert(W == 64 || W == 128, "blocked DMMA solver: windows of 64 and 128 cells");
+    static constexpr bool DMMA = true;
+    static constexpr int LPR = 1, RPL = 1;
+    static constexpr int TGS = W == 128 ? 512 : 128;
+    static constexpr int THREADS = 512, MINB = 1;
+    static constexpr int CS = THREADS / TGS;
+    static constexpr int S = 8;
+    static constexpr int LDX = S + 4, LDF = 8;
+    static constexpr int GT = TGS;
+    static constexpr int GEN_DIMS = 32 * (THREADS / S);
+    static constexpr int SH = dmma_sh_doubles(W);
+};
+
+template <int MODE, int W, typename Cfg = Rows2dCfg<W>>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) lognormal2d_rows_kernel(GenArgs g, Lognormal2dRowsArgs la, FinArgs fa,
                                                                                 double *__restrict__ samples,
                                                                                 long long tiles_per_shift) {
     static_assert(W >= 4, "the coarse solve needs W / 2 >= 2");
-    using Cfg = Rows2dCfg<W>;
     constexpr int THREADS = Cfg::THREADS, S = Cfg::S, LDX = Cfg::LDX, LDF = Cfg::LDF, TGS = Cfg::TGS, CS = Cfg::CS;
     constexpr int LPR = Cfg::LPR, RPL = Cfg::RPL, GT = Cfg::GT, NWARP = THREADS / 32, ST = S / 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int mpad = la.mpad, nks = mpad >> 2;
     double *xi = reinterpret_cast<double *>(smem_raw);                       // [mpad][LDX]
-    double *gsh = xi + (size_t)mpad * LDX;                                   // [CS][rows_sh_doubles(W)]
-    double *res = gsh + CS * rows_sh_doubles(W);                             // [S][2]
+    double *gsh = xi + (size_t)mpad * LDX;                                   // [CS][Cfg::SH]
+    double *res = gsh + CS * Cfg::SH;                                        // [S][2]
     Partial *mred = reinterpret_cast<Partial *>(res + 2 * S);                // [2][S]
     GenScratch sc;
     sc.wtot = reinterpret_cast<unsigned *>(mred + 2 * S);                    // [NWARP]
@@ -534,12 +950,24 @@ __global__ void __launch_bounds__(Rows2dCfg<W>::THREADS, Rows2dCfg<W>::MINB) log
         // C. solves: CS samples at a time
         for (int rd = 0; rd < S / CS; ++rd) {
             const int grp = tid / TGS, tg = tid % TGS, sigma = rd * CS + grp;
-            double *sh = gsh + grp * rows_sh_doubles(W);
+            double *sh = gsh + grp * Cfg::SH;
             FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
             double *park = la.park + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ROWS_PARK * THREADS + tid;
             // the solver of the view's window width: one row per lane (or a row over several lanes), or RPL rows per lane
             auto solve = [&](const FieldView &v, bool half_width) {
-                if constexpr (RPL > 1) {
+                if constexpr (Cfg::DMMA) {
+                    // multilevel differences on square grids only (the host dispatches nothing else here)
+                    if (!half_width) return frontal_mid_dmma<W, TGS / 32>(v, sh, park, THREADS, tg, 1 + grp);
+                    if constexpr (W == 128) {
+                        return frontal_mid_dmma<64, TGS / 32>(v, sh, park, THREADS, tg, 1 + grp);
+                    } else {
+                        // 32 cells: the register-window solver on the group's first warp; the others wait for it
+                        double u = 0.0;
+                        if (tg < 32) u = frontal_mid_rows<32, 1, 32>(v, sh, park, THREADS, tg, 1 + grp);
+                        rows_sync<GT>(1 + grp);
+                        return u;
+                    }
+                } else if constexpr (RPL > 1) {
                     if (half_width) return frontal_mid_rpl<W / 2, RPL>(v, sh, park, THREADS, tg);
                     return frontal_mid_rpl<W, RPL>(v, sh, park, THREADS, tg);
                 } else {
