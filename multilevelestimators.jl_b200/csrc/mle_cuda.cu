@@ -22,6 +22,7 @@ template <int MODE> static constexpr auto expsum_k = sample_simple_kernel<MODEL_
 template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MODEL_PROBLEM18, 26, MODE>;
 template <int MODE> static constexpr auto lognormal1d_k16 = lognormal1d_kernel<MODE, 16>;
 template <int MODE> static constexpr auto lognormal1d_kb = lognormal1d_block_kernel<MODE, 32>;
+template <int MODE> static constexpr auto lognormal1d_ks = lognormal1d_block_kernel<MODE, 32, true>;
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 template <int MODE> static constexpr auto lognormal2d_r4 = lognormal2d_rows_kernel<MODE, 4>;
@@ -99,6 +100,7 @@ struct mle_ctx_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     uint64_t launches = 0;
+    int ln_staged = -1;      // MLE_LN_STAGED=0|1: force / forbid the TMA-staged small-batch variant of the phase-synchronous kernel
     int ln_block = -1;       // MLE_LN_BLOCK=0|1: force the warp-autonomous / phase-synchronous lognormal1d kernel (default: by grid size)
     int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
     int ln2d_dmma = 1;       // MLE_2D_DMMA=0: register-window solver everywhere; 1: blocked DMMA solver at 128 cells; 2: also at 64
@@ -283,6 +285,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(problem18_k, 200 * 1024);
     MLE_SET_SMEM(lognormal1d_k16, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_kb, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_ks, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r4, 220 * 1024);
@@ -298,6 +301,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     if (const char *e = getenv("MLE_2D_WINDOW_SMEM")) ctx->ln2d_old = atoi(e) != 0;
     if (const char *e = getenv("MLE_2D_DMMA")) ctx->ln2d_dmma = atoi(e);
     if (const char *e = getenv("MLE_LN_BLOCK")) ctx->ln_block = atoi(e) != 0;
+    if (const char *e = getenv("MLE_LN_STAGED")) ctx->ln_staged = atoi(e) != 0;
     if (const char *e = getenv("MLE_NO_ZEROCOPY")) ctx->zero_copy = atoi(e) == 0;
     // the mapped completion flag (zero-copy result path); without it the library falls back to copy + synchronise
     if (ctx->zero_copy) {
@@ -974,13 +978,27 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
             const size_t smem = (size_t)la.mpad * lnb_ldx(bt) * 8 + fbytes + (size_t)3 * bt * sizeof(SweepState) +
                                 (size_t)bt * 8 + (size_t)la.mpad * 8 + ((W + 3) & ~3) * 4 +
                                 (lat ? (size_t)g.m * 16 : 0) + (qbytes <= fbytes ? 0 : qbytes) + 16;
-            const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_kb, threads, smem);
-            gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
-            rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
-            if (rc) return rc;
-            fa.partials = ctx->d_partials;
-            dim3 grid((unsigned)gx, (unsigned)R);
-            MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kb, grid, threads, smem, ctx->stream, g, la, fa, samples_dev, tps);
+            // small batches (the CTAs of the call do not even fill the SMs twice: every CTA is practically alone on its SM and
+            // bound by the L2 latency of the basis fragments): the variant that stages each chunk's A panel with a TMA bulk load
+            const bool staged = ctx->ln_staged >= 0 ? ctx->ln_staged != 0 : (unsigned long long)tps * (unsigned long long)R <= 2ull * (unsigned long long)ctx->sm_count;
+            const size_t smem_s = smem + 128 + (size_t)2 * 4 * (la.mpad / 4) * 32 * 8 + 16;
+            if (staged && smem_s <= 220 * 1024) {
+                const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_ks, threads, smem_s);
+                gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
+                rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+                if (rc) return rc;
+                fa.partials = ctx->d_partials;
+                dim3 grid((unsigned)gx, (unsigned)R);
+                MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_ks, grid, threads, smem_s, ctx->stream, g, la, fa, samples_dev, tps);
+            } else {
+                const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_kb, threads, smem);
+                gx = churn_grid_x(grid_x_for(ctx, tps, R, occ), tps);
+                rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+                if (rc) return rc;
+                fa.partials = ctx->d_partials;
+                dim3 grid((unsigned)gx, (unsigned)R);
+                MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kb, grid, threads, smem, ctx->stream, g, la, fa, samples_dev, tps);
+            }
         } else {
         const int ws = 16;  // samples per warp (the 8-sample instantiation never won a level and was dropped)
         const long long tps = (long long)((n + LN_BT - 1) / LN_BT);

@@ -13,7 +13,6 @@
 
 namespace mle {
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- TMA (bulk async copy) helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -26,7 +25,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-
 // ===================================================================================================================
 // K1 / K2: points -> HBM
 //   out[(r*n + i)*m + j].  One tile = P consecutive points of one shift = P*m consecutive doubles of `out`.
