@@ -12,6 +12,7 @@ merged in rank order with Chan's formula.
 
 Extra keys of the JSON line: `strong` (the same step with every level's points SPLIT over the ranks: fixed total
 work), `extra.c3` (config C3: MLMC on the 2-D lognormal model, 400 KL terms, levels 0-5, point slices per rank + merge),
+`extra.c4` (config C4: multi-index QMC batches on the 2-D anisotropic model over the indices of TD(2) up to size 3),
 `extra.c5` (config C5: 2^24 lattice points x 1000 dims, fused generate -> integrand -> moments), `run_e2e` (N = 1: wall time of
 run(estimator, tol) on the GPU backend vs the CPU oracle backend, tools/run_e2e.py).
 Launched WITHOUT torchrun and --gpus N > 1 the bench runs single-process on ONE multi-GPU context (mle_init_multi).
@@ -312,6 +313,40 @@ def bench_extras(eng, torch, dist, stream, world, rank):
         g3.close()
     except Exception as e:  # noqa: BLE001
         out["c3"] = {"error": repr(e)}
+    # ---- C4: multi-index QMC batches on the 2-D anisotropic model (BASELINE configs[3]: AD(2)/QMC), the indices of TD(2) up to ----
+    # size 3 as an adaptive run visits them, 100 KL terms, 16 shifts; rank r takes points [r n, (r+1) n) of every index
+    try:
+        C4_M, C4_R = 100, 16
+        idxs = [(lx, ly) for s_ in range(4) for lx in range(s_ + 1) for ly in [s_ - lx]]
+        z4 = eng.genvec("K_3600_32")[:C4_M]
+        lat4 = eng.lattice(z4, C4_M)
+        d4 = eng.dists([(mle_b200.NORMAL, [0.0, 1.0])] * C4_M)
+        g4 = eng.model("lognormal2d", 2, [4])
+        for idx in idxs:
+            g4.set_basis(idx, kl.kl_basis_2d(idx, m=C4_M))
+        n4 = [max(16, int(8192 * 2.0 ** (-1.5 * (lx + ly)))) for lx, ly in idxs]   # points per shift: N ~ 2^(-1.5 |index|)
+        sh4 = torch.from_numpy(splitmix_uniforms(4242, len(idxs) * C4_R * C4_M).reshape(len(idxs), C4_R, C4_M)).cuda()
+        mom4 = torch.zeros(len(idxs), C4_R * 6, dtype=torch.float64, device="cuda")
+
+        def step_c4():
+            for i, idx in enumerate(idxs):
+                eng.sample_batch_dev(g4, lat4, d4, list(idx), sh4[i].data_ptr(), C4_R, rank * n4[i], n4[i], C4_M, mom4[i].data_ptr())
+        step_c4(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record(stream)
+        for _ in range(reps):
+            step_c4()
+        b.record(stream); torch.cuda.synchronize()
+        ms4 = tmax(a.elapsed_time(b) / reps)
+        tot4 = sum(n4) * C4_R
+        out["c4"] = {"workload": "C4: multi-index QMC batches on the 2-D anisotropic lognormal model (mixed differences over diff(index)), "
+                                 "indices of TD(2) up to size 3 (grids 4*2^lx x 4*2^ly), 100 KL terms, 16 shifts, points per shift %s per rank" % n4,
+                     "value": tot4 * world / (ms4 * 1e-3), "unit": "samples/s", "ms_per_step": ms4, "scaling": "weak",
+                     "indices": [list(i) for i in idxs]}
+        g4.close(); lat4.close(); d4.close()
+    except Exception as e:  # noqa: BLE001
+        out["c4"] = {"error": repr(e)}
     # ---- C5: 2^24 lattice points x 1000 dims, 16 shifts, fused generate -> exp(sum a_j xi_j) -> moments ------------------------
     try:
         s5 = C5_DIMS

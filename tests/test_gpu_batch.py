@@ -491,3 +491,52 @@ def test_update_samples_matches_individual_calls(engine, oracle):
     import mle_b200
     with pytest.raises(mle_b200.MLEArgumentError):
         engine.update_samples(gm, lat, d, [([0], entries[0][1], 0, 0, 100)])    # n = 0 is refused like in mle_sample_batch
+
+
+def _engine_with_env(**env):
+    """a second context whose library switches (read in mle_init) differ from the session engine's"""
+    import os
+    import mle_b200
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return mle_b200.Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("level,n", [(1, 40), (3, 33), (6, 5)])
+def test_lognormal1d_small_batch_variant_is_bit_identical(oracle, level, n):
+    """the TMA-staged small-batch variant of the phase-synchronous kernel (basis panels by cp.async.bulk + mbarrier) against the
+    regular kernel and the oracle: same per-sample values bit for bit, with a partial last chunk (level 1) and many chunks (6)"""
+    outs = []
+    for staged in (0, 1):
+        eng = _engine_with_env(MLE_LN_STAGED=staged, MLE_LN_BLOCK=1)
+        z, lat, dl, d, gm, om = lognormal_setup(eng, oracle, 100, [level])
+        sh = splitmix_uniforms(31, 3 * 100).reshape(3, 100)
+        got, smp = eng.sample_batch(gm, lat, d, [level], sh, 7, n, want_samples=True)
+        outs.append((got, smp))
+        eng.close()
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, 7, n, want_samples=True)
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[1][1], smp_w)
+    assert np.array_equal(outs[0][0], outs[1][0])
+    check_moments(outs[1][0], want)
+
+
+def test_lognormal2d_blocked_dmma_solver_equals_register_window_solver(oracle):
+    """64 x 64 cells, where the register-window solver is the default: the blocked DMMA solver (MLE_2D_DMMA=2) and the solver
+    without any DMMA blocking (MLE_2D_DMMA=0) give the same bits as the oracle"""
+    outs = []
+    for mode in (0, 2):
+        eng = _engine_with_env(MLE_2D_DMMA=mode)
+        z, lat, dl, d, gm, om = lognormal2d_setup(eng, oracle, 40, [4])
+        sh = splitmix_uniforms(32, 2 * 40).reshape(2, 40)
+        got, smp = eng.sample_batch(gm, lat, d, [4], sh, 3, 9, want_samples=True)
+        outs.append(smp)
+        eng.close()
+    want, smp_w = oracle.sample_batch(om, z, dl, [4], sh, 3, 9, want_samples=True)
+    assert np.array_equal(outs[0], smp_w) and np.array_equal(outs[1], smp_w)
