@@ -73,3 +73,29 @@ def test_committed_bench_lines_carry_every_contract_key():
             assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
         else:
             assert 0.95 * n * single <= d["value"] <= 1.05 * n * single      # weak scaling
+
+
+def test_round2_bench_lines_carry_every_contract_key():
+    """round 2: the N = 1 and N = 8 lines under profiles/, with the extra keys this round added (strong scaling, C3 / C4 / C5,
+    run-level end-to-end, pipe-busy and traffic figures read from the committed ncu summary)"""
+    one = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_1gpu.json")).read().strip().splitlines()[-1])
+    eight = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_8gpu.json")).read().strip().splitlines()[-1])
+    for n, d in ((1, one), (8, eight)):
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "extra"):
+            assert key in d, (n, key)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["dtype"] == "f64" and d["vs_baseline"] is None
+        assert d["warmup"] >= 3 and d["gpu_launches"] == 7 * d["steps"]      # one launch per level and step, no finalize launch
+        r = d["roofline"]
+        assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6 and 0.3 < r["frac"] < 1
+        assert 0 < d["e2e"]["value"] <= d["value"] * 1.02 and d["e2e"]["h2d_bytes_per_step"] > 0
+        for cfg in ("c3", "c4", "c5"):
+            assert d["extra"][cfg]["value"] > 0, cfg
+        per_step = d["config"]["samples_per_step_per_gpu"] * n
+        assert abs(d["value"] - per_step / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    assert 0.95 * 8 * one["value"] <= eight["value"] <= 1.05 * 8 * one["value"]
+    assert eight["strong"]["scaling"] == "strong" and eight["strong"]["value"] > 5 * one["value"]
+    assert len(one["roofline"]["pipe_busy_ncu_per_level"]) == 7 and all(0.4 < x < 1 for x in one["roofline"]["pipe_busy_ncu_per_level"])
+    assert one["roofline"]["traffic"] > 0 and one["cpu_baseline"]["kind"] == "port"
+    tols = one["run_e2e"]["tols"]
+    assert len(tols) >= 3 and all(t["same_decisions"] for t in tols) and tols[-1]["speedup"] > 10
