@@ -23,6 +23,7 @@ template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MOD
 template <int MODE> static constexpr auto lognormal1d_k16 = lognormal1d_kernel<MODE, 16>;
 template <int MODE> static constexpr auto lognormal1d_kb = lognormal1d_block_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal1d_ks = lognormal1d_block_kernel<MODE, 32, true>;
+template <int MODE> static constexpr auto lognormal1d_kl = lognormal1d_small_kernel<MODE>;
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 template <int MODE> static constexpr auto lognormal2d_r4 = lognormal2d_rows_kernel<MODE, 4>;
@@ -101,6 +102,7 @@ struct mle_ctx_s {
     std::string err;
     uint64_t launches = 0;
     int ln_staged = -1;      // MLE_LN_STAGED=0|1: force / forbid the TMA-staged small-batch variant of the phase-synchronous kernel
+    int ln_small = -1;       // MLE_LN_SMALL=0|1: forbid / force (when it fits) the latency variant for tiny batches (mle_kernel_ln1d_small.cuh)
     int ln_block = -1;       // MLE_LN_BLOCK=0|1: force the warp-autonomous / phase-synchronous lognormal1d kernel (default: by grid size)
     int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
     int ln2d_dmma = 1;       // MLE_2D_DMMA=0: register-window solver everywhere; 1: blocked DMMA solver at 128 cells; 2: also at 64
@@ -286,6 +288,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(lognormal1d_k16, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_kb, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_ks, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_kl, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r4, 220 * 1024);
@@ -302,6 +305,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     if (const char *e = getenv("MLE_2D_DMMA")) ctx->ln2d_dmma = atoi(e);
     if (const char *e = getenv("MLE_LN_BLOCK")) ctx->ln_block = atoi(e) != 0;
     if (const char *e = getenv("MLE_LN_STAGED")) ctx->ln_staged = atoi(e) != 0;
+    if (const char *e = getenv("MLE_LN_SMALL")) ctx->ln_small = atoi(e) != 0;
     if (const char *e = getenv("MLE_NO_ZEROCOPY")) ctx->zero_copy = atoi(e) == 0;
     // the mapped completion flag (zero-copy result path); without it the library falls back to copy + synchronise
     if (ctx->zero_copy) {
@@ -970,7 +974,28 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         // every larger grid 7-15 % faster phase-synchronous (its four warps walk the basis together: L1 hits).
         // MLE_LN_BLOCK=0|1 forces one of them.
         const bool block = ctx->ln_block >= 0 ? ctx->ln_block != 0 : la.ntiles > 2;
-        if (block) {
+        // tiny batches (the 16 x (1 .. 100)-sample calls of the adaptive loop, src/run.jl:96-113): the latency variant -- 8-sample
+        // tiles, the whole field of a tile in shared memory, every phase but the flux sums spread over the CTA -- while its tiles
+        // fit in two waves of CTAs; measured 16-22 -> 8-10 us per launch at l <= 3 and 88 -> 19 us at l = 6 for 16 x 1 samples
+        bool small_done = false;
+        if (ctx->ln_small != 0 && g.m <= 1024 && la.N % 2 == 0 && (level == 0 || la.N % 4 == 0)) {
+            const size_t smem_l = lns_smem_bytes(la.mpad, lat ? g.m : 0, la.ntiles, g.m);
+            if (smem_l <= 220 * 1024) {
+                const long long tps = (long long)((n + LNS_BT - 1) / LNS_BT);
+                const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_kl, LNS_THREADS, smem_l);
+                if (ctx->ln_small > 0 || (unsigned long long)tps * (unsigned long long)R <= 2ull * (unsigned long long)ctx->sm_count * (unsigned long long)occ) {
+                    gx = grid_x_for(ctx, tps, R, occ);
+                    rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+                    if (rc) return rc;
+                    fa.partials = ctx->d_partials;
+                    dim3 grid((unsigned)gx, (unsigned)R);
+                    MLE_LAUNCH_BY_MODE(g.mode, lognormal1d_kl, grid, LNS_THREADS, smem_l, ctx->stream, g, la, fa, samples_dev, tps);
+                    small_done = true;
+                }
+            }
+        }
+        if (small_done) {
+        } else if (block) {
             const int bt = 32, threads = lnb_threads(bt), W = threads / 32;
             const long long tps = (long long)((n + bt - 1) / bt);
             const int qdims = g.m < 256 ? ((g.m + 3) & ~3) : 256;  // whole generator iterations: ceil(m / 4) * 4 dims

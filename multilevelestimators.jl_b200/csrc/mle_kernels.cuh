@@ -10,6 +10,7 @@
 #include "mle_device.cuh"
 #include "mle_kernel_ln1d.cuh"
 #include "mle_kernel_ln1d_block.cuh"
+#include "mle_kernel_ln1d_small.cuh"
 
 namespace mle {
 

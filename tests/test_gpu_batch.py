@@ -527,6 +527,45 @@ def test_lognormal1d_small_batch_variant_is_bit_identical(oracle, level, n):
     check_moments(outs[1][0], want)
 
 
+@pytest.mark.parametrize("level,n,k0", [(0, 1, 0), (0, 9, 5), (1, 8, 7), (2, 40, 3), (3, 33, 1), (5, 3, 11), (6, 5, 7), (6, 17, 2 ** 20 + 3)])
+def test_lognormal1d_latency_variant_is_bit_identical(oracle, level, n, k0):
+    """the latency variant for tiny batches (mle_kernel_ln1d_small.cuh: 8-sample tiles, whole field in shared memory, basis panels
+    by cp.async.bulk, reciprocals in parallel, flux sums in sequence) against the throughput kernels and the oracle: the same
+    per-sample values bit for bit -- one tile, partial tiles, several tiles per CTA, single and many panels"""
+    outs = []
+    for small in (0, 1):
+        eng = _engine_with_env(MLE_LN_SMALL=small)
+        z, lat, dl, d, gm, om = lognormal_setup(eng, oracle, 100, [level])
+        sh = splitmix_uniforms(31 + level, 3 * 100).reshape(3, 100)
+        got, smp = eng.sample_batch(gm, lat, d, [level], sh, k0, n, want_samples=True)
+        mom_only = eng.sample_batch(gm, lat, d, [level], sh, k0, n)   # zero-copy result path, one CTA per shift when n <= 8
+        outs.append((got, smp, mom_only))
+        eng.close()
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, k0, n, want_samples=True)
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[1][1], smp_w)
+    assert np.array_equal(outs[1][0], outs[1][2])
+    check_moments(outs[1][0], want)
+    check_moments(outs[0][2], want)
+
+
+def test_lognormal1d_latency_variant_mc_and_other_shapes(oracle):
+    """MC inputs (no lattice), a KL basis that is not a multiple of four terms, a grid with n0 = 4 (a single partial row tile)"""
+    for small in (0, 1):
+        eng = _engine_with_env(MLE_LN_SMALL=small)
+        z, lat, dl, d, gm, om = lognormal_setup(eng, oracle, 37, [0, 2], n0=4)
+        for level in (0, 2):
+            got, smp = eng.sample_batch(gm, None, d, [level], None, 3, 21, mc_seed=99 + level, want_samples=True)
+            want, smp_w = oracle.sample_batch(om, None, dl, [level], None, 3, 21, mc_seed=99 + level, want_samples=True)
+            assert np.array_equal(smp, smp_w)
+            check_moments(got, want)
+            sh = splitmix_uniforms(5, 2 * 37).reshape(2, 37)
+            got, smp = eng.sample_batch(gm, lat, d, [level], sh, 0, 13, want_samples=True)
+            want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, 0, 13, want_samples=True)
+            assert np.array_equal(smp, smp_w)
+            check_moments(got, want)
+        eng.close()
+
+
 def test_lognormal2d_blocked_dmma_solver_equals_register_window_solver(oracle):
     """64 x 64 cells, where the register-window solver is the default: the blocked DMMA solver (MLE_2D_DMMA=2) and the solver
     without any DMMA blocking (MLE_2D_DMMA=0) give the same bits as the oracle"""
