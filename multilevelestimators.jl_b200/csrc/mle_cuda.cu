@@ -23,7 +23,8 @@ template <int MODE> static constexpr auto problem18_k = sample_simple_kernel<MOD
 template <int MODE> static constexpr auto lognormal1d_k16 = lognormal1d_kernel<MODE, 16>;
 template <int MODE> static constexpr auto lognormal1d_kb = lognormal1d_block_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal1d_ks = lognormal1d_block_kernel<MODE, 32, true>;
-template <int MODE> static constexpr auto lognormal1d_kl = lognormal1d_small_kernel<MODE>;
+template <int MODE> static constexpr auto lognormal1d_kl = lognormal1d_small_kernel<MODE, false>;
+template <int MODE> static constexpr auto lognormal1d_kc = lognormal1d_small_kernel<MODE, true>;
 template <int MODE> static constexpr auto lognormal2d_w = lognormal2d_kernel<MODE, 32>;
 template <int MODE> static constexpr auto lognormal2d_c = lognormal2d_kernel<MODE, 256>;
 template <int MODE> static constexpr auto lognormal2d_r4 = lognormal2d_rows_kernel<MODE, 4>;
@@ -46,6 +47,69 @@ template <int MODE> static constexpr auto lognormal2d_d128 = lognormal2d_rows_ke
         default: K<GEN_GENERAL | GEN_MC><<<grid, block, smem, stream>>>(__VA_ARGS__); break;   \
         }                                                                                      \
     } while (0)
+
+// launch with a thread-block cluster of `cs` CTAs along x
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t stream, int cs, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#define MLE_LAUNCH_CLUSTER_BY_MODE(mode, K, grid, block, smem, stream, cs, ...)                                  \
+    do {                                                                                                           \
+        switch (mode) {                                                                                            \
+        case GEN_RAW: launch_cluster(K<GEN_RAW>, grid, block, smem, stream, cs, __VA_ARGS__); break;               \
+        case GEN_STDNORMAL: launch_cluster(K<GEN_STDNORMAL>, grid, block, smem, stream, cs, __VA_ARGS__); break;   \
+        case GEN_GENERAL: launch_cluster(K<GEN_GENERAL>, grid, block, smem, stream, cs, __VA_ARGS__); break;       \
+        case GEN_RAW | GEN_MC: launch_cluster(K<GEN_RAW | GEN_MC>, grid, block, smem, stream, cs, __VA_ARGS__); break; \
+        case GEN_STDNORMAL | GEN_MC: launch_cluster(K<GEN_STDNORMAL | GEN_MC>, grid, block, smem, stream, cs, __VA_ARGS__); break; \
+        default: launch_cluster(K<GEN_GENERAL | GEN_MC>, grid, block, smem, stream, cs, __VA_ARGS__); break;       \
+        }                                                                                                          \
+    } while (0)
+
+// clusters of `cs` CTAs of (kernel, block size, dynamic shared memory) the device can keep resident at once (GPC granularity:
+// a cluster lives inside one GPC); remembered like resident_ctas_per_sm
+template <typename K>
+static int resident_clusters(K kernel, int threads, size_t smem, int cs) {
+    struct Entry { const void *fn; int threads; size_t smem; int cs; int n; };
+    static std::vector<Entry> cache;
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    for (const Entry &e : cache)
+        if (e.fn == fn && e.threads == threads && e.smem == smem && e.cs == cs) return e.n;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)cs);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    if (getenv("MLE_DEBUG")) fprintf(stderr, "[mle] resident clusters of %d CTAs (%d threads, %zu bytes): %d\n", cs, threads, smem, n);
+    if (cache.size() < 256) cache.push_back(Entry{fn, threads, smem, cs, n});
+    return n;
+}
+#define MLE_CLUSTERS_BY_MODE(mode, K, threads, smem, cs)                                            \
+    ((mode) == GEN_RAW ? resident_clusters(K<GEN_RAW>, threads, smem, cs)                           \
+     : (mode) == GEN_STDNORMAL ? resident_clusters(K<GEN_STDNORMAL>, threads, smem, cs)             \
+     : (mode) == GEN_GENERAL ? resident_clusters(K<GEN_GENERAL>, threads, smem, cs)                 \
+     : (mode) == (GEN_RAW | GEN_MC) ? resident_clusters(K<GEN_RAW | GEN_MC>, threads, smem, cs)     \
+     : (mode) == (GEN_STDNORMAL | GEN_MC) ? resident_clusters(K<GEN_STDNORMAL | GEN_MC>, threads, smem, cs) \
+                                          : resident_clusters(K<GEN_GENERAL | GEN_MC>, threads, smem, cs))
 
 // resident CTAs per SM of (kernel, block size, dynamic shared memory); the query costs a few microseconds, so the answers are
 // remembered (one calling thread per context, see include/mle_cuda.h)
@@ -102,6 +166,7 @@ struct mle_ctx_s {
     std::string err;
     uint64_t launches = 0;
     int ln_staged = -1;      // MLE_LN_STAGED=0|1: force / forbid the TMA-staged small-batch variant of the phase-synchronous kernel
+    int ln_cluster = 1;      // MLE_LN_CLUSTER=0: the latency variant never spreads a sample tile over a thread-block cluster; 2|4|8: largest cluster tried
     int ln_small = -1;       // MLE_LN_SMALL=0|1: forbid / force (when it fits) the latency variant for tiny batches (mle_kernel_ln1d_small.cuh)
     int ln_block = -1;       // MLE_LN_BLOCK=0|1: force the warp-autonomous / phase-synchronous lognormal1d kernel (default: by grid size)
     int ln2d_old = 0;        // MLE_2D_WINDOW_SMEM=1: force the shared-memory-window lognormal2d kernel (A/B timing)
@@ -289,6 +354,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     MLE_SET_SMEM(lognormal1d_kb, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_ks, 220 * 1024);
     MLE_SET_SMEM(lognormal1d_kl, 220 * 1024);
+    MLE_SET_SMEM(lognormal1d_kc, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_w, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_c, 220 * 1024);
     MLE_SET_SMEM(lognormal2d_r4, 220 * 1024);
@@ -306,6 +372,7 @@ extern "C" int mle_init(int device, mle_ctx *out) {
     if (const char *e = getenv("MLE_LN_BLOCK")) ctx->ln_block = atoi(e) != 0;
     if (const char *e = getenv("MLE_LN_STAGED")) ctx->ln_staged = atoi(e) != 0;
     if (const char *e = getenv("MLE_LN_SMALL")) ctx->ln_small = atoi(e) != 0;
+    if (const char *e = getenv("MLE_LN_CLUSTER")) ctx->ln_cluster = atoi(e);
     if (const char *e = getenv("MLE_NO_ZEROCOPY")) ctx->zero_copy = atoi(e) == 0;
     // the mapped completion flag (zero-copy result path); without it the library falls back to copy + synchronise
     if (ctx->zero_copy) {
@@ -979,9 +1046,27 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         // fit in two waves of CTAs; measured 16-22 -> 8-10 us per launch at l <= 3 and 88 -> 19 us at l = 6 for 16 x 1 samples
         bool small_done = false;
         if (ctx->ln_small != 0 && g.m <= 1024 && la.N % 2 == 0 && (level == 0 || la.N % 4 == 0)) {
-            const size_t smem_l = lns_smem_bytes(la.mpad, lat ? g.m : 0, la.ntiles, g.m);
-            if (smem_l <= 220 * 1024) {
-                const long long tps = (long long)((n + LNS_BT - 1) / LNS_BT);
+            const long long tps = (long long)((n + LNS_BT - 1) / LNS_BT);
+            // fine grids: a thread-block cluster of cs CTAs per sample tile -- every rank contracts, exponentiates and inverts
+            // 1/cs of the rows (a single SM takes the level-6 basis in at ~28 bytes per clock: 14 us for its 819 KB) and stores
+            // its reciprocals into the leader's shared memory; at least 8 row tiles per rank, all clusters resident at once
+            int cs = 1;
+            if (ctx->ln_cluster != 0)
+                for (int c = ctx->ln_cluster > 1 ? ctx->ln_cluster : 8; c >= 2; c >>= 1) {
+                    if (la.ntiles < 8 * c || tps * R * c > ctx->sm_count) continue;
+                    const size_t sm_c = lns_smem_bytes(la.mpad, la.ntiles, g.m, c);
+                    if (sm_c <= 220 * 1024 && tps * R <= MLE_CLUSTERS_BY_MODE(g.mode, lognormal1d_kc, LNS_THREADS, sm_c, c)) { cs = c; break; }
+                }
+            const size_t smem_l = lns_smem_bytes(la.mpad, la.ntiles, g.m, cs);
+            if (smem_l <= 220 * 1024 && cs > 1) {
+                gx = tps;  // one cluster per sample tile, all of them resident at once
+                rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);
+                if (rc) return rc;
+                fa.partials = ctx->d_partials;
+                dim3 grid((unsigned)(gx * cs), (unsigned)R);
+                MLE_LAUNCH_CLUSTER_BY_MODE(g.mode, lognormal1d_kc, grid, LNS_THREADS, smem_l, ctx->stream, cs, g, la, fa, samples_dev, tps);
+                small_done = true;
+            } else if (smem_l <= 220 * 1024) {
                 const int occ = MLE_OCC_BY_MODE(g.mode, lognormal1d_kl, LNS_THREADS, smem_l);
                 if (ctx->ln_small > 0 || (unsigned long long)tps * (unsigned long long)R <= 2ull * (unsigned long long)ctx->sm_count * (unsigned long long)occ) {
                     gx = grid_x_for(ctx, tps, R, occ);
@@ -1150,6 +1235,10 @@ extern "C" int mle_sample_batch_dev(mle_ctx ctx, mle_model M, mle_lattice lat, m
     MLE_API_SCOPE;
     return launch_batch(ctx, M, lat, dists, index, d, shifts_dev, R, k0, n, m, mc_seed, moments_dev, samples_dev);
 }
+
+#ifdef MLE_LNS_TIMING
+extern "C" int mle_debug_lns_timing(long long *out16) { return cudaMemcpyFromSymbol(out16, g_lns_t, 16 * sizeof(long long)) == cudaSuccess ? 0 : -2; }
+#endif
 
 extern "C" int mle_moments_merge(double *acc, const double *part, size_t count);
 static int update_samples_group(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dists, int count, const int32_t *indices, int d,

@@ -527,14 +527,15 @@ def test_lognormal1d_small_batch_variant_is_bit_identical(oracle, level, n):
     check_moments(outs[1][0], want)
 
 
-@pytest.mark.parametrize("level,n,k0", [(0, 1, 0), (0, 9, 5), (1, 8, 7), (2, 40, 3), (3, 33, 1), (5, 3, 11), (6, 5, 7), (6, 17, 2 ** 20 + 3)])
+@pytest.mark.parametrize("level,n,k0", [(0, 1, 0), (0, 9, 5), (1, 8, 7), (2, 40, 3), (3, 33, 1), (4, 8, 0), (4, 30, 9), (5, 3, 11), (6, 5, 7), (6, 17, 2 ** 20 + 3)])
 def test_lognormal1d_latency_variant_is_bit_identical(oracle, level, n, k0):
     """the latency variant for tiny batches (mle_kernel_ln1d_small.cuh: 8-sample tiles, whole field in shared memory, basis panels
     by cp.async.bulk, reciprocals in parallel, flux sums in sequence) against the throughput kernels and the oracle: the same
     per-sample values bit for bit -- one tile, partial tiles, several tiles per CTA, single and many panels"""
     outs = []
-    for small in (0, 1):
-        eng = _engine_with_env(MLE_LN_SMALL=small)
+    # throughput kernels | latency variant, one CTA per sample tile | latency variant with thread-block clusters on the fine grids
+    for env in (dict(MLE_LN_SMALL=0), dict(MLE_LN_SMALL=1, MLE_LN_CLUSTER=0), dict(MLE_LN_SMALL=1)):
+        eng = _engine_with_env(**env)
         z, lat, dl, d, gm, om = lognormal_setup(eng, oracle, 100, [level])
         sh = splitmix_uniforms(31 + level, 3 * 100).reshape(3, 100)
         got, smp = eng.sample_batch(gm, lat, d, [level], sh, k0, n, want_samples=True)
@@ -542,10 +543,11 @@ def test_lognormal1d_latency_variant_is_bit_identical(oracle, level, n, k0):
         outs.append((got, smp, mom_only))
         eng.close()
     want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, k0, n, want_samples=True)
-    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[1][1], smp_w)
-    assert np.array_equal(outs[1][0], outs[1][2])
-    check_moments(outs[1][0], want)
-    check_moments(outs[0][2], want)
+    for got, smp, mom_only in outs:
+        assert np.array_equal(smp, smp_w)
+        check_moments(got, want)
+        check_moments(mom_only, want)
+    assert np.array_equal(outs[1][0], outs[1][2]) and np.array_equal(outs[2][0], outs[2][2]) and np.array_equal(outs[1][0], outs[2][0])
 
 
 def test_lognormal1d_latency_variant_mc_and_other_shapes(oracle):
