@@ -58,14 +58,6 @@ __host__ __device__ constexpr size_t lns_smem_bytes(int mpad, int ntiles, int m,
            + 128 + lns_region_bytes(mpad, ntiles, cs) + 16;              // alignment slack, panels / reciprocals, mbarriers
 }
 
-// store to shared memory under a predicate the compiler cannot turn into a branch around the value's computation: several
-// evaluations in flight stay ONE straight-line block (ptxas interleaves their dependent chains) even when the last group of a
-// loop is partial.  (With plain `if (ok) p[i] = f(x)` the four evaluations of an iteration were sunk into four conditional
-// blocks and ran one after the other: 920 cycles for four exp instead of 250.)
-__device__ __forceinline__ void st_shared_if(double *p, double v, bool ok) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.f64 [%0], %1;\n}" ::"r"(smem_u32(p)), "d"(v), "r"((unsigned)ok) : "memory");
-}
-
 // the same into the shared memory of CTA `rank` of the cluster (distributed shared memory): `p` is the address the datum has in
 // THIS CTA's window -- every CTA of the cluster lays its shared memory out identically
 __device__ __forceinline__ void st_cluster_if(double *p, unsigned rank, double v, bool ok) {

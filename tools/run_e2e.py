@@ -8,18 +8,25 @@ import numpy as np
 
 
 class Counting:
-    """backend wrapper: counts the calls that reach the device / the oracle"""
+    """backend wrapper: counts the calls that reach the device / the oracle and the wall time spent inside them (the rest of a
+    run is the Python twin of the reference's host loop, identical on both arms)"""
     def __init__(self, inner):
-        self.inner, self.calls, self.samples = inner, 0, 0
+        self.inner, self.calls, self.samples, self.seconds = inner, 0, 0, 0.0
     def lattice(self, *a, **k): return self.inner.lattice(*a, **k)
     def dists(self, *a, **k): return self.inner.dists(*a, **k)
     def model(self, spec): return self.inner.model(spec)
     def sample_batch(self, model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=False):
         self.calls += 1; self.samples += n * (1 if shifts is None else len(shifts))
-        return self.inner.sample_batch(model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=want_samples)
+        t0 = time.perf_counter()
+        out = self.inner.sample_batch(model, lattice, dists, index, shifts, k0, n, m, mc_seed, want_samples=want_samples)
+        self.seconds += time.perf_counter() - t0
+        return out
     def update_samples(self, model, lattice, dists, entries, mc_seed):
         self.calls += 1; self.samples += sum(e[3] * (1 if e[1] is None else len(e[1])) for e in entries)
-        return self.inner.update_samples(model, lattice, dists, entries, mc_seed)
+        t0 = time.perf_counter()
+        out = self.inner.update_samples(model, lattice, dists, entries, mc_seed)
+        self.seconds += time.perf_counter() - t0
+        return out
 
 
 def measure(gpus=1, tols=(1e-4, 2e-5, 5e-6), reps=3, with_cpu=True):
@@ -43,9 +50,10 @@ def measure(gpus=1, tols=(1e-4, 2e-5, 5e-6), reps=3, with_cpu=True):
             est = make(be)
             t0 = time.perf_counter(); h = H.run(est, tol); dt = time.perf_counter() - t0
             if best is None or dt < best[0]:
-                best = (dt, be.calls, be.samples, h)
-        dt, calls, samples, hg = best
-        row.update(gpu_seconds=dt, gpu_calls=calls, gpu_calls_per_s=calls / dt, samples=samples, mean=hg["mean"], rmse=hg["rmse"],
+                best = (dt, be.calls, be.samples, h, be.seconds)
+        dt, calls, samples, hg, inside = best
+        row.update(gpu_seconds=dt, gpu_calls=calls, gpu_calls_per_s=calls / dt, gpu_seconds_in_library=inside,
+                   gpu_us_per_call_in_library=inside / calls * 1e6, samples=samples, mean=hg["mean"], rmse=hg["rmse"],
                    levels=len(hg["current_index_set"]))
         if with_cpu:
             bestc = None
@@ -54,8 +62,8 @@ def measure(gpus=1, tols=(1e-4, 2e-5, 5e-6), reps=3, with_cpu=True):
                 est = make(be)
                 t0 = time.perf_counter(); ho = H.run(est, tol); dtc = time.perf_counter() - t0
                 if bestc is None or dtc < bestc[0]:
-                    bestc = (dtc, ho)
-            row.update(cpu_seconds=bestc[0], speedup=bestc[0] / dt, same_decisions=bestc[1]["nb_of_samples"] == hg["nb_of_samples"],
+                    bestc = (dtc, ho, be.seconds)
+            row.update(cpu_seconds=bestc[0], cpu_seconds_in_oracle=bestc[2], speedup=bestc[0] / dt, speedup_in_library=bestc[2] / inside, same_decisions=bestc[1]["nb_of_samples"] == hg["nb_of_samples"],
                        mean_rel_diff=abs(bestc[1]["mean"] - hg["mean"]) / abs(hg["mean"]))
         out["tols"].append(row)
     eng.close()
