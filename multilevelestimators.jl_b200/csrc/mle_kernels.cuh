@@ -32,8 +32,14 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 //   Persistent CTAs loop over tiles; two shared-memory tile buffers so the TMA store of tile t overlaps tile t+1.
 //   Algorithmic traffic: 8 B written per coordinate (z and the shifts stay in L1/L2).
 // ===================================================================================================================
-constexpr int POINTS_THREADS = 256;
-constexpr int POINTS_TILE_CAP = 4096;  // elements per tile buffer (32 KB)
+#ifndef MLE_POINTS_THREADS
+#define MLE_POINTS_THREADS 256
+#endif
+constexpr int POINTS_THREADS = MLE_POINTS_THREADS;
+#ifndef MLE_POINTS_TILE_CAP
+#define MLE_POINTS_TILE_CAP 4096
+#endif
+constexpr int POINTS_TILE_CAP = MLE_POINTS_TILE_CAP;  // elements per tile buffer (32 KB)
 
 template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__restrict__ out, int P,
