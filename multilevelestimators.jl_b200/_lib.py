@@ -73,5 +73,10 @@ def load():
             fn.argtypes = args
         if lib.mle_abi_version() != 1:
             raise ImportError("libmle_cuda.so ABI version mismatch")
+        # second prototype of the hot call with every pointer as a plain address: the per-call marshalling of ndarray.ctypes /
+        # POINTER objects costs more than the launch itself for the tiny batches of the adaptive loop (engine.Engine.sample_batch)
+        proto = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
+                            _vp, _vp, _vp)
+        lib.mle_sample_batch_addr = proto(("mle_sample_batch", lib))
         _lib = lib
     return _lib

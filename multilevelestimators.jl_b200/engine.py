@@ -83,6 +83,7 @@ class Engine:
             raise MLEError("mle_init failed (%d): %s" % (rc, msg))
         self.ctx = ctx
         self.device = device
+        self._idx_cache, self._shift_cache = {}, {}
         sm, hbm, cc, nd = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
         self.lib.mle_device_info(self.ctx, C.byref(sm), C.byref(hbm), C.byref(cc))
         self.lib.mle_device_count(self.ctx, C.byref(nd))
@@ -199,23 +200,40 @@ class Engine:
                      want_time=False):
         """One `parallel_sample!` call.  -> moments float64[R, nqoi, 2, 3] = (n, mean, M2) for X in (dQ, Qf)
         [, samples float64[R, nqoi, 2, n]] [, gpu_seconds]"""
-        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.int32)
+        # the adaptive loop calls this thousands of times with the same index / shift arrays and 16 x (1 .. 100) samples, where a
+        # call is ~23 us in the library: addresses of the (kept alive) input arrays are remembered, the output goes through
+        # plain addresses (mle_sample_batch_addr) -- ~5 instead of ~15 us of marshalling per call
+        key = index if isinstance(index, tuple) else tuple(np.atleast_1d(index).tolist())
+        ent = self._idx_cache.get(key)
+        if ent is None:
+            arr = np.ascontiguousarray(key, dtype=np.int32)
+            ent = self._idx_cache[key] = (arr, arr.ctypes.data, len(key))
         if shifts is not None:
-            shifts = np.ascontiguousarray(shifts, dtype=np.float64)
-            if lattice is None or shifts.ndim != 2 or shifts.shape[1] != lattice.s:
-                raise MLEArgumentError("shifts must have shape [R, s]")
-            R = shifts.shape[0]
+            sent = self._shift_cache.get(id(shifts))
+            if sent is None or sent[0] is not shifts:
+                a = np.ascontiguousarray(shifts, dtype=np.float64)
+                if lattice is None or a.ndim != 2 or a.shape[1] != lattice.s:
+                    raise MLEArgumentError("shifts must have shape [R, s]")
+                sent = (shifts, a, a.ctypes.data, a.shape[0])
+                if a is shifts:  # remembered only when no copy was made: the library then reads the caller's own memory on
+                    if len(self._shift_cache) > 4096:  # every call (in-place changes are seen); the object is kept alive with
+                        self._shift_cache.clear()      # the entry, so its id cannot be reused while the entry exists
+                    self._shift_cache[id(shifts)] = sent
+            sh_addr, R = sent[2], sent[3]
         else:
-            R = 1
+            sh_addr, R = None, 1
         if m is None:
             m = dists.m if dists is not None else lattice.s
         mom = np.empty((R, model.nqoi, 2, 3))
         smp = np.empty((R, model.nqoi, 2, int(n))) if want_samples else None
-        t = C.c_double(0.0)
-        self._check(self.lib.mle_sample_batch(self.ctx, model.handle, lattice.handle if lattice else None,
-                                              dists.handle if dists else None, idx.ctypes.data_as(C.POINTER(C.c_int32)),
-                                              len(idx), _as_dp(shifts), R, int(k0), int(n), int(m), int(mc_seed),
-                                              _as_dp(mom), _as_dp(smp), C.byref(t) if want_time else None))
+        t = C.c_double(0.0) if want_time else None
+        rc = self.lib.mle_sample_batch_addr(self.ctx, model.handle, lattice.handle if lattice else None,
+                                            dists.handle if dists else None, ent[1], ent[2], sh_addr, R, int(k0), int(n), int(m),
+                                            int(mc_seed), mom.__array_interface__["data"][0],
+                                            smp.__array_interface__["data"][0] if want_samples else None,
+                                            C.addressof(t) if want_time else None)
+        if rc:
+            self._check(rc)
         out = (mom,)
         if want_samples:
             out += (smp,)
