@@ -1148,8 +1148,15 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
                 ra.use_scratch = (fixed + fbytes + (qbytes > fbytes ? qbytes : 0) > 200 * 1024) ? 1 : 0;               \
                 const size_t smem = fixed + (ra.use_scratch ? qbytes : fbytes + (qbytes > fbytes ? qbytes : 0));       \
                 if (smem <= 220 * 1024) {                                                                              \
-                const long long tps = (long long)((n + Cfg::S - 1) / Cfg::S);                                          \
                 const int occ = MLE_OCC_BY_MODE(g.mode, KK, Cfg::THREADS, smem);                                       \
+                /* samples per tile: S when the batch fills the resident CTAs, else as few as spread it over all of them */ \
+                {                                                                                                      \
+                    const long long slots = std::max<long long>(1, (long long)ctx->sm_count * occ / R);               \
+                    long long spt = (long long)((n + (uint64_t)slots - 1) / (uint64_t)slots);                          \
+                    spt = (spt + Cfg::CS - 1) / Cfg::CS * Cfg::CS;                                                     \
+                    ra.spt = (int)std::min<long long>(Cfg::S, std::max<long long>(Cfg::CS, spt));                      \
+                }                                                                                                      \
+                const long long tps = (long long)((n + (uint64_t)ra.spt - 1) / (uint64_t)ra.spt);                      \
                 gx = grid_x_for(ctx, tps, R, occ);                                                                     \
                 rc = ensure_dev(ctx, &ctx->d_partials, &ctx->partials_cap, (size_t)R * V * (size_t)gx);                \
                 if (rc) return rc;                                                                                     \

@@ -43,6 +43,8 @@ struct Lognormal2dRowsArgs {
     int use_scratch;      // F in global scratch instead of shared memory
     double *scratch;      // [CTAs in grid][ntiles*8*LDF]
     double *park;         // [CTAs in grid][ROWS_PARK][THREADS]: the upper half's centre block of every thread
+    int spt;              // samples per tile, a multiple of the CS samples solved concurrently, <= S: small batches are spread
+                          // over more CTAs instead of filling the S slots of a few (a tile's surplus slots are never solved)
 };
 
 // node values a[((j*sty)*lda + i*stx) * ns] of an Nx x Ny-cell grid (optionally y-mirrored); ns = distance between nodes
@@ -915,10 +917,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) lognormal2d_rows_kern
     const int Nx = la.Nx, Ny = la.Ny;
 
     for (long long ti = blockIdx.x; ti < tiles_per_shift; ti += gridDim.x) {
-        const unsigned long long i0 = (unsigned long long)ti * S;
+        const unsigned long long i0 = (unsigned long long)ti * (unsigned long long)la.spt;
         const unsigned long long left = g.n - i0;
-        const int Pt = left < (unsigned long long)S ? (int)left : S;
-        // A. inputs (always a full tile: surplus points are masked out of the statistics)
+        const int Pt = left < (unsigned long long)la.spt ? (int)left : la.spt;
+        // A. inputs (always S points: the field synthesis works on whole 8-sample DMMA tiles; surplus points are never solved)
         for (int j0 = 0; j0 < g.m; j0 += Cfg::GEN_DIMS)
             gen_tile_owned<THREADS, S, MODE, LDX, unsigned, 4>(xi + (size_t)j0 * LDX, j0, min(Cfg::GEN_DIMS, g.m - j0),
                                                               g.k0 + i0, g, r, sc);
@@ -947,8 +949,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) lognormal2d_rows_kern
             }
         }
         __syncthreads();
-        // C. solves: CS samples at a time
-        for (int rd = 0; rd < S / CS; ++rd) {
+        // C. solves: CS samples at a time; rounds without a live sample are skipped (a round is a sequential elimination of
+        // thousands of pivots: a 128 x 128 call of one sample used to pay for eight)
+        for (int rd = 0; rd * CS < Pt; ++rd) {
             const int grp = tid / TGS, tg = tid % TGS, sigma = rd * CS + grp;
             double *sh = gsh + grp * Cfg::SH;
             FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};
