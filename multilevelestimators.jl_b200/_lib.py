@@ -78,5 +78,6 @@ def load():
         proto = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
                             _vp, _vp, _vp)
         lib.mle_sample_batch_addr = proto(("mle_sample_batch", lib))
+        lib.mle_moments_merge_addr = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_size_t)(("mle_moments_merge", lib))
         _lib = lib
     return _lib

@@ -308,7 +308,9 @@ def moments_merge(acc, part):
     modified"""
     lib = _lib.load()
     acc = np.array(acc, dtype=np.float64, order="C", copy=True)
-    part = np.ascontiguousarray(part, dtype=np.float64)
+    if not (isinstance(part, np.ndarray) and part.dtype == np.float64 and part.flags.c_contiguous):
+        part = np.ascontiguousarray(part, dtype=np.float64)
     assert acc.shape == part.shape and acc.shape[-1] == 3
-    lib.mle_moments_merge(_as_dp(acc), _as_dp(part), acc.size // 3)
+    # plain addresses (the marshalling of two ndarray.ctypes objects costs more than the merge of a 16 x 2 table)
+    lib.mle_moments_merge_addr(acc.__array_interface__["data"][0], part.__array_interface__["data"][0], acc.size // 3)
     return acc

@@ -636,6 +636,8 @@ class Estimator:
         # history); the values only change when samples arrive, so they are memoised until then (the reference recomputes them
         # from the stored sample vectors on every query)
         self._memo = {}
+        self._bias_deps = {}     # bias memo key -> indices whose means entered it
+        self._keys_cache = None
         self._boundary_cache = {}
         self.samples = {}  # save_samples: index -> list of [R, q, 2, n] blocks (X = 0: differences, 1: fine values)
         self.shifts = {}
@@ -758,6 +760,7 @@ class Estimator:
         if not sum(work) > 0:   # a cost model that returns 0: share the time out by sample counts
             work = [float(n) for _, n in due]
         self._memo.clear()
+        self._bias_deps.clear()
         for (index, n), mom, w in zip(due, moms, work):
             self.moments[index] = moments_merge(self.moments[index], mom) if index in self.moments else np.array(mom, dtype=np.float64)
             self.nb_of_samples[index] += n
@@ -803,10 +806,16 @@ class Estimator:
         """new samples at `index` (None: the index sets changed): per-index statistics of the other indices stay valid"""
         if index is None:
             drop = [k for k in self._memo if k[0] in ("rates", "bias")]
+            self._keys_cache = None
         else:
-            drop = [k for k in self._memo if k[0] in ("rates", "bias") or k[1] == index]
+            # a bias estimate depends on the means of a few boundary indices only (recorded when it was computed): new samples
+            # elsewhere -- the QMC loop mostly feeds the coarse levels -- leave it valid
+            deps = self._bias_deps
+            drop = [k for k in self._memo if k[0] == "rates" or k[1] == index or (k[0] == "bias" and index in deps.get(k, (index,)))]
         for k in drop:
             del self._memo[k]
+            if k[0] == "bias":
+                self._bias_deps.pop(k, None)
 
     def _per_qoi(self, index, X, f):
         return self._cached(("pq", index, X, f), lambda: self._per_qoi_now(index, X, f))
@@ -867,7 +876,11 @@ class Estimator:
         return self.total_time[index] / n if n else float("nan")
 
     def keys(self):
-        return sorted(self.current_index_set, key=lambda t: t[::-1])
+        # (the set only grows between two clear() calls, so its size is its version)
+        c = self._keys_cache
+        if c is None or c[0] != len(self.current_index_set):
+            c = self._keys_cache = (len(self.current_index_set), sorted(self.current_index_set, key=lambda t: t[::-1]))
+        return list(c[1])
 
     def all_keys(self):
         if self.unbiased:  # every idx <= a sampled index holds samples
@@ -1040,6 +1053,7 @@ class Estimator:
 
     def clear(self):  # src/internals.jl:116, :200-206: samples persist across tolerances, the index sets do not
         self.current_index_set.clear()
+        self._keys_cache = None
         self.active_set.clear()
         self.old_set.clear()
         self.max_index_set.clear()
@@ -1061,20 +1075,30 @@ class Estimator:
         if self.unbiased:
             return 0.0     # src/methods.jl:347
         sz = self.sz if sz is None else sz
-        return self._cached(("bias", sz, self.max_sz), lambda: self._bias_now(sz))
+        key = ("bias", sz, self.max_sz)
+        v = self._memo.get(key)
+        if v is None:
+            used = set()
+            v = self._memo[key] = self._bias_now(sz, used)
+            self._bias_deps[key] = used
+        return v
 
-    def _bias_now(self, sz):
+    def _bias_now(self, sz, used=None):
+        used = set() if used is None else used   # the indices whose means enter the estimate (see _invalidate)
         if self.adaptive:  # src/methods.jl:253-260
+            used.update(self.active_set)
+            used.update(self.ad_boundary)
             b = lambda indices: abs(sum(self.mean(i) for i in sorted(indices, key=lambda t: t[::-1])))
             return b(self.active_set) if sz != self.max_sz else min(b(self.active_set), b(self.ad_boundary))
         nxt = [i for i in self.boundary(sz + 1) if i in self.current_index_set]
         if nxt and not self.options["robustify_bias_estimate"]:
+            used.update(self.boundary(sz + 1))
             return abs(sum(self.mean(i) for i in self.boundary(sz + 1)))
         xs, ys = [], []
         for x in range(max(1, sz - 2), sz + 1):
-            with np.errstate(divide="ignore"):
-                v = abs(sum(self.mean(i) for i in self.boundary(x)))
-                y = math.log2(v) if v > 0 else float("-inf")
+            used.update(self.boundary(x))
+            v = abs(sum(self.mean(i) for i in self.boundary(x)))   # plain floats: no numpy warning to silence
+            y = math.log2(v) if v > 0 else float("-inf")
             if math.isfinite(y):
                 xs.append(x)
                 ys.append(y)
@@ -1138,8 +1162,15 @@ class Estimator:
 
     def find_index_with_max_var_over_cost(self):
         keys = self.keys()
-        vals = [self.varest(i) / self.cost(i) for i in keys]
-        return keys[int(np.argmax(vals))]
+        best, bv = 0, None
+        for pos, i in enumerate(keys):  # np.argmax semantics: the first maximum, and a NaN counts as the maximum
+            v = self.varest(i) / self.cost(i)
+            if v != v:
+                best = pos
+                break
+            if bv is None or v > bv:
+                best, bv = pos, v
+        return keys[best]
 
 
 # ---------------------------------------------------------------------------------------------------------------
