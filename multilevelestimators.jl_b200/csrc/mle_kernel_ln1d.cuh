@@ -63,8 +63,7 @@ __device__ __forceinline__ void sweep_step(SweepState &s, int ip, double a, int 
 // (exact, so the result is the same correctly rounded 1/kappa)
 __device__ __forceinline__ double rcp_kappa(double a0, double a1) {
     const double den = __dmul_rn(0.5, __dadd_rn(a0, a1));
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double r = rcp_seed(den);
     double e = __fma_rn(-den, r, 1.0);
     e = __fma_rn(e, e, e);
     r = __fma_rn(r, e, r);

@@ -488,8 +488,7 @@ __host__ __device__ constexpr int dmma_sh_doubles(int w) { return 12 * w + 6 * w
 
 // correctly rounded 1/d for d well inside the normal range: ddiv_normal(1.0, d) without its exact product 1.0 * r
 __device__ __forceinline__ double drcp_normal(double den) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double r = rcp_seed(den);
     double e = __fma_rn(-den, r, 1.0);
     e = __fma_rn(e, e, e);
     r = __fma_rn(r, e, r);

@@ -568,6 +568,28 @@ def test_lognormal1d_latency_variant_mc_and_other_shapes(oracle):
         eng.close()
 
 
+@pytest.mark.parametrize("level,n", [(0, 5), (0, 3000), (2, 7), (2, 2500), (4, 3)])
+def test_lognormal1d_reciprocal_of_all_ones_mantissa(engine, oracle, level, n):
+    """a field that is 1 - 2^-53 at every node (one KL term phi = -2^-53 everywhere, input Uniform(1, 1 + 2^-52)): every interface
+    coefficient has an all-ones mantissa, the case in which a Newton reciprocal started from a seed with a zero low word sticks on
+    a tie and returns 1 instead of 1 + 2^-52 (found by tools/fuzz_parity.py, fixed by rcp_seed in csrc/mle_device.cuh, isolated in
+    tools/ddiv_seed_test.cu) -- latency variant and throughput kernels, bit for bit against the oracle's IEEE division"""
+    n0, N = 16, 16 << level
+    gm = engine.model("lognormal1d", 1, [n0])
+    om = oracle.Model(oracle.MODEL_LOGNORMAL1D, 1, [float(n0)])
+    phi = np.full((N + 1, 1), -2.0 ** -53)
+    gm.set_basis(level, phi)
+    om.set_basis(level, phi)
+    dl = [(0, [1.0, 1.0 + 2.0 ** -52])]   # xi is 1 or 1 + 2^-52: exp(phi xi) rounds to 1 - 2^-53 either way
+    z = oracle.genvec("K_3600_32", 1)
+    sh = splitmix_uniforms(3, 2).reshape(2, 1)
+    got, smp = engine.sample_batch(gm, engine.lattice(z, 1), engine.dists(dl), [level], sh, 0, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [level], sh, 0, n, want_samples=True)
+    assert np.array_equal(smp, smp_w)
+    assert smp_w[0, 0, 1, 0] != 0.125   # the oracle's value carries the rounded-up reciprocals: not the exact 1/8 of a == 1
+    check_moments(got, want)
+
+
 def test_lognormal2d_blocked_dmma_solver_equals_register_window_solver(oracle):
     """64 x 64 cells, where the register-window solver is the default: the blocked DMMA solver (MLE_2D_DMMA=2) and the solver
     without any DMMA blocking (MLE_2D_DMMA=0) give the same bits as the oracle"""

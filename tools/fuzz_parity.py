@@ -19,7 +19,16 @@ eng = mle_b200.Engine(0)
 DISTS = [(1, [0.0, 1.0]), (0, [-1.0, 2.0]), (2, [0.0, 1.0, -2.0, 2.0]), (1, [0.3, 0.6]), (2, [0.5, 2.0, -1.0, 3.0])]
 t0 = time.time()
 bad = 0
+ONLY = set(int(x) for x in os.environ["FUZZ_ONLY"].split(",")) if os.environ.get("FUZZ_ONLY") else None  # replay selected cases
+
+
+class _Skip:
+    def set_basis(self, *a): pass
+    def close(self): pass
+
+
 for case in range(cases):
+    run = ONLY is None or case in ONLY
     model = rng.choice(["expsum", "problem18", "lognormal1d", "lognormal2d", "lognormal2d_mi"])
     mc = bool(rng.integers(0, 2))
     general = bool(rng.integers(0, 3) == 0)
@@ -28,18 +37,18 @@ for case in range(cases):
     if model == "expsum":
         m = int(rng.integers(1, 140)); index = [int(rng.integers(0, 4))]; ndims = 1
         w = list(rng.random(m) * 0.3)
-        gm, om = eng.model("expsum", 1, [2.0] + w), O.Model(O.MODEL_EXPSUM, 1, [2.0] + w)
+        gm, om = (eng.model("expsum", 1, [2.0] + w), O.Model(O.MODEL_EXPSUM, 1, [2.0] + w)) if run else (_Skip(), _Skip())
         n = int(rng.integers(1, 700))
     elif model == "problem18":
         ndims = int(rng.integers(1, 3)); m = ndims; index = [int(x) for x in rng.integers(0, 4, ndims)]
-        gm, om = eng.model("problem18", ndims), O.Model(O.MODEL_PROBLEM18, ndims, [])
+        gm, om = (eng.model("problem18", ndims), O.Model(O.MODEL_PROBLEM18, ndims, [])) if run else (_Skip(), _Skip())
         n = int(rng.integers(1, 500)); general = False
     elif model == "lognormal1d":
-        n0 = int(rng.choice([4, 8, 16, 24])); lev = int(rng.integers(0, 5)); m = int(rng.integers(1, 150)); index = [lev]; ndims = 1
+        n0 = int(rng.choice([4, 8, 16, 24])); lev = int(rng.integers(0, 7 if n0 == 16 else 5)); m = int(rng.integers(1, 150)); index = [lev]; ndims = 1
         # every tenth case: a nearly constant quantity of interest (|mean| / std of Qf between 1e5 and 1e9)
         amp = (0.2 + 0.6 * rng.random()) * (10.0 ** -rng.integers(5, 10) if rng.integers(0, 10) == 0 else 1.0)
         phi = amp * kl.kl_basis_1d(lev, m=m, n0=n0)
-        gm, om = eng.model("lognormal1d", 1, [n0]), O.Model(O.MODEL_LOGNORMAL1D, 1, [float(n0)])
+        gm, om = (eng.model("lognormal1d", 1, [n0]), O.Model(O.MODEL_LOGNORMAL1D, 1, [float(n0)])) if run else (_Skip(), _Skip())
         gm.set_basis(lev, phi); om.set_basis(lev, phi)
         n = int(rng.integers(1, 300))
     else:
@@ -52,7 +61,7 @@ for case in range(cases):
         m = int(rng.integers(1, 90))
         amp = (0.2 + 0.6 * rng.random()) * (10.0 ** -rng.integers(5, 10) if rng.integers(0, 10) == 0 else 1.0)
         phi = amp * kl.kl_basis_2d(key, m=m, n0=n0)
-        gm, om = eng.model("lognormal2d", ndims, [n0]), O.Model(O.MODEL_LOGNORMAL2D, ndims, [float(n0)])
+        gm, om = (eng.model("lognormal2d", ndims, [n0]), O.Model(O.MODEL_LOGNORMAL2D, ndims, [float(n0)])) if run else (_Skip(), _Skip())
         gm.set_basis(key, phi); om.set_basis(key, phi)
         cells = (n0 << index[0]) * (n0 << index[-1])
         n = int(rng.integers(1, max(2, 60000 // (cells * max(8, n0 << index[0])))))
@@ -63,14 +72,18 @@ for case in range(cases):
     else:
         dl = [DISTS[0]] * m
     s = m + int(rng.integers(0, 3)) if not mc else m
-    d = eng.dists(dl)
+    d = eng.dists(dl) if run else None
     if mc:
         seed = int(rng.integers(0, 2**31))
+        if not run:
+            continue
         got, smp = eng.sample_batch(gm, None, d, index, None, k0, n, m=m, mc_seed=seed, want_samples=True)
         want, smp_w = O.sample_batch(om, None, dl, index, None, k0, n, m=m, mc_seed=seed, want_samples=True)
     else:
         z = O.genvec("K_3600_32", s)
         sh = rng.random((R, s))
+        if not run:
+            continue
         got, smp = eng.sample_batch(gm, eng.lattice(z, s), d, index, sh, k0, n, m=m, want_samples=True)
         want, smp_w = O.sample_batch(om, z, dl, index, sh, k0, n, m=m, want_samples=True)
     ok = np.array_equal(smp, smp_w, equal_nan=True) and np.array_equal(got[..., 0], want[..., 0])
@@ -84,6 +97,11 @@ for case in range(cases):
         print("MISMATCH case %d: %s index=%s ndims=%d mc=%s general=%s R=%d k0=%d n=%d m=%d s=%d  max|d|=%.3e" % (
             case, model, index, ndims, mc, general, R, k0, n, m, s, np.nanmax(np.abs(smp - smp_w))), flush=True)
         print("   samples equal:", np.array_equal(smp, smp_w, equal_nan=True), " got", got.reshape(-1, 3)[:4].tolist(), " want", want.reshape(-1, 3)[:4].tolist())
+        if ONLY is not None:
+            w = np.argwhere(smp != smp_w)
+            print("   n0 / level:", locals().get("n0"), index, " differing entries [r, q, X, i]:", w[:6].tolist())
+            for r_, q_, x_, i_ in w[:4]:
+                print("      got %s want %s" % (float(smp[r_, q_, x_, i_]).hex(), float(smp_w[r_, q_, x_, i_]).hex()))
     gm.close()
 print("%d cases, %d mismatches, %.1f s" % (cases, bad, time.time() - t0))
 sys.exit(1 if bad else 0)
