@@ -16,7 +16,8 @@ cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 O.build()
 eng = mle_b200.Engine(0)
-DISTS = [(1, [0.0, 1.0]), (0, [-1.0, 2.0]), (2, [0.0, 1.0, -2.0, 2.0]), (1, [0.3, 0.6]), (2, [0.5, 2.0, -1.0, 3.0])]
+DISTS = [(1, [0.0, 1.0]), (0, [-1.0, 2.0]), (2, [0.0, 1.0, -2.0, 2.0]), (1, [0.3, 0.6]), (2, [0.5, 2.0, -1.0, 3.0]),
+         (3, [2.0, 1.5]), (3, [0.7, 0.3])]   # ... Weibull(k, lambda)
 t0 = time.time()
 bad = 0
 ONLY = set(int(x) for x in os.environ["FUZZ_ONLY"].split(",")) if os.environ.get("FUZZ_ONLY") else None  # replay selected cases
@@ -29,7 +30,29 @@ class _Skip:
 
 for case in range(cases):
     run = ONLY is None or case in ONLY
-    model = rng.choice(["expsum", "problem18", "lognormal1d", "lognormal2d", "lognormal2d_mi"])
+    model = rng.choice(["expsum", "problem18", "lognormal1d", "lognormal2d", "lognormal2d_mi", "points"])
+    if model == "points":  # stages 1-2 alone (mle_points): every coordinate bit for bit
+        mcp = bool(rng.integers(0, 4) == 0)
+        m = int(rng.integers(1, 300)); s_ = m + int(rng.integers(0, 3)) if not mcp else m
+        R = 1 if mcp else int(rng.integers(1, 5))
+        k0 = int(rng.choice([0, 1, 7, 1000, 2**20 + 3, 2**31 + 11, 2**32 - 700]))
+        n = int(rng.integers(1, 600))
+        kind = int(rng.integers(0, 3))  # raw points / all Normal(0,1) / a mix of every distribution
+        dl = None if kind == 0 else ([DISTS[0]] * m if kind == 1 else [DISTS[int(i)] for i in rng.integers(0, len(DISTS), m)])
+        seed = int(rng.integers(0, 2**31)); sh = rng.random((R, s_))
+        if not run:
+            continue
+        dd = eng.dists(dl) if dl is not None else None
+        if mcp:
+            got = eng.points(None, dd, None, k0, n, m=m, mc_seed=seed); want = O.points(None, dl, None, k0, n, m=m, mc_seed=seed)
+        else:
+            z = O.genvec("K_3600_32", s_)
+            got = eng.points(eng.lattice(z, s_), dd, sh, k0, n, m=m); want = O.points(z, dl, sh, k0, n, m=m)
+        if not np.array_equal(got, want, equal_nan=True):
+            bad += 1
+            print("MISMATCH case %d: points mc=%s kind=%d R=%d k0=%d n=%d m=%d s=%d  differing %d  max ulp-ish %.3e" % (
+                case, mcp, kind, R, k0, n, m, s_, int(np.sum(got != want)), np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))), flush=True)
+        continue
     mc = bool(rng.integers(0, 2))
     general = bool(rng.integers(0, 3) == 0)
     R = 1 if mc else int(rng.integers(1, 6))
