@@ -62,6 +62,8 @@ for case in range(cases):
         w = list(rng.random(m) * 0.3)
         gm, om = (eng.model("expsum", 1, [2.0] + w), O.Model(O.MODEL_EXPSUM, 1, [2.0] + w)) if run else (_Skip(), _Skip())
         n = int(rng.integers(1, 700))
+        if rng.integers(0, 25) == 0:
+            n = int(rng.integers(20000, 300000))
     elif model == "problem18":
         ndims = int(rng.integers(1, 3)); m = ndims; index = [int(x) for x in rng.integers(0, 4, ndims)]
         gm, om = (eng.model("problem18", ndims), O.Model(O.MODEL_PROBLEM18, ndims, [])) if run else (_Skip(), _Skip())
@@ -74,6 +76,8 @@ for case in range(cases):
         gm, om = (eng.model("lognormal1d", 1, [n0]), O.Model(O.MODEL_LOGNORMAL1D, 1, [float(n0)])) if run else (_Skip(), _Skip())
         gm.set_basis(lev, phi); om.set_basis(lev, phi)
         n = int(rng.integers(1, 300))
+        if rng.integers(0, 25) == 0 and lev <= 3:  # now and then a batch that fills the SMs: the throughput kernels, many-wave grids
+            n = int(rng.integers(3000, 60000))
     else:
         ndims = 2 if model == "lognormal2d_mi" else 1
         n0 = int(rng.choice([2, 4, 4, 4, 6]))
