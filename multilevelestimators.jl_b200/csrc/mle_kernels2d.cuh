@@ -950,7 +950,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) lognormal2d_rows_kern
         __syncthreads();
         // C. solves: CS samples at a time; rounds without a live sample are skipped (a round is a sequential elimination of
         // thousands of pivots: a 128 x 128 call of one sample used to pay for eight)
-        for (int rd = 0; rd * CS < Pt; ++rd) {
+        // (how the loop is bounded matters to ptxas at the register caps of these kernels: a trip count read back from shared
+        // memory keeps the blocked DMMA solver at its old spill level -- a register-held count cost it 9 % --, the constant bound
+        // with an early exit is the better form for the register-window solvers)
+        if constexpr (Cfg::DMMA) {
+            if (tid == 0) reinterpret_cast<int *>(mred)[0] = (Pt + CS - 1) / CS;
+            __syncthreads();
+        }
+        for (int rd = 0; Cfg::DMMA ? rd < reinterpret_cast<volatile int *>(mred)[0] : rd < S / CS; ++rd) {
+            if (!Cfg::DMMA && rd * CS >= Pt) break;
             const int grp = tid / TGS, tg = tid % TGS, sigma = rd * CS + grp;
             double *sh = gsh + grp * Cfg::SH;
             FieldView fv{F + sigma, LDF, Nx + 1, 1, 1, Nx, Ny, 0, (double)Nx * (double)Nx, (double)Ny * (double)Ny};

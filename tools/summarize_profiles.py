@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn the scratch ncu output under gpurun_out/ into the tracked summaries under profiles/.
 
-usage: python tools/summarize_profiles.py <round tag> <launches.csv> <full .ncu-rep>
+usage: python tools/summarize_profiles.py <round tag> <launches.csv> <full .ncu-rep | its --page raw --csv export>
   profiles/<tag>_launches.csv        per-kernel totals of the `--metrics gpu__time_duration.sum` launch list
   profiles/<tag>_kernels.csv         one row per profiled launch of the `--set full` capture (key metrics)
 """
@@ -31,7 +31,9 @@ with open(os.path.join(root, tag + "_launches.csv"), "w", newline="") as f:
     for (p, k), v in tot.most_common():
         w.writerow([p, k, cnt[(p, k)], "%.4f" % v, "%.2f" % (100 * v / ours) if "mle::" in k else ""])
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# the full capture: a .ncu-rep, or its `ncu -i <rep> --page raw --csv` export (made on the GPU box when the report itself is too
+# large to bring back)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
