@@ -134,7 +134,8 @@ __device__ __forceinline__ void finalize_single(const Partial &a, double *out3) 
     const double s2 = __dadd_rn(0.0, __fma_rn(dc, __fma_rn(2.0, a.s1, t), a.s2));
     out3[0] = a.n;
     out3[1] = __dadd_rn(mu, __ddiv_rn(s1, a.n));
-    out3[2] = fmax(__dsub_rn(s2, __ddiv_rn(__dmul_rn(s1, s1), a.n)), 0.0);
+    const double m2 = __dsub_rn(s2, __ddiv_rn(__dmul_rn(s1, s1), a.n));
+    out3[2] = m2 < 0.0 ? 0.0 : m2;  // (not fmax: NaN stays NaN)
 }
 
 template <int MODE, bool CL>

@@ -18,6 +18,22 @@ O.build()
 eng = mle_b200.Engine(0)
 DISTS = [(1, [0.0, 1.0]), (0, [-1.0, 2.0]), (2, [0.0, 1.0, -2.0, 2.0]), (1, [0.3, 0.6]), (2, [0.5, 2.0, -1.0, 3.0]),
          (3, [2.0, 1.5]), (3, [0.7, 0.3])]   # ... Weibull(k, lambda)
+
+
+def random_dist(rng):
+    """a distribution with random parameters (the host-side preprocessing -- Phi(alpha), Phi(beta), 1/k -- must match the oracle's)"""
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        a = float(rng.normal() * 3); return (0, [a, a + float(rng.random() * 5 + 1e-3)])
+    if kind == 1:
+        return (1, [float(rng.normal() * 2), float(rng.random() * 3 + 1e-3)])
+    if kind == 2:
+        mu, sg = float(rng.normal()), float(rng.random() * 2 + 0.1)
+        a = mu + sg * float(rng.normal() * 2)
+        return (2, [mu, sg, a, a + sg * float(rng.random() * 4 + 1e-2)])
+    return (3, [float(rng.random() * 4.7 + 0.3), float(rng.random() * 3 + 0.1)])
+
+
 t0 = time.time()
 bad = 0
 ONLY = set(int(x) for x in os.environ["FUZZ_ONLY"].split(",")) if os.environ.get("FUZZ_ONLY") else None  # replay selected cases
@@ -38,7 +54,7 @@ for case in range(cases):
         k0 = int(rng.choice([0, 1, 7, 1000, 2**20 + 3, 2**31 + 11, 2**32 - 700]))
         n = int(rng.integers(1, 600))
         kind = int(rng.integers(0, 3))  # raw points / all Normal(0,1) / a mix of every distribution
-        dl = None if kind == 0 else ([DISTS[0]] * m if kind == 1 else [DISTS[int(i)] for i in rng.integers(0, len(DISTS), m)])
+        dl = None if kind == 0 else ([DISTS[0]] * m if kind == 1 else [random_dist(rng) if rng.integers(0, 2) else DISTS[int(rng.integers(0, len(DISTS)))] for _ in range(m)])
         seed = int(rng.integers(0, 2**31)); sh = rng.random((R, s_))
         if not run:
             continue
@@ -95,7 +111,7 @@ for case in range(cases):
     if model == "problem18":
         dl = [(0, [-0.5, 0.5])] * m
     elif general:
-        dl = [DISTS[int(i)] for i in rng.integers(0, len(DISTS), m)]
+        dl = [random_dist(rng) if rng.integers(0, 2) else DISTS[int(rng.integers(0, len(DISTS)))] for _ in range(m)]
     else:
         dl = [DISTS[0]] * m
     s = m + int(rng.integers(0, 3)) if not mc else m
@@ -118,13 +134,26 @@ for case in range(cases):
     # mean and M2 within 1e-12 relative, nearly constant samples (|mean| / std up to 1e9) included: the kernels accumulate
     # pivoted sums, whose error does not grow with (mean / std)^2 -- like the reference's two-pass Statistics.var
     m2_tol = 1e-12 * np.abs(want[..., 2]) + 1e-300
-    ok = ok and np.all(np.abs(got[..., 1] - want[..., 1]) <= 1e-12 * scale) and np.all(np.abs(got[..., 2] - want[..., 2]) <= m2_tol)
+    # samples outside the model's domain (overflowing fields, heavy-tailed inputs) give NaN / Inf statistics: those entries must be
+    # the same non-finite value on both sides; finite ones agree to 1e-12
+    with np.errstate(all="ignore"):
+        # (which non-finite value is not compared: with an Inf among the samples the reference's mean is Inf and its variance NaN,
+        # the pivoted device sums give NaN for both -- outside the models' documented domain either way)
+        same = lambda a, b: (a == b) | (~np.isfinite(a) & ~np.isfinite(b))
+        std = np.sqrt(want[..., 2] / np.maximum(want[..., 0], 1))
+        mscale = np.abs(want[..., 1]) + np.where(np.isfinite(std), std, 0.0)
+        ok = ok and np.all(np.where(np.isfinite(want[..., 1]), np.abs(got[..., 1] - want[..., 1]) <= 1e-12 * mscale, same(got[..., 1], want[..., 1]))) \
+            and np.all(np.where(np.isfinite(want[..., 2]), np.abs(got[..., 2] - want[..., 2]) <= m2_tol, same(got[..., 2], want[..., 2])))
     if not ok:
         bad += 1
         print("MISMATCH case %d: %s index=%s ndims=%d mc=%s general=%s R=%d k0=%d n=%d m=%d s=%d  max|d|=%.3e" % (
             case, model, index, ndims, mc, general, R, k0, n, m, s, np.nanmax(np.abs(smp - smp_w))), flush=True)
         print("   samples equal:", np.array_equal(smp, smp_w, equal_nan=True), " got", got.reshape(-1, 3)[:4].tolist(), " want", want.reshape(-1, 3)[:4].tolist())
         if ONLY is not None:
+            with np.errstate(all="ignore"):
+                e1 = np.abs(got[..., 1] - want[..., 1]) / scale
+                e2 = np.abs(got[..., 2] - want[..., 2]) / np.abs(want[..., 2])
+            print("   worst mean error / scale %.3e, worst relative M2 error %.3e, n equal: %s" % (np.nanmax(e1), np.nanmax(e2), np.array_equal(got[..., 0], want[..., 0])))
             w = np.argwhere(smp != smp_w)
             print("   n0 / level:", locals().get("n0"), index, " differing entries [r, q, X, i]:", w[:6].tolist())
             for r_, q_, x_, i_ in w[:4]:
