@@ -590,6 +590,24 @@ def test_lognormal1d_reciprocal_of_all_ones_mantissa(engine, oracle, level, n):
     check_moments(got, want)
 
 
+@pytest.mark.parametrize("n", [64, 4000])
+def test_overflowing_samples_leave_non_finite_statistics(engine, oracle, n):
+    """exp(sum a_j xi_j) with a_j = 300 overflows for part of the inputs: the samples are Inf on both sides (one exp algorithm), and
+    the variance of a shift that contains them is non-finite like var() of the reference -- the M2 clamp must not turn the NaN
+    into 0 (it did, through fmax; found by tools/fuzz_parity.py with random distribution parameters)"""
+    s_ = 4
+    z = oracle.genvec("K_3600_32", s_)
+    w = [300.0] * s_
+    gm, om = engine.model("expsum", 1, [4.0] + w), oracle.Model(oracle.MODEL_EXPSUM, 1, [4.0] + w)
+    sh = splitmix_uniforms(11, 2 * s_).reshape(2, s_)
+    dl = [NORMAL01] * s_
+    got, smp = engine.sample_batch(gm, engine.lattice(z, s_), engine.dists(dl), [0], sh, 0, n, want_samples=True)
+    want, smp_w = oracle.sample_batch(om, z, dl, [0], sh, 0, n, want_samples=True)
+    assert np.array_equal(smp, smp_w, equal_nan=True)
+    assert np.any(np.isinf(smp_w))
+    assert np.array_equal(np.isfinite(got[..., 2]), np.isfinite(want[..., 2])) and not np.all(np.isfinite(want[..., 2]))
+
+
 def test_lognormal2d_blocked_dmma_solver_equals_register_window_solver(oracle):
     """64 x 64 cells, where the register-window solver is the default: the blocked DMMA solver (MLE_2D_DMMA=2) and the solver
     without any DMMA blocking (MLE_2D_DMMA=0) give the same bits as the oracle"""
