@@ -127,8 +127,20 @@ for case in range(cases):
         sh = rng.random((R, s))
         if not run:
             continue
-        got, smp = eng.sample_batch(gm, eng.lattice(z, s), d, index, sh, k0, n, m=m, want_samples=True)
+        lat_ = eng.lattice(z, s)
+        got, smp = eng.sample_batch(gm, lat_, d, index, sh, k0, n, m=m, want_samples=True)
         want, smp_w = O.sample_batch(om, z, dl, index, sh, k0, n, m=m, want_samples=True)
+        if case % 7 == 0 and k0 + 2 * n + 5 < 2**32:
+            # one update_samples call (several sample! requests, one synchronisation) against the same requests one by one: the
+            # moment tables must be the same bits (same kernels, same partition), whatever the arena / flag plumbing does
+            sh2 = sh[::-1].copy()
+            entries = [(index, sh, k0, n, m), (index, sh2, k0 + n, n + 3, m), (index, sh, k0 + 1, max(1, n // 2), m)]
+            many = eng.update_samples(gm, lat_, d, entries)
+            for (ix, shx, kx, nx, mx), tab in zip(entries, many):
+                one = eng.sample_batch(gm, lat_, d, ix, shx, kx, nx, m=mx)
+                if not np.array_equal(tab, one, equal_nan=True):
+                    bad += 1
+                    print("MISMATCH case %d: update_samples vs sample_batch, %s index=%s R=%d k0=%d n=%d m=%d" % (case, model, ix, R, kx, nx, mx), flush=True)
     ok = np.array_equal(smp, smp_w, equal_nan=True) and np.array_equal(got[..., 0], want[..., 0])
     scale = np.sqrt(want[..., 2] / np.maximum(want[..., 0], 1)) + np.abs(want[..., 1])
     # mean and M2 within 1e-12 relative, nearly constant samples (|mean| / std up to 1e9) included: the kernels accumulate
