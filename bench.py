@@ -584,6 +584,11 @@ def run_ours(args):
                     # FP64 + DMMA pipe-busy fractions of the 7 launches, read from the committed ncu summary of this command
                     # (profiles/r02_final_kernels.csv: sm__inst_executed_pipe_fp64 + sm__pipe_tensor_cycles_active); None when absent
                     "pipe_busy_ncu_per_level": ncu_pipe_busy(),
+                    # the same, weighted by this run's measured launch times: the share of the step during which the FP64 pipe
+                    # (the roof of these kernels) was busy -- `frac` counts algorithmic FLOPs against a roof only a pure FMA
+                    # stream reaches (at 100 % pipe utilisation `frac` would be 0.65)
+                    "pipe_busy_time_weighted": (lambda pb: None if not pb or len(pb) != len(lvl_ms) else
+                                                round(sum(p * t for p, t in zip(pb, lvl_ms)) / sum(lvl_ms), 4))(ncu_pipe_busy()),
                     "per_level_ms": lvl_ms,
                     "per_level_samples_per_s": [n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) for li in range(len(LEVELS))],
                     "per_level_tflops": [algorithmic_flops_per_sample(lev) * n_l[li] * R_SHIFTS / (lvl_ms[li] * 1e-3) * 1e-12

@@ -1043,7 +1043,7 @@ static int launch_batch(mle_ctx ctx, mle_model M, mle_lattice lat, mle_dists dis
         const bool block = ctx->ln_block >= 0 ? ctx->ln_block != 0 : la.ntiles > 2;
         // tiny batches (the 16 x (1 .. 100)-sample calls of the adaptive loop, src/run.jl:96-113): the latency variant -- 8-sample
         // tiles, the whole field of a tile in shared memory, every phase but the flux sums spread over the CTA -- while its tiles
-        // fit in two waves of CTAs; measured 16-22 -> 8-10 us per launch at l <= 3 and 88 -> 19 us at l = 6 for 16 x 1 samples
+        // fit in two waves of CTAs; measured (back-to-back launches of 16 x 1 samples) 16-22 -> 10-12 us at l <= 3, 88 -> 18 us at l = 6
         bool small_done = false;
         if (ctx->ln_small != 0 && g.m <= 1024 && la.N % 2 == 0 && (level == 0 || la.N % 4 == 0)) {
             const long long tps = (long long)((n + LNS_BT - 1) / LNS_BT);

@@ -8,7 +8,7 @@
 //
 // Same model, same arithmetic per sample and the same basis layout; the schedule is organised around the critical path instead:
 //   tile = 8 samples of one shift (ONE 8-wide DMMA sample tile), 256 threads, the whole field of the tile in shared memory.
-//   A. inputs: gen_tile_owned with 32 threads per point (3-4 coordinates each instead of 25-100 in sequence).
+//   A. inputs: gen_tile_wide (below): 32 threads per point, 3-4 coordinates each instead of 25-100 in sequence.
 //   B. KL contraction: the basis streams through two shared-memory panels of 8 row tiles (TMA bulk loads + mbarriers, two panels
 //      in flight); warp w takes row tile w of the panel: one chain of `nks` DMMAs (ascending k, as everywhere); the raw sums go
 //      to G[row][sample].  The mid-node chain rides along in warp 0's first panel.
@@ -16,7 +16,10 @@
 //   D. all reciprocals r = 1/kappa of the fine AND the coarse grid, all threads (rcp_kappa: the Newton sequence of the sweeps).
 //   E. the only sequential part: per (grid, side, sample) one thread adds its edges from the boundary towards the mid node,
 //      A += r, D = fma(w, r, D) -- the oracle's order (oracle/mle_oracle.c:tridiag_mid), two dependent operations per edge.
-//   F. the sides meet, (dQ, Qf), per-thread pivoted statistics, cta_finalize.
+//   F. the sides meet, (dQ, Qf), per-thread pivoted statistics, cta_finalize (moments in the CTA when it saw the whole shift).
+// Fine grids (>= 16 row tiles): a thread-block CLUSTER shares one sample tile -- every rank contracts, exponentiates and inverts
+// 1/cs of the rows and stores its reciprocals into the leader's shared memory (DSMEM), the leader runs E-F.  One SM takes the basis
+// in at ~28 bytes per clock, which at level 6 (819 KB) is 14 us: the split, not a faster inner loop, is what removes it.
 // Per-sample values are bit-identical to the other two schedules and to the oracle (tests/test_gpu_batch.py).
 #pragma once
 #include "mle_kernel_ln1d.cuh"
