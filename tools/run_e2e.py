@@ -70,10 +70,54 @@ def measure(gpus=1, tols=(1e-4, 2e-5, 5e-6), reps=3, with_cpu=True):
     return out
 
 
+def measure_2d(config="c4", gpus=1, tol=None, reps=2, with_cpu=True):
+    """the same for the 2-D models: c4 = AD(2)/QMC on the anisotropic multi-index model (100 KL terms, 16 shifts, indices up to size
+    4), c3 = ML()/MC() on the multilevel model (400 KL terms, levels <= 4)"""
+    import mle_b200, mle_b200.host as H, mle_b200.kl as kl
+    from oracle_backend import OracleBackend
+    if config == "c4":
+        m, L = 100, 4
+        bases = {i: kl.kl_basis_2d(i, m=m) for i in H.TD(2).get_index_set(L)}
+        spec = H.ModelSpec("lognormal2d", 2, [4], bases)
+        tol = 1e-5 if tol is None else tol
+        make = lambda be: H.Estimator(H.AD(2), H.QMC(), spec, [H.Normal()] * m, be, max_index_set_param=L, nb_of_shifts=16,
+                                      nb_of_warm_up_samples=8, cost_model=lambda i: 2.0 ** sum(i), nb_of_tols=4, min_index_set_param=1, shift_seed=7)
+        name = "C4: AD(2)/QMC(), lognormal2d multi-index, 16 shifts, 100 KL terms, indices of size <= 4, cost model 2^|index|"
+    else:
+        m, L = 400, 4
+        spec = H.ModelSpec("lognormal2d", 1, [4], {lev: kl.kl_basis_2d(lev, m=m) for lev in range(L + 1)})
+        tol = 2e-5 if tol is None else tol
+        make = lambda be: H.Estimator(H.ML(), H.MC(), spec, [H.Normal()] * m, be, max_index_set_param=L, cost_model=lambda i: 4.0 ** i[0],
+                                      nb_of_tols=4, mc_seed=11)
+        name = "C3: ML()/MC(), lognormal2d, 400 KL terms, levels <= 4, cost model 4^l"
+    eng = mle_b200.Engine(list(range(gpus)) if gpus > 1 else 0)
+    row = {"config": name + ", run(estimator, %g)" % tol, "gpus": gpus, "cpu_cores": os.cpu_count(), "tol": tol}
+    best = None
+    for _ in range(reps):
+        be = Counting(H.GpuBackend(eng)); est = make(be)
+        t0 = time.perf_counter(); h = H.run(est, tol); dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, be.calls, be.samples, h, be.seconds)
+    dt, calls, samples, hg, inside = best
+    row.update(gpu_seconds=dt, gpu_calls=calls, gpu_seconds_in_library=inside, samples=samples, mean=hg["mean"], rmse=hg["rmse"],
+               indices=len(hg["current_index_set"]))
+    if with_cpu:
+        be = Counting(OracleBackend()); est = make(be)
+        t0 = time.perf_counter(); ho = H.run(est, tol); dtc = time.perf_counter() - t0
+        row.update(cpu_seconds=dtc, cpu_seconds_in_oracle=be.seconds, speedup=dtc / dt, speedup_in_library=be.seconds / inside,
+                   same_decisions=ho["nb_of_samples"] == hg["nb_of_samples"], mean_rel_diff=abs(ho["mean"] - hg["mean"]) / abs(hg["mean"]))
+    eng.close()
+    return row
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--tols", default="1e-4,2e-5,5e-6")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"])
     a = ap.parse_args()
+    if a.config != "c2":
+        print(json.dumps(measure_2d(a.config, a.gpus, with_cpu=not a.no_cpu)))
+        sys.exit(0)
     print(json.dumps(measure(a.gpus, tuple(float(t) for t in a.tols.split(",")), with_cpu=not a.no_cpu)))
