@@ -636,6 +636,7 @@ class Estimator:
         # history); the values only change when samples arrive, so they are memoised until then (the reference recomputes them
         # from the stored sample vectors on every query)
         self._memo = {}
+        self._no_memo = False
         self._bias_deps = {}     # bias memo key -> indices whose means entered it
         self._keys_cache = None
         self._boundary_cache = {}
@@ -797,7 +798,7 @@ class Estimator:
         return float(values[self.options["qoi_with_max_var"] - 1])
 
     def _cached(self, key, fn):
-        v = self._memo.get(key)
+        v = None if self._no_memo else self._memo.get(key)   # (_no_memo: tests run the loop without any memoisation)
         if v is None:
             v = self._memo[key] = fn()
         return v
@@ -878,7 +879,7 @@ class Estimator:
     def keys(self):
         # (the set only grows between two clear() calls, so its size is its version)
         c = self._keys_cache
-        if c is None or c[0] != len(self.current_index_set):
+        if c is None or c[0] != len(self.current_index_set) or self._no_memo:
             c = self._keys_cache = (len(self.current_index_set), sorted(self.current_index_set, key=lambda t: t[::-1]))
         return list(c[1])
 
@@ -1076,7 +1077,7 @@ class Estimator:
             return 0.0     # src/methods.jl:347
         sz = self.sz if sz is None else sz
         key = ("bias", sz, self.max_sz)
-        v = self._memo.get(key)
+        v = None if self._no_memo else self._memo.get(key)
         if v is None:
             used = set()
             v = self._memo[key] = self._bias_now(sz, used)

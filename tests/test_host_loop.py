@@ -915,3 +915,33 @@ def test_verbose_report_follows_print_jl(capsys):
 
     out, h = run(H.SL(), "MC", 1, 5e-2)
     assert "Currently running on finest level." in out and "Checking convergence..." not in out
+
+
+@pytest.mark.parametrize("case", ["ml_qmc", "td_qmc", "ad_qmc", "ml_mc"])
+def test_memoisation_does_not_change_a_run(case):
+    """the host loop remembers statistics between queries (per-index moments, rates, bias estimates -- the latter invalidated only
+    by new samples on the indices they were computed from, sorted key lists); a run with every cache switched off must take the
+    same decisions and return the same History"""
+    H = host()
+
+    def make():
+        if case == "ml_qmc":
+            return H.Estimator(H.ML(), H.QMC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                               nb_of_shifts=8, cost_model=lambda i: 2.0 ** i[0], shift_seed=3, max_index_set_param=5)
+        if case == "td_qmc":
+            return H.Estimator(H.TD(2), H.QMC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(), nb_of_qoi=13,
+                               nb_of_shifts=8, cost_model=lambda i: 2.0 ** sum(i), shift_seed=3, max_index_set_param=4)
+        if case == "ad_qmc":
+            return H.Estimator(H.AD(2), H.QMC(), H.ModelSpec("problem18", 2), [H.Uniform(-0.5, 0.5)] * 2, OracleBackend(), nb_of_qoi=13,
+                               nb_of_shifts=8, cost_model=lambda i: 2.0 ** sum(i), shift_seed=3, max_index_set_param=4)
+        return H.Estimator(H.ML(), H.MC(), H.ModelSpec("problem18", 1), [H.Uniform(-0.5, 0.5)], OracleBackend(), nb_of_qoi=13,
+                           cost_model=lambda i: 2.0 ** i[0], mc_seed=5, max_index_set_param=5)
+    a, b = make(), make()
+    b._no_memo = True
+    ha, hb = H.run(a, 3e-4), H.run(b, 3e-4)   # ten tolerances, ~70 sample! calls on four levels (ml_qmc)
+    assert len(ha) == len(hb)
+    for i in range(len(ha)):
+        for key in ("nb_of_samples", "current_index_set", "mean", "varest", "bias", "rmse", "alpha", "beta", "gamma", "dE", "dV"):
+            assert repr(ha[i][key]) == repr(hb[i][key]), (i, key)
+    if case == "ad_qmc":
+        assert ha["logbook"] == hb["logbook"]
