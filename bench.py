@@ -14,7 +14,8 @@ Extra keys of the JSON line: `strong` (the same step with every le
 work), `extra.c3` (config C3: MLMC on the 2-D lognormal model, 400 KL terms, levels 0-5, point slices per rank + merge),
 `extra.c4` (config C4: multi-index QMC batches on the 2-D anisotropic model over the indices of TD(2) up to size 3),
 `extra.c5` (config C5: 2^24 lattice points x 1000 dims, fused generate -> integrand -> moments), `run_e2e` (N = 1: wall time of
-run(estimator, tol) on the GPU backend vs the CPU oracle backend, tools/run_e2e.py).
+run(estimator, tol) on the GPU backend vs the CPU oracle backend, tools/run_e2e.py; `run_e2e.two_d`: the same for whole runs of
+the 2-D configurations C4 and C3).
 Launched WITHOUT torchrun and --gpus N > 1 the bench runs single-process on ONE multi-GPU context (mle_init_multi).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -638,6 +639,8 @@ def run_ours(args):
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import run_e2e as RE
                 run_e2e = RE.measure(1, tols=(1e-4, 2e-5, 5e-6, 1e-6), reps=3)
+                # whole runs of the 2-D configurations (C4: AD(2)/QMC multi-index, C3: ML/MC), same two arms
+                run_e2e["two_d"] = [RE.measure_2d("c4", 1), RE.measure_2d("c3", 1)]
             except Exception as e:  # noqa: BLE001
                 run_e2e = {"error": repr(e)}
         cpu = None
