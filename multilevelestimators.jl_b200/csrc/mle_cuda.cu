@@ -903,7 +903,11 @@ extern "C" int mle_points_dev(mle_ctx ctx, mle_lattice lat, mle_dists dists, con
     const int P = POINTS_TILE_CAP / m > 0 ? POINTS_TILE_CAP / m : 1;
     const long long tps = (long long)((n + (uint64_t)P - 1) / (uint64_t)P);
     const long long ntiles = tps * R;
+#ifdef MLE_POINTS_DOUBLE_BUF
     const size_t smem = 2 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + (POINTS_THREADS / 32) * 4;
+#else
+    const size_t smem = 1 * POINTS_TILE_CAP * sizeof(double) + POINTS_TILE_CAP * sizeof(unsigned short) + (POINTS_THREADS / 32) * 4;
+#endif
     long long grid = (long long)ctx->sm_count * MLE_OCC_BY_MODE(g.mode, points_k, POINTS_THREADS, smem);
     if (grid > ntiles) grid = ntiles;
     grid = churn_grid_x(grid, ntiles);

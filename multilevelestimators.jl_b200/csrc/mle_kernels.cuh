@@ -29,7 +29,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // ===================================================================================================================
 // K1 / K2: points -> HBM
 //   out[(r*n + i)*m + j].  One tile = P consecutive points of one shift = P*m consecutive doubles of `out`.
-//   Persistent CTAs loop over tiles; two shared-memory tile buffers so the TMA store of tile t overlaps tile t+1.
+//   Persistent CTAs loop over tiles; the tile leaves through one TMA bulk store (five resident CTAs overlap each other's stores).
 //   Algorithmic traffic: 8 B written per coordinate (z and the shifts stay in L1/L2).
 // ===================================================================================================================
 #ifndef MLE_POINTS_THREADS
@@ -46,7 +46,14 @@ __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__re
                                                          long long tiles_per_shift, long long ntiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *buf0 = reinterpret_cast<double *>(smem_raw);
+#ifdef MLE_POINTS_DOUBLE_BUF  // A/B switch: two tile buffers (73.7 KB per CTA, 3 resident CTAs), the store of tile t overlapping tile t+1
     double *buf1 = buf0 + POINTS_TILE_CAP;
+#else
+    // ONE tile buffer: 41 KB per CTA -> 5 resident CTAs instead of 3.  The other CTAs of the SM cover the wait for the bulk store
+    // better than a second buffer did: raw points 5.28 -> 5.80 TB/s (0.81 -> 0.89 of the measured copy peak), with the Normal
+    // inverse CDF 1.81 -> 1.88 TB/s
+    double *buf1 = buf0;
+#endif
     GenScratch sc;
     sc.queue = reinterpret_cast<unsigned short *>(buf1 + POINTS_TILE_CAP);
     sc.wtot = reinterpret_cast<unsigned *>(sc.queue + POINTS_TILE_CAP);
@@ -60,9 +67,13 @@ __global__ void __launch_bounds__(THREADS) points_kernel(GenArgs g, double *__re
         const unsigned long long left = g.n - i0;
         const int Pt = left < (unsigned long long)P ? (int)left : P;
         double *buf = (it & 1) ? buf1 : buf0;
-        // the bulk store issued two iterations ago read this buffer: thread 0 waits until at most one store is still
-        // reading, and nobody writes the buffer before that wait has returned
+        // the previous bulk store of this CTA read this buffer: thread 0 waits until it has been read, and nobody writes the
+        // buffer before that wait has returned (the barrier below)
+#ifdef MLE_POINTS_DOUBLE_BUF
         if (threadIdx.x == 0) bulk_wait_read<1>();
+#else
+        if (threadIdx.x == 0) bulk_wait_read<0>();
+#endif
         __syncthreads();
         gen_tile_dense<THREADS, MODE>(buf, Pt, m, g.k0 + i0, g, r, sc);
         double *dst = out + ((size_t)r * g.n + i0) * (size_t)m;
