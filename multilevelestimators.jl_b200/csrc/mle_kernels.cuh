@@ -108,7 +108,10 @@ struct SimpleModelArgs {
 };
 
 constexpr int SIMPLE_THREADS = 128;       // = points per tile: every thread owns one point
-constexpr int SIMPLE_MC = 32;             // dims per chunk; tile[jj][point] (point fastest: conflict-free); 32 dims =
+#ifndef MLE_SIMPLE_MC
+#define MLE_SIMPLE_MC 32
+#endif
+constexpr int SIMPLE_MC = MLE_SIMPLE_MC;  // dims per chunk; tile[jj][point] (point fastest: conflict-free); 32 dims =
                                           // one 32-bit class mask per thread and 40 KB per CTA (5 CTAs per SM)
 
 // problem_18                                                      test/regression.jl:17-36 (1-d), :69-103 (2-d)
